@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI in include/dat_b200.h (libdat_b200.so).
+
+The library is the product; this file only marshals raw device pointers and the
+current CUDA stream.  There is no fallback: if the shared library is missing the
+import of the CUDA path fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdat_b200.so")
+
+DAT_F32, DAT_BF16 = 0, 1
+HEAD_DIM = 32
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_heads", C.c_int32),
+                ("n_groups", C.c_int32), ("stride", C.c_int32), ("ksize", C.c_int32),
+                ("table_h", C.c_int32), ("table_w", C.c_int32),
+                ("offset_range_factor", C.c_float), ("x_dtype", C.c_int32),
+                ("act_dtype", C.c_int32)]
+
+
+PARAM_FIELDS = ("off_dw_w", "off_dw_b", "off_ln_g", "off_ln_b", "off_pw_w", "wq", "bq", "wk", "bk",
+                "wv", "bv", "wo", "bo", "rpe_table")
+# state-dict key of every field (reference names, dat_blocks.py:51-104)
+PARAM_KEYS = ("conv_offset.0.weight", "conv_offset.0.bias", "conv_offset.1.norm.weight",
+              "conv_offset.1.norm.bias", "conv_offset.3.weight", "proj_q.weight", "proj_q.bias",
+              "proj_k.weight", "proj_k.bias", "proj_v.weight", "proj_v.bias", "proj_out.weight",
+              "proj_out.bias", "rpe_table")
+SAVED_FIELDS = ("q", "t_dw", "off_raw", "pos", "xs", "k", "v", "o", "lse")
+
+
+class BlockParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class BlockGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class BlockSaved(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in SAVED_FIELDS]
+
+
+class DatError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libdat_b200.so (built by dat_segmentation_b200/build.py).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DatError(f"{LIB_PATH} is missing — build it with `python -m dat_segmentation_b200.build` "
+                       "(there is no CPU or PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    dp = C.POINTER(BlockDesc)
+    L.dat_last_error.restype = C.c_char_p
+    L.dat_version.restype = C.c_char_p
+    L.dat_sample_grid.argtypes = [dp, C.POINTER(i32), C.POINTER(i32)]
+    L.dat_block_fwd_workspace_bytes.argtypes = [dp]
+    L.dat_block_fwd_workspace_bytes.restype = C.c_size_t
+    L.dat_block_bwd_workspace_bytes.argtypes = [dp]
+    L.dat_block_bwd_workspace_bytes.restype = C.c_size_t
+    L.dat_block_forward.argtypes = [dp, C.POINTER(BlockParams), vp, vp, C.POINTER(BlockSaved), vp,
+                                    C.c_size_t, vp]
+    L.dat_block_backward.argtypes = [dp, C.POINTER(BlockParams), vp, vp, C.POINTER(BlockSaved), vp,
+                                     C.POINTER(BlockGrads), vp, C.c_size_t, vp]
+    L.dat_pointwise_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, i64, i32, i32, vp]
+    L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
+    L.dat_ref_points.argtypes = [i32, i32, f32p, f32p, vp]
+    L.dat_sample_fwd.argtypes = [dp, vp, f32p, vp, vp, vp]
+    L.dat_attention_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp]
+    L.dat_rpe_bias.argtypes = [dp, f32p, f32p, f32p, vp]
+    for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
+                 "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd", "dat_attention_fwd",
+                 "dat_rpe_bias"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dat_last_error().decode("utf-8", "replace")
+        raise DatError(f"{what} failed (code {rc}): {msg}")
+
+
+def exported_symbols():
+    """Names declared in include/dat_b200.h (used by the CPU-side symbol test)."""
+    return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
+            "dat_last_error", "dat_version", "dat_block_forward", "dat_block_backward",
+            "dat_pointwise_fwd", "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd",
+            "dat_attention_fwd", "dat_rpe_bias"]

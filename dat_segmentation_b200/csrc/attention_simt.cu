@@ -1,0 +1,483 @@
+// Fused attention core of the block on CUDA cores, fp32 math throughout:
+//   S = (Q K^T) * hc^-0.5 + bilinear(rpe_table, (q_grid - pos) / 2);  P = softmax(S);  O = P V
+// (dat_blocks.py:180-223; bias branch :198-214, q grid :123-136), plus its backward.
+//
+// This is the exact-precision path (fp32 parity to 1e-5 needs fp32 products) and the
+// shape-generic fallback; the bf16 hot path is the tcgen05 kernel in attention_tc.cu.
+// The score matrix, displacement tensor and bias tensor of the reference (3 x 8.4 MB per
+// image at stage 2) are never materialised: each thread owns one query, streams the
+// sampled keys/values of its head through shared memory and evaluates the 4-tap bias
+// on the fly from a shared-memory copy of the head's table (online softmax).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dat {
+
+namespace {
+
+constexpr int HC = DAT_HEAD_DIM;  // 32
+constexpr int ATT_THREADS = 128;
+constexpr int KV_CHUNK = 64;
+constexpr int Q_CHUNK = 32;
+
+struct AttnArgs {
+  int B, H, W, HW, C, heads, G, hg, Ns, Th, Tw;
+  float scale;
+  int table_in_smem;
+};
+
+struct BiasEval {
+  float val, d_dix, d_diy;  // value, d/d(ix), d/d(iy) of the bilinear interpolant
+  int i00;                  // y0 * Tw + x0
+  float w00, w01, w10, w11; // tap weights with validity folded in (0 when out of range)
+};
+
+// Bilinear sample of one head's table at displacement ((gy - py)/2, (gx - px)/2);
+// same op order as the reference: sub, mul 0.5, then grid_sample's unnormalise.
+template <bool WITH_GRAD>
+__device__ __forceinline__ BiasEval rpe_bias_eval(const float* __restrict__ tab, int Th, int Tw,
+                                                  float gy, float gx, float py, float px) {
+  const float dy = __fmul_rn(__fsub_rn(gy, py), 0.5f);
+  const float dx = __fmul_rn(__fsub_rn(gx, px), 0.5f);
+  const Taps t = make_taps(dx, dy, Tw, Th);
+  BiasEval r;
+  r.i00 = t.y0 * Tw + t.x0;
+  const bool v00 = t.vx0 && t.vy0, v01 = t.vx1 && t.vy0, v10 = t.vx0 && t.vy1, v11 = t.vx1 && t.vy1;
+  const float t00 = v00 ? tab[r.i00] : 0.f;
+  const float t01 = v01 ? tab[r.i00 + 1] : 0.f;
+  const float t10 = v10 ? tab[r.i00 + Tw] : 0.f;
+  const float t11 = v11 ? tab[r.i00 + Tw + 1] : 0.f;
+  r.w00 = v00 ? __fmul_rn(t.wx0, t.wy0) : 0.f;
+  r.w01 = v01 ? __fmul_rn(t.wx1, t.wy0) : 0.f;
+  r.w10 = v10 ? __fmul_rn(t.wx0, t.wy1) : 0.f;
+  r.w11 = v11 ? __fmul_rn(t.wx1, t.wy1) : 0.f;
+  r.val = t00 * r.w00 + t01 * r.w01 + t10 * r.w10 + t11 * r.w11;
+  if (WITH_GRAD) {
+    r.d_dix = (t01 - t00) * t.wy0 + (t11 - t10) * t.wy1;
+    r.d_diy = (t10 - t00) * t.wx0 + (t11 - t01) * t.wx1;
+  } else {
+    r.d_dix = r.d_diy = 0.f;
+  }
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row32(const T* __restrict__ p, float* dst) {
+#pragma unroll
+  for (int i = 0; i < HC / 4; ++i) {
+    float4 v = load4(p + 4 * i);
+    dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_row32(T* __restrict__ p, const float* src) {
+#pragma unroll
+  for (int i = 0; i < HC / 4; ++i)
+    store4(p + 4 * i, make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]));
+}
+
+// cooperative stage of `rows` rows x 32 channels of one head into smem [rows][32]
+template <typename T>
+__device__ __forceinline__ void stage_rows(const T* __restrict__ src, long long row_stride,
+                                           int rows_valid, int rows, float* dst) {
+  for (int idx = threadIdx.x; idx < rows * (HC / 4); idx += blockDim.x) {
+    int r = idx / (HC / 4), c4 = idx % (HC / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows_valid) v = load4(src + (long long)r * row_stride + 4 * c4);
+    *reinterpret_cast<float4*>(dst + r * HC + 4 * c4) = v;
+  }
+}
+
+// smem layout: [table Th*Tw | ks KV_CHUNK*32 | vs KV_CHUNK*32 | ps KV_CHUNK*2]
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                     const float* __restrict__ pos, const float* __restrict__ table,
+                     T* __restrict__ o, float* __restrict__ lse, AttnArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int tsz = a.table_in_smem ? ((a.Th * a.Tw + 3) & ~3) : 0;
+  float* tab_s = smem;
+  float* ks = smem + tsz;
+  float* vs = ks + KV_CHUNK * HC;
+  float* ps = vs + KV_CHUNK * HC;
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
+  if (a.table_in_smem)
+    for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) tab_s[i] = tab_g[i];
+  const float* tab = a.table_in_smem ? tab_s : tab_g;
+
+  const int m_raw = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const bool valid = m_raw < a.HW;
+  const int m = valid ? m_raw : a.HW - 1;
+  const float gy = query_point(m / a.W, a.H), gx = query_point(m % a.W, a.W);
+  float qr[HC], acc[HC];
+  load_row32(q + ((long long)b * a.HW + m) * a.C + eta * HC, qr);
+#pragma unroll
+  for (int c = 0; c < HC; ++c) acc[c] = 0.f;
+  float mx = -INFINITY, l = 0.f;
+
+  const T* kbase = k + (long long)b * a.Ns * a.C + eta * HC;
+  const T* vbase = v + (long long)b * a.Ns * a.C + eta * HC;
+  const float* pbase = pos + ((long long)b * a.G + g) * a.Ns * 2;
+  for (int n0 = 0; n0 < a.Ns; n0 += KV_CHUNK) {
+    const int nv = min(KV_CHUNK, a.Ns - n0);
+    __syncthreads();
+    stage_rows(kbase + (long long)n0 * a.C, a.C, nv, KV_CHUNK, ks);
+    stage_rows(vbase + (long long)n0 * a.C, a.C, nv, KV_CHUNK, vs);
+    for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) ps[i] = pbase[2 * n0 + i];
+    __syncthreads();
+    for (int n = 0; n < nv; ++n) {
+      const float* kr = ks + n * HC;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) s = fmaf(qr[c], kr[c], s);
+      s = s * a.scale + rpe_bias_eval<false>(tab, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]).val;
+      if (s > mx) {
+        const float corr = expf(mx - s);  // exp(-inf) = 0 on the first key
+        l *= corr;
+#pragma unroll
+        for (int c = 0; c < HC; ++c) acc[c] *= corr;
+        mx = s;
+      }
+      const float p = expf(s - mx);
+      l += p;
+      const float* vr = vs + n * HC;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) acc[c] = fmaf(p, vr[c], acc[c]);
+    }
+  }
+  if (valid) {
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int c = 0; c < HC; ++c) acc[c] *= inv;
+    store_row32(o + ((long long)b * a.HW + m) * a.C + eta * HC, acc);
+    lse[(long long)bh * a.HW + m] = mx + logf(l);
+  }
+}
+
+// bias (B, heads, HW, Ns) alone — test hook for the rpe path
+__global__ void rpe_bias_kernel(const float* __restrict__ pos, const float* __restrict__ table,
+                                float* __restrict__ bias, AttnArgs a, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % a.Ns);
+  const int m = (int)((idx / a.Ns) % a.HW);
+  const int bh = (int)(idx / ((long long)a.Ns * a.HW));
+  const int b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  const float* pp = pos + (((long long)b * a.G + g) * a.Ns + n) * 2;
+  bias[idx] = rpe_bias_eval<false>(table + (long long)eta * a.Th * a.Tw, a.Th, a.Tw,
+                                   query_point(m / a.W, a.H), query_point(m % a.W, a.W), pp[0],
+                                   pp[1]).val;
+}
+
+// delta[b, eta, m] = sum_c dO * O over the head's 32 channels
+template <typename T>
+__global__ void attn_delta_kernel(const T* __restrict__ d_o, const T* __restrict__ o,
+                                  float* __restrict__ delta, int HW, int C, int heads,
+                                  long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, m, eta)
+  if (idx >= total) return;
+  const int eta = (int)(idx % heads);
+  const long long bm = idx / heads;
+  const int m = (int)(bm % HW);
+  const int b = (int)(bm / HW);
+  const T* pa = d_o + bm * C + eta * HC;
+  const T* pb = o + bm * C + eta * HC;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HC / 4; ++i) {
+    float4 x = load4(pa + 4 * i), y = load4(pb + 4 * i);
+    s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  }
+  delta[((long long)b * heads + eta) * HW + m] = s;
+}
+
+// Query-parallel backward: dQ and the rpe-table gradient.
+// The table gradient is accumulated in a per-CTA shared-memory copy (shared atomics) and
+// flushed with one global atomicAdd per touched cell; d_table must be zeroed beforehand.
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                   const T* __restrict__ d_o, const float* __restrict__ lse,
+                   const float* __restrict__ delta, const float* __restrict__ pos,
+                   const float* __restrict__ table, T* __restrict__ dq,
+                   float* __restrict__ d_table, AttnArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int tsz = (a.Th * a.Tw + 3) & ~3;
+  float* tab_s = smem;
+  float* dtab_s = smem + tsz;
+  float* ks = dtab_s + tsz;
+  float* vs = ks + KV_CHUNK * HC;
+  float* ps = vs + KV_CHUNK * HC;
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
+  for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
+    tab_s[i] = tab_g[i];
+    dtab_s[i] = 0.f;
+  }
+  const int m_raw = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const bool valid = m_raw < a.HW;
+  const int m = valid ? m_raw : a.HW - 1;
+  const float gy = query_point(m / a.W, a.H), gx = query_point(m % a.W, a.W);
+  float qr[HC], dor[HC], acc[HC];
+  load_row32(q + ((long long)b * a.HW + m) * a.C + eta * HC, qr);
+  load_row32(d_o + ((long long)b * a.HW + m) * a.C + eta * HC, dor);
+#pragma unroll
+  for (int c = 0; c < HC; ++c) acc[c] = 0.f;
+  const float lse_m = lse[(long long)bh * a.HW + m];
+  const float dl_m = delta[(long long)bh * a.HW + m];
+
+  const T* kbase = k + (long long)b * a.Ns * a.C + eta * HC;
+  const T* vbase = v + (long long)b * a.Ns * a.C + eta * HC;
+  const float* pbase = pos + ((long long)b * a.G + g) * a.Ns * 2;
+  for (int n0 = 0; n0 < a.Ns; n0 += KV_CHUNK) {
+    const int nv = min(KV_CHUNK, a.Ns - n0);
+    __syncthreads();
+    stage_rows(kbase + (long long)n0 * a.C, a.C, nv, KV_CHUNK, ks);
+    stage_rows(vbase + (long long)n0 * a.C, a.C, nv, KV_CHUNK, vs);
+    for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) ps[i] = pbase[2 * n0 + i];
+    __syncthreads();
+    for (int n = 0; n < nv; ++n) {
+      const float* kr = ks + n * HC;
+      const float* vr = vs + n * HC;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        s = fmaf(qr[c], kr[c], s);
+        dp = fmaf(dor[c], vr[c], dp);
+      }
+      const BiasEval be = rpe_bias_eval<false>(tab_s, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]);
+      const float p = expf(s * a.scale + be.val - lse_m);
+      const float ds = valid ? p * (dp - dl_m) : 0.f;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) acc[c] = fmaf(ds, kr[c], acc[c]);
+      if (be.w00 != 0.f) atomicAdd(dtab_s + be.i00, ds * be.w00);
+      if (be.w01 != 0.f) atomicAdd(dtab_s + be.i00 + 1, ds * be.w01);
+      if (be.w10 != 0.f) atomicAdd(dtab_s + be.i00 + a.Tw, ds * be.w10);
+      if (be.w11 != 0.f) atomicAdd(dtab_s + be.i00 + a.Tw + 1, ds * be.w11);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < HC; ++c) acc[c] *= a.scale;
+    store_row32(dq + ((long long)b * a.HW + m) * a.C + eta * HC, acc);
+  }
+  __syncthreads();
+  float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
+  for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
+    float vv = dtab_s[i];
+    if (vv != 0.f) atomicAdd(dt_g + i, vv);
+  }
+}
+
+// Key-parallel backward: dK, dV and the rpe-bias part of d pos.  Each thread owns one
+// sampled key; queries of the CTA's q-split stream through shared memory.  Outputs are
+// per-split partials (fixed-order reduction afterwards): no atomics.
+//   dk_part/dv_part: (qsplit, B, Ns, C) fp32;  dpos_part: (B, heads, qsplit, Ns, 2) fp32
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                    const T* __restrict__ d_o, const float* __restrict__ lse,
+                    const float* __restrict__ delta, const float* __restrict__ pos,
+                    const float* __restrict__ table, float* __restrict__ dk_part,
+                    float* __restrict__ dv_part, float* __restrict__ dpos_part, int q_per_split,
+                    AttnArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int tsz = a.table_in_smem ? ((a.Th * a.Tw + 3) & ~3) : 0;
+  float* tab_s = smem;
+  float* qs = smem + tsz;
+  float* dos = qs + Q_CHUNK * HC;
+  float* ls = dos + Q_CHUNK * HC;     // lse
+  float* dls = ls + Q_CHUNK;          // delta
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  const int z = blockIdx.z, qsplit = gridDim.z;
+  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
+  if (a.table_in_smem)
+    for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) tab_s[i] = tab_g[i];
+  const float* tab = a.table_in_smem ? tab_s : tab_g;
+
+  const int n_raw = blockIdx.x * ATT_THREADS + threadIdx.x;
+  const bool valid = n_raw < a.Ns;
+  const int n = valid ? n_raw : a.Ns - 1;
+  float kr[HC], vr[HC], dk[HC], dv[HC];
+  load_row32(k + ((long long)b * a.Ns + n) * a.C + eta * HC, kr);
+  load_row32(v + ((long long)b * a.Ns + n) * a.C + eta * HC, vr);
+#pragma unroll
+  for (int c = 0; c < HC; ++c) dk[c] = dv[c] = 0.f;
+  const float* pp = pos + (((long long)b * a.G + g) * a.Ns + n) * 2;
+  const float py = pp[0], px = pp[1];
+  float dpy = 0.f, dpx = 0.f;
+
+  const int m_begin = z * q_per_split, m_end = min(a.HW, m_begin + q_per_split);
+  const T* qbase = q + (long long)b * a.HW * a.C + eta * HC;
+  const T* dobase = d_o + (long long)b * a.HW * a.C + eta * HC;
+  for (int m0 = m_begin; m0 < m_end; m0 += Q_CHUNK) {
+    const int mv = min(Q_CHUNK, m_end - m0);
+    __syncthreads();
+    stage_rows(qbase + (long long)m0 * a.C, a.C, mv, Q_CHUNK, qs);
+    stage_rows(dobase + (long long)m0 * a.C, a.C, mv, Q_CHUNK, dos);
+    for (int i = threadIdx.x; i < mv; i += blockDim.x) {
+      ls[i] = lse[(long long)bh * a.HW + m0 + i];
+      dls[i] = delta[(long long)bh * a.HW + m0 + i];
+    }
+    __syncthreads();
+    for (int mi = 0; mi < mv; ++mi) {
+      const int m = m0 + mi;
+      const float* qr = qs + mi * HC;
+      const float* dor = dos + mi * HC;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        s = fmaf(qr[c], kr[c], s);
+        dp = fmaf(dor[c], vr[c], dp);
+      }
+      const BiasEval be = rpe_bias_eval<true>(tab, a.Th, a.Tw, query_point(m / a.W, a.H),
+                                              query_point(m % a.W, a.W), py, px);
+      const float p = expf(s * a.scale + be.val - ls[mi]);
+      const float ds = p * (dp - dls[mi]);
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        dv[c] = fmaf(p, dor[c], dv[c]);
+        dk[c] = fmaf(ds, qr[c], dk[c]);
+      }
+      dpx = fmaf(ds, be.d_dix, dpx);
+      dpy = fmaf(ds, be.d_diy, dpy);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < HC; ++c) dk[c] *= a.scale;
+    const long long row = ((long long)z * a.B + b) * a.Ns + n;
+    store_row32(dk_part + row * a.C + eta * HC, dk);
+    store_row32(dv_part + row * a.C + eta * HC, dv);
+    float* dpo = dpos_part + ((((long long)b * a.heads + eta) * qsplit + z) * a.Ns + n) * 2;
+    // ix = ((d + 1)/2)(Tw - 1), d = (grid - pos)/2  ->  d ix / d pos = -(Tw - 1)/4
+    dpo[0] = dpy * (-0.25f * (float)(a.Th - 1));
+    dpo[1] = dpx * (-0.25f * (float)(a.Tw - 1));
+  }
+}
+
+AttnArgs make_args(const Shape& s) {
+  AttnArgs a;
+  a.B = s.B; a.H = s.H; a.W = s.W; a.HW = s.HW; a.C = s.C; a.heads = s.heads; a.G = s.G;
+  a.hg = s.hg; a.Ns = s.Ns; a.Th = s.Th; a.Tw = s.Tw;
+  a.scale = 1.0f / sqrtf((float)HC);
+  a.table_in_smem = ((size_t)s.Th * s.Tw * sizeof(float) <= 96 * 1024) ? 1 : 0;
+  return a;
+}
+
+template <typename K>
+int set_smem(K kern, size_t smem) {
+  if (smem > 48 * 1024)
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return DAT_OK;
+}
+
+}  // namespace
+
+int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void* v,
+                       const float* pos, const float* table, void* o, float* lse,
+                       cudaStream_t st) {
+  AttnArgs a = make_args(s);
+  const size_t tsz = a.table_in_smem ? (size_t)((s.Th * s.Tw + 3) & ~3) : 0;
+  size_t smem = (tsz + 2 * KV_CHUNK * HC + 2 * KV_CHUNK) * sizeof(float);
+  dim3 grid(ceil_div(s.HW, ATT_THREADS), s.B * s.heads);
+  if (s.act_dtype == DAT_F32) {
+    DAT_FWD(set_smem(attn_fwd_simt_kernel<float>, smem));
+    attn_fwd_simt_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
+        (const float*)q, (const float*)k, (const float*)v, pos, table, (float*)o, lse, a);
+  } else {
+    DAT_FWD(set_smem(attn_fwd_simt_kernel<bf16>, smem));
+    attn_fwd_simt_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
+        (const bf16*)q, (const bf16*)k, (const bf16*)v, pos, table, (bf16*)o, lse, a);
+  }
+  DAT_LAUNCH_OK("attn_fwd_simt_kernel");
+  return DAT_OK;
+}
+
+int rpe_bias(const Shape& s, const float* pos, const float* table, float* bias, cudaStream_t st) {
+  AttnArgs a = make_args(s);
+  long long total = (long long)s.B * s.heads * s.HW * s.Ns;
+  rpe_bias_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pos, table, bias, a, total);
+  DAT_LAUNCH_OK("rpe_bias_kernel");
+  return DAT_OK;
+}
+
+int attention_bwd_qsplit(const Shape& s) {
+  long long base = (long long)s.B * s.heads * ceil_div(s.Ns, ATT_THREADS);
+  long long want = (2 * 148 + base - 1) / base;
+  long long cap = (s.HW + 255) / 256;
+  long long r = want < cap ? want : cap;
+  return (int)(r < 1 ? 1 : r);
+}
+
+size_t attention_bwd_workspace(const Shape& s) {
+  int qs = attention_bwd_qsplit(s);
+  size_t delta = align_up((size_t)s.B * s.heads * s.HW * 4, 256);
+  size_t part = align_up((size_t)qs * s.B * s.Ns * s.C * 4, 256);
+  return delta + 2 * part;
+}
+
+// dq, dk, dv (act dtype), d_table (fp32, overwritten), dpos_part (B,heads,qsplit,Ns,2).
+int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void* v, const void* o,
+                       const void* d_o, const float* lse, const float* pos, const float* table,
+                       void* dq, void* dk, void* dv, float* d_table, float* dpos_part,
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+  DAT_REQUIRE(ws_bytes >= attention_bwd_workspace(s), "attention_bwd: workspace too small");
+  DAT_REQUIRE((size_t)s.Th * s.Tw * 4 <= 48 * 1024 + 32 * 1024,
+              "attention_bwd: rpe table %dx%d too large for the shared-memory gradient copy", s.Th, s.Tw);
+  AttnArgs a = make_args(s);
+  const int qsplit = attention_bwd_qsplit(s);
+  float* delta = (float*)ws;
+  float* dk_part = (float*)((char*)ws + align_up((size_t)s.B * s.heads * s.HW * 4, 256));
+  float* dv_part = (float*)((char*)dk_part + align_up((size_t)qsplit * s.B * s.Ns * s.C * 4, 256));
+  const bool f32 = s.act_dtype == DAT_F32;
+
+  long long tot = (long long)s.B * s.HW * s.heads;
+  if (f32) attn_delta_kernel<float><<<ceil_div(tot, 256), 256, 0, st>>>((const float*)d_o, (const float*)o, delta, s.HW, s.C, s.heads, tot);
+  else attn_delta_kernel<bf16><<<ceil_div(tot, 256), 256, 0, st>>>((const bf16*)d_o, (const bf16*)o, delta, s.HW, s.C, s.heads, tot);
+  DAT_LAUNCH_OK("attn_delta_kernel");
+
+  DAT_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
+  {
+    const size_t tsz = (size_t)((s.Th * s.Tw + 3) & ~3);
+    size_t smem = (2 * tsz + 2 * KV_CHUNK * HC + 2 * KV_CHUNK) * sizeof(float);
+    dim3 grid(ceil_div(s.HW, ATT_THREADS), s.B * s.heads);
+    if (f32) {
+      DAT_FWD(set_smem(attn_bwd_dq_kernel<float>, smem));
+      attn_bwd_dq_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
+          (const float*)q, (const float*)k, (const float*)v, (const float*)d_o, lse, delta, pos,
+          table, (float*)dq, d_table, a);
+    } else {
+      DAT_FWD(set_smem(attn_bwd_dq_kernel<bf16>, smem));
+      attn_bwd_dq_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
+          (const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta, pos,
+          table, (bf16*)dq, d_table, a);
+    }
+    DAT_LAUNCH_OK("attn_bwd_dq_kernel");
+  }
+  {
+    const size_t tsz = a.table_in_smem ? (size_t)((s.Th * s.Tw + 3) & ~3) : 0;
+    size_t smem = (tsz + 2 * Q_CHUNK * HC + 2 * Q_CHUNK) * sizeof(float);
+    dim3 grid(ceil_div(s.Ns, ATT_THREADS), s.B * s.heads, qsplit);
+    int qps = ceil_div(ceil_div(s.HW, qsplit), Q_CHUNK) * Q_CHUNK;
+    if (f32) {
+      DAT_FWD(set_smem(attn_bwd_dkv_kernel<float>, smem));
+      attn_bwd_dkv_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
+          (const float*)q, (const float*)k, (const float*)v, (const float*)d_o, lse, delta, pos,
+          table, dk_part, dv_part, dpos_part, qps, a);
+    } else {
+      DAT_FWD(set_smem(attn_bwd_dkv_kernel<bf16>, smem));
+      attn_bwd_dkv_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
+          (const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta, pos,
+          table, dk_part, dv_part, dpos_part, qps, a);
+    }
+    DAT_LAUNCH_OK("attn_bwd_dkv_kernel");
+  }
+  long long cnt = (long long)s.B * s.Ns * s.C;
+  DAT_FWD(reduce_partials(dk_part, qsplit, cnt, dk, s.act_dtype, st));
+  DAT_FWD(reduce_partials(dv_part, qsplit, cnt, dv, s.act_dtype, st));
+  return DAT_OK;
+}
+
+}  // namespace dat

@@ -1,0 +1,219 @@
+// C ABI (include/dat_b200.h): argument validation, workspace planning and the host-side
+// sequencing of the kernels of one deformable-attention block.  No allocation, no host
+// synchronisation: everything is enqueued on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dat {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int make_shape(const dat_block_desc* d, Shape* s) {
+  DAT_REQUIRE(d != nullptr, "descriptor is NULL");
+  DAT_REQUIRE(d->B > 0 && d->H > 1 && d->W > 1, "bad B/H/W = %d/%d/%d (H, W must be > 1)", d->B, d->H, d->W);
+  DAT_REQUIRE(d->n_heads > 0 && d->n_groups > 0 && d->n_heads % d->n_groups == 0,
+              "n_heads=%d must be a positive multiple of n_groups=%d", d->n_heads, d->n_groups);
+  DAT_REQUIRE(d->stride > 0 && d->ksize > 0, "bad stride/ksize");
+  DAT_REQUIRE(d->table_h > 0 && d->table_w > 0, "bad rpe table size");
+  DAT_REQUIRE((d->x_dtype == DAT_F32 || d->x_dtype == DAT_BF16) &&
+                  (d->act_dtype == DAT_F32 || d->act_dtype == DAT_BF16), "bad dtype code");
+  s->B = d->B; s->H = d->H; s->W = d->W; s->HW = d->H * d->W;
+  s->heads = d->n_heads; s->G = d->n_groups;
+  s->C = d->n_heads * DAT_HEAD_DIM;
+  s->Cg = s->C / s->G; s->hg = s->heads / s->G;
+  s->stride = d->stride; s->ksize = d->ksize;
+  s->pad = d->ksize != d->stride ? d->ksize / 2 : 0;
+  DAT_REQUIRE(d->H + 2 * s->pad >= d->ksize && d->W + 2 * s->pad >= d->ksize, "map smaller than the offset kernel");
+  s->Hk = (d->H + 2 * s->pad - d->ksize) / d->stride + 1;
+  s->Wk = (d->W + 2 * s->pad - d->ksize) / d->stride + 1;
+  DAT_REQUIRE(s->Hk > 1 && s->Wk > 1, "sample grid %dx%d: the reference divides by (Hk-1), (Wk-1)", s->Hk, s->Wk);
+  s->Ns = s->Hk * s->Wk;
+  s->Th = d->table_h; s->Tw = d->table_w;
+  s->orf = d->offset_range_factor;
+  s->x_dtype = d->x_dtype; s->act_dtype = d->act_dtype;
+  DAT_REQUIRE((long long)s->B * s->HW * s->C < (1ll << 40), "tensor too large");
+  return DAT_OK;
+}
+
+namespace {
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base((char*)p) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  }
+};
+
+struct BwdPlan {
+  void *d_o, *dq, *dk, *dv, *dxs;
+  float *dpos_part, *dpos;
+  void* sub;        // shared scratch of the individual stages (used one at a time)
+  size_t sub_bytes, total;
+};
+
+BwdPlan plan_bwd(const Shape& s, void* ws) {
+  BwdPlan p;
+  Carver c(ws);
+  const size_t e = dtype_size(s.act_dtype);
+  p.d_o = c.take((size_t)s.B * s.HW * s.C * e);
+  p.dq = c.take((size_t)s.B * s.HW * s.C * e);
+  p.dk = c.take((size_t)s.B * s.Ns * s.C * e);
+  p.dv = c.take((size_t)s.B * s.Ns * s.C * e);
+  p.dxs = c.take((size_t)s.B * s.Ns * s.C * e);
+  p.dpos_part = (float*)c.take((size_t)s.B * s.heads * attention_bwd_qsplit(s) * s.Ns * 2 * 4);
+  p.dpos = (float*)c.take((size_t)s.B * s.G * s.Ns * 2 * 4);
+  size_t sub = attention_bwd_workspace(s);
+  size_t w1 = pointwise_wgrad_workspace((long long)s.B * s.HW, s.C, s.C);
+  size_t w2 = pointwise_wgrad_workspace((long long)s.B * s.Ns, s.C, s.C);
+  size_t w3 = offset_bwd_workspace(s);
+  if (w1 > sub) sub = w1;
+  if (w2 > sub) sub = w2;
+  if (w3 > sub) sub = w3;
+  p.sub_bytes = sub;
+  p.sub = c.take(sub);
+  p.total = c.off;
+  return p;
+}
+
+}  // namespace
+}  // namespace dat
+
+using namespace dat;
+
+extern "C" {
+
+const char* dat_last_error(void) { return g_err; }
+const char* dat_version(void) { return "dat_b200 0.1 sm_100a"; }
+
+int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  if (Hk) *Hk = s.Hk;
+  if (Wk) *Wk = s.Wk;
+  return DAT_OK;
+}
+
+size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d) {
+  (void)d;
+  return 0;
+}
+
+size_t dat_block_bwd_workspace_bytes(const dat_block_desc* d) {
+  Shape s;
+  if (make_shape(d, &s) != DAT_OK) return 0;
+  return plan_bwd(s, nullptr).total;
+}
+
+int dat_pointwise_fwd(const void* X, int32_t x_dtype, const float* W, const float* b, void* Y,
+                      int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream) {
+  DAT_REQUIRE(X && W && Y, "pointwise_fwd: NULL pointer");
+  return pointwise_fwd_simt(X, x_dtype, W, b, Y, y_dtype, M, N, K, (cudaStream_t)stream);
+}
+
+int dat_offset_pos_fwd(const dat_block_desc* d, const dat_block_params* p, const void* q,
+                       float* t_dw, float* off_raw, float* pos, void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(p && q && t_dw && off_raw && pos, "offset_pos_fwd: NULL pointer");
+  return offset_pos_fwd(s, p, q, t_dw, off_raw, pos, (cudaStream_t)stream);
+}
+
+int dat_ref_points(int32_t Hk, int32_t Wk, float* ref_y, float* ref_x, void* stream) {
+  DAT_REQUIRE(ref_y && ref_x, "ref_points: NULL pointer");
+  return ref_points(Hk, Wk, ref_y, ref_x, (cudaStream_t)stream);
+}
+
+int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, void* xs,
+                   int32_t* taps, void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(x && pos && xs, "sample_fwd: NULL pointer");
+  return sample_fwd(s, x, pos, xs, taps, (cudaStream_t)stream);
+}
+
+int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, const void* v,
+                      const float* pos, const float* rpe_table, void* o, float* lse,
+                      void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(q && k && v && pos && rpe_table && o && lse, "attention_fwd: NULL pointer");
+  return attention_fwd_simt(s, q, k, v, pos, rpe_table, o, lse, (cudaStream_t)stream);
+}
+
+int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table, float* bias,
+                 void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(pos && rpe_table && bias, "rpe_bias: NULL pointer");
+  return rpe_bias(s, pos, rpe_table, bias, (cudaStream_t)stream);
+}
+
+int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const void* x, void* y,
+                      const dat_block_saved* sv, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(p && x && y && sv, "block_forward: NULL pointer");
+  DAT_REQUIRE(sv->q && sv->t_dw && sv->off_raw && sv->pos && sv->xs && sv->k && sv->v && sv->o && sv->lse,
+              "block_forward: every dat_block_saved buffer must be provided");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long M = (long long)s.B * s.HW, Mk = (long long)s.B * s.Ns;
+  DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, s.act_dtype, M, s.C, s.C, st));
+  DAT_FWD(offset_pos_fwd(s, p, sv->q, sv->t_dw, sv->off_raw, sv->pos, st));
+  DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
+  DAT_FWD(pointwise_fwd_simt(sv->xs, s.act_dtype, p->wk, p->bk, sv->k, s.act_dtype, Mk, s.C, s.C, st));
+  DAT_FWD(pointwise_fwd_simt(sv->xs, s.act_dtype, p->wv, p->bv, sv->v, s.act_dtype, Mk, s.C, s.C, st));
+  DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st));
+  DAT_FWD(pointwise_fwd_simt(sv->o, s.act_dtype, p->wo, p->bo, y, s.act_dtype, M, s.C, s.C, st));
+  return DAT_OK;
+}
+
+int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const void* x,
+                       const void* dy, const dat_block_saved* sv, float* dx,
+                       const dat_block_grads* g, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(p && x && dy && sv && dx && g && workspace, "block_backward: NULL pointer");
+  BwdPlan w = plan_bwd(s, workspace);
+  DAT_REQUIRE(workspace_bytes >= w.total, "block_backward: workspace %zu < %zu bytes", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long M = (long long)s.B * s.HW, Mk = (long long)s.B * s.Ns;
+  const int C = s.C, adt = s.act_dtype;
+  // proj_out
+  DAT_FWD(pointwise_wgrad_simt(dy, adt, sv->o, adt, g->wo, g->bo, M, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
+  // attention core
+  DAT_FWD(attention_bwd_simt(s, sv->q, sv->k, sv->v, sv->o, w.d_o, sv->lse, sv->pos, p->rpe_table,
+                             w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
+  // proj_k / proj_v
+  DAT_FWD(pointwise_wgrad_simt(w.dk, adt, sv->xs, adt, g->wk, g->bk, Mk, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(pointwise_wgrad_simt(w.dv, adt, sv->xs, adt, g->wv, g->bv, Mk, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(pointwise_dgrad_simt(w.dk, adt, p->wk, w.dxs, adt, Mk, C, C, 0, st));
+  DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
+  // sampling -> d pos; offset network -> dq
+  DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, attention_bwd_qsplit(s), w.dpos, st));
+  DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
+  // proj_q, then the sampling scatter on top of its data gradient
+  DAT_FWD(pointwise_wgrad_simt(w.dq, adt, x, s.x_dtype, g->wq, g->bq, M, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
+  DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
+  return DAT_OK;
+}
+
+}  // extern "C"

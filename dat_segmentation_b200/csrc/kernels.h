@@ -1,0 +1,54 @@
+// Internal (non-ABI) launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/dat_b200.h"
+
+namespace dat {
+
+struct Shape;
+
+// gemm_simt.cu — fp32-accumulate CUDA-core GEMMs (exact path)
+int pointwise_fwd_simt(const void* X, int x_dt, const float* W, const float* b, void* Y, int y_dt,
+                       long long M, int N, int K, cudaStream_t st);
+int pointwise_dgrad_simt(const void* dY, int dy_dt, const float* W, void* dX, int dx_dt,
+                         long long M, int N, int K, int accumulate, cudaStream_t st);
+int wgrad_splits(long long M, int N, int K);
+int colsum_splits(long long M);
+size_t pointwise_wgrad_workspace(long long M, int N, int K);
+int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, float* dW, float* db,
+                         long long M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+int reduce_partials(const float* part, int nsplit, long long count, void* out, int out_dt,
+                    cudaStream_t st);
+
+// offset_net.cu
+int offset_pos_fwd(const Shape& s, const dat_block_params* p, const void* q, float* t_dw,
+                   float* off_raw, float* pos, cudaStream_t st);
+int ref_points(int Hk, int Wk, float* ry, float* rx, cudaStream_t st);
+size_t offset_bwd_workspace(const Shape& s);
+int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const float* t_dw,
+               const float* off_raw, const float* dpos, void* dq, const dat_block_grads* g,
+               void* ws, size_t ws_bytes, cudaStream_t st);
+
+// gather.cu
+int sample_fwd(const Shape& s, const void* x, const float* pos, void* xs, int32_t* taps,
+               cudaStream_t st);
+int sample_bwd_dpos(const Shape& s, const void* x, const float* pos, const void* dxs,
+                    const float* dpos_bias_part, int qsplit, float* dpos, cudaStream_t st);
+int sample_bwd_dx(const Shape& s, const float* pos, const void* dxs, float* dx, cudaStream_t st);
+
+// attention_simt.cu
+int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void* v,
+                       const float* pos, const float* table, void* o, float* lse,
+                       cudaStream_t st);
+int rpe_bias(const Shape& s, const float* pos, const float* table, float* bias, cudaStream_t st);
+int attention_bwd_qsplit(const Shape& s);
+size_t attention_bwd_workspace(const Shape& s);
+int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void* v, const void* o,
+                       const void* d_o, const float* lse, const float* pos, const float* table,
+                       void* dq, void* dk, void* dv, float* d_table, float* dpos_part, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+
+}  // namespace dat

@@ -1,0 +1,461 @@
+// Offset network of the deformable-attention block, fused into one kernel:
+//   depthwise k x k strided conv (+bias) -> LayerNorm over Cg -> exact GELU ->
+//   1x1 conv Cg->2 (no bias) -> tanh*range*orf | clamp -> + reference point -> pos
+// (dat_blocks.py:51-56, :144-162, _get_ref_points :108-121).
+//
+// Mapping: one warp per sample point (b, g, i, j); lanes stride the Cg channels, so every
+// tap of the k x k window is one coalesced channel-last row read of q.  The transposed
+// depthwise weights live in shared memory.  LayerNorm statistics and the 2-vector dot are
+// warp-shuffle reductions; nothing but pos (and the small saved tensors) is written.
+// HBM-bound: algorithmic bytes per launch = B*HW*C*e (q) + B*G*Ns*(Cg*4 + 16) (t, off, pos).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dat {
+
+namespace {
+
+constexpr int OFF_WARPS = 8;
+
+struct OffsetArgs {
+  int B, H, W, C, G, Cg, stride, ksize, pad, Hk, Wk, Ns;
+  float orf, range_y, range_x;
+  long long n_points;  // B * G * Ns
+};
+
+__device__ __forceinline__ float gelu_exact(float z) {
+  return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad(float z) {
+  float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+  float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
+  return cdf + z * pdf;
+}
+
+// dynamic smem: transposed depthwise weights [k*k][Cg]
+template <typename TQ, int MAXCPL>
+__global__ void __launch_bounds__(OFF_WARPS * 32)
+offset_pos_fwd_kernel(const TQ* __restrict__ q, const float* __restrict__ w_dw,
+                      const float* __restrict__ b_dw, const float* __restrict__ ln_g,
+                      const float* __restrict__ ln_b, const float* __restrict__ w_pw,
+                      float* __restrict__ t_dw, float* __restrict__ off_raw,
+                      float* __restrict__ pos, OffsetArgs a) {
+  extern __shared__ float wsm[];
+  const int kk = a.ksize * a.ksize;
+  for (int idx = threadIdx.x; idx < kk * a.Cg; idx += blockDim.x) {
+    int c = idx % a.Cg, uv = idx / a.Cg;
+    wsm[idx] = w_dw[c * kk + uv];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long sp = (long long)blockIdx.x * OFF_WARPS + warp;
+  if (sp >= a.n_points) return;
+  const int n = (int)(sp % a.Ns);
+  const int g = (int)((sp / a.Ns) % a.G);
+  const int b = (int)(sp / ((long long)a.Ns * a.G));
+  const int i = n / a.Wk, j = n % a.Wk;
+
+  float acc[MAXCPL];
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) {
+    int c = lane + 32 * cc;
+    acc[cc] = c < a.Cg ? b_dw[c] : 0.f;
+  }
+  for (int u = 0; u < a.ksize; ++u) {
+    int y = i * a.stride - a.pad + u;
+    if (y < 0 || y >= a.H) continue;
+    for (int v = 0; v < a.ksize; ++v) {
+      int x = j * a.stride - a.pad + v;
+      if (x < 0 || x >= a.W) continue;
+      const TQ* row = q + (((long long)b * a.H + y) * a.W + x) * a.C + g * a.Cg;
+      const float* wrow = wsm + (u * a.ksize + v) * a.Cg;
+#pragma unroll
+      for (int cc = 0; cc < MAXCPL; ++cc) {
+        int c = lane + 32 * cc;
+        if (c < a.Cg) acc[cc] = fmaf(wrow[c], to_f32(row[c]), acc[cc]);
+      }
+    }
+  }
+  float s1 = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) {
+    int c = lane + 32 * cc;
+    if (c < a.Cg) {
+      t_dw[sp * a.Cg + c] = acc[cc];
+      s1 += acc[cc];
+    }
+  }
+  const float inv_n = 1.0f / (float)a.Cg;
+  const float mean = warp_sum(s1) * inv_n;
+  float s2 = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) {
+    int c = lane + 32 * cc;
+    if (c < a.Cg) {
+      float dlt = acc[cc] - mean;
+      s2 = fmaf(dlt, dlt, s2);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(s2) * inv_n + 1e-5f);
+  float oy = 0.f, ox = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) {
+    int c = lane + 32 * cc;
+    if (c < a.Cg) {
+      float z = (acc[cc] - mean) * rstd * ln_g[c] + ln_b[c];
+      float act = gelu_exact(z);
+      oy = fmaf(act, w_pw[c], oy);
+      ox = fmaf(act, w_pw[a.Cg + c], ox);
+    }
+  }
+  oy = warp_sum(oy);
+  ox = warp_sum(ox);
+  if (lane == 0) {
+    off_raw[sp * 2 + 0] = oy;
+    off_raw[sp * 2 + 1] = ox;
+    float ry = ref_point(i, a.Hk), rx = ref_point(j, a.Wk);
+    float py, px;
+    if (a.orf >= 0.f) {
+      py = __fadd_rn(__fmul_rn(__fmul_rn(tanhf(oy), a.range_y), a.orf), ry);
+      px = __fadd_rn(__fmul_rn(__fmul_rn(tanhf(ox), a.range_x), a.orf), rx);
+    } else {
+      py = fminf(fmaxf(__fadd_rn(oy, ry), -1.0f), 1.0f);
+      px = fminf(fmaxf(__fadd_rn(ox, rx), -1.0f), 1.0f);
+    }
+    pos[sp * 2 + 0] = py;
+    pos[sp * 2 + 1] = px;
+  }
+}
+
+__global__ void ref_points_kernel(int Hk, int Wk, float* ry, float* rx) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < Hk) ry[t] = ref_point(t, Hk);
+  if (t < Wk) rx[t] = ref_point(t, Wk);
+}
+
+// ---- backward ---------------------------------------------------------------------
+// Per sample point: d pos -> d raw offset -> 1x1^T -> GELU' -> LayerNorm backward -> dt
+// (stored for the two depthwise-conv gradient kernels) plus per-channel parameter sums.
+// Grid-stride over points; per-CTA partial sums [5][Cg] (pw_y, pw_x, ln_g, ln_b, dw_b),
+// reduced in a fixed order by offset_bwd_reduce_kernel: deterministic, no atomics.
+template <int MAXCPL>
+__global__ void __launch_bounds__(OFF_WARPS * 32)
+offset_bwd_point_kernel(const float* __restrict__ dpos, const float* __restrict__ off_raw,
+                        const float* __restrict__ t_dw, const float* __restrict__ ln_g,
+                        const float* __restrict__ ln_b, const float* __restrict__ w_pw,
+                        float* __restrict__ dt, float* __restrict__ partial, OffsetArgs a) {
+  extern __shared__ float red[];  // [OFF_WARPS][5][Cg]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float g_py[MAXCPL], g_px[MAXCPL], g_g[MAXCPL], g_b[MAXCPL], g_b0[MAXCPL];
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) g_py[cc] = g_px[cc] = g_g[cc] = g_b[cc] = g_b0[cc] = 0.f;
+  const float inv_n = 1.0f / (float)a.Cg;
+
+  for (long long sp = (long long)blockIdx.x * OFF_WARPS + warp; sp < a.n_points;
+       sp += (long long)gridDim.x * OFF_WARPS) {
+    const int n = (int)(sp % a.Ns);
+    const int i = n / a.Wk, j = n % a.Wk;
+    float oy = off_raw[sp * 2], ox = off_raw[sp * 2 + 1];
+    float dy = dpos[sp * 2], dx = dpos[sp * 2 + 1];
+    if (a.orf >= 0.f) {
+      float ty = tanhf(oy), tx = tanhf(ox);
+      dy = dy * a.range_y * a.orf * (1.0f - ty * ty);
+      dx = dx * a.range_x * a.orf * (1.0f - tx * tx);
+    } else {
+      float py = __fadd_rn(oy, ref_point(i, a.Hk)), px = __fadd_rn(ox, ref_point(j, a.Wk));
+      if (!(py >= -1.0f && py <= 1.0f)) dy = 0.f;
+      if (!(px >= -1.0f && px <= 1.0f)) dx = 0.f;
+    }
+    float tv[MAXCPL];
+    float s1 = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < MAXCPL; ++cc) {
+      int c = lane + 32 * cc;
+      tv[cc] = c < a.Cg ? t_dw[sp * a.Cg + c] : 0.f;
+      s1 += tv[cc];
+    }
+    const float mean = warp_sum(s1) * inv_n;
+    float s2 = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < MAXCPL; ++cc) {
+      int c = lane + 32 * cc;
+      if (c < a.Cg) {
+        float dlt = tv[cc] - mean;
+        s2 = fmaf(dlt, dlt, s2);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(s2) * inv_n + 1e-5f);
+    float dth[MAXCPL];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < MAXCPL; ++cc) {
+      int c = lane + 32 * cc;
+      dth[cc] = 0.f;
+      if (c < a.Cg) {
+        float that = (tv[cc] - mean) * rstd;
+        float gam = ln_g[c];
+        float z = that * gam + ln_b[c];
+        float act = gelu_exact(z);
+        float dact = dy * w_pw[c] + dx * w_pw[a.Cg + c];
+        float dln = dact * gelu_grad(z);
+        g_py[cc] = fmaf(dy, act, g_py[cc]);
+        g_px[cc] = fmaf(dx, act, g_px[cc]);
+        g_g[cc] = fmaf(dln, that, g_g[cc]);
+        g_b[cc] += dln;
+        dth[cc] = dln * gam;
+        m1 += dth[cc];
+        m2 = fmaf(dth[cc], that, m2);
+        tv[cc] = that;
+      }
+    }
+    m1 = warp_sum(m1) * inv_n;
+    m2 = warp_sum(m2) * inv_n;
+#pragma unroll
+    for (int cc = 0; cc < MAXCPL; ++cc) {
+      int c = lane + 32 * cc;
+      if (c < a.Cg) {
+        float d = rstd * (dth[cc] - m1 - tv[cc] * m2);
+        dt[sp * a.Cg + c] = d;
+        g_b0[cc] += d;
+      }
+    }
+  }
+  // CTA reduction in a fixed warp order
+#pragma unroll
+  for (int cc = 0; cc < MAXCPL; ++cc) {
+    int c = lane + 32 * cc;
+    if (c < a.Cg) {
+      float* r = red + (size_t)warp * 5 * a.Cg;
+      r[0 * a.Cg + c] = g_py[cc];
+      r[1 * a.Cg + c] = g_px[cc];
+      r[2 * a.Cg + c] = g_g[cc];
+      r[3 * a.Cg + c] = g_b[cc];
+      r[4 * a.Cg + c] = g_b0[cc];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 5 * a.Cg; idx += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < OFF_WARPS; ++w) s += red[(size_t)w * 5 * a.Cg + idx];
+    partial[(size_t)blockIdx.x * 5 * a.Cg + idx] = s;
+  }
+}
+
+__global__ void offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cg,
+                                         float* __restrict__ g_pw, float* __restrict__ g_ln_g,
+                                         float* __restrict__ g_ln_b, float* __restrict__ g_dw_b) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 5 * Cg) return;
+  float s = 0.f;
+  for (int blk = 0; blk < nblocks; ++blk) s += partial[(size_t)blk * 5 * Cg + idx];
+  int row = idx / Cg, c = idx % Cg;
+  if (row < 2) g_pw[row * Cg + c] = s;
+  else if (row == 2) g_ln_g[c] = s;
+  else if (row == 3) g_ln_b[c] = s;
+  else g_dw_b[c] = s;
+}
+
+// Depthwise weight gradient: dw[c,u,v] = sum_points dt[point, c] * q[window(point,u,v), c].
+// grid = (k*k, nsplit), one thread per channel; partial[split][uv][c].
+template <typename TQ>
+__global__ void offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
+                                        float* __restrict__ partial, long long pts_per_split,
+                                        OffsetArgs a) {
+  const int c = threadIdx.x;
+  const int uv = blockIdx.x, u = uv / a.ksize, v = uv % a.ksize;
+  long long p0 = (long long)blockIdx.y * pts_per_split;
+  long long p1 = min(a.n_points, p0 + pts_per_split);
+  float s = 0.f;
+  if (c < a.Cg) {
+    for (long long sp = p0; sp < p1; ++sp) {
+      const int n = (int)(sp % a.Ns);
+      const int g = (int)((sp / a.Ns) % a.G);
+      const int b = (int)(sp / ((long long)a.Ns * a.G));
+      const int y = (n / a.Wk) * a.stride - a.pad + u;
+      const int x = (n % a.Wk) * a.stride - a.pad + v;
+      if (y < 0 || y >= a.H || x < 0 || x >= a.W) continue;
+      float qv = to_f32(q[(((long long)b * a.H + y) * a.W + x) * a.C + g * a.Cg + c]);
+      s = fmaf(dt[sp * a.Cg + c], qv, s);
+    }
+    partial[((size_t)blockIdx.y * gridDim.x + uv) * a.Cg + c] = s;
+  }
+}
+
+__global__ void offset_bwd_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit,
+                                               int kk, int Cg, float* __restrict__ g_dw_w) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // uv * Cg + c
+  if (idx >= kk * Cg) return;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += partial[(size_t)z * kk * Cg + idx];
+  int uv = idx / Cg, c = idx % Cg;
+  g_dw_w[c * kk + uv] = s;
+}
+
+// Depthwise data gradient in gather form (no atomics): every q element sums the <=
+// ceil(k/s)^2 sample points whose window covers it, and adds that to dq in place.
+template <typename TQ>
+__global__ void offset_bwd_dgrad_kernel(const float* __restrict__ dt,
+                                        const float* __restrict__ w_dw, TQ* __restrict__ dq,
+                                        long long total, OffsetArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cf = (int)(idx % a.C);
+  const long long pix = idx / a.C;
+  const int x = (int)(pix % a.W);
+  const int y = (int)((pix / a.W) % a.H);
+  const int b = (int)(pix / ((long long)a.W * a.H));
+  const int g = cf / a.Cg, c = cf % a.Cg;
+  const int kk = a.ksize * a.ksize;
+  // i*s - p + u = y, 0 <= u < k  ->  (y + p - k + 1)/s <= i <= (y + p)/s
+  int i_lo = y + a.pad - a.ksize + 1;
+  i_lo = i_lo <= 0 ? 0 : (i_lo + a.stride - 1) / a.stride;
+  int i_hi = min(a.Hk - 1, (y + a.pad) / a.stride);
+  int j_lo = x + a.pad - a.ksize + 1;
+  j_lo = j_lo <= 0 ? 0 : (j_lo + a.stride - 1) / a.stride;
+  int j_hi = min(a.Wk - 1, (x + a.pad) / a.stride);
+  float s = 0.f;
+  for (int i = i_lo; i <= i_hi; ++i) {
+    int u = y + a.pad - i * a.stride;
+    for (int j = j_lo; j <= j_hi; ++j) {
+      int v = x + a.pad - j * a.stride;
+      long long sp = ((long long)b * a.G + g) * a.Ns + i * a.Wk + j;
+      s = fmaf(w_dw[c * kk + u * a.ksize + v], dt[sp * a.Cg + c], s);
+    }
+  }
+  dq[idx] = from_f32<TQ>(to_f32(dq[idx]) + s);
+}
+
+OffsetArgs make_args(const Shape& s) {
+  OffsetArgs a;
+  a.B = s.B; a.H = s.H; a.W = s.W; a.C = s.C; a.G = s.G; a.Cg = s.Cg;
+  a.stride = s.stride; a.ksize = s.ksize; a.pad = s.pad; a.Hk = s.Hk; a.Wk = s.Wk; a.Ns = s.Ns;
+  a.orf = s.orf;
+  // the reference builds the range as a Python double rounded to fp32 (dat_blocks.py:150)
+  a.range_y = (float)(1.0 / ((double)s.Hk - 1.0));
+  a.range_x = (float)(1.0 / ((double)s.Wk - 1.0));
+  a.n_points = (long long)s.B * s.G * s.Ns;
+  return a;
+}
+
+int pick_cpl(int Cg) {
+  int cpl = (Cg + 31) / 32;
+  if (cpl <= 2) return 2;
+  if (cpl <= 4) return 4;
+  if (cpl <= 8) return 8;
+  return 16;
+}
+
+}  // namespace
+
+int offset_pos_fwd(const Shape& s, const dat_block_params* p, const void* q, float* t_dw,
+                   float* off_raw, float* pos, cudaStream_t st) {
+  DAT_REQUIRE(s.Cg <= 512, "offset net: Cg=%d > 512 unsupported", s.Cg);
+  OffsetArgs a = make_args(s);
+  size_t smem = (size_t)s.ksize * s.ksize * s.Cg * sizeof(float);
+  DAT_REQUIRE(smem <= 200 * 1024, "offset net: k*k*Cg too large for shared memory");
+  int grid = ceil_div(a.n_points, OFF_WARPS);
+  int cpl = pick_cpl(s.Cg);
+#define LAUNCH(TQ, CPL)                                                                        \
+  do {                                                                                         \
+    auto kern = offset_pos_fwd_kernel<TQ, CPL>;                                                \
+    if (smem > 48 * 1024)                                                                      \
+      DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                       (int)smem));                                            \
+    kern<<<grid, OFF_WARPS * 32, smem, st>>>((const TQ*)q, p->off_dw_w, p->off_dw_b,           \
+                                             p->off_ln_g, p->off_ln_b, p->off_pw_w, t_dw,      \
+                                             off_raw, pos, a);                                 \
+  } while (0)
+#define LAUNCH_T(TQ)                                    \
+  do {                                                  \
+    if (cpl == 2) LAUNCH(TQ, 2);                        \
+    else if (cpl == 4) LAUNCH(TQ, 4);                   \
+    else if (cpl == 8) LAUNCH(TQ, 8);                   \
+    else LAUNCH(TQ, 16);                                \
+  } while (0)
+  if (s.act_dtype == DAT_F32) LAUNCH_T(float); else LAUNCH_T(bf16);
+#undef LAUNCH_T
+#undef LAUNCH
+  DAT_LAUNCH_OK("offset_pos_fwd_kernel");
+  return DAT_OK;
+}
+
+int ref_points(int Hk, int Wk, float* ry, float* rx, cudaStream_t st) {
+  DAT_REQUIRE(Hk > 1 && Wk > 1, "ref_points: Hk, Wk must be > 1");
+  int n = Hk > Wk ? Hk : Wk;
+  ref_points_kernel<<<ceil_div(n, 128), 128, 0, st>>>(Hk, Wk, ry, rx);
+  DAT_LAUNCH_OK("ref_points_kernel");
+  return DAT_OK;
+}
+
+static int offset_bwd_blocks(const Shape& s) {
+  long long pts = (long long)s.B * s.G * s.Ns;
+  long long want = (pts + OFF_WARPS - 1) / OFF_WARPS;
+  return (int)(want < 296 ? want : 296);  // 2 CTAs per SM
+}
+static int offset_wgrad_splits(const Shape& s) {
+  long long pts = (long long)s.B * s.G * s.Ns;
+  long long sp = (pts + 511) / 512;
+  return (int)(sp < 1 ? 1 : (sp > 32 ? 32 : sp));
+}
+
+size_t offset_bwd_workspace(const Shape& s) {
+  size_t dt = align_up((size_t)s.B * s.G * s.Ns * s.Cg * sizeof(float), 256);
+  size_t p1 = align_up((size_t)offset_bwd_blocks(s) * 5 * s.Cg * sizeof(float), 256);
+  size_t p2 = align_up((size_t)offset_wgrad_splits(s) * s.ksize * s.ksize * s.Cg * sizeof(float), 256);
+  return dt + p1 + p2;
+}
+
+// dpos (B,G,Ns,2) -> parameter grads of the offset net, and dq += depthwise data gradient.
+int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const float* t_dw,
+               const float* off_raw, const float* dpos, void* dq, const dat_block_grads* g,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+  DAT_REQUIRE(s.Cg <= 512, "offset net: Cg=%d > 512 unsupported", s.Cg);
+  DAT_REQUIRE(ws_bytes >= offset_bwd_workspace(s), "offset_bwd: workspace too small");
+  OffsetArgs a = make_args(s);
+  const int kk = s.ksize * s.ksize;
+  float* dt = (float*)ws;
+  float* part1 = (float*)((char*)ws + align_up((size_t)a.n_points * s.Cg * sizeof(float), 256));
+  int nblk = offset_bwd_blocks(s);
+  float* part2 = (float*)((char*)part1 + align_up((size_t)nblk * 5 * s.Cg * sizeof(float), 256));
+  size_t smem = (size_t)OFF_WARPS * 5 * s.Cg * sizeof(float);
+  int cpl = pick_cpl(s.Cg);
+#define LAUNCH(CPL)                                                                          \
+  do {                                                                                       \
+    auto kern = offset_bwd_point_kernel<CPL>;                                                \
+    if (smem > 48 * 1024)                                                                    \
+      DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                       (int)smem));                                          \
+    kern<<<nblk, OFF_WARPS * 32, smem, st>>>(dpos, off_raw, t_dw, p->off_ln_g, p->off_ln_b,  \
+                                             p->off_pw_w, dt, part1, a);                     \
+  } while (0)
+  if (cpl == 2) LAUNCH(2); else if (cpl == 4) LAUNCH(4); else if (cpl == 8) LAUNCH(8); else LAUNCH(16);
+#undef LAUNCH
+  DAT_LAUNCH_OK("offset_bwd_point_kernel");
+  offset_bwd_reduce_kernel<<<ceil_div(5 * s.Cg, 128), 128, 0, st>>>(
+      part1, nblk, s.Cg, g->off_pw_w, g->off_ln_g, g->off_ln_b, g->off_dw_b);
+  DAT_LAUNCH_OK("offset_bwd_reduce_kernel");
+
+  int nsplit = offset_wgrad_splits(s);
+  long long pps = (a.n_points + nsplit - 1) / nsplit;
+  int threads = ((s.Cg + 31) / 32) * 32;
+  dim3 grid(kk, nsplit);
+  if (s.act_dtype == DAT_F32)
+    offset_bwd_wgrad_kernel<float><<<grid, threads, 0, st>>>((const float*)q, dt, part2, pps, a);
+  else
+    offset_bwd_wgrad_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)q, dt, part2, pps, a);
+  DAT_LAUNCH_OK("offset_bwd_wgrad_kernel");
+  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 128), 128, 0, st>>>(part2, nsplit, kk, s.Cg,
+                                                                            g->off_dw_w);
+  DAT_LAUNCH_OK("offset_bwd_wgrad_reduce_kernel");
+
+  long long total = (long long)s.B * s.HW * s.C;
+  if (s.act_dtype == DAT_F32)
+    offset_bwd_dgrad_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>(dt, p->off_dw_w, (float*)dq, total, a);
+  else
+    offset_bwd_dgrad_kernel<bf16><<<ceil_div(total, 256), 256, 0, st>>>(dt, p->off_dw_w, (bf16*)dq, total, a);
+  DAT_LAUNCH_OK("offset_bwd_dgrad_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

@@ -1,0 +1,153 @@
+/*
+ * dat_b200 — C ABI of the B200-native deformable-attention block (DAT / DAT++).
+ *
+ * The reference (hehe717/DAT-Segmentation) is pure Python and has no FFI: the block
+ * is `DAttentionBaseline.forward` (models/utils/dat_blocks.py:138-227), a straight
+ * line of ~20 PyTorch operator calls.  This header is the boundary a maintainer binds
+ * instead (ctypes stub in INTEGRATION.md): every entry point names the reference
+ * lines it replaces.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers owned by the caller (PyTorch's allocator);
+ *     nothing here allocates, frees or keeps a pointer after returning.
+ *   - Activations are channel-last: x (B, H, W, C) == (B, HW, C), C = n_heads * 32.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     (CUDA-graph capturable; no host synchronisation inside).
+ *   - Return value: DAT_OK (0) or a negative DAT_ERR_* code; never aborts.
+ *     `dat_last_error()` returns a static, thread-local message for the last failure.
+ *   - Re-entrant; no global mutable state.
+ *   - dtype codes: DAT_F32 = 0, DAT_BF16 = 1.  Parameters and all gradients of
+ *     parameters are fp32.  pos / lse / offsets are always fp32.
+ */
+#ifndef DAT_B200_H_
+#define DAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAT_OK 0
+#define DAT_ERR_ARG (-1)      /* bad shape / null pointer / unsupported configuration */
+#define DAT_ERR_CUDA (-2)     /* a CUDA runtime call or kernel launch failed            */
+#define DAT_ERR_UNSUPPORTED (-3)
+
+#define DAT_F32 0
+#define DAT_BF16 1
+
+#define DAT_HEAD_DIM 32       /* n_head_channels; 32 in every DAT++ variant (dat.py:57) */
+
+/* Shape / hyper-parameters of one block call.  Mirrors the constructor arguments of
+ * DAttentionBaseline (dat_blocks.py:21-50) plus the runtime (B, H, W). */
+typedef struct dat_block_desc {
+  int32_t B, H, W;            /* runtime query map; C = n_heads * 32                    */
+  int32_t n_heads;            /* dat_blocks.py:33                                        */
+  int32_t n_groups;           /* :38; Cg = C / n_groups, hg = n_heads / n_groups         */
+  int32_t stride, ksize;      /* :46-47; pad = ksize/2 if ksize != stride else 0 (:50)   */
+  int32_t table_h, table_w;   /* rpe_table spatial size 2*q_h-1, 2*q_w-1 (:101-103)      */
+  float offset_range_factor;  /* :45; < 0 selects the clamp(-1, 1) branch (:159-162)     */
+  int32_t x_dtype;            /* dtype of x and of dx                                    */
+  int32_t act_dtype;          /* dtype of q, xs, k, v, o, y, dy and of d{o,q,k,v,xs}     */
+} dat_block_desc;
+
+/* The 14 reference parameters (state-dict names in comments), fp32. */
+typedef struct dat_block_params {
+  const float* off_dw_w;   /* conv_offset.0.weight      (Cg, 1, k, k) */
+  const float* off_dw_b;   /* conv_offset.0.bias        (Cg)          */
+  const float* off_ln_g;   /* conv_offset.1.norm.weight (Cg)          */
+  const float* off_ln_b;   /* conv_offset.1.norm.bias   (Cg)          */
+  const float* off_pw_w;   /* conv_offset.3.weight      (2, Cg, 1, 1) */
+  const float* wq; const float* bq;   /* proj_q.weight (C, C, 1, 1), proj_q.bias (C) */
+  const float* wk; const float* bk;   /* proj_k.*                                     */
+  const float* wv; const float* bv;   /* proj_v.*                                     */
+  const float* wo; const float* bo;   /* proj_out.*                                   */
+  const float* rpe_table;  /* rpe_table (n_heads, table_h, table_w) */
+} dat_block_params;
+
+/* Gradients of the same 14 tensors (fp32, OVERWRITTEN, not accumulated). */
+typedef struct dat_block_grads {
+  float* off_dw_w; float* off_dw_b; float* off_ln_g; float* off_ln_b; float* off_pw_w;
+  float* wq; float* bq; float* wk; float* bk; float* wv; float* bv; float* wo; float* bo;
+  float* rpe_table;
+} dat_block_grads;
+
+/* Activations kept between forward and backward; caller allocates each buffer.
+ * Ns = Hk * Wk, G = n_groups. */
+typedef struct dat_block_saved {
+  void* q;          /* (B, HW, C)      act_dtype                                   */
+  float* t_dw;      /* (B, G, Ns, Cg)  fp32  depthwise-conv output, pre-LayerNorm  */
+  float* off_raw;   /* (B, G, Ns, 2)   fp32  output of conv_offset.3 (dy, dx)      */
+  float* pos;       /* (B, G, Ns, 2)   fp32  sampling positions (y, x) in [-1, 1]  */
+  void* xs;         /* (B, Ns, C)      act_dtype  sampled features                 */
+  void* k;          /* (B, Ns, C)      act_dtype                                   */
+  void* v;          /* (B, Ns, C)      act_dtype                                   */
+  void* o;          /* (B, HW, C)      act_dtype  attention output before proj_out */
+  float* lse;       /* (B, n_heads, HW) fp32 log-sum-exp of the score rows         */
+} dat_block_saved;
+
+/* ---- queries ------------------------------------------------------------------- */
+
+/* Sample-grid size of the offset network's strided depthwise conv (dat_blocks.py:52,146). */
+int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk);
+
+/* Bytes of scratch `dat_block_forward` / `dat_block_backward` need (0 is possible). */
+size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d);
+size_t dat_block_bwd_workspace_bytes(const dat_block_desc* d);
+
+const char* dat_last_error(void);
+/* Build identification: "dat_b200 <git-free version> sm_100a". */
+const char* dat_version(void);
+
+/* ---- whole block (replaces DAttentionBaseline.forward, dat_blocks.py:138-227) ---- */
+
+int dat_block_forward(const dat_block_desc* d, const dat_block_params* p,
+                      const void* x,            /* (B, HW, C) x_dtype   */
+                      void* y,                  /* (B, HW, C) act_dtype */
+                      const dat_block_saved* s, /* all buffers filled   */
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Autograd of the above (what torch.autograd derives for the reference). */
+int dat_block_backward(const dat_block_desc* d, const dat_block_params* p,
+                       const void* x, const void* dy, const dat_block_saved* s,
+                       float* dx,                /* (B, HW, C) fp32, overwritten */
+                       const dat_block_grads* g,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- individual stages (unit-parity entry points) ------------------------------- */
+
+/* 1x1 conv + bias, channel-last: Y[M,N] = X[M,K] W[N,K]^T + b[N].
+ * Replaces proj_q/proj_k/proj_v/proj_out (dat_blocks.py:143,177-178,225). */
+int dat_pointwise_fwd(const void* X, int32_t x_dtype, const float* W, const float* b,
+                      void* Y, int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream);
+
+/* Offset network + reference points + range/clamp → pos
+ * (dat_blocks.py:144-162 and _get_ref_points :108-121).
+ * q (B,HW,C) act_dtype → t_dw, off_raw, pos as in dat_block_saved. */
+int dat_offset_pos_fwd(const dat_block_desc* d, const dat_block_params* p, const void* q,
+                       float* t_dw, float* off_raw, float* pos, void* stream);
+
+/* Reference points alone, (Hk) + (Wk) floats: ((i + .5) / (n - 1)) * 2 - 1, bit-exact
+ * with dat_blocks.py:111-118. */
+int dat_ref_points(int32_t Hk, int32_t Wk, float* ref_y, float* ref_x, void* stream);
+
+/* Bilinear gather of x at pos (F.grid_sample bilinear/zeros/align_corners=True,
+ * dat_blocks.py:169-172).  taps (optional, may be NULL): (B, G, Ns, 2) int32 = (y0, x0)
+ * north-west integer tap of every sample, for index bit-exactness tests. */
+int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, void* xs,
+                   int32_t* taps, void* stream);
+
+/* QK^T*scale + bilinear rpe bias + softmax + PV (dat_blocks.py:180-223). */
+int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, const void* v,
+                      const float* pos, const float* rpe_table, void* o, float* lse,
+                      void* stream);
+
+/* The rpe bias alone, (B, n_heads, HW, Ns) fp32 (dat_blocks.py:198-212); test hook. */
+int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table,
+                 float* bias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAT_B200_H_ */

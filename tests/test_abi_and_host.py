@@ -1,0 +1,102 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol declared in
+include/dat_b200.h; host-only entry points validate arguments; the Python module
+mirrors the reference's constructor / state-dict surface.  No GPU compute."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from golden_util import load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cab():
+    from dat_segmentation_b200 import _cabi, build
+    build.build()
+    return _cabi
+
+
+def test_header_symbols_all_exported(cab):
+    hdr = open(os.path.join(ROOT, "include", "dat_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dat_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = cab.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in dat_b200.h but not exported"
+    assert declared == set(cab.exported_symbols())
+
+
+def test_sample_grid_matches_conv_arithmetic(cab):
+    lib = cab.lib()
+    for (H, W, s, k) in [(128, 128, 8, 9), (64, 64, 4, 7), (32, 32, 2, 5), (16, 16, 1, 3), (43, 22, 2, 5),
+                         (12, 10, 2, 2), (128, 512, 8, 9)]:
+        d = cab.BlockDesc(1, H, W, 2, 1, s, k, 27, 27, -1.0, 0, 0)
+        hk, wk = C.c_int32(), C.c_int32()
+        assert lib.dat_sample_grid(C.byref(d), C.byref(hk), C.byref(wk)) == 0
+        pad = k // 2 if k != s else 0
+        conv = torch.nn.Conv2d(1, 1, k, s, pad)
+        out = conv(torch.zeros(1, 1, H, W))
+        assert (hk.value, wk.value) == tuple(out.shape[2:])
+
+
+def test_bad_descriptor_is_an_error_not_a_crash(cab):
+    lib = cab.lib()
+    hk, wk = C.c_int32(), C.c_int32()
+    d = cab.BlockDesc(1, 32, 32, 6, 4, 2, 5, 27, 27, -1.0, 0, 0)   # heads % groups != 0
+    assert lib.dat_sample_grid(C.byref(d), C.byref(hk), C.byref(wk)) == -1
+    assert b"n_heads" in lib.dat_last_error()
+    d = cab.BlockDesc(1, 8, 8, 2, 1, 8, 9, 27, 27, -1.0, 0, 0)     # Hk = 1 → reference divides by 0
+    assert lib.dat_sample_grid(C.byref(d), C.byref(hk), C.byref(wk)) == -1
+    assert lib.dat_block_bwd_workspace_bytes(C.byref(d)) == 0
+
+
+def test_workspace_query(cab):
+    d = cab.BlockDesc(16, 32, 32, 8, 4, 2, 5, 27, 27, -1.0, 0, 1)
+    n = cab.lib().dat_block_bwd_workspace_bytes(C.byref(d))
+    assert 0 < n < (1 << 31)
+
+
+def test_module_surface_matches_reference():
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    cfg, x, dy, rec = load_case("cfg1_stage2")
+    m = DAttentionBaseline((14, 14), (14, 14), 8, 32, 4, 0.0, 0.0, 2, -1, True, False, False, False, 5, False, 2)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(rec["params"].keys())          # same names, same order
+    assert all(sd[k].shape == rec["params"][k].shape for k in sd)
+    m.load_state_dict(rec["params"], strict=True)
+    names = [n for n, _ in m.named_parameters()]
+    assert "rpe_table" in names and any("norm" in n for n in names)  # weight-decay filters (new_train.py:146-157)
+    with pytest.raises(RuntimeError):
+        m(x)   # CPU tensor: no fallback
+
+
+def test_default_init_matches_reference_rng_stream():
+    """Same seed → same initial weights as the reference constructor (fixtures were
+    generated with manual_seed(7) and two rescalings)."""
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    cfg, x, dy, rec = load_case("k_eq_s_orf1")
+    torch.manual_seed(7)
+    m = DAttentionBaseline((12, 12), (12, 12), 2, 32, 2, 0.0, 0.0, 2, 1, True, False, False, False, 2, False, 2)
+    with torch.no_grad():
+        m.conv_offset[3].weight.mul_(2.0)
+        m.rpe_table.mul_(10.0)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, rec["params"][k]), k
+
+
+@pytest.mark.parametrize("flag", ["dwc_pe", "no_off", "fixed_pe", "log_cpb", "no_pe"])
+def test_unimplemented_variants_raise(flag):
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    kw = dict(use_pe=True, dwc_pe=False, no_off=False, fixed_pe=False, log_cpb=False)
+    if flag == "no_pe":
+        kw["use_pe"] = False
+    else:
+        kw[flag] = True
+    with pytest.raises(NotImplementedError):
+        DAttentionBaseline((14, 14), (14, 14), 8, 32, 4, 0.0, 0.0, 2, -1, kw["use_pe"], kw["dwc_pe"],
+                           kw["no_off"], kw["fixed_pe"], 5, kw["log_cpb"], 2)

@@ -1,0 +1,288 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI
+(ctypes → libdat_b200.so), against the CPU oracle and the golden vectors generated
+from the unmodified reference.  fp32: 1e-5 relative (max|a-b| / max|b|), integer taps
+and reference points bit-exact; bf16: 2e-2 max-abs (north_star tolerances)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from golden_util import CASES, load_case, nhwc, rel_err
+from oracle import dattn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [n for n in CASES if n != "cfg1_stage2"]
+FP32_TOL = 1e-5
+
+
+def _lib():
+    from dat_segmentation_b200 import _cabi
+    return _cabi, _cabi.lib()
+
+
+def _desc(cab, cfg, B, H, W, x_dt=0, act_dt=0):
+    th, tw = cfg.table_hw
+    return cab.BlockDesc(B, H, W, cfg.n_heads, cfg.n_groups, cfg.stride, cfg.ksize, th, tw,
+                         float(cfg.offset_range_factor), x_dt, act_dt)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _params_struct(cab, params, keep):
+    st = cab.BlockParams()
+    for f, k in zip(cab.PARAM_FIELDS, cab.PARAM_KEYS):
+        t = params[k].detach().float().contiguous().cuda()
+        keep.append(t)
+        setattr(st, f, t.data_ptr())
+    return st
+
+
+def _module(cfg, params, q_size):
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    m = DAttentionBaseline(q_size, q_size, cfg.n_heads, 32, cfg.n_groups, 0.0, 0.0, cfg.stride,
+                           cfg.offset_range_factor, True, False, False, False, cfg.ksize, False, 2)
+    m.load_state_dict(params, strict=True)   # reference state dict, strict
+    return m.cuda()
+
+
+def test_library_loads_and_reports_version():
+    cab, lib = _lib()
+    assert b"sm_100a" in lib.dat_version()
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 7, 16, 17, 32, 64, 112, 128, 512])
+def test_ref_points_bit_exact(n):
+    cab, lib = _lib()
+    ry = torch.empty(n, device="cuda")
+    rx = torch.empty(n + 1, device="cuda")
+    cab.check(lib.dat_ref_points(n, n + 1, _p(ry), _p(rx), _stream()), "ref_points")
+    ref_y = torch.linspace(0.5, n - 0.5, n).div_(n - 1.0).mul_(2.0).sub_(1.0)      # dat_blocks.py:111-118
+    ref_x = torch.linspace(0.5, n + 0.5, n + 1).div_(float(n)).mul_(2.0).sub_(1.0)
+    assert torch.equal(ry.cpu(), ref_y)
+    assert torch.equal(rx.cpu(), ref_x)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (513, 96, 96), (4096, 256, 256), (77, 512, 512)])
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_pointwise_fwd(M, N, K, dt):
+    cab, lib = _lib()
+    g = torch.Generator().manual_seed(M + N)
+    X = torch.randn(M, K, generator=g)
+    Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = X @ Wt.T + b
+    if dt == "f32":
+        Xd, Y = X.cuda(), torch.empty(M, N, device="cuda")
+        code = 0
+    else:
+        Xd, Y = X.cuda().bfloat16(), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ref = Xd.float().cpu() @ Wt.T + b
+        code = 1
+    Wd, bd = Wt.cuda(), b.cuda()
+    cab.check(lib.dat_pointwise_fwd(_p(Xd), code, _p(Wd), _p(bd), _p(Y), code, M, N, K, _stream()), "pw")
+    err = rel_err(Y.float().cpu(), ref)
+    assert err < (FP32_TOL if dt == "f32" else 8e-3), err
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_offset_net_and_positions(name):
+    cab, lib = _lib()
+    cfg, x, dy, rec = load_case(name)
+    fw = orc.forward_explicit(nhwc(x), rec["params"], cfg)
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    keep = []
+    ps = _params_struct(cab, rec["params"], keep)
+    d = _desc(cab, cfg, B, H, W)
+    q = fw["q"].contiguous().cuda()
+    G, Cg = cfg.n_groups, cfg.cg
+    Ns = fw["pos"].shape[2] * fw["pos"].shape[3]
+    t = torch.empty(B, G, Ns, Cg, device="cuda")
+    off = torch.empty(B, G, Ns, 2, device="cuda")
+    pos = torch.empty(B, G, Ns, 2, device="cuda")
+    cab.check(lib.dat_offset_pos_fwd(C.byref(d), C.byref(ps), _p(q), _p(t), _p(off), _p(pos), _stream()), "off")
+    t_ref = fw["off_t"].permute(0, 3, 1, 2, 4).reshape(B, G, Ns, Cg)
+    assert rel_err(t.cpu(), t_ref) < FP32_TOL
+    assert rel_err(off.cpu(), fw["off_raw"].reshape(B, G, Ns, 2)) < 2e-5
+    assert rel_err(pos.cpu(), fw["pos"].reshape(B, G, Ns, 2)) < FP32_TOL
+    assert rel_err(pos.cpu(), rec["pos_l"].reshape(B, G, Ns, 2)) < FP32_TOL   # vs the reference itself
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_sampling_taps_bit_exact_and_values(name):
+    """Reference pos injected → integer taps identical to ATen's floor(((g+1)/2)(size-1)),
+    sampled features equal to the reference's F.grid_sample output."""
+    cab, lib = _lib()
+    cfg, x, dy, rec = load_case(name)
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    d = _desc(cab, cfg, B, H, W)
+    pos = rec["pos_l"].contiguous()
+    G, Ns = cfg.n_groups, pos.shape[2] * pos.shape[3]
+    xs_ref, (x0, y0) = orc.sample_features_explicit(nhwc(x), pos, cfg)
+    xd, posd = nhwc(x).cuda(), pos.cuda()
+    xs = torch.empty(B, Ns, cfg.nc, device="cuda")
+    taps = torch.empty(B, G, Ns, 2, device="cuda", dtype=torch.int32)
+    cab.check(lib.dat_sample_fwd(C.byref(d), _p(xd), _p(posd), _p(xs), _p(taps), _stream()), "sample")
+    assert torch.equal(taps[..., 0].cpu().long(), y0)
+    assert torch.equal(taps[..., 1].cpu().long(), x0)
+    assert rel_err(xs.cpu(), rec["xs_l"]) < 2e-6
+    assert rel_err(xs.cpu(), xs_ref) < 2e-6
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_rpe_bias_matches_reference(name):
+    cab, lib = _lib()
+    cfg, x, dy, rec = load_case(name)
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    d = _desc(cab, cfg, B, H, W)
+    posd = rec["pos_l"].contiguous().cuda()
+    tab = rec["params"]["rpe_table"].contiguous().cuda()
+    Ns = rec["pos_l"].shape[2] * rec["pos_l"].shape[3]
+    bias = torch.empty(B, cfg.n_heads, H * W, Ns, device="cuda")
+    cab.check(lib.dat_rpe_bias(C.byref(d), _p(posd), _p(tab), _p(bias), _stream()), "bias")
+    assert rel_err(bias.cpu(), rec["bias_l"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_attention_core_fwd(name):
+    cab, lib = _lib()
+    cfg, x, dy, rec = load_case(name)
+    fw = orc.forward_explicit(nhwc(x), rec["params"], cfg)
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    d = _desc(cab, cfg, B, H, W)
+    q = fw["q"].reshape(B, H * W, -1).contiguous().cuda()
+    k, v = fw["k"].contiguous().cuda(), fw["v"].contiguous().cuda()
+    pos = fw["pos"].contiguous().cuda()
+    tab = rec["params"]["rpe_table"].contiguous().cuda()
+    o = torch.empty_like(q)
+    lse = torch.empty(B, cfg.n_heads, H * W, device="cuda")
+    cab.check(lib.dat_attention_fwd(C.byref(d), _p(q), _p(k), _p(v), _p(pos), _p(tab), _p(o), _p(lse), _stream()), "attn")
+    assert rel_err(o.cpu(), fw["o"].reshape(B, H * W, -1)) < FP32_TOL
+    assert rel_err(lse.cpu(), fw["lse"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+def test_block_forward_fp32_vs_reference(name, layout):
+    cfg, x, dy, rec = load_case(name)
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    xd = x.cuda()
+    if layout == "channels_last":   # in-situ layout: permuted view of an NHWC buffer (dat.py:147)
+        xd = nhwc(x).cuda().permute(0, 3, 1, 2)
+    with torch.no_grad():
+        y, p_, r_ = m(xd)
+    assert p_ is None and r_ is None and y.shape == x.shape
+    err = rel_err(y.cpu(), rec["y"])
+    assert err < FP32_TOL, err
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_block_backward_fp32_vs_reference(name):
+    cfg, x, dy, rec = load_case(name)
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    xd = x.cuda().requires_grad_(True)
+    y, _, _ = m(xd)
+    y.backward(dy.cuda())
+    report = {"dx": rel_err(xd.grad.cpu(), rec["dx"])}
+    for key, p in m.named_parameters():
+        if key == "proj_k.bias":   # analytically zero; compare absolutely
+            report[key] = p.grad.abs().max().item()
+            continue
+        report[key] = rel_err(p.grad.cpu(), rec["grads"][key])
+    print(name, {k: f"{v:.2e}" for k, v in report.items()})
+    bad = {k: v for k, v in report.items() if v > (1e-4 if k == "proj_k.bias" else 5e-5)}
+    assert not bad, bad
+
+
+def test_pos_and_ref_opt_in():
+    cfg, x, dy, rec = load_case("stage1_orf2")
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    m.return_pos_ref = True
+    with torch.no_grad():
+        y, pos, ref = m(x.cuda())
+    assert rel_err(pos.cpu(), rec["pos"]) < FP32_TOL
+    hk, wk = rec["pos"].shape[1:3]
+    ry, rx = orc.ref_points(hk, wk)
+    assert torch.equal(ref[0, :, 0, 0].cpu(), ry) and torch.equal(ref[0, 0, :, 1].cpu(), rx)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_block_forward_bf16_autocast_vs_reference(name):
+    """bf16 parity mode = torch.autocast(bfloat16) of the reference."""
+    cfg, x, dy, rec = load_case(name)
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y, _, _ = m(x.cuda())
+    assert y.dtype == torch.bfloat16
+    d_bf = (y.float().cpu() - rec["y_autocast_bf16"].float()).abs().max().item()
+    d_32 = (y.float().cpu() - rec["y"]).abs().max().item()
+    ref_gap = (rec["y_autocast_bf16"].float() - rec["y"]).abs().max().item()
+    print(name, f"vs ref-bf16 {d_bf:.2e}  vs ref-fp32 {d_32:.2e}  (ref bf16 vs fp32 {ref_gap:.2e})")
+    # the reference's own bf16 run is up to ref_gap away from its fp32 run
+    assert d_32 < 2e-2 or d_bf < 2e-2
+    assert d_32 < max(2e-2, 2 * ref_gap)
+
+
+@pytest.mark.parametrize("name", ["cfg1_stage2", "stage1_orf2", "stage3_small"])
+def test_block_backward_bf16(name):
+    cfg, x, dy, rec = load_case(name)
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y, _, _ = m(xd)
+    y.backward(dy.cuda().bfloat16())
+    report = {"dx": rel_err(xd.grad.cpu(), rec["dx"])}
+    for key, p in m.named_parameters():
+        if key != "proj_k.bias":
+            report[key] = rel_err(p.grad.cpu(), rec["grads"][key])
+    print(name, {k: f"{v:.2e}" for k, v in report.items()})
+    assert all(v < 6e-2 for v in report.values()), report
+
+
+def test_cpu_tensor_raises_no_fallback():
+    cfg, x, dy, rec = load_case("k_eq_s_orf1")
+    m = _module(cfg, rec["params"], rec["meta"]["q_size"])
+    with pytest.raises(RuntimeError):
+        m(x)   # CPU tensor
+
+
+# ---- full-size (BASELINE.json configs[1] shapes): size-independent properties -------------
+
+STAGES = [  # DAT-T++ @512²: (H, heads, groups, stride, ksize, q_size)
+    (128, 2, 1, 8, 9, 56), (64, 4, 2, 4, 7, 28), (32, 8, 4, 2, 5, 14), (16, 16, 8, 1, 3, 7)]
+
+
+@pytest.mark.parametrize("stage", range(4))
+def test_full_size_batch_independence_and_determinism(stage):
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    H, heads, groups, stride, ksize, qs = STAGES[stage]
+    torch.manual_seed(stage)
+    m = DAttentionBaseline((qs, qs), (qs, qs), heads, 32, groups, 0.0, 0.0, stride, -1, True, False,
+                           False, False, ksize, False, stage).cuda()
+    with torch.no_grad():
+        m.conv_offset[3].weight.mul_(2.0)
+        m.rpe_table.mul_(10.0)
+    B = 16
+    x = torch.randn(B, heads * 32, H, H, device="cuda")
+    with torch.no_grad():
+        y1, _, _ = m(x)
+        y2, _, _ = m(x)
+        y_one, _, _ = m(x[5:6])
+    assert torch.equal(y1, y2)                      # deterministic
+    assert torch.equal(y1[5:6], y_one)              # samples are independent (batch sharding is exact)
+    # oracle on a 2-image slice at full spatial size
+    cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, -1)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    y_ref = orc.forward_libops(x[:2].cpu(), params, cfg)
+    assert rel_err(y1[:2].cpu(), y_ref) < FP32_TOL
+    # softmax shift invariance: a constant added to every key logit changes nothing
+    with torch.no_grad():
+        m.proj_k.bias.add_(0.37)
+        y3, _, _ = m(x)
+    assert rel_err(y3.cpu(), y1.cpu()) < 5e-5
