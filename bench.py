@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: DAT-T++ backbone fwd+bwd images/s @512x512 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: the backbone of dat_segmentation_b200/backbone.py with the 14 deformable-attention
+blocks running in the hand-written sm_100a kernels (C ABI, libdat_b200.so), bf16 autocast,
+batch 16 per GPU, synthetic ADE20K-shaped input, random-init weights.  `value` = device-timed
+images/s with inputs resident in HBM; `e2e` = the same step fed from pinned host memory with a
+device->host read of the loss every step.  `roofline` = the dominant hand-written kernel timed
+alone with CUDA events (L2 flushed between launches).  `cpu_baseline` / `--impl reference` =
+the oracle port of the reference (library-operator form) on the host cores, bounded sample.
+Under torchrun (N > 1): one process per GPU, batch-sharded, gradients all-reduced by NCCL
+(DistributedDataParallel), max-over-ranks timing.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DAT-T++ backbone fwd+bwd images/sec @512x512"
+UNIT = "images/s"
+IMG = 512
+PER_GPU_BATCH = 16
+STAGES = [  # DAT-T++ @512²: (H=W, C, heads, groups, stride, ksize, q_size, n_blocks)
+    (128, 64, 2, 1, 8, 9, 56, 1), (64, 128, 4, 2, 4, 7, 28, 2),
+    (32, 256, 8, 4, 2, 5, 14, 9), (16, 512, 16, 8, 1, 3, 7, 2)]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def loss_of(outs):
+    return sum(o.float().square().mean() for o in outs)
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port of the reference on the host cores
+# --------------------------------------------------------------------------------------
+
+def cpu_port_run(steps, warmup, batch):
+    from dat_segmentation_b200.backbone import build_dat
+    from oracle.dattn_oracle import OracleDAttention
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = build_dat(attn_cls=OracleDAttention).train()
+    imgs = torch.randn(batch, 3, IMG, IMG)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            outs = model(imgs)
+        loss_of(outs).backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=batch / dt, ms_per_step=dt * 1e3, cores=cores, threads=torch.get_num_threads(),
+                sample=f"{steps} steps of batch {batch} @512x512 fwd+bwd, bf16 autocast, {warmup} warm-up")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_port_run(max(1, min(args.steps, 4)), max(1, min(args.warmup, 1)), 2)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "DAT-T++ backbone fwd+bwd 512x512 (configs[1]), CPU sample batch 2",
+                   "per_gpu_batch": PER_GPU_BATCH},
+        "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# roofline leg: the dominant hand-written kernel, timed alone on its launch stream
+# --------------------------------------------------------------------------------------
+
+def kernel_roofline(dev, pk):
+    """Attention core (QK^T + rpe bias + softmax + PV) at the stage-2 shape (9 of the 14 blocks),
+    batch 16, bf16.  Algorithmic FLOPs = 4*HW*Ns*C per image; algorithmic
+    bytes = q + o + k + v + pos + table."""
+    from dat_segmentation_b200 import _cabi
+    lib = _cabi.lib()
+    H, Cc, heads, groups, stride, ksize, qs, _ = STAGES[2]
+    B, HW, Ns = PER_GPU_BATCH, H * H, 256
+    d = _cabi.BlockDesc(B, H, H, heads, groups, stride, ksize, 2 * qs - 1, 2 * qs - 1, -1.0, _cabi.DAT_F32, _cabi.DAT_BF16)
+    g = torch.Generator(device=dev).manual_seed(0)
+    bf = torch.bfloat16
+    q = torch.randn(B, HW, Cc, device=dev, generator=g).to(bf)
+    k = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
+    v = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
+    pos = (torch.rand(B, groups, Ns, 2, device=dev, generator=g) * 2 - 1)
+    tab = torch.randn(heads, 2 * qs - 1, 2 * qs - 1, device=dev, generator=g) * 0.1
+    o = torch.empty_like(q)
+    lse = torch.empty(B, heads, HW, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(st.cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def launch():
+        _cabi.check(lib.dat_attention_fwd(C.byref(d), p(q), p(k), p(v), p(pos), p(tab), p(o), p(lse), sp), "attention_fwd")
+
+    for _ in range(3):
+        launch()
+    times = []
+    for _ in range(10):
+        flush.zero_()                       # > L2 (126 MB): next launch starts cold
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        launch()
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    flops = 4.0 * HW * Ns * Cc * B
+    byts = (2 * B * HW * Cc + 2 * B * Ns * Cc) * 2 + B * groups * Ns * 8 + heads * (2 * qs - 1) ** 2 * 4
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "dat_attention_fwd (stage-2 shape, B=16, bf16)", "bound": "tensor",
+            "achieved": round(achieved, 3), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": round(achieved / pk["bf16_tflops"], 5), "traffic": None, "ms": round(ms, 4),
+            "algorithmic_bytes": byts, "hbm_gbs_at_this_time": round(byts / (ms * 1e-3) / 1e9, 1),
+            "peak_source": pk["source"]}
+
+
+# --------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dat_b200", choices=["dat_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from dat_segmentation_b200 import _cabi
+    from dat_segmentation_b200.backbone import build_dat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.pop("NCCL_P2P_DISABLE", None)   # the reference's launch scripts set it; NVSwitch wants P2P
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+    warmup = max(3, args.warmup)
+
+    torch.manual_seed(0)
+    model = build_dat().to(dev).train()          # drop_path_rate 0.3 as in the shipped config
+    step_model = model
+    if world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev, generator=gen)
+    host = torch.randn(PER_GPU_BATCH, 3, IMG, IMG).pin_memory()
+    dev_in = torch.empty_like(imgs)
+
+    def step(x):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = step_model(x)
+        loss = loss_of(outs)
+        loss.backward()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step(imgs)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = lib.dat_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(imgs)
+    e1.record()
+    sync_all()
+    launches = lib.dat_launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+
+    # end-to-end: pinned host -> device every step, loss read back every step
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_in.copy_(host, non_blocking=True)
+        _ = step(dev_in).item()
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.summary() if sampler else None
+
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        roof = kernel_roofline(dev, pk)
+        total = PER_GPU_BATCH * world
+        line = {
+            "metric": METRIC, "value": round(total / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "DAT-T++ backbone fwd+bwd, 512x512, batch 16 per GPU, bf16 autocast "
+                                   "(BASELINE.json configs[1]); 14 deformable-attention blocks in dat_b200 kernels, "
+                                   "rest of the backbone in PyTorch library ops",
+                       "per_gpu_batch": PER_GPU_BATCH, "global_batch": total,
+                       "parallelism": f"dp{world} (batch-sharded, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+                       "l2": "working set per step >> 126 MB L2 (no flush needed); roofline leg flushes L2 per launch",
+                       "drop_path_rate": 0.3},
+            "e2e": {"value": round(total / (e2e_ms * 1e-3), 2), "unit": UNIT,
+                    "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_port_run(3, 1, 2)
+            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"],
+                                    "kind": "port", "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

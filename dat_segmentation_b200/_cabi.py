@@ -64,6 +64,7 @@ def lib():
     dp = C.POINTER(BlockDesc)
     L.dat_last_error.restype = C.c_char_p
     L.dat_version.restype = C.c_char_p
+    L.dat_launch_count.restype = C.c_uint64
     L.dat_sample_grid.argtypes = [dp, C.POINTER(i32), C.POINTER(i32)]
     L.dat_block_fwd_workspace_bytes.argtypes = [dp]
     L.dat_block_fwd_workspace_bytes.restype = C.c_size_t
@@ -96,6 +97,6 @@ def check(rc, what):
 def exported_symbols():
     """Names declared in include/dat_b200.h (used by the CPU-side symbol test)."""
     return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
-            "dat_last_error", "dat_version", "dat_block_forward", "dat_block_backward",
+            "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
             "dat_pointwise_fwd", "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd",
             "dat_attention_fwd", "dat_rpe_bias"]

@@ -1,0 +1,222 @@
+"""Host-side DAT / DAT++ backbone that calls the B200 deformable-attention block.
+
+Row "next" of the scope table: the caller of the hot path
+(`models/backbones/dat.py:34-312` in the reference).  Only the deformable-attention
+block is hand-written CUDA; everything else in this file is plain PyTorch plumbing
+(library convolutions / LayerNorm), kept so that `bench.py` can measure the headline
+metric (DAT-T++ images/s fwd+bwd @512²) on a GPU box where the reference tree does not
+exist.  Module and parameter names follow the reference, so a reference DAT++ state
+dict loads with `strict=True`.
+"""
+from typing import Callable, Sequence
+
+import torch
+import torch.nn as nn
+
+from .dattention import DAttentionBaseline, LayerNormProxy, _pair
+
+__all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat"]
+
+# DAT-T++ backbone hyper-parameters (configs/dat/upn_tiny_160k_dp03_lr6.py:9-32)
+DAT_TINY_PP = dict(
+    dim_stem=64, dims=[64, 128, 256, 512], depths=[2, 4, 18, 2],
+    stage_spec=[["X", "D"], ["X", "D"] * 2, ["X", "D"] * 9, ["D", "D"]],
+    heads=[2, 4, 8, 16], groups=[1, 2, 4, 8], use_pes=[True] * 4, strides=[8, 4, 2, 1],
+    offset_range_factor=[-1, -1, -1, -1], use_dwc_mlps=[True] * 4, use_lpus=[True] * 4,
+    use_conv_patches=True, ksizes=[9, 7, 5, 3], nat_ksizes=[7, 7, 7, 7], drop_path_rate=0.3,
+    use_checkpoint=False)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth, per sample, kept-path rescaled by 1/(1-p) (timm semantics)."""
+
+    def __init__(self, p=0.0):
+        super().__init__()
+        self.p = float(p)
+
+    def forward(self, x):
+        if not self.training or self.p == 0.0:
+            return x
+        keep = 1.0 - self.p
+        mask = torch.empty(x.shape[0], 1, 1, 1, device=x.device, dtype=x.dtype).bernoulli_(keep)
+        return x * mask / keep
+
+
+class LayerScale(nn.Module):
+    def __init__(self, dim, init_values=1e-5):
+        super().__init__()
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+    def forward(self, x):
+        return x * self.gamma.view(1, -1, 1, 1)
+
+
+class TransformerMLP(nn.Module):
+    """Linear-GELU-Linear over channels (dat_blocks.py:244-265)."""
+
+    def __init__(self, channels, expansion, drop):
+        super().__init__()
+        self.chunk = nn.Sequential()
+        self.chunk.add_module("linear1", nn.Linear(channels, channels * expansion))
+        self.chunk.add_module("act", nn.GELU())
+        self.chunk.add_module("drop1", nn.Dropout(drop))
+        self.chunk.add_module("linear2", nn.Linear(channels * expansion, channels))
+        self.chunk.add_module("drop2", nn.Dropout(drop))
+
+    def forward(self, x):
+        return self.chunk(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+class TransformerMLPWithConv(nn.Module):
+    """1x1 -> (+ depthwise 3x3) -> GELU -> 1x1 (dat_blocks.py:316-348)."""
+
+    def __init__(self, channels, expansion, drop):
+        super().__init__()
+        hidden = channels * expansion
+        self.linear1 = nn.Sequential(nn.Conv2d(channels, hidden, 1))
+        self.drop1 = nn.Dropout(drop)
+        self.act = nn.GELU()
+        self.linear2 = nn.Sequential(nn.Conv2d(hidden, channels, 1))
+        self.drop2 = nn.Dropout(drop)
+        self.dwc = nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden)
+
+    def forward(self, x):
+        x = self.drop1(self.linear1(x))
+        x = self.act(x + self.dwc(x))
+        return self.drop2(self.linear2(x))
+
+
+class TransformerStage(nn.Module):
+    """One resolution stage (dat.py:34-165).  Spec letters: 'D' deformable attention,
+    'X' depthwise conv mixer.  `attn_cls` lets tests / the CPU baseline substitute the
+    block implementation (reference class, oracle port) without touching the wiring."""
+
+    def __init__(self, fmap_size, window_size, dim_in, dim_embed, depths, stage_spec, n_groups,
+                 use_pe, heads, stride, offset_range_factor, dwc_pe, no_off, fixed_pe, attn_drop,
+                 proj_drop, expansion, drop, drop_path_rate, use_dwc_mlp, ksize, layer_scale_value,
+                 use_lpu, log_cpb, stage_i, use_checkpoint, attn_cls: Callable = DAttentionBaseline):
+        super().__init__()
+        fmap_size = _pair(fmap_size)
+        self.depths, self.stage_spec = depths, list(stage_spec)
+        self.use_lpu, self.use_checkpoint = use_lpu, use_checkpoint
+        hc = dim_embed // heads
+        assert dim_embed == heads * hc
+        self.proj = nn.Conv2d(dim_in, dim_embed, 1) if dim_in != dim_embed else nn.Identity()
+        self.ln_cnvnxt = nn.ModuleDict(
+            {str(d): LayerNormProxy(dim_embed) for d in range(depths) if stage_spec[d] == "X"})
+        self.layer_norms = nn.ModuleList(
+            [LayerNormProxy(dim_embed) if stage_spec[d // 2] != "X" else nn.Identity()
+             for d in range(2 * depths)])
+        mlp_cls = TransformerMLPWithConv if use_dwc_mlp else TransformerMLP
+        self.mlps = nn.ModuleList([mlp_cls(dim_embed, expansion, drop) for _ in range(depths)])
+        self.attns = nn.ModuleList()
+        self.drop_path = nn.ModuleList()
+        self.layer_scales = nn.ModuleList(
+            [LayerScale(dim_embed, layer_scale_value) if layer_scale_value > 0.0 else nn.Identity()
+             for _ in range(2 * depths)])
+        self.local_perception_units = nn.ModuleList(
+            [nn.Conv2d(dim_embed, dim_embed, 3, 1, 1, groups=dim_embed) if use_lpu else nn.Identity()
+             for _ in range(depths)])
+        for d in range(depths):
+            if stage_spec[d] == "D":
+                self.attns.append(attn_cls(fmap_size, fmap_size, heads, hc, n_groups, attn_drop,
+                                           proj_drop, stride, offset_range_factor, use_pe, dwc_pe,
+                                           no_off, fixed_pe, ksize, log_cpb, stage_i))
+            elif stage_spec[d] == "X":
+                self.attns.append(nn.Conv2d(dim_embed, dim_embed, window_size, padding=window_size // 2,
+                                            groups=dim_embed))
+            else:
+                raise NotImplementedError(f"Spec: {stage_spec[d]} is not supported.")
+            self.drop_path.append(DropPath(drop_path_rate[d]) if drop_path_rate[d] > 0.0 else nn.Identity())
+
+    def _inner_forward(self, x):
+        x = self.proj(x)
+        for d in range(self.depths):
+            if self.use_lpu:
+                x = self.local_perception_units[d](x.contiguous()) + x
+            if self.stage_spec[d] == "X":   # note: no residual around mixer+MLP (dat.py:140-144)
+                x = self.attns[d](self.layer_norms[2 * d](x))
+                x = self.drop_path[d](self.mlps[d](self.ln_cnvnxt[str(d)](x)))
+            else:
+                a, _, _ = self.attns[d](self.layer_norms[2 * d](x))
+                x = self.drop_path[d](self.layer_scales[2 * d](a)) + x
+                m = self.mlps[d](self.layer_norms[2 * d + 1](x))
+                x = self.drop_path[d](self.layer_scales[2 * d + 1](m)) + x
+        return x
+
+    def forward(self, x):
+        if self.training and x.requires_grad and self.use_checkpoint:
+            return torch.utils.checkpoint.checkpoint(self._inner_forward, x, use_reentrant=False)
+        return self._inner_forward(x)
+
+
+class DAT(nn.Module):
+    """DAT / DAT++ backbone (dat.py:167-312): conv stem, 4 stages, 3 down-projections,
+    per-stage output norms; returns the 4 feature maps."""
+
+    def __init__(self, img_size=224, patch_size=4, num_classes=1000, expansion=4, dim_stem=96,
+                 dims=(96, 192, 384, 768), depths=(2, 2, 6, 2), heads=(3, 6, 12, 24),
+                 heads_q=(6, 12, 24, 48), window_sizes=(7, 7, 7, 7), drop_rate=0.0,
+                 attn_drop_rate=0.0, drop_path_rate=0.0, strides=(-1, -1, -1, -1),
+                 offset_range_factor=(1, 2, 3, 4), local_orf=(-1,) * 4, local_kv_sizes=(-1,) * 4,
+                 offset_pes=(False,) * 4,
+                 stage_spec=(("L", "D"), ("L", "D"), ("L", "D") * 3, ("L", "D")),
+                 groups=(-1, -1, 3, 6), use_pes=(False,) * 4, dwc_pes=(False,) * 4,
+                 sr_ratios=(8, 4, 2, 1), lower_lr_kvs=None, fixed_pes=(False,) * 4,
+                 no_offs=(False,) * 4, ns_per_pts=(4,) * 4, use_dwc_mlps=(False,) * 4,
+                 use_conv_patches=False, ksizes=(9, 7, 5, 3), ksize_qnas=(3,) * 4, nqs=(2,) * 4,
+                 qna_activation="exp", deform_groups=(0,) * 4, nat_ksizes=(3,) * 4,
+                 layer_scale_values=(-1,) * 4, use_lpus=(False,) * 4, use_cmt_mlps=(False,) * 4,
+                 log_cpb=(False,) * 4, out_indices=(0, 1, 2, 3), use_checkpoint=True,
+                 init_cfg=None, attn_cls: Callable = DAttentionBaseline, **kwargs):
+        super().__init__()
+        if any(use_cmt_mlps):
+            raise NotImplementedError("use_cmt_mlps (BatchNorm MLP variant) is not implemented")
+        self.out_indices = out_indices
+        half = dim_stem // 2
+        if use_conv_patches:
+            self.patch_proj = nn.Sequential(
+                nn.Conv2d(3, half, 3, patch_size // 2, 1), LayerNormProxy(half), nn.GELU(),
+                nn.Conv2d(half, dim_stem, 3, patch_size // 2, 1), LayerNormProxy(dim_stem))
+        else:
+            self.patch_proj = nn.Sequential(nn.Conv2d(3, dim_stem, patch_size, patch_size, 0),
+                                            LayerNormProxy(dim_stem))
+        fmap = img_size // patch_size
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.stages = nn.ModuleList()
+        self.norms = nn.ModuleList()
+        for i in range(4):
+            dim_in = dim_stem if i == 0 else dims[i - 1] * 2
+            lo, hi = sum(depths[:i]), sum(depths[:i + 1])
+            self.stages.append(TransformerStage(
+                fmap, window_sizes[i], dim_in, dims[i], depths[i], stage_spec[i], groups[i],
+                use_pes[i], heads[i], strides[i], offset_range_factor[i], dwc_pes[i], no_offs[i],
+                fixed_pes[i], attn_drop_rate, drop_rate, expansion, drop_rate, dpr[lo:hi],
+                use_dwc_mlps[i], ksizes[i], layer_scale_values[i], use_lpus[i], log_cpb[i], i,
+                use_checkpoint, attn_cls=attn_cls))
+            self.norms.append(LayerNormProxy(dims[i]) if i in out_indices else nn.Identity())
+            fmap //= 2
+        self.down_projs = nn.ModuleList()
+        for i in range(3):
+            conv = (nn.Conv2d(dims[i], dims[i + 1], 3, 2, 1, bias=False) if use_conv_patches
+                    else nn.Conv2d(dims[i], dims[i + 1], 2, 2, 0, bias=False))
+            self.down_projs.append(nn.Sequential(conv, LayerNormProxy(dims[i + 1])))
+
+    def forward(self, x):
+        x = self.patch_proj(x)
+        outs = []
+        for i in range(4):
+            x = self.stages[i](x)
+            outs.append(self.norms[i](x).contiguous())
+            if i < 3:
+                x = self.down_projs[i](x)
+        return outs
+
+
+def build_dat(cfg: dict = None, attn_cls: Callable = DAttentionBaseline, **override) -> DAT:
+    """DAT(**cfg) as `models/builder.py:93-102` does (init_cfg / type keys dropped)."""
+    kw = dict(DAT_TINY_PP if cfg is None else cfg)
+    kw.update(override)
+    kw.pop("type", None)
+    kw.pop("init_cfg", None)
+    return DAT(attn_cls=attn_cls, **kw)

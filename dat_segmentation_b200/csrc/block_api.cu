@@ -10,6 +10,9 @@
 namespace dat {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // statistics only (relaxed atomic increments)
+
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -98,6 +101,7 @@ extern "C" {
 
 const char* dat_last_error(void) { return g_err; }
 const char* dat_version(void) { return "dat_b200 0.1 sm_100a"; }
+uint64_t dat_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk) {
   Shape s;

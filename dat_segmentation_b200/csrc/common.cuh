@@ -12,6 +12,7 @@ namespace dat {
 
 // ---- error plumbing --------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launch();  // host-side counter behind dat_launch_count()
 
 #define DAT_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -38,6 +39,7 @@ void set_error(const char* fmt, ...);
       ::dat::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));     \
       return DAT_ERR_CUDA;                                                            \
     }                                                                                 \
+    ::dat::count_launch();                                                            \
   } while (0)
 
 #define DAT_FWD(expr)             \

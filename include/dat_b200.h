@@ -99,6 +99,8 @@ size_t dat_block_bwd_workspace_bytes(const dat_block_desc* d);
 const char* dat_last_error(void);
 /* Build identification: "dat_b200 <git-free version> sm_100a". */
 const char* dat_version(void);
+/* Number of kernels this library has launched in this process (statistics; bench.py). */
+uint64_t dat_launch_count(void);
 
 /* ---- whole block (replaces DAttentionBaseline.forward, dat_blocks.py:138-227) ---- */
 

@@ -481,10 +481,16 @@ def forward_libops(x_nchw: Tensor, p: Dict[str, Tensor], cfg: BlockCfg) -> Tenso
     return F.conv2d(out, p["proj_out.weight"], p["proj_out.bias"])
 
 
+class _LNHolder(torch.nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = torch.nn.LayerNorm(dim)
+
+
 class OracleDAttention(torch.nn.Module):
     """nn.Module wrapper over `forward_libops` with the reference's constructor
     signature (dat_blocks.py:21-26) and state-dict keys, so it can stand in for
-    the block inside a backbone for CPU baseline timing."""
+    the block inside a backbone (CPU baseline timing, backbone-level parity)."""
 
     def __init__(self, q_size, kv_size, n_heads, n_head_channels, n_groups, attn_drop, proj_drop,
                  stride, offset_range_factor, use_pe, dwc_pe, no_off, fixed_pe, ksize, log_cpb,
@@ -492,21 +498,19 @@ class OracleDAttention(torch.nn.Module):
         super().__init__()
         if not use_pe or dwc_pe or no_off or fixed_pe or log_cpb:
             raise NotImplementedError("oracle covers the rpe_table (bilinear bias) variant only")
+        nn = torch.nn
+        q_size = tuple(q_size) if isinstance(q_size, (tuple, list)) else (q_size, q_size)
         self.cfg = BlockCfg(q_size[0], q_size[1], n_heads, n_head_channels, n_groups, stride, ksize,
                             offset_range_factor)
-        self._keys = []
-        for key, val in init_params(self.cfg, seed=stage_i).items():
-            name = key.replace(".", "__")
-            self.register_parameter(name, torch.nn.Parameter(val))
-            self._keys.append((key, name))
-
-    def params(self):
-        return {key: getattr(self, name) for key, name in self._keys}
-
-    def load_reference_state(self, sd):
-        with torch.no_grad():
-            for key, name in self._keys:
-                getattr(self, name).copy_(sd[key])
+        c, cg = self.cfg.nc, self.cfg.cg
+        self.conv_offset = nn.Sequential(nn.Conv2d(cg, cg, ksize, stride, self.cfg.pad, groups=cg),
+                                         _LNHolder(cg), nn.GELU(), nn.Conv2d(cg, 2, 1, bias=False))
+        self.proj_q, self.proj_k = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 1)
+        self.proj_v, self.proj_out = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 1)
+        th, tw = self.cfg.table_hw
+        self.rpe_table = nn.Parameter(torch.zeros(n_heads, th, tw))
+        nn.init.trunc_normal_(self.rpe_table, std=0.01)
 
     def forward(self, x):
-        return forward_libops(x, self.params(), self.cfg), None, None
+        params = dict(self.named_parameters())
+        return forward_libops(x, params, self.cfg), None, None

@@ -94,6 +94,20 @@ def main():
         with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
             yb, _, _ = mod(x.detach())
         rec["y_autocast_bf16"] = yb.clone()
+        # the reference's own autocast-bf16 backward, as a gap to its fp32 gradients
+        # (max|a-b|/max|b| per tensor): the yardstick for the bf16 backward tests
+        mod.zero_grad()
+        xb = x.detach().clone().requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb2, _, _ = mod(xb)
+        yb2.backward(dy.bfloat16())
+
+        def gap(a, b):
+            return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+
+        rec["bf16_grad_gap"] = {"dx": gap(xb.grad, rec["dx"])}
+        for k, v in mod.named_parameters():
+            rec["bf16_grad_gap"][k] = gap(v.grad, rec["grads"][k])
         path = os.path.join(HERE, f"{name}.pt")
         torch.save(rec, path)
         print(f"{name}: y {tuple(y.shape)} |y|max {y.abs().max():.4f}  "

@@ -1,0 +1,77 @@
+"""Host-side DAT backbone (dat_segmentation_b200/backbone.py): wiring and state-dict parity
+with the reference DAT (container only: needs /root/reference), and CUDA-vs-oracle parity
+of the whole backbone on the GPU box."""
+import pytest
+import torch
+
+from oracle import dattn_oracle as orc
+from oracle.ref_shim import import_reference, reference_available
+
+from dat_segmentation_b200.backbone import DAT_TINY_PP, build_dat
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_backbone_matches_reference_dat_on_cpu():
+    blocks, dat = import_reference()
+    cfg = dict(DAT_TINY_PP)
+    torch.manual_seed(3)
+    ref = dat.DAT(**cfg).eval()
+    torch.manual_seed(3)
+    mine = build_dat(cfg, attn_cls=blocks.DAttentionBaseline).eval()
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert list(sd_ref.keys()) == list(sd_mine.keys())
+    assert all(torch.equal(sd_ref[k], sd_mine[k]) for k in sd_ref)     # same init RNG stream
+    mine.load_state_dict(sd_ref, strict=True)
+    x = torch.randn(1, 3, 128, 128)
+    with torch.no_grad():
+        o_ref, o_mine = ref(x), mine(x)
+    for a, b in zip(o_ref, o_mine):
+        assert a.shape == b.shape and torch.equal(a, b)
+    # and with the oracle port of the block in place of the reference block
+    port = build_dat(cfg, attn_cls=orc.OracleDAttention).eval()
+    port.load_state_dict(sd_ref, strict=True)
+    with torch.no_grad():
+        o_port = port(x)
+    for a, b in zip(o_ref, o_port):
+        assert _rel(b, a) < 1e-5
+
+
+def test_backbone_cuda_class_shares_state_dict_with_port():
+    """Keys/shapes of the CUDA-backed backbone == the oracle-port backbone (CPU only: no forward)."""
+    a = build_dat(attn_cls=orc.OracleDAttention)
+    b = build_dat()
+    assert {k: v.shape for k, v in a.state_dict().items()} == {k: v.shape for k, v in b.state_dict().items()}
+    n_attn = sum(1 for m in b.modules() if type(m).__name__ == "DAttentionBaseline")
+    assert n_attn == 14       # DAT-T++: 1 + 2 + 9 + 2 deformable blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(128, 128), (96, 160)])
+def test_backbone_cuda_vs_oracle_port(size):
+    torch.manual_seed(5)
+    gpu = build_dat(drop_path_rate=0.0).cuda()
+    with torch.no_grad():
+        for m in gpu.modules():
+            if type(m).__name__ == "DAttentionBaseline":
+                m.conv_offset[3].weight.mul_(2.0)
+                m.rpe_table.mul_(10.0)
+    cpu = build_dat(drop_path_rate=0.0, attn_cls=orc.OracleDAttention)
+    cpu.load_state_dict({k: v.cpu() for k, v in gpu.state_dict().items()}, strict=True)
+    x = torch.randn(2, 3, *size)
+    xg = x.cuda().requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    og, oc = gpu(xg), cpu(xc)
+    for a, b in zip(og, oc):
+        assert _rel(a.detach().cpu(), b.detach()) < 2e-4     # 14 blocks deep, fp32, library convs differ too
+    sum(o.square().mean() for o in og).backward()
+    sum(o.square().mean() for o in oc).backward()
+    assert _rel(xg.grad.cpu(), xc.grad) < 5e-3
+    gp, cp = dict(gpu.named_parameters()), dict(cpu.named_parameters())
+    worst = max((_rel(gp[k].grad.cpu(), cp[k].grad), k) for k in gp if cp[k].grad is not None
+                and cp[k].grad.abs().max() > 1e-6)
+    print("worst param-grad rel err", worst)
+    assert worst[0] < 2e-2

@@ -242,7 +242,12 @@ def test_block_backward_bf16(name):
         if key != "proj_k.bias":
             report[key] = rel_err(p.grad.cpu(), rec["grads"][key])
     print(name, {k: f"{v:.2e}" for k, v in report.items()})
-    assert all(v < 6e-2 for v in report.values()), report
+    # Gradients through the offsets are discontinuous (clamp mask, floor of the taps), so
+    # bf16 rounding moves them a lot — in the reference as well.  Yardstick: the reference's
+    # own autocast-bf16 backward vs its fp32 backward, stored per tensor in the fixture.
+    gap = rec["bf16_grad_gap"]
+    bad = {k: (v, gap[k]) for k, v in report.items() if v > max(3e-2, 1.25 * gap[k])}
+    assert not bad, bad
 
 
 def test_cpu_tensor_raises_no_fallback():
