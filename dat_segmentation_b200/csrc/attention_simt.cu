@@ -30,6 +30,8 @@ struct BiasEval {
   float val, d_dix, d_diy;  // value, d/d(ix), d/d(iy) of the bilinear interpolant
   int i00;                  // y0 * Tw + x0
   float w00, w01, w10, w11; // tap weights with validity folded in (0 when out of range)
+  float wx0, wx1, wy0, wy1; // separable factors (w00 = wx0 * wy0, ...)
+  int vmask;                // validity bits: 1 = (y0,x0), 2 = (y0,x0+1), 4 = (y0+1,x0), 8 = (y0+1,x0+1)
 };
 
 // Bilinear sample of one head's table at displacement ((gy - py)/2, (gx - px)/2);
@@ -52,6 +54,8 @@ __device__ __forceinline__ BiasEval rpe_bias_eval(const float* __restrict__ tab,
   r.w10 = v10 ? __fmul_rn(t.wx0, t.wy1) : 0.f;
   r.w11 = v11 ? __fmul_rn(t.wx1, t.wy1) : 0.f;
   r.val = t00 * r.w00 + t01 * r.w01 + t10 * r.w10 + t11 * r.w11;
+  r.wx0 = t.wx0; r.wx1 = t.wx1; r.wy0 = t.wy0; r.wy1 = t.wy1;
+  r.vmask = (v00 ? 1 : 0) | (v01 ? 2 : 0) | (v10 ? 4 : 0) | (v11 ? 8 : 0);
   if (WITH_GRAD) {
     r.d_dix = (t01 - t00) * t.wy0 + (t11 - t10) * t.wy1;
     r.d_diy = (t10 - t00) * t.wx0 + (t11 - t01) * t.wx1;
@@ -59,6 +63,37 @@ __device__ __forceinline__ BiasEval rpe_bias_eval(const float* __restrict__ tab,
     r.d_dix = r.d_diy = 0.f;
   }
   return r;
+}
+
+// d table += ds * (4 tap weights), warp-aggregated.  Lanes are consecutive queries of one
+// image row, so neighbouring lanes hit the same table cell (the table step per query is
+// < 1 cell): runs of lanes with the same (row, north-west cell) are summed with a
+// segmented shuffle reduction (windows of 8 lanes) and only the window leaders issue the
+// shared-memory atomics - ~3x fewer, conflict-free within the warp.  Must be called by all
+// 32 lanes.
+__device__ __forceinline__ void table_grad_scatter(float* dtab, int Tw, const BiasEval& be,
+                                                   float ds, int row) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int pk = __shfl_up_sync(FULL, be.i00, 1);
+  const int pr = __shfl_up_sync(FULL, row, 1);
+  const bool head = lane == 0 || pk != be.i00 || pr != row;
+  const unsigned heads = __ballot_sync(FULL, head);
+  const int start = 31 - __clz((int)(heads & (FULL >> (31 - lane))));
+  float P = ds * be.wx0, Q = ds * be.wx1;
+#pragma unroll
+  for (int d = 1; d <= 4; d <<= 1) {
+    const float oP = __shfl_down_sync(FULL, P, d), oQ = __shfl_down_sync(FULL, Q, d);
+    const int os = __shfl_down_sync(FULL, start, d);
+    if (lane + d < 32 && os == start) { P += oP; Q += oQ; }
+  }
+  if (((lane - start) & 7) == 0 && (P != 0.f || Q != 0.f)) {
+    float* cell = dtab + be.i00;
+    if (be.vmask & 1) atomicAdd(cell, P * be.wy0);
+    if (be.vmask & 2) atomicAdd(cell + 1, Q * be.wy0);
+    if (be.vmask & 4) atomicAdd(cell + Tw, P * be.wy1);
+    if (be.vmask & 8) atomicAdd(cell + Tw + 1, Q * be.wy1);
+  }
 }
 
 template <typename T>
@@ -251,10 +286,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
       const float ds = valid ? p * (dp - dl_m) : 0.f;
 #pragma unroll
       for (int c = 0; c < HC; ++c) acc[c] = fmaf(ds, kr[c], acc[c]);
-      if (be.w00 != 0.f) atomicAdd(dtab_s + be.i00, ds * be.w00);
-      if (be.w01 != 0.f) atomicAdd(dtab_s + be.i00 + 1, ds * be.w01);
-      if (be.w10 != 0.f) atomicAdd(dtab_s + be.i00 + a.Tw, ds * be.w10);
-      if (be.w11 != 0.f) atomicAdd(dtab_s + be.i00 + a.Tw + 1, ds * be.w11);
+      table_grad_scatter(dtab_s, a.Tw, be, ds, m / a.W);
     }
   }
   if (valid) {

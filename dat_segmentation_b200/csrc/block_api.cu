@@ -2,6 +2,7 @@
 // sequencing of the kernels of one deformable-attention block.  No allocation, no host
 // synchronisation: everything is enqueued on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -49,6 +50,12 @@ int make_shape(const dat_block_desc* d, Shape* s) {
 }
 
 namespace {
+
+// DAT_B200_DISABLE_TC=1 forces the CUDA-core kernels everywhere (A/B measurements, debugging).
+bool tc_enabled() {
+  static const int off = [] { const char* e = getenv("DAT_B200_DISABLE_TC"); return e && e[0] == '1' ? 1 : 0; }();
+  return off == 0;
+}
 
 struct Carver {
   char* base;
@@ -112,8 +119,25 @@ int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk) {
 }
 
 size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d) {
-  (void)d;
-  return 0;
+  Shape s;
+  if (make_shape(d, &s) != DAT_OK) return 0;
+  // bf16 copies of (wk, wv, wo) and of wq for the tensor-core projections
+  return s.act_dtype == DAT_BF16 ? align_up((size_t)4 * s.C * s.C * 2, 256) : 0;
+}
+
+int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b, void* Y,
+                         int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream) {
+  DAT_REQUIRE(X && W && Y, "pointwise_fwd_tc: NULL pointer");
+  if (!pointwise_fwd_tc_supported(x_dtype, M, N, K)) {
+    set_error("pointwise_fwd_tc: shape M=%lld N=%d K=%d not tileable", (long long)M, N, K);
+    return DAT_ERR_UNSUPPORTED;
+  }
+  return pointwise_fwd_tc(X, x_dtype, W, b, Y, y_dtype, M, N, K, (cudaStream_t)stream);
+}
+
+int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  DAT_REQUIRE(src && dst && n > 0, "cast_bf16: bad arguments");
+  return cast_weights_bf16(src, nullptr, nullptr, dst, n, (cudaStream_t)stream);
 }
 
 size_t dat_block_bwd_workspace_bytes(const dat_block_desc* d) {
@@ -169,7 +193,6 @@ int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_tab
 int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const void* x, void* y,
                       const dat_block_saved* sv, void* workspace, size_t workspace_bytes,
                       void* stream) {
-  (void)workspace; (void)workspace_bytes;
   Shape s;
   DAT_FWD(make_shape(d, &s));
   DAT_REQUIRE(p && x && y && sv, "block_forward: NULL pointer");
@@ -177,13 +200,34 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
               "block_forward: every dat_block_saved buffer must be provided");
   cudaStream_t st = (cudaStream_t)stream;
   const long long M = (long long)s.B * s.HW, Mk = (long long)s.B * s.Ns;
-  DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, s.act_dtype, M, s.C, s.C, st));
+  const int C = s.C, adt = s.act_dtype;
+  // bf16 mode: projections on the tensor cores when the shape tiles (else CUDA-core GEMM)
+  const bool tc = adt == DAT_BF16 && tc_enabled() && workspace != nullptr &&
+                  workspace_bytes >= (size_t)4 * C * C * 2 &&
+                  pointwise_fwd_tc_supported(DAT_BF16, Mk, C, C) &&
+                  pointwise_fwd_tc_supported(s.x_dtype, M, C, C);
+  const size_t wsz = (size_t)C * C;
+  bf16* wbf = (bf16*)workspace;   // [wk | wv | wo | wq]
+  if (tc) {
+    DAT_FWD(cast_weights_bf16(p->wk, p->wv, p->wo, wbf, (long long)wsz, st));
+    if (s.x_dtype == DAT_BF16) DAT_FWD(cast_weights_bf16(p->wq, nullptr, nullptr, wbf + 3 * wsz, (long long)wsz, st));
+    const void* wq = s.x_dtype == DAT_BF16 ? (const void*)(wbf + 3 * wsz) : (const void*)p->wq;
+    DAT_FWD(pointwise_fwd_tc(x, s.x_dtype, wq, p->bq, sv->q, adt, M, C, C, st));
+  } else {
+    DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, adt, M, C, C, st));
+  }
   DAT_FWD(offset_pos_fwd(s, p, sv->q, sv->t_dw, sv->off_raw, sv->pos, st));
   DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
-  DAT_FWD(pointwise_fwd_simt(sv->xs, s.act_dtype, p->wk, p->bk, sv->k, s.act_dtype, Mk, s.C, s.C, st));
-  DAT_FWD(pointwise_fwd_simt(sv->xs, s.act_dtype, p->wv, p->bv, sv->v, s.act_dtype, Mk, s.C, s.C, st));
+  if (tc) {
+    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf, p->bk, sv->k, adt, Mk, C, C, st));
+    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf + wsz, p->bv, sv->v, adt, Mk, C, C, st));
+  } else {
+    DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wk, p->bk, sv->k, adt, Mk, C, C, st));
+    DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wv, p->bv, sv->v, adt, Mk, C, C, st));
+  }
   DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st));
-  DAT_FWD(pointwise_fwd_simt(sv->o, s.act_dtype, p->wo, p->bo, y, s.act_dtype, M, s.C, s.C, st));
+  if (tc) DAT_FWD(pointwise_fwd_tc(sv->o, adt, wbf + 2 * wsz, p->bo, y, adt, M, C, C, st));
+  else DAT_FWD(pointwise_fwd_simt(sv->o, adt, p->wo, p->bo, y, adt, M, C, C, st));
   return DAT_OK;
 }
 

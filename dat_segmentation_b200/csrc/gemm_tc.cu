@@ -1,0 +1,247 @@
+// 1x1-convolution GEMMs of the block on the 5th-generation tensor cores (tcgen05):
+//     Y[M, N] = X[M, K] * W[N, K]^T + b[N]        (proj_q / proj_k / proj_v / proj_out,
+//                                                  dat_blocks.py:143,177-178,225)
+// Both operands are K-major and are staged by TMA (128-byte swizzle) into a 4-stage
+// shared-memory ring; one elected thread issues tcgen05.mma (M = 128, N = tile width,
+// K step = 32 bytes) with the fp32 accumulator in tensor memory; four epilogue warps read
+// it back with tcgen05.ld, add the bias, convert and store channel-last rows.
+//
+// Two operand kinds share the code:
+//   bf16 : X and W are bf16 (W pre-cast once per call into the workspace).
+//   tf32 : X is the fp32 block input straight from the preceding LayerNorm and W the fp32
+//          parameter — no cast pass at all; x is read exactly once at 4 B/element, which
+//          is what bounds proj_q (HBM-bound: 4 B in + 2 B out per element, ~64 FLOP/B).
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace dat {
+
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;   // benign race: every thread resolves the same pointer
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool is_float32,
+                 uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
+                 uint32_t box_cols, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encoder();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return DAT_ERR_CUDA;
+  }
+  DAT_REQUIRE(((uintptr_t)base & 15) == 0 && (pitch_bytes & 15) == 0, "TMA: base / pitch must be 16-byte aligned");
+  DAT_REQUIRE(box_rows <= 256 && box_cols <= 256, "TMA: box too large");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMapDataType dt = is_float32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DAT_ERR_CUDA;
+  }
+  return DAT_OK;
+}
+
+}  // namespace tc
+
+namespace {
+
+using namespace tc;
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+constexpr int CHUNK_BYTES = 128;          // K bytes per pipeline stage row (one swizzle atom)
+constexpr int A_STAGE_BYTES = TC_BM * CHUNK_BYTES;
+
+template <bool TF32, typename TOut>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
+               int BN, int stages, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int b_stage_bytes = BN * CHUNK_BYTES;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + stages * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  constexpr int CHUNK_ELEMS = TF32 ? 32 : 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+        tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kc * CHUNK_ELEMS, m0);
+        tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], kc * CHUNK_ELEMS, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TC_BM, (uint32_t)BN);
+      for (int kc = 0; kc < k_chunks; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+#pragma unroll
+        for (int k4 = 0; k4 < CHUNK_BYTES / 32; ++k4) {
+          const uint64_t ad = make_smem_desc(a_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t bd = make_smem_desc(b_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+          if (TF32) mma_tf32_ss(tmem_base, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+          else mma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+        }
+        tc_commit(&empty[s]);        // frees the smem slot when these MMAs have read it
+      }
+      tc_commit(tmem_full);          // accumulator complete
+    }
+  } else {
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after_sync();
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_wait_ld();
+      if (row < M) {
+        const float* bp = bias + n0 + c * 32;
+        TOut* dst = Y + (long long)row * N + n0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (bias != nullptr) {
+            float4 bb = *reinterpret_cast<const float4*>(bp + j);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          store4(dst + j, v);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// fp32 -> bf16 for up to 3 equally sized matrices in one launch (weights of a block)
+__global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                 const float* __restrict__ c, bf16* __restrict__ out, long long n) {
+  const float* src = blockIdx.y == 0 ? a : (blockIdx.y == 1 ? b : c);
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (src == nullptr || i >= n) return;
+  store4(out + (long long)blockIdx.y * n + i, load4(src + i));
+}
+
+int pick_bn(int N) {
+  int tiles = (N + 255) / 256;
+  if (N % tiles != 0) return 0;
+  int bn = N / tiles;
+  return (bn % 32 == 0 && bn >= 32) ? bn : 0;
+}
+
+}  // namespace
+
+bool pointwise_fwd_tc_supported(int x_dt, long long M, int N, int K) {
+  if (M <= 0 || pick_bn(N) == 0) return false;
+  return x_dt == DAT_F32 ? (K % 32 == 0) : (K % 8 == 0);
+}
+
+int cast_weights_bf16(const float* a, const float* b, const float* c, void* out, long long n,
+                      cudaStream_t st) {
+  DAT_REQUIRE(n % 4 == 0, "cast_weights: n must be a multiple of 4");
+  dim3 grid(ceil_div(n / 4, 256), 3);
+  cast_bf16_kernel<<<grid, 256, 0, st>>>(a, b, c, (bf16*)out, n);
+  DAT_LAUNCH_OK("cast_bf16_kernel");
+  return DAT_OK;
+}
+
+// W: fp32 when x_dt == DAT_F32 (tf32 MMA), bf16 when x_dt == DAT_BF16.
+int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, void* Y, int y_dt,
+                     long long M, int N, int K, cudaStream_t st) {
+  DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
+  const bool tf32 = x_dt == DAT_F32;
+  const int eb = tf32 ? 4 : 2;
+  const int chunk_elems = CHUNK_BYTES / eb;
+  const int BN = pick_bn(N);
+  const int k_chunks = (K + chunk_elems - 1) / chunk_elems;
+  CUtensorMap tmA, tmB;
+  DAT_FWD(tc::make_tmap_2d(&tmA, X, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
+  DAT_FWD(tc::make_tmap_2d(&tmB, W, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
+  const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
+  int stages = 200 * 1024 / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > k_chunks) stages = k_chunks;
+  if (stages < 1) stages = 1;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  int tmem_cols = 32;
+  while (tmem_cols < BN) tmem_cols <<= 1;
+  dim3 grid(ceil_div(M, TC_BM), N / BN);
+#define LAUNCH(TF, TO)                                                                          \
+  do {                                                                                          \
+    auto kern = gemm_tc_kernel<TF, TO>;                                                         \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, b, (TO*)Y, (int)M, N, k_chunks, BN, stages, tmem_cols); \
+  } while (0)
+  if (tf32 && y_dt == DAT_F32) LAUNCH(true, float);
+  else if (tf32) LAUNCH(true, bf16);
+  else if (y_dt == DAT_F32) LAUNCH(false, float);
+  else LAUNCH(false, bf16);
+#undef LAUNCH
+  DAT_LAUNCH_OK("gemm_tc_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

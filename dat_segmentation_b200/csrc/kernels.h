@@ -52,3 +52,12 @@ int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void*
                        size_t ws_bytes, cudaStream_t st);
 
 }  // namespace dat
+
+namespace dat {
+// gemm_tc.cu — tcgen05 / TMA GEMMs (bf16 hot path)
+bool pointwise_fwd_tc_supported(int x_dt, long long M, int N, int K);
+int cast_weights_bf16(const float* a, const float* b, const float* c, void* out, long long n,
+                      cudaStream_t st);
+int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, void* Y, int y_dt,
+                     long long M, int N, int K, cudaStream_t st);
+}  // namespace dat

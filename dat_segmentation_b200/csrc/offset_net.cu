@@ -257,28 +257,49 @@ __global__ void offset_bwd_reduce_kernel(const float* __restrict__ partial, int 
 }
 
 // Depthwise weight gradient: dw[c,u,v] = sum_points dt[point, c] * q[window(point,u,v), c].
-// grid = (k*k, nsplit), one thread per channel; partial[split][uv][c].
+// One CTA per chunk of sample points; thread = (channel, tap group) with up to WG_ACC taps
+// accumulated in registers, so every q / dt access is a coalesced channel row and the taps
+// give independent loads in flight.  partial[chunk][uv][c], reduced in a fixed order.
+constexpr int WG_ACC = 24;
 template <typename TQ>
-__global__ void offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
-                                        float* __restrict__ partial, long long pts_per_split,
-                                        OffsetArgs a) {
-  const int c = threadIdx.x;
-  const int uv = blockIdx.x, u = uv / a.ksize, v = uv % a.ksize;
-  long long p0 = (long long)blockIdx.y * pts_per_split;
-  long long p1 = min(a.n_points, p0 + pts_per_split);
-  float s = 0.f;
-  if (c < a.Cg) {
-    for (long long sp = p0; sp < p1; ++sp) {
-      const int n = (int)(sp % a.Ns);
-      const int g = (int)((sp / a.Ns) % a.G);
-      const int b = (int)(sp / ((long long)a.Ns * a.G));
-      const int y = (n / a.Wk) * a.stride - a.pad + u;
-      const int x = (n % a.Wk) * a.stride - a.pad + v;
-      if (y < 0 || y >= a.H || x < 0 || x >= a.W) continue;
-      float qv = to_f32(q[(((long long)b * a.H + y) * a.W + x) * a.C + g * a.Cg + c]);
-      s = fmaf(dt[sp * a.Cg + c], qv, s);
+__global__ void __launch_bounds__(256)
+offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
+                        float* __restrict__ partial, long long pts_per_split, OffsetArgs a) {
+  const int kk = a.ksize * a.ksize;
+  const int cthreads = a.Cg < (int)blockDim.x ? a.Cg : (int)blockDim.x;   // channels per pass
+  const int uvg_n = blockDim.x / cthreads;                                // tap groups
+  const int cl = threadIdx.x % cthreads, uvg = threadIdx.x / cthreads;
+  const long long p0 = (long long)blockIdx.x * pts_per_split;
+  const long long p1 = min(a.n_points, p0 + pts_per_split);
+  if (uvg >= uvg_n) return;
+  for (int c = cl; c < a.Cg; c += cthreads) {
+    for (int uv0 = 0; uv0 < kk; uv0 += uvg_n * WG_ACC) {
+      float acc[WG_ACC];
+#pragma unroll
+      for (int t = 0; t < WG_ACC; ++t) acc[t] = 0.f;
+      for (long long sp = p0; sp < p1; ++sp) {
+        const int n = (int)(sp % a.Ns);
+        const int g = (int)((sp / a.Ns) % a.G);
+        const int b = (int)(sp / ((long long)a.Ns * a.G));
+        const int yb = (n / a.Wk) * a.stride - a.pad, xb = (n % a.Wk) * a.stride - a.pad;
+        const float dtv = dt[sp * a.Cg + c];
+        const TQ* qb = q + (long long)b * a.H * a.W * a.C + g * a.Cg + c;
+#pragma unroll
+        for (int t = 0; t < WG_ACC; ++t) {
+          const int uv = uv0 + uvg + t * uvg_n;
+          if (uv < kk) {
+            const int y = yb + uv / a.ksize, x = xb + uv % a.ksize;
+            if (y >= 0 && y < a.H && x >= 0 && x < a.W)
+              acc[t] = fmaf(dtv, to_f32(qb[((long long)y * a.W + x) * a.C]), acc[t]);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < WG_ACC; ++t) {
+        const int uv = uv0 + uvg + t * uvg_n;
+        if (uv < kk) partial[((size_t)blockIdx.x * kk + uv) * a.Cg + c] = acc[t];
+      }
     }
-    partial[((size_t)blockIdx.y * gridDim.x + uv) * a.Cg + c] = s;
   }
 }
 
@@ -395,8 +416,8 @@ static int offset_bwd_blocks(const Shape& s) {
 }
 static int offset_wgrad_splits(const Shape& s) {
   long long pts = (long long)s.B * s.G * s.Ns;
-  long long sp = (pts + 511) / 512;
-  return (int)(sp < 1 ? 1 : (sp > 32 ? 32 : sp));
+  long long sp = (pts + 63) / 64;
+  return (int)(sp < 1 ? 1 : (sp > 148 ? 148 : sp));
 }
 
 size_t offset_bwd_workspace(const Shape& s) {
@@ -438,12 +459,10 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
 
   int nsplit = offset_wgrad_splits(s);
   long long pps = (a.n_points + nsplit - 1) / nsplit;
-  int threads = ((s.Cg + 31) / 32) * 32;
-  dim3 grid(kk, nsplit);
   if (s.act_dtype == DAT_F32)
-    offset_bwd_wgrad_kernel<float><<<grid, threads, 0, st>>>((const float*)q, dt, part2, pps, a);
+    offset_bwd_wgrad_kernel<float><<<nsplit, 256, 0, st>>>((const float*)q, dt, part2, pps, a);
   else
-    offset_bwd_wgrad_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)q, dt, part2, pps, a);
+    offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, st>>>((const bf16*)q, dt, part2, pps, a);
   DAT_LAUNCH_OK("offset_bwd_wgrad_kernel");
   offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 128), 128, 0, st>>>(part2, nsplit, kk, s.Cg,
                                                                             g->off_dw_w);

@@ -81,8 +81,11 @@ class _BlockFn(torch.autograd.Function):
             pstruct = _fill_struct(_cabi.BlockParams(), _cabi.PARAM_FIELDS, p32)
             sstruct = _fill_struct(_cabi.BlockSaved(), _cabi.SAVED_FIELDS, saved)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            nbytes = lib.dat_block_fwd_workspace_bytes(C.byref(desc))
+            ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
             _cabi.check(lib.dat_block_forward(C.byref(desc), C.byref(pstruct), _ptr(x_l), _ptr(y_l),
-                                              C.byref(sstruct), None, 0, stream), "dat_block_forward")
+                                              C.byref(sstruct), _ptr(ws), nbytes, stream),
+                        "dat_block_forward")
         ctx.meta = meta
         ctx.desc = desc
         ctx.param_dtypes = [p.dtype for p in params]

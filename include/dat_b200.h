@@ -124,6 +124,16 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p,
 int dat_pointwise_fwd(const void* X, int32_t x_dtype, const float* W, const float* b,
                       void* Y, int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream);
 
+/* Same contraction on the tcgen05 tensor cores (TMA-fed, accumulator in tensor memory).
+ * x_dtype DAT_F32: tf32 MMA straight on fp32 X and fp32 W (no cast pass);
+ * x_dtype DAT_BF16: bf16 MMA, W must then point to a bf16 copy of the weight
+ * (dat_cast_bf16).  Returns DAT_ERR_UNSUPPORTED for shapes it cannot tile
+ * (the block driver then uses the CUDA-core path). */
+int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b,
+                         void* Y, int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream);
+/* fp32 -> bf16 copy of n elements (n % 4 == 0), used for the weight operands above. */
+int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 /* Offset network + reference points + range/clamp → pos
  * (dat_blocks.py:144-162 and _get_ref_points :108-121).
  * q (B,HW,C) act_dtype → t_dw, off_raw, pos as in dat_block_saved. */
