@@ -105,9 +105,14 @@ def main():
         def gap(a, b):
             return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
 
+        def gap_l2(a, b):
+            return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
         rec["bf16_grad_gap"] = {"dx": gap(xb.grad, rec["dx"])}
+        rec["bf16_grad_gap_l2"] = {"dx": gap_l2(xb.grad, rec["dx"])}
         for k, v in mod.named_parameters():
             rec["bf16_grad_gap"][k] = gap(v.grad, rec["grads"][k])
+            rec["bf16_grad_gap_l2"][k] = gap_l2(v.grad, rec["grads"][k])
         path = os.path.join(HERE, f"{name}.pt")
         torch.save(rec, path)
         print(f"{name}: y {tuple(y.shape)} |y|max {y.abs().max():.4f}  "

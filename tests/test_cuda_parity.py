@@ -269,16 +269,20 @@ def test_block_backward_bf16(name):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y, _, _ = m(xd)
     y.backward(dy.cuda().bfloat16())
-    report = {"dx": rel_err(xd.grad.cpu(), rec["dx"])}
+    def l2(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    report = {"dx": l2(xd.grad.cpu(), rec["dx"])}
     for key, p in m.named_parameters():
         if key != "proj_k.bias":
-            report[key] = rel_err(p.grad.cpu(), rec["grads"][key])
+            report[key] = l2(p.grad.cpu(), rec["grads"][key])
     print(name, {k: f"{v:.2e}" for k, v in report.items()})
     # Gradients through the offsets are discontinuous (clamp mask, floor of the taps), so
-    # bf16 rounding moves them a lot — in the reference as well.  Yardstick: the reference's
-    # own autocast-bf16 backward vs its fp32 backward, stored per tensor in the fixture.
-    gap = rec["bf16_grad_gap"]
-    bad = {k: (v, gap[k]) for k, v in report.items() if v > max(5e-2, 2.0 * gap[k])}
+    # bf16 rounding moves individual entries a lot — in the reference as well.  Metric:
+    # relative L2 error; yardstick: the reference's own autocast-bf16 backward vs its fp32
+    # backward, stored per tensor in the fixture (a different realisation of the same noise).
+    gap = rec["bf16_grad_gap_l2"]
+    bad = {k: (v, gap[k]) for k, v in report.items() if v > max(5e-2, 2.5 * gap[k])}
     assert not bad, bad
 
 
