@@ -156,8 +156,12 @@ def kernel_roofline(dev, pk):
     sp = C.c_void_p(st.cuda_stream)
     p = lambda t: C.c_void_p(t.data_ptr())
 
+    nws = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
+    ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+
     def launch():
-        _cabi.check(lib.dat_attention_fwd(C.byref(d), p(q), p(k), p(v), p(pos), p(tab), p(o), p(lse), sp), "attention_fwd")
+        _cabi.check(lib.dat_attention_fwd(C.byref(d), p(q), p(k), p(v), p(pos), p(tab), p(o), p(lse),
+                                          p(ws), nws, 0, sp), "attention_fwd")
 
     for _ in range(3):
         launch()

@@ -80,7 +80,9 @@ def lib():
     L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
     L.dat_ref_points.argtypes = [i32, i32, f32p, f32p, vp]
     L.dat_sample_fwd.argtypes = [dp, vp, f32p, vp, vp, vp]
-    L.dat_attention_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp]
+    L.dat_attention_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp, C.c_size_t, i32, vp]
+    L.dat_attention_fwd_workspace_bytes.argtypes = [dp]
+    L.dat_attention_fwd_workspace_bytes.restype = C.c_size_t
     L.dat_rpe_bias.argtypes = [dp, f32p, f32p, f32p, vp]
     for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
                  "dat_pointwise_fwd_tc", "dat_cast_bf16",
@@ -103,4 +105,4 @@ def exported_symbols():
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
             "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_offset_pos_fwd",
             "dat_ref_points", "dat_sample_fwd",
-            "dat_attention_fwd", "dat_rpe_bias"]
+            "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias"]

@@ -1,0 +1,414 @@
+// Fused attention core of the block on the tcgen05 tensor cores (bf16 hot path):
+//   S = Q K^T (tcgen05, fp32 in tensor memory)  ->  + bilinear rpe bias, softmax (CUDA cores)
+//   ->  P (bf16, shared memory)  ->  O = P V (tcgen05)  ->  O / rowsum -> bf16, channel-last
+// (dat_blocks.py:180-223; bias branch :198-214, q grid :123-136).
+//
+// One CTA owns one (batch, head) and walks a strided list of 128-query tiles.  K, V
+// (Ns x 32 bf16 each) are TMA-loaded once per CTA; Q tiles are TMA double-buffered.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 idle,
+// 4-11 = softmax / epilogue (thread = one query row x half of the Ns columns; the score
+// row lives in registers between the two softmax passes, registers are moved to these
+// warps with setmaxnreg).
+//
+// The kernel is bound by the per-score scalar work, not by the tensor pipe (128 MMA FLOP
+// vs ~25 CUDA-core instructions per score), so that work is cut to the bone:
+//  * the displacement is separable, ix depends on (query column, n), iy on (query row, n):
+//    the y part (row offset into the table, fraction) is tabulated once per tile per image
+//    row in shared memory; the x part is one FADD from a per-n constant;
+//  * floor() is the magic-number trick (no F2I / MUFU), the 4 taps are ONE 8-byte LDS from
+//    a zero-padded table packed as bf16 {t00, t01-t00, t10, t11-t10} (pre-multiplied by
+//    log2 e), so zero padding needs no bounds checks and the blend is 3 FMA + 1 FADD;
+//  * scale * log2(e) is folded into the S -> exp2 FMA; normalisation is deferred to O.
+// No score / bias / displacement tensor ever reaches HBM: algorithmic bytes per launch =
+// B*HW*C*2 (q) + B*HW*C*2 (o) + 2*B*Ns*C*2 (k, v) + pos + table + lse.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace dat {
+
+namespace {
+
+using namespace tc;
+
+constexpr int TQ = 128;             // queries per tile (UMMA M)
+constexpr int ATC_THREADS = 384;    // 4 control warps + 8 softmax warps
+constexpr int SOFT_THREADS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float MAGIC = 12582912.0f;           // 1.5 * 2^23: float -> integer rounding trick
+constexpr int MAGIC_BITS = 0x4B400000;
+
+struct AtcArgs {
+  int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
+  int n_tiles, rows_max;
+  float c1;        // hc^-0.5 * log2(e)
+  float kx, ky;    // 0.25 * (Tw - 1), 0.25 * (Th - 1)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void soft_bar_sync() {   // the 256 softmax threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// rpe table -> zero-padded, tap-packed, log2(e)-scaled copy:
+// entry (y, x), y in [-2, Th], x in [-2, Tw]  at  (y + 2) * Wp + (x + 2):
+//   .x = bf16x2 {T[y][x],   T[y][x+1]   - T[y][x]}      .y = bf16x2 {T[y+1][x], T[y+1][x+1] - T[y+1][x]}
+__global__ void pack_table_kernel(const float* __restrict__ table, uint2* __restrict__ out,
+                                  int heads, int Th, int Tw) {
+  const int Wp = Tw + 3, Hp = Th + 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= heads * Hp * Wp) return;
+  const int eta = idx / (Hp * Wp), rem = idx % (Hp * Wp);
+  const int y = rem / Wp - 2, x = rem % Wp - 2;
+  const float* t = table + (long long)eta * Th * Tw;
+  auto at = [&](int yy, int xx) {
+    return (yy >= 0 && yy < Th && xx >= 0 && xx < Tw) ? t[yy * Tw + xx] * LOG2E : 0.f;
+  };
+  const float t00 = at(y, x), t01 = at(y, x + 1), t10 = at(y + 1, x), t11 = at(y + 1, x + 1);
+  out[idx] = make_uint2(pack_bf16x2(t00, t01 - t00), pack_bf16x2(t10, t11 - t10));
+}
+
+struct SmemPlan {
+  uint32_t q[2], k, v, p, tab, yt, xk, yk, red, bars, total;
+};
+__host__ __device__ inline SmemPlan plan_smem(int NS, int Hp, int Wp, int rows_max) {
+  SmemPlan s;
+  uint32_t off = 0;
+  s.q[0] = off; off += TQ * 64;
+  s.q[1] = off; off += TQ * 64;
+  s.k = off; off += NS * 64;
+  s.v = off; off += NS * 64;
+  s.p = off; off += (NS / 64) * 16384;
+  s.tab = off; off += ((uint32_t)(Hp * Wp) * 8 + 15) & ~15u;
+  s.yt = off; off += (uint32_t)rows_max * NS * 8;
+  s.xk = off; off += NS * 4;
+  s.yk = off; off += NS * 4;
+  s.red = off; off += 4 * TQ * 4;
+  s.bars = off; off += 16 * 8;
+  s.total = off + 1024;   // slack for the manual 1024-byte alignment
+  return s;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const float* __restrict__ pos,
+                   const uint2* __restrict__ tab_packed, bf16* __restrict__ o,
+                   float* __restrict__ lse, AtcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  const SmemPlan sp = plan_smem(NS, a.Hp, a.Wp, a.rows_max);
+  uint8_t* sQ0 = smem + sp.q[0];
+  uint8_t* sK = smem + sp.k;
+  uint8_t* sV = smem + sp.v;
+  uint8_t* sP = smem + sp.p;
+  uint2* sTab = reinterpret_cast<uint2*>(smem + sp.tab);
+  int2* sYt = reinterpret_cast<int2*>(smem + sp.yt);
+  float* sXk = reinterpret_cast<float*>(smem + sp.xk);
+  float* sYk = reinterpret_cast<float*>(smem + sp.yk);
+  float* sMax = reinterpret_cast<float*>(smem + sp.red);      // [2][128]
+  float* sSum = sMax + 2 * TQ;                                // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint64_t* s_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  constexpr uint32_t TMEM_COLS = NS < 32 ? 32 : NS;   // NS is a power of two here
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1);
+    mbar_init(&q_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, SOFT_THREADS);
+    mbar_init(o_full, 1);
+    mbar_init(s_free, SOFT_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  {
+    const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
+    for (int i = threadIdx.x; i < a.Hp * a.Wp; i += ATC_THREADS) sTab[i] = src[i];
+    const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
+    for (int n = threadIdx.x; n < NS; n += ATC_THREADS) {
+      sYk[n] = pp[2 * n] * a.ky;
+      sXk[n] = pp[2 * n + 1] * a.kx;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer ------------------------------------------------------------
+      mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
+      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * NS);
+      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * NS);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&q_empty[slot], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&q_full[slot], TQ * 64u);
+        tma_load_2d(sQ0 + slot * (TQ * 64), &tmQ, &q_full[slot], eta * 32, b * a.HW + tile * TQ);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer ---------------------------------------------------------------
+      const uint32_t idesc_s = make_instr_desc(FMT_BF16, TQ, NS);
+      const uint32_t idesc_o = make_instr_desc(FMT_BF16, TQ, 32, 0, 1);   // B (= V) is MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      mbar_wait(kv_full, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&q_full[slot], ((uint32_t)it >> 1) & 1u);
+        if (it > 0) mbar_wait(s_free, (uint32_t)(it - 1) & 1u);
+        tc_fence_after_sync();
+        const uint32_t q_addr = smem_u32(sQ0 + slot * (TQ * 64));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {     // head dim 32 = 2 x K16
+          const uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
+          const uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
+          mma_bf16_ss(tmem_base, ad, bd, idesc_s, (uint32_t)k);
+        }
+        tc_commit(&q_empty[slot]);
+        tc_commit(s_full);
+        mbar_wait(p_ready, (uint32_t)it & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < NS / 16; ++kk) {
+          const uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
+          mma_bf16_ss(tmem_base, ad, bd, idesc_o, (uint32_t)(kk > 0));
+        }
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ---- softmax + epilogue -------------------------------------------------------------
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int stid = threadIdx.x - 128;
+    constexpr int NH = NS / 2;                       // columns per thread
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int m = tile * TQ + row;
+      const bool valid = m < a.HW;
+      const int mm = valid ? m : a.HW - 1;
+      const int r = mm / a.W, c = mm - r * a.W;
+      const int r0 = (tile * TQ) / a.W;
+      const int r_last = min(a.HW - 1, tile * TQ + TQ - 1) / a.W;
+      // y part of the bias footprint, once per (image row of the tile, n)
+      for (int e = stid; e < (r_last - r0 + 1) * NS; e += SOFT_THREADS) {
+        const int rr = e / NS, n = e - rr * NS;
+        const float ay = (query_point(r0 + rr, a.H) * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
+        float u = ay - sYk[n];
+        u = fminf(fmaxf(u, -1.5f), (float)a.Th - 0.5f);
+        const float aa = u + MAGIC;
+        const float fy = (u - (aa - MAGIC)) + 0.5f;
+        const int y0 = __float_as_int(aa) - MAGIC_BITS;            // in [-2, Th]
+        sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
+      }
+      soft_bar_sync();
+      const float ax = (query_point(c, a.W) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
+      const float xhi = (float)a.Tw - 0.5f;
+
+      mbar_wait(s_full, (uint32_t)it & 1u);
+      tc_fence_after_sync();
+      uint32_t t[NH];
+#pragma unroll
+      for (int c4 = 0; c4 < NH / 32; ++c4)
+        tmem_ld_32x32(t_lane + (uint32_t)(half * NH + c4 * 32),
+                      *reinterpret_cast<uint32_t(*)[32]>(&t[c4 * 32]));
+      tmem_wait_ld();
+
+      // pass 1: t = s * scale*log2e + bias*log2e, running max
+      const int2* yt = sYt + (r - r0) * NS + half * NH;
+      const float* xk = sXk + half * NH;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        const int2 ye = yt[j];
+        float u = ax - xk[j];
+        u = fminf(fmaxf(u, -1.5f), xhi);
+        const float aa = u + MAGIC;
+        const float fx = (u - (aa - MAGIC)) + 0.5f;
+        const uint2 e = sTab[ye.x + __float_as_int(aa)];
+        const float t00 = __uint_as_float(e.x << 16), d0 = __uint_as_float(e.x & 0xffff0000u);
+        const float t10 = __uint_as_float(e.y << 16), d1 = __uint_as_float(e.y & 0xffff0000u);
+        const float top = fmaf(fx, d0, t00), bot = fmaf(fx, d1, t10);
+        const float bias = fmaf(__int_as_float(ye.y), bot - top, top);
+        const float val = fmaf(__uint_as_float(t[j]), a.c1, bias);
+        t[j] = __float_as_uint(val);
+        mx = fmaxf(mx, val);
+      }
+      sMax[half * TQ + row] = mx;
+      soft_bar_sync();
+      mx = fmaxf(mx, sMax[(half ^ 1) * TQ + row]);
+
+      // pass 2: p = 2^(t - max), row sum, bf16 -> shared memory (K-major, 128B swizzle)
+      float l = 0.f;
+      uint8_t* prow = sP + row * 128;
+#pragma unroll
+      for (int j = 0; j < NH; j += 8) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pv[i] = ex2(__uint_as_float(t[j + i]) - mx);
+          l += pv[i];
+        }
+        const int n = half * NH + j;
+        const int kb = n >> 6, ch = (n & 63) >> 3;
+        uint4 w = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
+                             pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+        *reinterpret_cast<uint4*>(prow + kb * 16384 + ((ch ^ (row & 7)) << 4)) = w;
+      }
+      sSum[half * TQ + row] = l;
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+      soft_bar_sync();
+      l += sSum[(half ^ 1) * TQ + row];
+
+      // epilogue: O (fp32, TMEM columns [0, 32) of the S buffer) / l -> bf16
+      mbar_wait(o_full, (uint32_t)it & 1u);
+      tc_fence_after_sync();
+      uint32_t ov[16];
+      tmem_ld_32x16(t_lane + (uint32_t)(half * 16), ov);
+      tmem_wait_ld();
+      tc_fence_before_sync();
+      mbar_arrive(s_free);
+      if (valid) {
+        const float inv = 1.0f / l;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pk[i] = pack_bf16x2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(o + ((long long)b * a.HW + m) * a.C + eta * 32 + half * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (half == 0) lse[(long long)bh * a.HW + m] = (mx + log2f(l)) * LN2;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int rows_spanned_max(int HW, int W) {
+  int n_tiles = (HW + TQ - 1) / TQ, best = 1;
+  for (int t = 0; t < n_tiles; ++t) {
+    int first = (t * TQ) / W;
+    int last_m = t * TQ + TQ - 1;
+    if (last_m > HW - 1) last_m = HW - 1;
+    int rows = last_m / W - first + 1;
+    if (rows > best) best = rows;
+  }
+  return best;
+}
+
+// number of CTAs per (batch, head): minimise waves * (tiles per CTA + prologue)
+int pick_chunks(int pairs, int n_tiles) {
+  double best_cost = 1e30;
+  int best = 1;
+  for (int ch = 1; ch <= n_tiles; ++ch) {
+    long long ctas = (long long)pairs * ch;
+    long long waves = (ctas + 147) / 148;
+    int per = (n_tiles + ch - 1) / ch;
+    double cost = (double)waves * (per + 0.6);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ch; }
+  }
+  return best;
+}
+
+AtcArgs make_args(const Shape& s) {
+  AtcArgs a;
+  a.B = s.B; a.H = s.H; a.W = s.W; a.HW = s.HW; a.C = s.C; a.heads = s.heads; a.G = s.G; a.hg = s.hg;
+  a.Th = s.Th; a.Tw = s.Tw; a.Wp = s.Tw + 3; a.Hp = s.Th + 3;
+  a.n_tiles = (s.HW + TQ - 1) / TQ;
+  a.rows_max = rows_spanned_max(s.HW, s.W);
+  a.c1 = (1.0f / sqrtf((float)DAT_HEAD_DIM)) * LOG2E;
+  a.kx = 0.25f * (float)(s.Tw - 1);
+  a.ky = 0.25f * (float)(s.Th - 1);
+  return a;
+}
+
+}  // namespace
+
+size_t attention_fwd_tc_workspace(const Shape& s) {
+  return align_up((size_t)s.heads * (s.Th + 3) * (s.Tw + 3) * 8, 256);
+}
+
+bool attention_fwd_tc_supported(const Shape& s) {
+  if (s.act_dtype != DAT_BF16) return false;
+  if (!(s.Ns == 64 || s.Ns == 128 || s.Ns == 256)) return false;
+  if (s.C % 8 != 0) return false;
+  SmemPlan sp = plan_smem(s.Ns, s.Th + 3, s.Tw + 3, rows_spanned_max(s.HW, s.W));
+  return sp.total <= 227 * 1024;
+}
+
+int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v, const float* pos,
+                     const float* table, void* o, float* lse, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  DAT_REQUIRE(attention_fwd_tc_supported(s), "attention_fwd_tc: unsupported shape");
+  DAT_REQUIRE(ws != nullptr && ws_bytes >= attention_fwd_tc_workspace(s), "attention_fwd_tc: workspace too small");
+  AtcArgs a = make_args(s);
+  const int ntab = s.heads * a.Hp * a.Wp;
+  pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
+  DAT_LAUNCH_OK("pack_table_kernel");
+  CUtensorMap tmQ, tmK, tmV;
+  DAT_FWD(tc::make_tmap_2d(&tmQ, q, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, (uint64_t)s.C * 2, TQ, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, s.Ns, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, s.Ns, 32, 64));
+  SmemPlan sp = plan_smem(s.Ns, a.Hp, a.Wp, a.rows_max);
+  dim3 grid(pick_chunks(s.B * s.heads, a.n_tiles), s.B * s.heads);
+#define LAUNCH(NSV)                                                                              \
+  do {                                                                                           \
+    auto kern = attn_fwd_tc_kernel<NSV>;                                                         \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
+    kern<<<grid, ATC_THREADS, sp.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, (bf16*)o, lse, a); \
+  } while (0)
+  if (s.Ns == 256) LAUNCH(256);
+  else if (s.Ns == 128) LAUNCH(128);
+  else LAUNCH(64);
+#undef LAUNCH
+  DAT_LAUNCH_OK("attn_fwd_tc_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

@@ -121,8 +121,11 @@ int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk) {
 size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d) {
   Shape s;
   if (make_shape(d, &s) != DAT_OK) return 0;
-  // bf16 copies of (wk, wv, wo) and of wq for the tensor-core projections
-  return s.act_dtype == DAT_BF16 ? align_up((size_t)4 * s.C * s.C * 2, 256) : 0;
+  // bf16 copies of (wk, wv, wo) and of wq for the tensor-core projections, then the packed
+  // rpe table of the tensor-core attention kernel
+  if (s.act_dtype != DAT_BF16) return 0;
+  return align_up((size_t)4 * s.C * s.C * 2, 256) +
+         (attention_fwd_tc_supported(s) ? attention_fwd_tc_workspace(s) : 0);
 }
 
 int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b, void* Y,
@@ -173,12 +176,21 @@ int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, voi
   return sample_fwd(s, x, pos, xs, taps, (cudaStream_t)stream);
 }
 
+size_t dat_attention_fwd_workspace_bytes(const dat_block_desc* d) {
+  Shape s;
+  if (make_shape(d, &s) != DAT_OK) return 0;
+  return attention_fwd_tc_supported(s) ? attention_fwd_tc_workspace(s) : 0;
+}
+
 int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, const void* v,
                       const float* pos, const float* rpe_table, void* o, float* lse,
-                      void* stream) {
+                      void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
   Shape s;
   DAT_FWD(make_shape(d, &s));
   DAT_REQUIRE(q && k && v && pos && rpe_table && o && lse, "attention_fwd: NULL pointer");
+  if (impl == 0 && tc_enabled() && attention_fwd_tc_supported(s))
+    return attention_fwd_tc(s, q, k, v, pos, rpe_table, o, lse, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
   return attention_fwd_simt(s, q, k, v, pos, rpe_table, o, lse, (cudaStream_t)stream);
 }
 
@@ -225,7 +237,13 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
     DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wk, p->bk, sv->k, adt, Mk, C, C, st));
     DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wv, p->bv, sv->v, adt, Mk, C, C, st));
   }
-  DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st));
+  const size_t w_bytes = align_up((size_t)4 * C * C * 2, 256);
+  if (adt == DAT_BF16 && tc_enabled() && attention_fwd_tc_supported(s) && workspace != nullptr &&
+      workspace_bytes >= w_bytes + attention_fwd_tc_workspace(s))
+    DAT_FWD(attention_fwd_tc(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse,
+                             (char*)workspace + w_bytes, workspace_bytes - w_bytes, st));
+  else
+    DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st));
   if (tc) DAT_FWD(pointwise_fwd_tc(sv->o, adt, wbf + 2 * wsz, p->bo, y, adt, M, C, C, st));
   else DAT_FWD(pointwise_fwd_simt(sv->o, adt, p->wo, p->bo, y, adt, M, C, C, st));
   return DAT_OK;

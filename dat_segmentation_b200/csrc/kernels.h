@@ -61,3 +61,12 @@ int cast_weights_bf16(const float* a, const float* b, const float* c, void* out,
 int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, void* Y, int y_dt,
                      long long M, int N, int K, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// attention_tc.cu — tcgen05 fused attention forward (bf16, Ns in {64,128,256})
+bool attention_fwd_tc_supported(const Shape& s);
+size_t attention_fwd_tc_workspace(const Shape& s);
+int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v, const float* pos,
+                     const float* table, void* o, float* lse, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+}  // namespace dat

@@ -150,10 +150,15 @@ int dat_ref_points(int32_t Hk, int32_t Wk, float* ref_y, float* ref_x, void* str
 int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, void* xs,
                    int32_t* taps, void* stream);
 
-/* QK^T*scale + bilinear rpe bias + softmax + PV (dat_blocks.py:180-223). */
+/* QK^T*scale + bilinear rpe bias + softmax + PV (dat_blocks.py:180-223).
+ * act_dtype DAT_BF16 with Ns in {64,128,256} runs the tcgen05 kernel and needs
+ * `dat_attention_fwd_workspace_bytes` of scratch (packed rpe table); any other case runs
+ * the fp32 CUDA-core kernel (workspace may be NULL).  `impl`: 0 = automatic,
+ * 1 = force the CUDA-core kernel. */
+size_t dat_attention_fwd_workspace_bytes(const dat_block_desc* d);
 int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, const void* v,
                       const float* pos, const float* rpe_table, void* o, float* lse,
-                      void* stream);
+                      void* workspace, size_t workspace_bytes, int32_t impl, void* stream);
 
 /* The rpe bias alone, (B, n_heads, HW, Ns) fp32 (dat_blocks.py:198-212); test hook. */
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table,

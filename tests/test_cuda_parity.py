@@ -194,9 +194,64 @@ def test_attention_core_fwd(name):
     tab = rec["params"]["rpe_table"].contiguous().cuda()
     o = torch.empty_like(q)
     lse = torch.empty(B, cfg.n_heads, H * W, device="cuda")
-    cab.check(lib.dat_attention_fwd(C.byref(d), _p(q), _p(k), _p(v), _p(pos), _p(tab), _p(o), _p(lse), _stream()), "attn")
+    cab.check(lib.dat_attention_fwd(C.byref(d), _p(q), _p(k), _p(v), _p(pos), _p(tab), _p(o), _p(lse),
+                                    None, 0, 0, _stream()), "attn")
     assert rel_err(o.cpu(), fw["o"].reshape(B, H * W, -1)) < FP32_TOL
     assert rel_err(lse.cpu(), fw["lse"]) < FP32_TOL
+
+
+def _attention_case(stage, B, seed):
+    """Random q/k/v/pos/table at a DAT-T++ stage shape, as bf16 device tensors + fp32 oracle."""
+    H, heads, groups, stride, ksize, qs = STAGES[stage]
+    cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, -1)
+    g = torch.Generator().manual_seed(seed)
+    C_, HW, Ns = heads * 32, H * H, 256
+    q = torch.randn(B, HW, C_, generator=g).bfloat16()
+    k = torch.randn(B, Ns, C_, generator=g).bfloat16()
+    v = torch.randn(B, Ns, C_, generator=g).bfloat16()
+    pos = (torch.rand(B, groups, 16, 16, 2, generator=g) * 2.4 - 1.2).clamp(-1, 1)
+    tab = torch.randn(heads, 2 * qs - 1, 2 * qs - 1, generator=g)
+    return cfg, H, q, k, v, pos, tab
+
+
+def _attention_oracle(cfg, H, q, k, v, pos, tab):
+    B, HW, C_ = q.shape
+    h = cfg.n_heads
+    qh = q.float().reshape(B, HW, h, 32).permute(0, 2, 1, 3)
+    kh = k.float().reshape(B, -1, h, 32).permute(0, 2, 1, 3)
+    vh = v.float().reshape(B, -1, h, 32).permute(0, 2, 1, 3)
+    s = (qh @ kh.transpose(-1, -2)) * 32 ** -0.5 + orc.rpe_bias_explicit(pos, tab, H, H, cfg)
+    lse = torch.logsumexp(s, -1)
+    o = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B, HW, C_)
+    return o, lse
+
+
+@pytest.mark.parametrize("stage", range(4))
+def test_attention_core_fwd_tensor_core(stage):
+    """tcgen05 attention kernel vs the fp32 oracle on the same bf16 q/k/v (full-size DAT-T++
+    stage shapes, B=2), and vs the CUDA-core kernel."""
+    cab, lib = _lib()
+    B = 2
+    cfg, H, q, k, v, pos, tab = _attention_case(stage, B, 100 + stage)
+    o_ref, lse_ref = _attention_oracle(cfg, H, q, k, v, pos, tab)
+    d = _desc(cab, cfg, B, H, H, 0, 1)
+    qd, kd, vd, posd, tabd = q.cuda(), k.cuda(), v.cuda(), pos.reshape(B, cfg.n_groups, 256, 2).contiguous().cuda(), tab.cuda()
+    res = {}
+    for impl in (0, 1):
+        o = torch.zeros_like(qd)
+        lse = torch.zeros(B, cfg.n_heads, H * H, device="cuda")
+        nb = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
+        assert nb > 0
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        cab.check(lib.dat_attention_fwd(C.byref(d), _p(qd), _p(kd), _p(vd), _p(posd), _p(tabd), _p(o), _p(lse),
+                                        _p(ws), nb, impl, _stream()), "attn")
+        torch.cuda.synchronize()
+        res[impl] = (o.float().cpu(), lse.cpu())
+    for impl, (o, lse) in res.items():
+        e_o = (o - o_ref).abs().max().item()
+        e_l = (lse - lse_ref).abs().max().item()
+        print(f"stage {stage} impl {impl}: |o - ref| max {e_o:.2e} (|ref| max {o_ref.abs().max():.2f}), |lse - ref| {e_l:.2e}")
+        assert e_o < 2e-2 and e_l < 2e-2
 
 
 @pytest.mark.parametrize("name", list(CASES))
