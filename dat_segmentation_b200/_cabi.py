@@ -77,6 +77,8 @@ def lib():
     L.dat_pointwise_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_pointwise_fwd_tc.argtypes = [vp, i32, vp, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_cast_bf16.argtypes = [f32p, vp, i64, vp]
+    L.dat_debug_gemm_timing.argtypes = [C.POINTER(C.c_uint64)]
+    L.dat_debug_gemm_timing.restype = C.c_int
     L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
     L.dat_ref_points.argtypes = [i32, i32, f32p, f32p, vp]
     L.dat_sample_fwd.argtypes = [dp, vp, f32p, vp, vp, vp]
@@ -103,6 +105,7 @@ def exported_symbols():
     """Names declared in include/dat_b200.h (used by the CPU-side symbol test)."""
     return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
-            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_offset_pos_fwd",
+            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing",
+            "dat_offset_pos_fwd",
             "dat_ref_points", "dat_sample_fwd",
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias"]

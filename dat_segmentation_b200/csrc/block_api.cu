@@ -138,6 +138,12 @@ int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const fl
   return pointwise_fwd_tc(X, x_dtype, W, b, Y, y_dtype, M, N, K, (cudaStream_t)stream);
 }
 
+int dat_debug_gemm_timing(uint64_t* out8) {
+  DAT_REQUIRE(out8 != nullptr, "debug_gemm_timing: NULL pointer");
+  DAT_CUDA_OK(cudaDeviceSynchronize());
+  return debug_gemm_timing((unsigned long long*)out8);
+}
+
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   DAT_REQUIRE(src && dst && n > 0, "cast_bf16: bad arguments");
   return cast_weights_bf16(src, nullptr, nullptr, dst, n, (cudaStream_t)stream);

@@ -147,24 +147,42 @@ sample_bwd_dx_kernel(const float* __restrict__ pos, const TD* __restrict__ dxs,
       __syncthreads();
     }
   }
-  const int c = g * Cg + blockIdx.y * 32 + lane;
+  // One THREAD per run head, 32 channels (this CTA's slice) as 8 independent 4-wide
+  // vector accumulators: every global access is a full 32-byte+ segment and the runs of
+  // different threads overlap their memory latency (the previous warp-per-run loop
+  // serialised ~1 us of latency per run).
+  (void)lane; (void)warp; (void)nwarps;
+  const int c = g * Cg + blockIdx.y * 32;
   const TD* dbase = dxs + (long long)b * Ns * C + c;
   float* xbase = dx + (long long)b * H * W * C + c;
-  for (int p = warp; p < P; p += nwarps) {
+  for (int p = tid; p < P; p += blockDim.x) {
     const uint32_t key = keys[p];
     if (key == 0xffffffffu) break;          // sorted: only invalid entries follow
     const uint32_t pix = key >> 14;
     if (p > 0 && (keys[p - 1] >> 14) == pix) continue;  // not a run head
-    float acc = 0.f;
+    float4* xrow = reinterpret_cast<float4*>(xbase + (long long)pix * C);
+    float4 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = xrow[i];
     int r = p;
     uint32_t kr = key;
     do {
       const int e = (int)(kr & 0x3fffu);
-      acc = fmaf(wts[e], to_f32(dbase[(long long)(e >> 2) * C]), acc);
+      const float w = wts[e];
+      const TD* drow = dbase + (long long)(e >> 2) * C;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 d = load4(drow + 4 * i);
+        acc[i].x = fmaf(w, d.x, acc[i].x);
+        acc[i].y = fmaf(w, d.y, acc[i].y);
+        acc[i].z = fmaf(w, d.z, acc[i].z);
+        acc[i].w = fmaf(w, d.w, acc[i].w);
+      }
       ++r;
       kr = r < P ? keys[r] : 0xffffffffu;
     } while (kr != 0xffffffffu && (kr >> 14) == pix);
-    xbase[(long long)pix * C] += acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xrow[i] = acc[i];
   }
 }
 

@@ -69,9 +69,21 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool is_flo
 
 }  // namespace tc
 
+// Phase timestamps (globaltimer ns) of CTA (0,0) of the last tensor-core GEMM launch:
+// [0] entry, [1] setup done, [2] first stage landed, [3] MMAs issued, [4] accumulator
+// ready, [5] epilogue done.  Debug aid read back by dat_debug_gemm_timing().
+__device__ unsigned long long g_gemm_timing[8];
+
 namespace {
 
 using namespace tc;
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TSTAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_gemm_timing[i] = gtime(); } while (0)
 
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;
@@ -97,6 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   constexpr int CHUNK_ELEMS = TF32 ? 32 : 64;
+  if (threadIdx.x == 0) TSTAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -113,6 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TSTAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -133,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (uint32_t)(kc / stages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after_sync();
+        if (kc == 0) TSTAMP(2);
         const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
         const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
 #pragma unroll
@@ -145,12 +160,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_commit(&empty[s]);        // frees the smem slot when these MMAs have read it
       }
       tc_commit(tmem_full);          // accumulator complete
+      TSTAMP(3);
     }
   } else {
     const int quad = warp & 3;       // TMEM lane quadrant this warp may access
     const int row = m0 + quad * 32 + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
+    if (warp == 2 && lane == 0) TSTAMP(4);
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
@@ -173,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) TSTAMP(5);
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -193,6 +211,11 @@ int pick_bn(int N) {
 }
 
 }  // namespace
+
+int debug_gemm_timing(unsigned long long* out8) {
+  DAT_CUDA_OK(cudaMemcpyFromSymbol(out8, g_gemm_timing, sizeof(unsigned long long) * 8));
+  return DAT_OK;
+}
 
 bool pointwise_fwd_tc_supported(int x_dt, long long M, int N, int K) {
   if (M <= 0 || pick_bn(N) == 0) return false;

@@ -70,3 +70,14 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
                      const float* table, void* o, float* lse, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+int debug_gemm_timing(unsigned long long* out8);
+}
+
+namespace dat {
+// offset_net_vec.cu — vectorised offset-network forward (Cg in {32,64,128,256})
+bool offset_pos_fwd_vec_supported(const Shape& s);
+int offset_pos_fwd_vec(const Shape& s, const dat_block_params* p, const void* q, float* t_dw,
+                       float* off_raw, float* pos, cudaStream_t st);
+}  // namespace dat

@@ -371,6 +371,7 @@ int pick_cpl(int Cg) {
 
 int offset_pos_fwd(const Shape& s, const dat_block_params* p, const void* q, float* t_dw,
                    float* off_raw, float* pos, cudaStream_t st) {
+  if (offset_pos_fwd_vec_supported(s)) return offset_pos_fwd_vec(s, p, q, t_dw, off_raw, pos, st);
   DAT_REQUIRE(s.Cg <= 512, "offset net: Cg=%d > 512 unsupported", s.Cg);
   OffsetArgs a = make_args(s);
   size_t smem = (size_t)s.ksize * s.ksize * s.Cg * sizeof(float);

@@ -131,6 +131,10 @@ int dat_pointwise_fwd(const void* X, int32_t x_dtype, const float* W, const floa
  * (the block driver then uses the CUDA-core path). */
 int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b,
                          void* Y, int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream);
+/* Debug aid: globaltimer (ns) phase stamps of CTA (0,0) of the last dat_pointwise_fwd_tc
+ * launch: entry, setup done, first TMA stage landed, MMAs issued, accumulator ready,
+ * epilogue done (6 of 8 slots used).  Synchronises the device. */
+int dat_debug_gemm_timing(uint64_t* out8);
 /* fp32 -> bf16 copy of n elements (n % 4 == 0), used for the weight operands above. */
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 
