@@ -6,9 +6,10 @@
 // One CTA owns one (batch, head) and walks a strided list of 128-query tiles.  K, V
 // (Ns x 32 bf16 each) are TMA-loaded once per CTA; Q tiles are TMA double-buffered.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 idle,
-// 4-11 = softmax / epilogue (thread = one query row x half of the Ns columns; the score
-// row lives in registers between the two softmax passes, registers are moved to these
-// warps with setmaxnreg).
+// 4-19 = softmax / epilogue (thread = one query row x a quarter of the Ns columns; the
+// score row lives in registers between the two softmax passes; 16 warps = 4 per scheduler
+// hide the LDS / MUFU latencies of the scalar work, registers are rebalanced with
+// setmaxnreg).
 //
 // The kernel is bound by the per-score scalar work, not by the tensor pipe (128 MMA FLOP
 // vs ~25 CUDA-core instructions per score), so that work is cut to the bone:
@@ -31,8 +32,9 @@ namespace {
 using namespace tc;
 
 constexpr int TQ = 128;             // queries per tile (UMMA M)
-constexpr int ATC_THREADS = 384;    // 4 control warps + 8 softmax warps
-constexpr int SOFT_THREADS = 256;
+constexpr int ATC_THREADS = 640;    // 4 control warps + 16 softmax warps
+constexpr int SOFT_THREADS = 512;
+constexpr int NPART = 4;            // column parts per query row (one per softmax warp group)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float MAGIC = 12582912.0f;           // 1.5 * 2^23: float -> integer rounding trick
@@ -51,7 +53,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 __device__ __forceinline__ void soft_bar_sync() {   // the 256 softmax threads only
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, 512;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -101,7 +103,7 @@ __host__ __device__ inline SmemPlan plan_smem(int NS, int Hp, int Wp, int rows_m
   s.yt = off; off += (uint32_t)rows_max * NS * 8;
   s.xk = off; off += NS * 4;
   s.yk = off; off += NS * 4;
-  s.red = off; off += 4 * TQ * 4;
+  s.red = off; off += 2 * NPART * TQ * 4;
   s.bars = off; off += 16 * 8;
   s.total = off + 1024;   // slack for the manual 1024-byte alignment
   return s;
@@ -125,8 +127,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   int2* sYt = reinterpret_cast<int2*>(smem + sp.yt);
   float* sXk = reinterpret_cast<float*>(smem + sp.xk);
   float* sYk = reinterpret_cast<float*>(smem + sp.yk);
-  float* sMax = reinterpret_cast<float*>(smem + sp.red);      // [2][128]
-  float* sSum = sMax + 2 * TQ;                                // [2][128]
+  float* sMax = reinterpret_cast<float*>(smem + sp.red);      // [NPART][128]
+  float* sSum = sMax + NPART * TQ;                            // [NPART][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;    // [2]
@@ -218,12 +220,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ---- softmax + epilogue -------------------------------------------------------------
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int quad = warp & 3, half = (warp - 4) >> 2;   // `half` = column part 0..NPART-1
     const int row = quad * 32 + lane;
     const int stid = threadIdx.x - 128;
-    constexpr int NH = NS / 2;                       // columns per thread
+    constexpr int NH = NS / NPART;                   // columns per thread
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -251,10 +253,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(s_full, (uint32_t)it & 1u);
       tc_fence_after_sync();
       uint32_t t[NH];
+      if constexpr (NH >= 32) {
 #pragma unroll
-      for (int c4 = 0; c4 < NH / 32; ++c4)
-        tmem_ld_32x32(t_lane + (uint32_t)(half * NH + c4 * 32),
-                      *reinterpret_cast<uint32_t(*)[32]>(&t[c4 * 32]));
+        for (int c4 = 0; c4 < NH / 32; ++c4)
+          tmem_ld_32x32(t_lane + (uint32_t)(half * NH + c4 * 32),
+                        *reinterpret_cast<uint32_t(*)[32]>(&t[c4 * 32]));
+      } else {
+        tmem_ld_32x16(t_lane + (uint32_t)(half * NH), *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
+      }
       tmem_wait_ld();
 
       // pass 1: t = s * scale*log2e + bias*log2e, running max
@@ -279,7 +285,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       sMax[half * TQ + row] = mx;
       soft_bar_sync();
-      mx = fmaxf(mx, sMax[(half ^ 1) * TQ + row]);
+#pragma unroll
+      for (int pp = 0; pp < NPART; ++pp) mx = fmaxf(mx, sMax[pp * TQ + row]);
 
       // pass 2: p = 2^(t - max), row sum, bf16 -> shared memory (K-major, 128B swizzle)
       float l = 0.f;
@@ -302,17 +309,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async_smem();
       mbar_arrive(p_ready);
       soft_bar_sync();
-      l += sSum[(half ^ 1) * TQ + row];
+      l = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < NPART; ++pp) l += sSum[pp * TQ + row];
 
       // epilogue: O (fp32, TMEM columns [0, 32) of the S buffer) / l -> bf16
       mbar_wait(o_full, (uint32_t)it & 1u);
       tc_fence_after_sync();
       uint32_t ov[16];
-      tmem_ld_32x16(t_lane + (uint32_t)(half * 16), ov);
-      tmem_wait_ld();
+      if (half < 2) {                       // parts 0 and 1 write 16 output channels each
+        tmem_ld_32x16(t_lane + (uint32_t)(half * 16), ov);
+        tmem_wait_ld();
+      }
       tc_fence_before_sync();
       mbar_arrive(s_free);
-      if (valid) {
+      if (valid && half < 2) {
         const float inv = 1.0f / l;
         uint32_t pk[8];
 #pragma unroll

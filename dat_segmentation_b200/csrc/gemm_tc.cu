@@ -99,12 +99,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int b_stage_bytes = BN * CHUNK_BYTES;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + stages * A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * b_stage_bytes);
+  // [barriers: 1 KB][A stages][B stages]; the stage buffers double as the epilogue's
+  // output staging area once the accumulator is complete
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint8_t* sA = smem + 1024;
+  uint8_t* sB = sA + stages * A_STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
@@ -168,24 +170,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
     if (warp == 2 && lane == 0) TSTAMP(4);
+    // TMEM -> registers (+bias, convert) -> this warp's 32 x BN staging tile in shared
+    // memory (row pitch padded by 16 B: conflict-free 16-byte accesses) -> global memory
+    // one whole output row per store instruction (fully coalesced 512 B+ segments; the
+    // per-thread row-strided 8-byte stores this replaces cost 5.5 us per tile).
+    const int row_bytes = BN * (int)sizeof(TOut);
+    const int pitch = row_bytes + 16;
+    uint8_t* stage = sA + (warp - 2) * 32 * pitch;
+    (void)row;
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_wait_ld();
-      if (row < M) {
-        const float* bp = bias + n0 + c * 32;
-        TOut* dst = Y + (long long)row * N + n0 + c * 32;
+      const float* bp = bias + n0 + c * 32;
+      TOut* dst = reinterpret_cast<TOut*>(stage + lane * pitch) + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          if (bias != nullptr) {
-            float4 bb = *reinterpret_cast<const float4*>(bp + j);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-          }
-          store4(dst + j, v);
+      for (int j = 0; j < 32; j += 4) {
+        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        if (bias != nullptr) {
+          float4 bb = *reinterpret_cast<const float4*>(bp + j);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
         }
+        store4(dst + j, v);
       }
+    }
+    __syncwarp();
+    const int rows_here = min(32, M - (m0 + quad * 32));
+    for (int rr = 0; rr < rows_here; ++rr) {
+      uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0);
+      const uint8_t* srow = stage + rr * pitch;
+      for (int off = lane * 16; off < row_bytes; off += 512)
+        *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
     }
   }
   tc_fence_before_sync();
@@ -248,7 +264,10 @@ int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, voi
   if (stages > 6) stages = 6;
   if (stages > k_chunks) stages = k_chunks;
   if (stages < 1) stages = 1;
-  size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16;
+  const size_t out_stage = (size_t)4 * 32 * (BN * dtype_size(y_dt) + 16);
+  size_t buf = (size_t)stages * stage_bytes;
+  if (out_stage > buf) buf = out_stage;
+  size_t smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + buf;
   int tmem_cols = 32;
   while (tmem_cols < BN) tmem_cols <<= 1;
   dim3 grid(ceil_div(M, TC_BM), N / BN);
