@@ -8,8 +8,7 @@
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 idle,
 // 4-19 = softmax / epilogue (thread = one query row x a quarter of the Ns columns; the
 // score row lives in registers between the two softmax passes; 16 warps = 4 per scheduler
-// hide the LDS / MUFU latencies of the scalar work, registers are rebalanced with
-// setmaxnreg).
+// hide the LDS / MUFU latencies of the scalar work).
 //
 // The kernel is bound by the per-score scalar work, not by the tensor pipe (128 MMA FLOP
 // vs ~25 CUDA-core instructions per score), so that work is cut to the bone:
@@ -174,7 +173,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // ---- TMA producer ------------------------------------------------------------
       mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
@@ -220,7 +218,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ---- softmax + epilogue -------------------------------------------------------------
     const int quad = warp & 3, half = (warp - 4) >> 2;   // `half` = column part 0..NPART-1
     const int row = quad * 32 + lane;
