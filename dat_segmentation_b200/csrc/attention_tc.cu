@@ -44,6 +44,7 @@ struct AtcArgs {
   int n_tiles, rows_max;
   float c1;        // hc^-0.5 * log2(e)
   float kx, ky;    // 0.25 * (Tw - 1), 0.25 * (Th - 1)
+  float gsx, gsy;  // 2 / (W - 1), 2 / (H - 1): query grid step (no IEEE division in the kernel)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -235,7 +236,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // y part of the bias footprint, once per (image row of the tile, n)
       for (int e = stid; e < (r_last - r0 + 1) * NS; e += SOFT_THREADS) {
         const int rr = e / NS, n = e - rr * NS;
-        const float ay = (query_point(r0 + rr, a.H) * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
+        const float gy = fmaf((float)(r0 + rr), a.gsy, -1.0f);
+        const float ay = (gy * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
         float u = ay - sYk[n];
         u = fminf(fmaxf(u, -1.5f), (float)a.Th - 0.5f);
         const float aa = u + MAGIC;
@@ -244,7 +246,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
       }
       soft_bar_sync();
-      const float ax = (query_point(c, a.W) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
+      const float ax = (fmaf((float)c, a.gsx, -1.0f) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
       const float xhi = (float)a.Tw - 0.5f;
 
       mbar_wait(s_full, (uint32_t)it & 1u);
@@ -321,7 +323,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before_sync();
       mbar_arrive(s_free);
       if (valid && half < 2) {
-        const float inv = 1.0f / l;
+        const float inv = __fdividef(1.0f, l);
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -329,7 +331,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint4* dst = reinterpret_cast<uint4*>(o + ((long long)b * a.HW + m) * a.C + eta * 32 + half * 16);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (half == 0) lse[(long long)bh * a.HW + m] = (mx + log2f(l)) * LN2;
+        if (half == 0) lse[(long long)bh * a.HW + m] = (mx + __log2f(l)) * LN2;
       }
     }
   }
@@ -373,6 +375,8 @@ AtcArgs make_args(const Shape& s) {
   a.c1 = (1.0f / sqrtf((float)DAT_HEAD_DIM)) * LOG2E;
   a.kx = 0.25f * (float)(s.Tw - 1);
   a.ky = 0.25f * (float)(s.Th - 1);
+  a.gsx = 2.0f / (float)(s.W - 1);
+  a.gsy = 2.0f / (float)(s.H - 1);
   return a;
 }
 
@@ -380,6 +384,14 @@ AtcArgs make_args(const Shape& s) {
 
 size_t attention_fwd_tc_workspace(const Shape& s) {
   return align_up((size_t)s.heads * (s.Th + 3) * (s.Tw + 3) * 8, 256);
+}
+
+// packed table (see pack_table_kernel) into `out`, attention_fwd_tc_workspace(s) bytes
+int attention_pack_table(const Shape& s, const float* table, void* out, cudaStream_t st) {
+  const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
+  pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)out, s.heads, s.Th, s.Tw);
+  DAT_LAUNCH_OK("pack_table_kernel");
+  return DAT_OK;
 }
 
 bool attention_fwd_tc_supported(const Shape& s) {

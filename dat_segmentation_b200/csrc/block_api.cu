@@ -71,6 +71,7 @@ struct Carver {
 struct BwdPlan {
   void *d_o, *dq, *dk, *dv, *dxs;
   float *dpos_part, *dpos;
+  void* wT;         // bf16 transposed copies of (wo, wk, wv, wq) for the tensor-core data gradients
   void* sub;        // shared scratch of the individual stages (used one at a time)
   size_t sub_bytes, total;
 };
@@ -86,6 +87,7 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   p.dxs = c.take((size_t)s.B * s.Ns * s.C * e);
   p.dpos_part = (float*)c.take((size_t)s.B * s.heads * attention_bwd_qsplit(s) * s.Ns * 2 * 4);
   p.dpos = (float*)c.take((size_t)s.B * s.G * s.Ns * 2 * 4);
+  p.wT = c.take((size_t)4 * s.C * s.C * 2);
   size_t sub = attention_bwd_workspace(s);
   size_t w1 = pointwise_wgrad_workspace((long long)s.B * s.HW, s.C, s.C);
   size_t w2 = pointwise_wgrad_workspace((long long)s.B * s.Ns, s.C, s.C);
@@ -267,23 +269,36 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   cudaStream_t st = (cudaStream_t)stream;
   const long long M = (long long)s.B * s.HW, Mk = (long long)s.B * s.Ns;
   const int C = s.C, adt = s.act_dtype;
+  // bf16 mode: data gradients dX = dY W run on the tensor cores as K-major GEMMs against
+  // transposed bf16 copies of the weights (one tiny transpose launch per backward)
+  const bool tc = adt == DAT_BF16 && tc_enabled() && pointwise_fwd_tc_supported(DAT_BF16, M, C, C) &&
+                  pointwise_fwd_tc_supported(DAT_BF16, Mk, C, C);
+  bf16* wT = (bf16*)w.wT;
+  const size_t wsz = (size_t)C * C;
+  if (tc) DAT_FWD(cast_transpose_weights_bf16(p->wo, p->wk, p->wv, p->wq, wT, C, st));
   // proj_out
   DAT_FWD(pointwise_wgrad_simt(dy, adt, sv->o, adt, g->wo, g->bo, M, C, C, w.sub, w.sub_bytes, st));
-  DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
+  if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
+  else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
   // attention core
   DAT_FWD(attention_bwd_simt(s, sv->q, sv->k, sv->v, sv->o, w.d_o, sv->lse, sv->pos, p->rpe_table,
                              w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
   // proj_k / proj_v
   DAT_FWD(pointwise_wgrad_simt(w.dk, adt, sv->xs, adt, g->wk, g->bk, Mk, C, C, w.sub, w.sub_bytes, st));
   DAT_FWD(pointwise_wgrad_simt(w.dv, adt, sv->xs, adt, g->wv, g->bv, Mk, C, C, w.sub, w.sub_bytes, st));
-  DAT_FWD(pointwise_dgrad_simt(w.dk, adt, p->wk, w.dxs, adt, Mk, C, C, 0, st));
-  DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
+  if (tc) {
+    DAT_FWD(pointwise_fwd_tc_dual(w.dk, wT + wsz, w.dv, wT + 2 * wsz, adt, nullptr, w.dxs, adt, Mk, C, C, st));
+  } else {
+    DAT_FWD(pointwise_dgrad_simt(w.dk, adt, p->wk, w.dxs, adt, Mk, C, C, 0, st));
+    DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
+  }
   // sampling -> d pos; offset network -> dq
   DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, attention_bwd_qsplit(s), w.dpos, st));
   DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
   // proj_q, then the sampling scatter on top of its data gradient
   DAT_FWD(pointwise_wgrad_simt(w.dq, adt, x, s.x_dtype, g->wq, g->bq, M, C, C, w.sub, w.sub_bytes, st));
-  DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
+  if (tc) DAT_FWD(pointwise_fwd_tc(w.dq, adt, wT + 3 * wsz, nullptr, dx, DAT_F32, M, C, C, st));
+  else DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
   DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
   return DAT_OK;
 }

@@ -93,8 +93,9 @@ constexpr int A_STAGE_BYTES = TC_BM * CHUNK_BYTES;
 template <bool TF32, typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
-               int BN, int stages, int tmem_cols) {
+               int k_chunks1, int BN, int stages, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -117,6 +118,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (k_chunks1 < k_chunks) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -141,8 +146,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (uint32_t)(kc / stages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
-        tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full[s], kc * CHUNK_ELEMS, m0);
-        tma_load_2d(sB + s * b_stage_bytes, &tmB, &full[s], kc * CHUNK_ELEMS, n0);
+        // optional second operand pair: Y = X1 W1^T + X2 W2^T as one K-concatenated GEMM
+        const bool second = kc >= k_chunks1;
+        const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
+        tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
+        tma_load_2d(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
       }
     }
   } else if (warp == 1) {
@@ -212,6 +220,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// fp32 (C x C) -> transposed bf16 for up to 4 matrices in one launch: out[z][k][n] = w_z[n][k].
+// The data-gradient GEMMs dX = dY W are then plain K-major products with "weight" W^T.
+__global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                           const float* __restrict__ w2, const float* __restrict__ w3,
+                                           bf16* __restrict__ out, int C) {
+  __shared__ float tile[32][33];
+  const float* src = blockIdx.z == 0 ? w0 : (blockIdx.z == 1 ? w1 : (blockIdx.z == 2 ? w2 : w3));
+  if (src == nullptr) return;
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, k = k0 + threadIdx.x;
+    tile[r][threadIdx.x] = (n < C && k < C) ? src[(long long)n * C + k] : 0.f;
+  }
+  __syncthreads();
+  bf16* dst = out + (long long)blockIdx.z * C * C;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, n = n0 + threadIdx.x;
+    if (k < C && n < C) dst[(long long)k * C + n] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+
 // fp32 -> bf16 for up to 3 equally sized matrices in one launch (weights of a block)
 __global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                  const float* __restrict__ c, bf16* __restrict__ out, long long n) {
@@ -249,18 +278,39 @@ int cast_weights_bf16(const float* a, const float* b, const float* c, void* out,
   return DAT_OK;
 }
 
-// W: fp32 when x_dt == DAT_F32 (tf32 MMA), bf16 when x_dt == DAT_BF16.
+int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w2, const float* w3,
+                                void* out, int C, cudaStream_t st) {
+  dim3 grid(ceil_div(C, 32), ceil_div(C, 32), 4), block(32, 8);
+  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w0, w1, w2, w3, (bf16*)out, C);
+  DAT_LAUNCH_OK("cast_transpose_bf16_kernel");
+  return DAT_OK;
+}
+
 int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, void* Y, int y_dt,
                      long long M, int N, int K, cudaStream_t st) {
+  return pointwise_fwd_tc_dual(X, W, nullptr, nullptr, x_dt, b, Y, y_dt, M, N, K, st);
+}
+
+// Y = X W^T (+ X2 W2^T) + b.  W: fp32 when x_dt == DAT_F32 (tf32 MMA), bf16 when x_dt == DAT_BF16.
+int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
+                          const float* b, void* Y, int y_dt, long long M, int N, int K,
+                          cudaStream_t st) {
   DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
   const bool tf32 = x_dt == DAT_F32;
   const int eb = tf32 ? 4 : 2;
   const int chunk_elems = CHUNK_BYTES / eb;
   const int BN = pick_bn(N);
-  const int k_chunks = (K + chunk_elems - 1) / chunk_elems;
-  CUtensorMap tmA, tmB;
+  const int k_chunks1 = (K + chunk_elems - 1) / chunk_elems;
+  const int k_chunks = X2 != nullptr ? 2 * k_chunks1 : k_chunks1;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
   DAT_FWD(tc::make_tmap_2d(&tmA, X, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
   DAT_FWD(tc::make_tmap_2d(&tmB, W, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
+  tmA2 = tmA;
+  tmB2 = tmB;
+  if (X2 != nullptr) {
+    DAT_FWD(tc::make_tmap_2d(&tmA2, X2, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
+    DAT_FWD(tc::make_tmap_2d(&tmB2, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
+  }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
   int stages = 200 * 1024 / stage_bytes;
   if (stages > 6) stages = 6;
@@ -277,7 +327,8 @@ int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, voi
   do {                                                                                          \
     auto kern = gemm_tc_kernel<TF, TO>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, b, (TO*)Y, (int)M, N, k_chunks, BN, stages, tmem_cols); \
+    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,    \
+                                         k_chunks1, BN, stages, tmem_cols);                       \
   } while (0)
   if (tf32 && y_dt == DAT_F32) LAUNCH(true, float);
   else if (tf32) LAUNCH(true, bf16);

@@ -81,3 +81,11 @@ bool offset_pos_fwd_vec_supported(const Shape& s);
 int offset_pos_fwd_vec(const Shape& s, const dat_block_params* p, const void* q, float* t_dw,
                        float* off_raw, float* pos, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w2, const float* w3,
+                                void* out, int C, cudaStream_t st);
+int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
+                          const float* b, void* Y, int y_dt, long long M, int N, int K,
+                          cudaStream_t st);
+}  // namespace dat

@@ -277,6 +277,7 @@ offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
       float acc[WG_ACC];
 #pragma unroll
       for (int t = 0; t < WG_ACC; ++t) acc[t] = 0.f;
+#pragma unroll 2
       for (long long sp = p0; sp < p1; ++sp) {
         const int n = (int)(sp % a.Ns);
         const int g = (int)((sp / a.Ns) % a.G);
@@ -417,8 +418,8 @@ static int offset_bwd_blocks(const Shape& s) {
 }
 static int offset_wgrad_splits(const Shape& s) {
   long long pts = (long long)s.B * s.G * s.Ns;
-  long long sp = (pts + 63) / 64;
-  return (int)(sp < 1 ? 1 : (sp > 148 ? 148 : sp));
+  long long sp = (pts + 7) / 8;      // ~8 points per CTA: latency-bound loop, so go wide
+  return (int)(sp < 1 ? 1 : (sp > 4096 ? 4096 : sp));
 }
 
 size_t offset_bwd_workspace(const Shape& s) {
