@@ -1,0 +1,537 @@
+// Backward of the fused attention core on the tcgen05 tensor cores (bf16 hot path):
+// autograd of  S = QK^T*scale + bias(pos, rpe_table);  P = softmax(S);  O = PV
+// (dat_blocks.py:180-223).  Given dO, lse and delta = rowsum(dO*O):
+//   dP = dO V^T;  dS = P*(dP - delta);  dQ = scale*dS K;  dK = scale*dS^T Q;  dV = P^T dO
+//   d rpe_table += dS * (4 bilinear tap weights);   d pos = -k * sum_q dS * d bias/d(ix, iy)
+//
+// One CTA owns one (batch, head) and walks 128-query tiles; the Ns sampled keys are processed
+// in halves of 128 columns.  Five GEMMs per half run on the tensor cores, all operands in
+// shared memory, all accumulators in tensor memory:
+//   S_h = Q K_h^T, dP_h = dO V_h^T          (K-major A and B, 64B swizzle)      -> TMEM [0,256)
+//   dQ += dS_h K_h                           (A = dS_h K-major, B = K_h MN-major)
+//   dK_h += dS_h^T Q,  dV_h += P_h^T dO      (A = the same dS_h / P_h tiles read MN-major,
+//                                             B = Q / dO tiles read MN-major)
+// dK/dV accumulate over all tiles of the CTA in TMEM and are written once at the end.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2-3 idle, 4-11 = compute
+// (thread = query row x 64 columns of the half, in two 32-column steps): recompute the bias
+// (same separable / packed-table scheme as the forward), P and dS -> bf16 tiles in shared
+// memory (128B swizzle), and the two bias gradients:
+//   * d pos: per-column sums over the 32 rows of a warp by a register transpose-reduction
+//     (31 shuffles per 32 columns), accumulated in registers over all tiles - no atomics;
+//   * d rpe_table: lanes are consecutive queries of one image row and hit the same table cell
+//     in runs (table step per query < 1), so runs are pre-summed with a segmented shuffle
+//     reduction and only run leaders issue shared-memory atomics into a per-CTA padded fp32
+//     copy of the table, flushed with one global atomic per cell at the end.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace dat {
+
+namespace {
+
+using namespace tc;
+
+constexpr int TQ = 128;
+constexpr int NHC = 128;             // key columns per half
+constexpr int BTC_THREADS = 384;     // 4 control + 8 compute warps
+constexpr int COMP_THREADS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float MAGIC = 12582912.0f;
+constexpr int MAGIC_BITS = 0x4B400000;
+constexpr unsigned FULL = 0xffffffffu;
+
+// TMEM column map (512 columns allocated)
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 288, TM_DV = 352;
+
+struct BtcArgs {
+  int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
+  int n_tiles, rows_max, chunks;
+  float c1, scale, kx, ky, gsx, gsy;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void comp_bar_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// sum over the 32 lanes of v[lane-th column]: lane L returns sum_rows v_row[L]  (31 shuffles)
+__device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, w);
+    }
+  }
+  return v[0];
+}
+
+struct SmemPlanB {
+  uint32_t q[2], d_o[2], k, v, p, ds, tab, dtab, yt, xk, yk, dpos, bars, total;
+};
+__host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int rows_max) {
+  SmemPlanB s;
+  uint32_t off = 0;
+  s.q[0] = off; off += TQ * 64;
+  s.q[1] = off; off += TQ * 64;
+  s.d_o[0] = off; off += TQ * 64;
+  s.d_o[1] = off; off += TQ * 64;
+  s.k = off; off += NS * 64;
+  s.v = off; off += NS * 64;
+  s.p = off; off += 2 * 16384;      // [128 x 128] bf16, two 64-column K-blocks
+  s.ds = off; off += 2 * 16384;
+  s.tab = off; off += ((uint32_t)(Hp * Wp) * 8 + 15) & ~15u;
+  s.dtab = off; off += ((uint32_t)(Hp * Wp) * 4 + 15) & ~15u;
+  s.yt = off; off += (uint32_t)rows_max * NS * 8;
+  s.xk = off; off += NS * 4;
+  s.yk = off; off += NS * 4;
+  s.dpos = off; off += 8 * NS * 2 * 4;     // per compute warp column sums [8][NS][2]
+  s.bars = off; off += 16 * 8;
+  s.total = off + 1024;
+  return s;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(BTC_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const float* __restrict__ pos, const uint2* __restrict__ tab_packed,
+                   const float* __restrict__ lse, const float* __restrict__ delta,
+                   bf16* __restrict__ dq, float* __restrict__ dk_part, float* __restrict__ dv_part,
+                   float* __restrict__ d_table, float* __restrict__ dpos_part, BtcArgs a) {
+  constexpr int NHALF = NS / NHC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  const SmemPlanB sp = plan_smem_b(NS, a.Hp, a.Wp, a.rows_max);
+  uint8_t* sQ0 = smem + sp.q[0];
+  uint8_t* sDO0 = smem + sp.d_o[0];
+  uint8_t* sK = smem + sp.k;
+  uint8_t* sV = smem + sp.v;
+  uint8_t* sP = smem + sp.p;
+  uint8_t* sDS = smem + sp.ds;
+  uint2* sTab = reinterpret_cast<uint2*>(smem + sp.tab);
+  float* sDTab = reinterpret_cast<float*>(smem + sp.dtab);
+  int2* sYt = reinterpret_cast<int2*>(smem + sp.yt);
+  float* sXk = reinterpret_cast<float*>(smem + sp.xk);
+  float* sYk = reinterpret_cast<float*>(smem + sp.yk);
+  float* sDpos = reinterpret_cast<float*>(smem + sp.dpos);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;    // [2]
+  uint64_t* qdo_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_ready = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, COMP_THREADS);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, COMP_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  {
+    const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
+    for (int i = threadIdx.x; i < a.Hp * a.Wp; i += BTC_THREADS) {
+      sTab[i] = src[i];
+      sDTab[i] = 0.f;
+    }
+    const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
+    for (int n = threadIdx.x; n < NS; n += BTC_THREADS) {
+      sYk[n] = pp[2 * n] * a.ky;
+      sXk[n] = pp[2 * n + 1] * a.kx;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ------------------------------------------------------------------
+      mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
+      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * NS);
+      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * NS);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&qdo_empty[slot], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&qdo_full[slot], 2u * TQ * 64u);
+        tma_load_2d(sQ0 + slot * (TQ * 64), &tmQ, &qdo_full[slot], eta * 32, b * a.HW + tile * TQ);
+        tma_load_2d(sDO0 + slot * (TQ * 64), &tmDO, &qdo_full[slot], eta * 32, b * a.HW + tile * TQ);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ---------------------------------------------------------------------
+      const uint32_t idesc_s = make_instr_desc(FMT_BF16, TQ, NHC);             // S, dP
+      const uint32_t idesc_q = make_instr_desc(FMT_BF16, TQ, 32, 0, 1);        // dQ: B MN-major
+      const uint32_t idesc_kv = make_instr_desc(FMT_BF16, NHC, 32, 1, 1);      // dK, dV: A and B MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      mbar_wait(kv_full, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&qdo_full[slot], ((uint32_t)it >> 1) & 1u);
+        const uint32_t q_addr = smem_u32(sQ0 + slot * (TQ * 64));
+        const uint32_t do_addr = smem_u32(sDO0 + slot * (TQ * 64));
+#pragma unroll
+        for (int h = 0; h < NHALF; ++h) {
+          const uint32_t e = (uint32_t)(it * NHALF + h);
+          tc_fence_after_sync();
+          // S_h = Q K_h^T, dP_h = dO V_h^T  (in-order tensor pipe: the previous half's
+          // consumers of TMEM S/dP finished before pds_ready, which was waited below)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            mma_bf16_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64),
+                        make_smem_desc(k_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s,
+                        (uint32_t)k);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            mma_bf16_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16, 512, LAYOUT_SW64),
+                        make_smem_desc(v_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s,
+                        (uint32_t)k);
+          }
+          tc_commit(sdp_full);
+          mbar_wait(pds_ready, e & 1u);
+          if (h == 0 && it > 0) mbar_wait(dq_free, (uint32_t)(it - 1) & 1u);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int j = 0; j < NHC / 16; ++j) {     // contraction over the 128 queries of the tile
+            const uint64_t a_p = make_smem_desc(p_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
+            const uint64_t a_ds = make_smem_desc(ds_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
+            const uint64_t b_do = make_smem_desc(do_addr + j * 1024, 512, 512, LAYOUT_SW64);
+            const uint64_t b_q = make_smem_desc(q_addr + j * 1024, 512, 512, LAYOUT_SW64);
+            const uint32_t acc = (uint32_t)((it | j) != 0);
+            mma_bf16_ss(tmem_base + TM_DV + h * 32, a_p, b_do, idesc_kv, acc);
+            mma_bf16_ss(tmem_base + TM_DK + h * 32, a_ds, b_q, idesc_kv, acc);
+          }
+#pragma unroll
+          for (int kk = 0; kk < NHC / 16; ++kk) {  // contraction over the 128 keys of the half
+            const uint64_t a_ds = make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t b_k = make_smem_desc(k_addr + (h * NHC + kk * 16) * 64, 512, 512, LAYOUT_SW64);
+            mma_bf16_ss(tmem_base + TM_DQ, a_ds, b_k, idesc_q, (uint32_t)((h | kk) != 0));
+          }
+          if (h == NHALF - 1) {
+            tc_commit(dq_full);
+            tc_commit(&qdo_empty[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- compute warps ------------------------------------------------------------------------
+    const int quad = warp & 3, chalf = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int ctid = threadIdx.x - 128;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float dpx_acc[NHALF * 2], dpy_acc[NHALF * 2];
+#pragma unroll
+    for (int i = 0; i < NHALF * 2; ++i) dpx_acc[i] = dpy_acc[i] = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int m = tile * TQ + row;
+      const bool valid = m < a.HW;
+      const int mm = valid ? m : a.HW - 1;
+      const int r = mm / a.W, c = mm - r * a.W;
+      const int r0 = (tile * TQ) / a.W;
+      const int r_last = min(a.HW - 1, tile * TQ + TQ - 1) / a.W;
+      comp_bar_sync();     // previous tile finished with sYt
+      for (int e = ctid; e < (r_last - r0 + 1) * NS; e += COMP_THREADS) {
+        const int rr = e / NS, n = e - rr * NS;
+        const float gy = fmaf((float)(r0 + rr), a.gsy, -1.0f);
+        const float ay = (gy * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
+        float u = ay - sYk[n];
+        u = fminf(fmaxf(u, -1.5f), (float)a.Th - 0.5f);
+        const float aa = u + MAGIC;
+        const float fy = (u - (aa - MAGIC)) + 0.5f;
+        const int y0 = __float_as_int(aa) - MAGIC_BITS;
+        sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
+      }
+      comp_bar_sync();
+      const float ax = (fmaf((float)c, a.gsx, -1.0f) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
+      const float xhi = (float)a.Tw - 0.5f;
+      const float lse2 = lse[(long long)bh * a.HW + mm] * LOG2E;
+      const float dl = delta[(long long)bh * a.HW + mm];
+
+#pragma unroll 1
+      for (int h = 0; h < NHALF; ++h) {
+        const uint32_t e_idx = (uint32_t)(it * NHALF + h);
+        mbar_wait(sdp_full, e_idx & 1u);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int col0 = chalf * 64 + sub * 32;          // column within the half
+          uint32_t sv[32], dpv[32];
+          tmem_ld_32x32(t_lane + TM_S + (uint32_t)col0, sv);
+          tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
+          tmem_wait_ld();
+          const int nbase = h * NHC + col0;
+          const int2* yt = sYt + (r - r0) * NS + nbase;
+          const float* xk = sXk + nbase;
+          float gxs[32], gys[32];
+          uint32_t pp[16], dd[16];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int2 ye = yt[j];
+            float u = ax - xk[j];
+            u = fminf(fmaxf(u, -1.5f), xhi);
+            const float aa = u + MAGIC;
+            const float fx = (u - (aa - MAGIC)) + 0.5f;
+            const float fy = __int_as_float(ye.y);
+            const int idx = ye.x + __float_as_int(aa);
+            const uint2 e = sTab[idx];
+            const float t00 = __uint_as_float(e.x << 16), d0 = __uint_as_float(e.x & 0xffff0000u);
+            const float t10 = __uint_as_float(e.y << 16), d1 = __uint_as_float(e.y & 0xffff0000u);
+            const float top = fmaf(fx, d0, t00), bot = fmaf(fx, d1, t10);
+            const float dyb = bot - top;                         // d bias / d iy  (x log2e)
+            const float bias = fmaf(fy, dyb, top);
+            const float dxb = fmaf(fy, d1 - d0, d0);             // d bias / d ix  (x log2e)
+            const float tv = fmaf(__uint_as_float(sv[j]), a.c1, bias);
+            const float p = valid ? ex2(tv - lse2) : 0.f;
+            const float ds = p * (__uint_as_float(dpv[j]) - dl);
+            gxs[j] = ds * dxb;
+            gys[j] = ds * dyb;
+            if (j & 1) {
+              pp[(j >> 1) & 3] = pack_bf16x2(__uint_as_float(sv[j - 1]), p);
+              dd[(j >> 1) & 3] = pack_bf16x2(__uint_as_float(dpv[j - 1]), ds);
+            } else {                                             // park p, ds until the pair is complete
+              sv[j] = __float_as_uint(p);
+              dpv[j] = __float_as_uint(ds);
+            }
+            if ((j & 7) == 7) {
+              // P_h, dS_h -> shared memory (K-major, 128B swizzle), 16 bytes per 8 columns
+              const int ch = sub * 4 + (j >> 3);
+              const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(sP + chalf * 16384 + row * 128 + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+              *reinterpret_cast<uint4*>(sDS + chalf * 16384 + row * 128 + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+            }
+            // ---- d rpe_table: segmented (run-wise) pre-reduction across the warp ----
+            {
+              const int pk = __shfl_up_sync(FULL, idx, 1);
+              const int pr = __shfl_up_sync(FULL, r, 1);
+              const bool head = lane == 0 || pk != idx || pr != r;
+              const unsigned heads = __ballot_sync(FULL, head);
+              const int start = 31 - __clz((int)(heads & (FULL >> (31 - lane))));
+              float Pw = ds * (1.0f - fx), Qw = ds * fx;
+#pragma unroll
+              for (int dsh = 1; dsh <= 4; dsh <<= 1) {
+                const float oP = __shfl_down_sync(FULL, Pw, dsh), oQ = __shfl_down_sync(FULL, Qw, dsh);
+                const int os = __shfl_down_sync(FULL, start, dsh);
+                if (lane + dsh < 32 && os == start) { Pw += oP; Qw += oQ; }
+              }
+              if (((lane - start) & 7) == 0 && (Pw != 0.f || Qw != 0.f)) {
+                float* cell = sDTab + idx;                 // padded index: no bounds checks
+                const float wy1 = fy, wy0 = 1.0f - fy;
+                atomicAdd(cell, Pw * wy0);
+                atomicAdd(cell + 1, Qw * wy0);
+                atomicAdd(cell + a.Wp, Pw * wy1);
+                atomicAdd(cell + a.Wp + 1, Qw * wy1);
+              }
+            }
+          }
+          // d pos: column sums over this warp's 32 rows (lane L ends up with column L)
+          dpx_acc[h * 2 + sub] += column_sums32(gxs, lane);
+          dpy_acc[h * 2 + sub] += column_sums32(gys, lane);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(pds_ready);
+      }
+
+      // dQ tile: TMEM -> * scale -> bf16 -> global (each compute warp writes 16 channels)
+      mbar_wait(dq_full, (uint32_t)it & 1u);
+      tc_fence_after_sync();
+      uint32_t qv[16];
+      tmem_ld_32x16(t_lane + TM_DQ + (uint32_t)(chalf * 16), qv);
+      tmem_wait_ld();
+      tc_fence_before_sync();
+      mbar_arrive(dq_free);
+      if (valid) {
+        uint32_t pk8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pk8[i] = pack_bf16x2(__uint_as_float(qv[2 * i]) * a.scale, __uint_as_float(qv[2 * i + 1]) * a.scale);
+        uint4* dst = reinterpret_cast<uint4*>(dq + ((long long)b * a.HW + m) * a.C + eta * 32 + chalf * 16);
+        dst[0] = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
+        dst[1] = make_uint4(pk8[4], pk8[5], pk8[6], pk8[7]);
+      }
+    }
+
+    // ---- end of CTA: dK / dV accumulators, d pos, d table --------------------------------------
+    // every MMA of this CTA has completed: the last dq_full commit covers all earlier MMAs
+    {
+      const uint32_t acc_base = chalf == 0 ? TM_DK : TM_DV;
+      float* outp = chalf == 0 ? dk_part : dv_part;
+      const float mul = chalf == 0 ? a.scale : 1.0f;
+#pragma unroll
+      for (int h = 0; h < NHALF; ++h) {
+        const int n = h * NHC + row;
+        float* dst = outp + (((long long)blockIdx.x * a.B + b) * NS + n) * a.C + eta * 32;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t kv[16];
+          tmem_ld_32x16(t_lane + acc_base + (uint32_t)(h * 32 + c2 * 16), kv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(dst + c2 * 16 + i) =
+                make_float4(__uint_as_float(kv[i]) * mul, __uint_as_float(kv[i + 1]) * mul,
+                            __uint_as_float(kv[i + 2]) * mul, __uint_as_float(kv[i + 3]) * mul);
+        }
+      }
+    }
+    // per-warp column sums -> shared memory -> sum over the 4 row-quads
+    {
+      float* mine = sDpos + (size_t)(warp - 4) * NS * 2;
+#pragma unroll
+      for (int h = 0; h < NHALF; ++h)
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int n = h * NHC + chalf * 64 + sub * 32 + lane;
+          mine[2 * n] = dpy_acc[h * 2 + sub];
+          mine[2 * n + 1] = dpx_acc[h * 2 + sub];
+        }
+    }
+    comp_bar_sync();
+    for (int n = ctid; n < NS; n += COMP_THREADS) {
+      const int ch = (n % NHC) / 64;                 // which column-half group of warps owns n
+      float sy = 0.f, sx = 0.f;
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        const float* src = sDpos + (size_t)(ch * 4 + qd) * NS * 2;
+        sy += src[2 * n];
+        sx += src[2 * n + 1];
+      }
+      float* dpo = dpos_part + ((((long long)b * a.heads + eta) * a.chunks + blockIdx.x) * NS + n) * 2;
+      dpo[0] = sy * (-a.ky / LOG2E);
+      dpo[1] = sx * (-a.kx / LOG2E);
+    }
+    // padded shared-memory table gradient -> global (one atomic per touched in-range cell)
+    float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
+    for (int i = ctid; i < a.Hp * a.Wp; i += COMP_THREADS) {
+      const int y = i / a.Wp - 2, x = i - (i / a.Wp) * a.Wp - 2;
+      const float vv = sDTab[i];
+      if (vv != 0.f && y >= 0 && y < a.Th && x >= 0 && x < a.Tw) atomicAdd(dt_g + y * a.Tw + x, vv);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int rows_spanned_max_b(int HW, int W) {
+  int n_tiles = (HW + TQ - 1) / TQ, best = 1;
+  for (int t = 0; t < n_tiles; ++t) {
+    int first = (t * TQ) / W;
+    int last_m = t * TQ + TQ - 1;
+    if (last_m > HW - 1) last_m = HW - 1;
+    int rows = last_m / W - first + 1;
+    if (rows > best) best = rows;
+  }
+  return best;
+}
+
+}  // namespace
+
+int attention_bwd_tc_chunks(const Shape& s) {
+  const int pairs = s.B * s.heads, n_tiles = (s.HW + TQ - 1) / TQ;
+  double best_cost = 1e30;
+  int best = 1;
+  for (int ch = 1; ch <= n_tiles && ch <= 16; ++ch) {
+    long long ctas = (long long)pairs * ch;
+    long long waves = (ctas + 147) / 148;
+    int per = (n_tiles + ch - 1) / ch;
+    double cost = (double)waves * (per + 1.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ch; }
+  }
+  return best;
+}
+
+bool attention_bwd_tc_supported(const Shape& s) {
+  if (s.act_dtype != DAT_BF16) return false;
+  if (!(s.Ns == 128 || s.Ns == 256)) return false;
+  if (s.C % 8 != 0) return false;
+  SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows_spanned_max_b(s.HW, s.W));
+  return sp.total <= 227 * 1024;
+}
+
+// dq (bf16); dk_part / dv_part: (chunks, B, Ns, C) fp32; dpos_part: (B, heads, chunks, Ns, 2);
+// d_table must be zeroed by the caller; tab_packed from attention_pack_table().
+int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
+                     const float* lse, const float* delta, const float* pos, const void* tab_packed,
+                     void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
+                     cudaStream_t st) {
+  DAT_REQUIRE(attention_bwd_tc_supported(s), "attention_bwd_tc: unsupported shape");
+  BtcArgs a;
+  a.B = s.B; a.H = s.H; a.W = s.W; a.HW = s.HW; a.C = s.C; a.heads = s.heads; a.G = s.G; a.hg = s.hg;
+  a.Th = s.Th; a.Tw = s.Tw; a.Wp = s.Tw + 3; a.Hp = s.Th + 3;
+  a.n_tiles = (s.HW + TQ - 1) / TQ;
+  a.rows_max = rows_spanned_max_b(s.HW, s.W);
+  a.chunks = attention_bwd_tc_chunks(s);
+  a.scale = 1.0f / sqrtf((float)DAT_HEAD_DIM);
+  a.c1 = a.scale * LOG2E;
+  a.kx = 0.25f * (float)(s.Tw - 1);
+  a.ky = 0.25f * (float)(s.Th - 1);
+  a.gsx = 2.0f / (float)(s.W - 1);
+  a.gsy = 2.0f / (float)(s.H - 1);
+  CUtensorMap tmQ, tmDO, tmK, tmV;
+  const uint64_t pitch = (uint64_t)s.C * 2;
+  DAT_FWD(tc::make_tmap_2d(&tmQ, q, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, pitch, TQ, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmDO, d_o, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, pitch, TQ, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
+  SmemPlanB sp = plan_smem_b(s.Ns, a.Hp, a.Wp, a.rows_max);
+  dim3 grid(a.chunks, s.B * s.heads);
+#define LAUNCH(NSV)                                                                              \
+  do {                                                                                           \
+    auto kern = attn_bwd_tc_kernel<NSV>;                                                         \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
+    kern<<<grid, BTC_THREADS, sp.total, st>>>(tmQ, tmDO, tmK, tmV, pos, (const uint2*)tab_packed, lse, \
+                                              delta, (bf16*)dq, dk_part, dv_part, d_table, dpos_part, a); \
+  } while (0)
+  if (s.Ns == 256) LAUNCH(256); else LAUNCH(128);
+#undef LAUNCH
+  DAT_LAUNCH_OK("attn_bwd_tc_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

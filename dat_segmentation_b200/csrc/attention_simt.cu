@@ -443,6 +443,17 @@ int attention_bwd_qsplit(const Shape& s) {
   return (int)(r < 1 ? 1 : r);
 }
 
+// delta[b, eta, m] = sum_c dO * O (shared by the CUDA-core and tensor-core backward paths)
+int attention_delta(const Shape& s, const void* d_o, const void* o, float* delta, cudaStream_t st) {
+  long long tot = (long long)s.B * s.HW * s.heads;
+  if (s.act_dtype == DAT_F32)
+    attn_delta_kernel<float><<<ceil_div(tot, 256), 256, 0, st>>>((const float*)d_o, (const float*)o, delta, s.HW, s.C, s.heads, tot);
+  else
+    attn_delta_kernel<bf16><<<ceil_div(tot, 256), 256, 0, st>>>((const bf16*)d_o, (const bf16*)o, delta, s.HW, s.C, s.heads, tot);
+  DAT_LAUNCH_OK("attn_delta_kernel");
+  return DAT_OK;
+}
+
 size_t attention_bwd_workspace(const Shape& s) {
   int qs = attention_bwd_qsplit(s);
   size_t delta = align_up((size_t)s.B * s.heads * s.HW * 4, 256);

@@ -76,6 +76,17 @@ struct BwdPlan {
   size_t sub_bytes, total;
 };
 
+bool use_tc_attn_bwd(const Shape& s) { return tc_enabled() && attention_bwd_tc_supported(s); }
+// number of query splits whose partial dK / dV / dpos the backward produces
+int bwd_qsplit(const Shape& s) {
+  return use_tc_attn_bwd(s) ? attention_bwd_tc_chunks(s) : attention_bwd_qsplit(s);
+}
+// scratch of the tensor-core attention backward: delta | dk_part | dv_part | packed table
+size_t tc_attn_bwd_scratch(const Shape& s) {
+  const size_t part = align_up((size_t)attention_bwd_tc_chunks(s) * s.B * s.Ns * s.C * 4, 256);
+  return align_up((size_t)s.B * s.heads * s.HW * 4, 256) + 2 * part + attention_fwd_tc_workspace(s);
+}
+
 BwdPlan plan_bwd(const Shape& s, void* ws) {
   BwdPlan p;
   Carver c(ws);
@@ -85,10 +96,11 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   p.dk = c.take((size_t)s.B * s.Ns * s.C * e);
   p.dv = c.take((size_t)s.B * s.Ns * s.C * e);
   p.dxs = c.take((size_t)s.B * s.Ns * s.C * e);
-  p.dpos_part = (float*)c.take((size_t)s.B * s.heads * attention_bwd_qsplit(s) * s.Ns * 2 * 4);
+  p.dpos_part = (float*)c.take((size_t)s.B * s.heads * bwd_qsplit(s) * s.Ns * 2 * 4);
   p.dpos = (float*)c.take((size_t)s.B * s.G * s.Ns * 2 * 4);
   p.wT = c.take((size_t)4 * s.C * s.C * 2);
   size_t sub = attention_bwd_workspace(s);
+  if (use_tc_attn_bwd(s) && tc_attn_bwd_scratch(s) > sub) sub = tc_attn_bwd_scratch(s);
   size_t w1 = pointwise_wgrad_workspace((long long)s.B * s.HW, s.C, s.C);
   size_t w2 = pointwise_wgrad_workspace((long long)s.B * s.Ns, s.C, s.C);
   size_t w3 = offset_bwd_workspace(s);
@@ -281,8 +293,24 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
   // attention core
-  DAT_FWD(attention_bwd_simt(s, sv->q, sv->k, sv->v, sv->o, w.d_o, sv->lse, sv->pos, p->rpe_table,
-                             w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
+  if (use_tc_attn_bwd(s)) {
+    const int chunks = attention_bwd_tc_chunks(s);
+    const size_t part = align_up((size_t)chunks * s.B * s.Ns * C * 4, 256);
+    float* delta = (float*)w.sub;
+    float* dk_part = (float*)((char*)w.sub + align_up((size_t)s.B * s.heads * s.HW * 4, 256));
+    float* dv_part = (float*)((char*)dk_part + part);
+    void* tabp = (char*)dv_part + part;
+    DAT_FWD(attention_delta(s, w.d_o, sv->o, delta, st));
+    DAT_CUDA_OK(cudaMemsetAsync(g->rpe_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
+    DAT_FWD(attention_pack_table(s, p->rpe_table, tabp, st));
+    DAT_FWD(attention_bwd_tc(s, sv->q, sv->k, sv->v, w.d_o, sv->lse, delta, sv->pos, tabp, w.dq, dk_part,
+                             dv_part, g->rpe_table, w.dpos_part, st));
+    DAT_FWD(reduce_partials(dk_part, chunks, (long long)s.B * s.Ns * C, w.dk, adt, st));
+    DAT_FWD(reduce_partials(dv_part, chunks, (long long)s.B * s.Ns * C, w.dv, adt, st));
+  } else {
+    DAT_FWD(attention_bwd_simt(s, sv->q, sv->k, sv->v, sv->o, w.d_o, sv->lse, sv->pos, p->rpe_table,
+                               w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
+  }
   // proj_k / proj_v
   DAT_FWD(pointwise_wgrad_simt(w.dk, adt, sv->xs, adt, g->wk, g->bk, Mk, C, C, w.sub, w.sub_bytes, st));
   DAT_FWD(pointwise_wgrad_simt(w.dv, adt, sv->xs, adt, g->wv, g->bv, Mk, C, C, w.sub, w.sub_bytes, st));
@@ -293,7 +321,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
   }
   // sampling -> d pos; offset network -> dq
-  DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, attention_bwd_qsplit(s), w.dpos, st));
+  DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
   DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
   // proj_q, then the sampling scatter on top of its data gradient
   DAT_FWD(pointwise_wgrad_simt(w.dq, adt, x, s.x_dtype, g->wq, g->bq, M, C, C, w.sub, w.sub_bytes, st));

@@ -89,3 +89,15 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
                           cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// attention_bwd_tc.cu — tcgen05 attention backward (bf16, Ns in {128, 256}, table fits smem)
+int attention_delta(const Shape& s, const void* d_o, const void* o, float* delta, cudaStream_t st);
+int attention_pack_table(const Shape& s, const float* table, void* out, cudaStream_t st);
+bool attention_bwd_tc_supported(const Shape& s);
+int attention_bwd_tc_chunks(const Shape& s);
+int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
+                     const float* lse, const float* delta, const float* pos, const void* tab_packed,
+                     void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
+                     cudaStream_t st);
+}  // namespace dat

@@ -382,3 +382,39 @@ def test_full_size_batch_independence_and_determinism(stage):
         m.proj_k.bias.add_(0.37)
         y3, _, _ = m(x)
     assert rel_err(y3.cpu(), y1.cpu()) < 5e-5
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3])
+def test_block_backward_bf16_full_size_vs_oracle(stage):
+    """bf16 block fwd+bwd at full DAT-T++ stage shapes (tensor-core attention backward for
+    Ns = 256) against the fp32 analytic oracle.  tanh offsets (orf = 2): no clamp mask, so the
+    gradients are continuous and a plain relative-L2 tolerance applies."""
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    H, heads, groups, stride, ksize, qs = STAGES[stage]
+    torch.manual_seed(20 + stage)
+    m = DAttentionBaseline((qs, qs), (qs, qs), heads, 32, groups, 0.0, 0.0, stride, 2, True, False,
+                           False, False, ksize, False, stage).cuda()
+    with torch.no_grad():
+        m.conv_offset[3].weight.mul_(2.0)
+        m.rpe_table.mul_(10.0)
+    B = 2
+    x = torch.randn(B, heads * 32, H, H)
+    dy = torch.randn(B, heads * 32, H, H)
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y, _, _ = m(xd)
+    y.backward(dy.cuda().bfloat16())
+    cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, 2)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    dx_ref, g_ref, _ = orc.backward_explicit(nhwc(x), params, cfg, nhwc(dy))
+
+    def l2(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    report = {"dx": l2(nhwc(xd.grad.cpu()), dx_ref)}
+    for key, p in m.named_parameters():
+        if key != "proj_k.bias":
+            report[key] = l2(p.grad.cpu(), g_ref[key])
+    print(f"stage {stage}", {k: f"{v:.2e}" for k, v in report.items()})
+    bad = {k: v for k, v in report.items() if v > 4e-2}
+    assert not bad, bad
