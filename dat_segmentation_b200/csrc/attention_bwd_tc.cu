@@ -45,7 +45,7 @@ constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 288, TM_DV = 352;
 
 struct BtcArgs {
   int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
-  int n_tiles, rows_max, chunks;
+  int n_tiles, rows_max, chunks, nslots;
   float c1, scale, kx, ky, gsx, gsy;
 };
 
@@ -85,44 +85,67 @@ __device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// compact packed table: entry (y, x) at (y + 2) * Wp + (x + 2) = bf16x2 {T[y][x], T[y][x+1]} * log2(e),
+// zero outside the table
+__global__ void pack_table_compact_kernel(const float* __restrict__ table, uint32_t* __restrict__ out,
+                                          int heads, int Th, int Tw) {
+  const int Wp = Tw + 3, Hp = Th + 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= heads * Hp * Wp) return;
+  const int eta = idx / (Hp * Wp), rem = idx % (Hp * Wp);
+  const int y = rem / Wp - 2, x = rem % Wp - 2;
+  const float* t = table + (long long)eta * Th * Tw;
+  auto at = [&](int yy, int xx) {
+    return (yy >= 0 && yy < Th && xx >= 0 && xx < Tw) ? t[yy * Tw + xx] * LOG2E : 0.f;
+  };
+  out[idx] = pack_bf16x2(at(y, x), at(y, x + 1));
+}
+
 struct SmemPlanB {
   uint32_t q[2], d_o[2], k, v, p, ds, tab, dtab, yt, xk, yk, dpos, bars, total;
 };
-__host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int rows_max) {
+__host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int rows_max, bool compact,
+                                                 int ndt, int nslots) {
   SmemPlanB s;
   uint32_t off = 0;
-  s.q[0] = off; off += TQ * 64;
-  s.q[1] = off; off += TQ * 64;
+  s.q[0] = off; off += TQ * 64;          // Q slots are contiguous: slot i at q[0] + i * 8 KB
+  s.q[1] = off; off += (nslots > 1 ? TQ * 64 : 0);
   s.d_o[0] = off; off += TQ * 64;
-  s.d_o[1] = off; off += TQ * 64;
+  s.d_o[1] = off; off += (nslots > 1 ? TQ * 64 : 0);
   s.k = off; off += NS * 64;
   s.v = off; off += NS * 64;
   s.p = off; off += 2 * 16384;      // [128 x 128] bf16, two 64-column K-blocks
   s.ds = off; off += 2 * 16384;
-  s.tab = off; off += ((uint32_t)(Hp * Wp) * 8 + 15) & ~15u;
-  s.dtab = off; off += ((uint32_t)(Hp * Wp) * 4 + 15) & ~15u;
+  s.tab = off; off += ((uint32_t)(Hp * Wp) * (compact ? 4 : 8) + 15) & ~15u;
+  s.dtab = off; off += ((uint32_t)(ndt * Hp * Wp) * 4 + 15) & ~15u;
   s.yt = off; off += (uint32_t)rows_max * NS * 8;
   s.xk = off; off += NS * 4;
   s.yk = off; off += NS * 4;
-  s.dpos = off; off += 8 * NS * 2 * 4;     // per compute warp column sums [8][NS][2]
+  s.dpos = s.p;                            // per-warp column sums [8][NS][2] alias P/dS at the end
   s.bars = off; off += 16 * 8;
   s.total = off + 1024;
   return s;
 }
 
-template <int NS>
+// COMPACT: table entries are 4 bytes {T[y][x], T[y][x+1]} (two LDS per score) instead of the
+//          8-byte 4-tap entries: halves the table footprint for the 111 x 111 stage-0 table.
+// PRIV:    every compute warp owns a private padded copy of the table gradient and updates it
+//          with plain read-modify-writes (no atomics); needs W % 32 == 0 (a warp's 32 queries
+//          lie in one image row, so its run leaders hit distinct cells).
+template <int NS, bool COMPACT, bool PRIV>
 __global__ void __launch_bounds__(BTC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const float* __restrict__ pos, const uint2* __restrict__ tab_packed,
+                   const float* __restrict__ pos, const void* __restrict__ tab_packed,
                    const float* __restrict__ lse, const float* __restrict__ delta,
                    bf16* __restrict__ dq, float* __restrict__ dk_part, float* __restrict__ dv_part,
                    float* __restrict__ d_table, float* __restrict__ dpos_part, BtcArgs a) {
   constexpr int NHALF = NS / NHC;
+  constexpr int NDT = PRIV ? 8 : 1;          // copies of the table gradient
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
-  const SmemPlanB sp = plan_smem_b(NS, a.Hp, a.Wp, a.rows_max);
+  const SmemPlanB sp = plan_smem_b(NS, a.Hp, a.Wp, a.rows_max, COMPACT, NDT, a.nslots);
   uint8_t* sQ0 = smem + sp.q[0];
   uint8_t* sDO0 = smem + sp.d_o[0];
   uint8_t* sK = smem + sp.k;
@@ -130,11 +153,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sP = smem + sp.p;
   uint8_t* sDS = smem + sp.ds;
   uint2* sTab = reinterpret_cast<uint2*>(smem + sp.tab);
+  uint32_t* sTabC = reinterpret_cast<uint32_t*>(smem + sp.tab);
   float* sDTab = reinterpret_cast<float*>(smem + sp.dtab);
   int2* sYt = reinterpret_cast<int2*>(smem + sp.yt);
   float* sXk = reinterpret_cast<float*>(smem + sp.xk);
   float* sYk = reinterpret_cast<float*>(smem + sp.yk);
-  float* sDpos = reinterpret_cast<float*>(smem + sp.dpos);
+  float* sDpos = reinterpret_cast<float*>(smem + sp.p);   // aliases the P / dS tiles (used after the last MMA)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;    // [2]
@@ -166,11 +190,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   {
-    const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
-    for (int i = threadIdx.x; i < a.Hp * a.Wp; i += BTC_THREADS) {
-      sTab[i] = src[i];
-      sDTab[i] = 0.f;
+    if (COMPACT) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(tab_packed) + (long long)eta * a.Hp * a.Wp;
+      for (int i = threadIdx.x; i < a.Hp * a.Wp; i += BTC_THREADS) sTabC[i] = src[i];
+    } else {
+      const uint2* src = reinterpret_cast<const uint2*>(tab_packed) + (long long)eta * a.Hp * a.Wp;
+      for (int i = threadIdx.x; i < a.Hp * a.Wp; i += BTC_THREADS) sTab[i] = src[i];
     }
+    for (int i = threadIdx.x; i < NDT * a.Hp * a.Wp; i += BTC_THREADS) sDTab[i] = 0.f;
     const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
     for (int n = threadIdx.x; n < NS; n += BTC_THREADS) {
       sYk[n] = pp[2 * n] * a.ky;
@@ -190,8 +217,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(sV, &tmV, kv_full, eta * 32, b * NS);
       int it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int slot = it & 1;
-        mbar_wait(&qdo_empty[slot], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int slot = it % a.nslots;
+        mbar_wait(&qdo_empty[slot], ((uint32_t)(it / a.nslots) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&qdo_full[slot], 2u * TQ * 64u);
         tma_load_2d(sQ0 + slot * (TQ * 64), &tmQ, &qdo_full[slot], eta * 32, b * a.HW + tile * TQ);
         tma_load_2d(sDO0 + slot * (TQ * 64), &tmDO, &qdo_full[slot], eta * 32, b * a.HW + tile * TQ);
@@ -208,8 +235,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(kv_full, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int slot = it & 1;
-        mbar_wait(&qdo_full[slot], ((uint32_t)it >> 1) & 1u);
+        const int slot = it % a.nslots;
+        mbar_wait(&qdo_full[slot], (uint32_t)(it / a.nslots) & 1u);
         const uint32_t q_addr = smem_u32(sQ0 + slot * (TQ * 64));
         const uint32_t do_addr = smem_u32(sDO0 + slot * (TQ * 64));
 #pragma unroll
@@ -291,6 +318,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float xhi = (float)a.Tw - 0.5f;
       const float lse2 = lse[(long long)bh * a.HW + mm] * LOG2E;
       const float dl = delta[(long long)bh * a.HW + mm];
+      const int r_up = __shfl_up_sync(FULL, r, 1);
+      const bool row_head = lane == 0 || r_up != r;
+      float* mytab = sDTab + (PRIV ? (warp - 4) * a.Hp * a.Wp : 0);
+      uint8_t* prow_p = sP + chalf * 16384 + row * 128;
+      uint8_t* prow_d = sDS + chalf * 16384 + row * 128;
 
 #pragma unroll 1
       for (int h = 0; h < NHALF; ++h) {
@@ -318,9 +350,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float fx = (u - (aa - MAGIC)) + 0.5f;
             const float fy = __int_as_float(ye.y);
             const int idx = ye.x + __float_as_int(aa);
-            const uint2 e = sTab[idx];
-            const float t00 = __uint_as_float(e.x << 16), d0 = __uint_as_float(e.x & 0xffff0000u);
-            const float t10 = __uint_as_float(e.y << 16), d1 = __uint_as_float(e.y & 0xffff0000u);
+            float t00, d0, t10, d1;
+            if (COMPACT) {
+              const uint32_t e0 = sTabC[idx], e1 = sTabC[idx + a.Wp];
+              t00 = __uint_as_float(e0 << 16);
+              d0 = __uint_as_float(e0 & 0xffff0000u) - t00;
+              t10 = __uint_as_float(e1 << 16);
+              d1 = __uint_as_float(e1 & 0xffff0000u) - t10;
+            } else {
+              const uint2 e = sTab[idx];
+              t00 = __uint_as_float(e.x << 16); d0 = __uint_as_float(e.x & 0xffff0000u);
+              t10 = __uint_as_float(e.y << 16); d1 = __uint_as_float(e.y & 0xffff0000u);
+            }
             const float top = fmaf(fx, d0, t00), bot = fmaf(fx, d1, t10);
             const float dyb = bot - top;                         // d bias / d iy  (x log2e)
             const float bias = fmaf(fy, dyb, top);
@@ -341,30 +382,59 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               // P_h, dS_h -> shared memory (K-major, 128B swizzle), 16 bytes per 8 columns
               const int ch = sub * 4 + (j >> 3);
               const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(sP + chalf * 16384 + row * 128 + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-              *reinterpret_cast<uint4*>(sDS + chalf * 16384 + row * 128 + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+              *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+              *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
             }
-            // ---- d rpe_table: segmented (run-wise) pre-reduction across the warp ----
+            // ---- d rpe_table ----------------------------------------------------------------
+            // Lanes = consecutive queries of an image row; the table step per query is < 1 cell,
+            // so lanes form runs with the same north-west cell.  (1) segmented shuffle reduction
+            // of P = ds(1-fx) -> cell x0 and Q = ds*fx -> cell x0+1 over each run (windows of 8);
+            // (2) a run head also takes the Q of the previous run when that run is its left
+            // neighbour (same image row, cell x0-1, single window), so a run usually issues 2
+            // updates (rows y0, y0+1 of one cell) instead of 4.
             {
               const int pk = __shfl_up_sync(FULL, idx, 1);
-              const int pr = __shfl_up_sync(FULL, r, 1);
-              const bool head = lane == 0 || pk != idx || pr != r;
+              const bool head = row_head || pk != idx;
               const unsigned heads = __ballot_sync(FULL, head);
               const int start = 31 - __clz((int)(heads & (FULL >> (31 - lane))));
-              float Pw = ds * (1.0f - fx), Qw = ds * fx;
+              float Qw = ds * fx, Pw = ds - Qw;
 #pragma unroll
               for (int dsh = 1; dsh <= 4; dsh <<= 1) {
                 const float oP = __shfl_down_sync(FULL, Pw, dsh), oQ = __shfl_down_sync(FULL, Qw, dsh);
                 const int os = __shfl_down_sync(FULL, start, dsh);
-                if (lane + dsh < 32 && os == start) { Pw += oP; Qw += oQ; }
+                const bool same = (lane + dsh < 32) && (os == start);
+                Pw += same ? oP : 0.f;
+                Qw += same ? oQ : 0.f;
               }
-              if (((lane - start) & 7) == 0 && (Pw != 0.f || Qw != 0.f)) {
-                float* cell = sDTab + idx;                 // padded index: no bounds checks
-                const float wy1 = fy, wy0 = 1.0f - fy;
-                atomicAdd(cell, Pw * wy0);
-                atomicAdd(cell + 1, Qw * wy0);
-                atomicAdd(cell + a.Wp, Pw * wy1);
-                atomicAdd(cell + a.Wp + 1, Qw * wy1);
+              const unsigned above = (heads >> lane) >> 1;              // heads strictly above my lane
+              const int nh = above ? lane + __ffs((int)above) : 32;    // next run head (32: none)
+              const int src_n = nh & 31;
+              const int idx_n = __shfl_sync(FULL, idx, src_n);
+              const int r_n = __shfl_sync(FULL, r, src_n);
+              const bool is_head = lane == start;
+              // my Q is absorbed by the next run's head
+              const bool absorbed = is_head && nh < 32 && (nh - lane) <= 8 && idx_n == idx + 1 && r_n == r;
+              // I (a run head) absorb the previous run's Q: previous head lane
+              const unsigned below = heads & ((1u << lane) - 1u);
+              const int ph = below ? 31 - __clz((int)below) : 0;
+              const float q_prev = __shfl_sync(FULL, Qw, ph);
+              const bool take = is_head && below != 0u && (lane - ph) <= 8 && pk + 1 == idx && r_up == r;
+              const float Uw = Pw + (take ? q_prev : 0.f);
+              const bool leader = ((lane - start) & 7) == 0;
+              float* cell = mytab + idx;                  // padded index: no bounds checks
+              const float wy1 = fy, wy0 = 1.0f - fy;
+              if (PRIV) {
+                if (leader) { cell[0] += Uw * wy0; cell[a.Wp] += Uw * wy1; }
+                __syncwarp();
+                if (leader && !absorbed) { cell[1] += Qw * wy0; cell[a.Wp + 1] += Qw * wy1; }
+                __syncwarp();
+              } else if (leader) {
+                atomicAdd(cell, Uw * wy0);
+                atomicAdd(cell + a.Wp, Uw * wy1);
+                if (!absorbed) {
+                  atomicAdd(cell + 1, Qw * wy0);
+                  atomicAdd(cell + a.Wp + 1, Qw * wy1);
+                }
               }
             }
           }
@@ -449,7 +519,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
     for (int i = ctid; i < a.Hp * a.Wp; i += COMP_THREADS) {
       const int y = i / a.Wp - 2, x = i - (i / a.Wp) * a.Wp - 2;
-      const float vv = sDTab[i];
+      float vv = 0.f;
+#pragma unroll
+      for (int cpy = 0; cpy < NDT; ++cpy) vv += sDTab[cpy * a.Hp * a.Wp + i];
       if (vv != 0.f && y >= 0 && y < a.Th && x >= 0 && x < a.Tw) atomicAdd(dt_g + y * a.Tw + x, vv);
     }
   }
@@ -486,12 +558,37 @@ int attention_bwd_tc_chunks(const Shape& s) {
   return best;
 }
 
-bool attention_bwd_tc_supported(const Shape& s) {
-  if (s.act_dtype != DAT_BF16) return false;
-  if (!(s.Ns == 128 || s.Ns == 256)) return false;
-  if (s.C % 8 != 0) return false;
-  SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows_spanned_max_b(s.HW, s.W));
-  return sp.total <= 227 * 1024;
+// kernel variant for a shape: private table-gradient copies and 8-byte table entries when they
+// fit, else shared copy (atomics) / compact table / single Q,dO slot.  variant < 0: unsupported.
+struct BtcVariant { int ok, compact, priv, nslots; uint32_t smem; };
+BtcVariant pick_variant(const Shape& s) {
+  BtcVariant v = {0, 0, 0, 2, 0};
+  if (s.act_dtype != DAT_BF16 || !(s.Ns == 128 || s.Ns == 256) || s.C % 8 != 0) return v;
+  const int rows = rows_spanned_max_b(s.HW, s.W);
+  const uint32_t lim = 227 * 1024;
+  // private copies: a warp's queries lie in one image row, and runs of equal cells stay within
+  // one 8-lane reduction window (table step per query >= 0.2 cells)
+  const bool priv_ok = (s.W % 32) == 0 && (s.Tw - 1) * 5 >= (s.W - 1);
+  const int tries[4][3] = {{0, 1, 2}, {0, 0, 2}, {1, 0, 2}, {1, 0, 1}};   // {compact, priv, nslots}
+  for (int t = 0; t < 4; ++t) {
+    if (tries[t][1] && !priv_ok) continue;
+    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, tries[t][1] ? 8 : 1, tries[t][2]);
+    if (sp.total <= lim) {
+      v.ok = 1; v.compact = tries[t][0]; v.priv = tries[t][1]; v.nslots = tries[t][2]; v.smem = sp.total;
+      return v;
+    }
+  }
+  return v;
+}
+
+bool attention_bwd_tc_supported(const Shape& s) { return pick_variant(s).ok != 0; }
+bool attention_bwd_tc_compact_table(const Shape& s) { return pick_variant(s).compact != 0; }
+
+int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st) {
+  const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
+  pack_table_compact_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint32_t*)out, s.heads, s.Th, s.Tw);
+  DAT_LAUNCH_OK("pack_table_compact_kernel");
+  return DAT_OK;
 }
 
 // dq (bf16); dk_part / dv_part: (chunks, B, Ns, C) fp32; dpos_part: (B, heads, chunks, Ns, 2);
@@ -500,8 +597,10 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
                      const float* lse, const float* delta, const float* pos, const void* tab_packed,
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
                      cudaStream_t st) {
-  DAT_REQUIRE(attention_bwd_tc_supported(s), "attention_bwd_tc: unsupported shape");
+  const BtcVariant var = pick_variant(s);
+  DAT_REQUIRE(var.ok, "attention_bwd_tc: unsupported shape");
   BtcArgs a;
+  a.nslots = var.nslots;
   a.B = s.B; a.H = s.H; a.W = s.W; a.HW = s.HW; a.C = s.C; a.heads = s.heads; a.G = s.G; a.hg = s.hg;
   a.Th = s.Th; a.Tw = s.Tw; a.Wp = s.Tw + 3; a.Hp = s.Th + 3;
   a.n_tiles = (s.HW + TQ - 1) / TQ;
@@ -519,16 +618,22 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
   DAT_FWD(tc::make_tmap_2d(&tmDO, d_o, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, pitch, TQ, 32, 64));
   DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
   DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
-  SmemPlanB sp = plan_smem_b(s.Ns, a.Hp, a.Wp, a.rows_max);
   dim3 grid(a.chunks, s.B * s.heads);
-#define LAUNCH(NSV)                                                                              \
+#define LAUNCH(NSV, CP, PV)                                                                      \
   do {                                                                                           \
-    auto kern = attn_bwd_tc_kernel<NSV>;                                                         \
-    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
-    kern<<<grid, BTC_THREADS, sp.total, st>>>(tmQ, tmDO, tmK, tmV, pos, (const uint2*)tab_packed, lse, \
-                                              delta, (bf16*)dq, dk_part, dv_part, d_table, dpos_part, a); \
+    auto kern = attn_bwd_tc_kernel<NSV, CP, PV>;                                                 \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem)); \
+    kern<<<grid, BTC_THREADS, var.smem, st>>>(tmQ, tmDO, tmK, tmV, pos, tab_packed, lse, delta,  \
+                                              (bf16*)dq, dk_part, dv_part, d_table, dpos_part, a); \
   } while (0)
-  if (s.Ns == 256) LAUNCH(256); else LAUNCH(128);
+#define LAUNCH_NS(NSV)                                   \
+  do {                                                   \
+    if (var.compact) LAUNCH(NSV, true, false);           \
+    else if (var.priv) LAUNCH(NSV, false, true);         \
+    else LAUNCH(NSV, false, false);                      \
+  } while (0)
+  if (s.Ns == 256) LAUNCH_NS(256); else LAUNCH_NS(128);
+#undef LAUNCH_NS
 #undef LAUNCH
   DAT_LAUNCH_OK("attn_bwd_tc_kernel");
   return DAT_OK;

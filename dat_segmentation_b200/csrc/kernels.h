@@ -101,3 +101,8 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
                      cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+bool attention_bwd_tc_compact_table(const Shape& s);
+int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st);
+}  // namespace dat
