@@ -72,6 +72,7 @@ struct BwdPlan {
   void *d_o, *dq, *dk, *dv, *dxs;
   float *dpos_part, *dpos;
   void* wT;         // bf16 transposed copies of (wo, wk, wv, wq) for the tensor-core data gradients
+  void* x_bf;       // bf16 copy of an fp32 x for the tensor-core weight gradient of proj_q
   void* sub;        // shared scratch of the individual stages (used one at a time)
   size_t sub_bytes, total;
 };
@@ -99,6 +100,7 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   p.dpos_part = (float*)c.take((size_t)s.B * s.heads * bwd_qsplit(s) * s.Ns * 2 * 4);
   p.dpos = (float*)c.take((size_t)s.B * s.G * s.Ns * 2 * 4);
   p.wT = c.take((size_t)4 * s.C * s.C * 2);
+  p.x_bf = c.take(s.act_dtype == DAT_BF16 && s.x_dtype == DAT_F32 ? (size_t)s.B * s.HW * s.C * 2 : 0);
   size_t sub = attention_bwd_workspace(s);
   if (use_tc_attn_bwd(s) && tc_attn_bwd_scratch(s) > sub) sub = tc_attn_bwd_scratch(s);
   size_t w1 = pointwise_wgrad_workspace((long long)s.B * s.HW, s.C, s.C);
@@ -106,6 +108,10 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   size_t w3 = offset_bwd_workspace(s);
   if (w1 > sub) sub = w1;
   if (w2 > sub) sub = w2;
+  if (s.act_dtype == DAT_BF16 && pointwise_wgrad_tc_supported((long long)s.B * s.HW, s.C, s.C)) {
+    size_t w4 = pointwise_wgrad_tc_workspace((long long)s.B * s.HW, s.C, s.C) + align_up((size_t)64 * s.C * 4, 256);
+    if (w4 > sub) sub = w4;
+  }
   if (w3 > sub) sub = w3;
   p.sub_bytes = sub;
   p.sub = c.take(sub);
@@ -288,8 +294,17 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   bf16* wT = (bf16*)w.wT;
   const size_t wsz = (size_t)C * C;
   if (tc) DAT_FWD(cast_transpose_weights_bf16(p->wo, p->wk, p->wv, p->wq, wT, C, st));
+  // weight gradients dW = dY^T X on the tensor cores (both operands read MN-major), bias
+  // gradients as column sums
+  const bool tcw = tc && pointwise_wgrad_tc_supported(M, C, C) && pointwise_wgrad_tc_supported(Mk, C, C);
+  auto wgrad = [&](const void* dY, const void* X, int x_dt, float* dW, float* db, long long rows) -> int {
+    if (!tcw) return pointwise_wgrad_simt(dY, adt, X, x_dt, dW, db, rows, C, C, w.sub, w.sub_bytes, st);
+    const size_t wsz_tc = pointwise_wgrad_tc_workspace(rows, C, C);
+    DAT_FWD(pointwise_wgrad_tc(dY, X, dW, rows, C, C, w.sub, wsz_tc, st));
+    return bias_grad(dY, adt, db, rows, C, (char*)w.sub + wsz_tc, w.sub_bytes - wsz_tc, st);
+  };
   // proj_out
-  DAT_FWD(pointwise_wgrad_simt(dy, adt, sv->o, adt, g->wo, g->bo, M, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(wgrad(dy, sv->o, adt, g->wo, g->bo, M));
   if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
   // attention core
@@ -313,8 +328,8 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
                                w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
   }
   // proj_k / proj_v
-  DAT_FWD(pointwise_wgrad_simt(w.dk, adt, sv->xs, adt, g->wk, g->bk, Mk, C, C, w.sub, w.sub_bytes, st));
-  DAT_FWD(pointwise_wgrad_simt(w.dv, adt, sv->xs, adt, g->wv, g->bv, Mk, C, C, w.sub, w.sub_bytes, st));
+  DAT_FWD(wgrad(w.dk, sv->xs, adt, g->wk, g->bk, Mk));
+  DAT_FWD(wgrad(w.dv, sv->xs, adt, g->wv, g->bv, Mk));
   if (tc) {
     DAT_FWD(pointwise_fwd_tc_dual(w.dk, wT + wsz, w.dv, wT + 2 * wsz, adt, nullptr, w.dxs, adt, Mk, C, C, st));
   } else {
@@ -325,7 +340,12 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
   DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
   // proj_q, then the sampling scatter on top of its data gradient
-  DAT_FWD(pointwise_wgrad_simt(w.dq, adt, x, s.x_dtype, g->wq, g->bq, M, C, C, w.sub, w.sub_bytes, st));
+  if (tcw && s.x_dtype == DAT_F32) {
+    DAT_FWD(cast_weights_bf16((const float*)x, nullptr, nullptr, w.x_bf, M * C, st));
+    DAT_FWD(wgrad(w.dq, w.x_bf, DAT_BF16, g->wq, g->bq, M));
+  } else {
+    DAT_FWD(wgrad(w.dq, x, s.x_dtype, g->wq, g->bq, M));
+  }
   if (tc) DAT_FWD(pointwise_fwd_tc(w.dq, adt, wT + 3 * wsz, nullptr, dx, DAT_F32, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
   DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));

@@ -234,6 +234,22 @@ int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, flo
   return DAT_OK;
 }
 
+// db[N] = column sums of dY[M,N] (two-stage, fixed order).  ws: colsum_splits(M) * N floats.
+int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+  const int cs = colsum_splits(M);
+  DAT_REQUIRE(ws_bytes >= (size_t)cs * N * sizeof(float), "bias_grad: workspace too small");
+  float* cpart = (float*)ws;
+  const long long rows = (M + cs - 1) / cs;
+  dim3 grid(ceil_div(N, 32), cs);
+  if (dy_dt == DAT_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, M, N, rows, cpart);
+  else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, M, N, rows, cpart);
+  DAT_LAUNCH_OK("colsum_kernel");
+  reduce_partials_kernel<float><<<ceil_div(N, 256), 256, 0, st>>>(cpart, cs, N, N, nullptr, db);
+  DAT_LAUNCH_OK("reduce_partials_kernel");
+  return DAT_OK;
+}
+
 // Generic deterministic reduction used by other stages: out[idx] = sum_z part[z][idx].
 int reduce_partials(const float* part, int nsplit, long long count, void* out, int out_dt,
                     cudaStream_t st) {

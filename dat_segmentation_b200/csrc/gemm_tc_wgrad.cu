@@ -1,0 +1,184 @@
+// Weight gradients of the 1x1 convolutions on the tcgen05 tensor cores:
+//     dW[N, K] = sum_m dY[m, n] * X[m, k]          (autograd of dat_blocks.py:143,177-178,225)
+// The contraction runs over the pixels m, i.e. over the ROWS of both channel-last matrices,
+// so both operands are MN-major: TMA boxes of 64 rows x 64 columns (128B swizzle) are used
+// directly as the canonical MN-major core-matrix layout (8-row groups 1 KB apart, 64-column
+// blocks 8 KB apart) - no transposed copy of either activation is ever made.
+// One CTA = one 128 (out-channel) x BNK (in-channel, <= 256) tile of dW over one slice of the
+// pixels; fp32 partial tiles per slice are reduced in a fixed order afterwards (deterministic).
+// Warp roles as in gemm_tc.cu: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace dat {
+
+namespace {
+
+using namespace tc;
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_BM = 128;           // out-channel rows of dW per CTA (UMMA M)
+constexpr int WG_CHUNK = 64;         // pixels per pipeline stage
+constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column bf16 box
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                     float* __restrict__ partial, int N, int K, int BNK, int rows_per_split,
+                     long long M, int stages, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int a_bytes = 2 * BOX_BYTES, b_bytes = (BNK / 64) * BOX_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint8_t* sA = smem + 1024;
+  uint8_t* sB = sA + stages * a_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * WG_BM, k0 = blockIdx.y * BNK, split = blockIdx.z;
+  const long long m_begin = (long long)split * rows_per_split;
+  long long m_end = m_begin + rows_per_split;
+  if (m_end > M) m_end = M;
+  const int chunks = m_end > m_begin ? (int)((m_end - m_begin + WG_CHUNK - 1) / WG_CHUNK) : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < chunks; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
+        // rows past m_end belong to the next slice: they are loaded but must not count, so the
+        // last chunk of a slice is clipped by construction (rows_per_split is a multiple of 64)
+        const int mrow = (int)(m_begin + (long long)kc * WG_CHUNK);
+        for (int i = 0; i < 2; ++i)
+          tma_load_2d(sA + s * a_bytes + i * BOX_BYTES, &tmDY, &full[s], n0 + 64 * i, mrow);
+        for (int i = 0; i < BNK / 64; ++i)
+          tma_load_2d(sB + s * b_bytes + i * BOX_BYTES, &tmX, &full[s], k0 + 64 * i, mrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(FMT_BF16, WG_BM, (uint32_t)BNK, 1, 1);   // A, B MN-major
+      for (int kc = 0; kc < chunks; ++kc) {
+        const int s = kc % stages;
+        const uint32_t ph = (uint32_t)(kc / stages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(sA + s * a_bytes), b_addr = smem_u32(sB + s * b_bytes);
+#pragma unroll
+        for (int j = 0; j < WG_CHUNK / 16; ++j) {      // 16 pixels per MMA
+          const uint64_t ad = make_smem_desc(a_addr + j * 2048, BOX_BYTES, 1024, LAYOUT_SW128);
+          const uint64_t bd = make_smem_desc(b_addr + j * 2048, BOX_BYTES, 1024, LAYOUT_SW128);
+          mma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)((kc | j) != 0));
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+  } else {
+    const int quad = warp & 3;
+    float* out = partial + ((long long)split * N + n0 + quad * 32) * K + k0;
+    const int row_bytes = BNK * 4, pitch = row_bytes + 16;
+    uint8_t* stage = sA + (warp - 2) * 32 * pitch;
+    if (chunks > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after_sync();
+    }
+    for (int c = 0; c < BNK / 32; ++c) {
+      uint32_t r[32];
+      if (chunks > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      float* dst = reinterpret_cast<float*>(stage + lane * pitch) + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    __syncwarp();
+    const int rows_here = min(32, N - (n0 + quad * 32));
+    for (int rr = 0; rr < rows_here; ++rr) {
+      uint8_t* grow = reinterpret_cast<uint8_t*>(out + (long long)rr * K);
+      const uint8_t* srow = stage + rr * pitch;
+      for (int off = lane * 16; off < row_bytes; off += 512)
+        *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+int wg_bnk(int C) { return C >= 256 ? 256 : C; }
+
+}  // namespace
+
+bool pointwise_wgrad_tc_supported(long long M, int N, int K) {
+  return M >= 64 && N % 128 == 0 && K % 128 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
+}
+
+int pointwise_wgrad_tc_splits(long long M, int N, int K) {
+  const int tiles = (N / WG_BM) * (K / wg_bnk(K));
+  long long want = (148 + tiles - 1) / tiles;
+  long long cap = (M + 127) / 128;            // at least 2 chunks per slice
+  long long s = want < cap ? want : cap;
+  return (int)(s < 1 ? 1 : s);
+}
+
+size_t pointwise_wgrad_tc_workspace(long long M, int N, int K) {
+  return align_up((size_t)pointwise_wgrad_tc_splits(M, N, K) * N * K * 4, 256);
+}
+
+// dW[N,K] (fp32, overwritten) = dY[M,N]^T X[M,K]; dY, X bf16 channel-last.
+int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, int N, int K,
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+  DAT_REQUIRE(pointwise_wgrad_tc_supported(M, N, K), "pointwise_wgrad_tc: unsupported shape");
+  DAT_REQUIRE(ws_bytes >= pointwise_wgrad_tc_workspace(M, N, K), "pointwise_wgrad_tc: workspace too small");
+  const int BNK = wg_bnk(K);
+  const int splits = pointwise_wgrad_tc_splits(M, N, K);
+  long long rps = (M + splits - 1) / splits;
+  rps = (rps + WG_CHUNK - 1) / WG_CHUNK * WG_CHUNK;
+  CUtensorMap tmDY, tmX;
+  DAT_FWD(tc::make_tmap_2d(&tmDY, dY, 2, false, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 64, 64, 128));
+  DAT_FWD(tc::make_tmap_2d(&tmX, X, 2, false, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, 64, 64, 128));
+  const int stage_bytes = 2 * BOX_BYTES + (BNK / 64) * BOX_BYTES;
+  int stages = 192 * 1024 / stage_bytes;
+  if (stages > 6) stages = 6;
+  size_t buf = (size_t)stages * stage_bytes;
+  const size_t out_stage = (size_t)4 * 32 * (BNK * 4 + 16);
+  if (out_stage > buf) buf = out_stage;
+  const size_t smem = 1024 + 1024 + buf;
+  int tmem_cols = 32;
+  while (tmem_cols < BNK) tmem_cols <<= 1;
+  float* part = splits > 1 ? (float*)ws : dW;
+  dim3 grid(N / WG_BM, K / BNK, splits);
+  DAT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gemm_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, part, N, K, BNK, (int)rps, M, stages, tmem_cols);
+  DAT_LAUNCH_OK("gemm_tc_wgrad_kernel");
+  if (splits > 1) DAT_FWD(reduce_partials((const float*)ws, splits, (long long)N * K, dW, DAT_F32, st));
+  return DAT_OK;
+}
+
+}  // namespace dat

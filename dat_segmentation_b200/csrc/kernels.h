@@ -106,3 +106,13 @@ namespace dat {
 bool attention_bwd_tc_compact_table(const Shape& s);
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// gemm_tc_wgrad.cu / gemm_simt.cu
+int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws, size_t ws_bytes,
+              cudaStream_t st);
+bool pointwise_wgrad_tc_supported(long long M, int N, int K);
+size_t pointwise_wgrad_tc_workspace(long long M, int N, int K);
+int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, int N, int K, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+}  // namespace dat

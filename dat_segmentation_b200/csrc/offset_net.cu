@@ -304,14 +304,25 @@ offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
   }
 }
 
+// block (32, 32): threadIdx.x = output within a 32-wide slice, threadIdx.y = partial lane.
+// Fixed summation order (lane-strided partial sums, then lanes 0..31): deterministic.
 __global__ void offset_bwd_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit,
                                                int kk, int Cg, float* __restrict__ g_dw_w) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // uv * Cg + c
-  if (idx >= kk * Cg) return;
+  __shared__ float red[32][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x;  // uv * Cg + c
+  const int n_out = kk * Cg;
   float s = 0.f;
-  for (int z = 0; z < nsplit; ++z) s += partial[(size_t)z * kk * Cg + idx];
-  int uv = idx / Cg, c = idx % Cg;
-  g_dw_w[c * kk + uv] = s;
+  if (idx < n_out)
+    for (int z = threadIdx.y; z < nsplit; z += 32) s += partial[(size_t)z * n_out + idx];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < n_out) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
+    const int uv = idx / Cg, c = idx % Cg;
+    g_dw_w[c * kk + uv] = t;
+  }
 }
 
 // Depthwise data gradient in gather form (no atomics): every q element sums the <=
@@ -466,8 +477,8 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   else
     offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, st>>>((const bf16*)q, dt, part2, pps, a);
   DAT_LAUNCH_OK("offset_bwd_wgrad_kernel");
-  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 128), 128, 0, st>>>(part2, nsplit, kk, s.Cg,
-                                                                            g->off_dw_w);
+  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 32), dim3(32, 32), 0, st>>>(part2, nsplit, kk, s.Cg,
+                                                                                    g->off_dw_w);
   DAT_LAUNCH_OK("offset_bwd_wgrad_reduce_kernel");
 
   long long total = (long long)s.B * s.HW * s.C;
