@@ -86,6 +86,13 @@ def lib():
     L.dat_attention_fwd_workspace_bytes.argtypes = [dp]
     L.dat_attention_fwd_workspace_bytes.restype = C.c_size_t
     L.dat_rpe_bias.argtypes = [dp, f32p, f32p, f32p, vp]
+    L.dat_layernorm_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, f32p, f32p, i64, i32, C.c_float, vp]
+    L.dat_layernorm_bwd_workspace_bytes.argtypes = [i64, i32]
+    L.dat_layernorm_bwd_workspace_bytes.restype = C.c_size_t
+    L.dat_layernorm_bwd.argtypes = [vp, i32, vp, i32, f32p, f32p, f32p, vp, f32p, f32p, i64, i32, vp,
+                                    C.c_size_t, vp]
+    L.dat_layernorm_fwd.restype = C.c_int
+    L.dat_layernorm_bwd.restype = C.c_int
     for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
                  "dat_pointwise_fwd_tc", "dat_cast_bf16",
                  "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd", "dat_attention_fwd",
@@ -108,4 +115,5 @@ def exported_symbols():
             "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing",
             "dat_offset_pos_fwd",
             "dat_ref_points", "dat_sample_fwd",
-            "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias"]
+            "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
+            "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd"]

@@ -13,9 +13,10 @@ from typing import Callable, Sequence
 import torch
 import torch.nn as nn
 
-from .dattention import DAttentionBaseline, LayerNormProxy, _pair
+from .dattention import DAttentionBaseline, _pair
+from .layernorm import LayerNormProxy, TorchLayerNormProxy
 
-__all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat"]
+__all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
 
 # DAT-T++ backbone hyper-parameters (configs/dat/upn_tiny_160k_dp03_lr6.py:9-32)
 DAT_TINY_PP = dict(
@@ -94,7 +95,8 @@ class TransformerStage(nn.Module):
     def __init__(self, fmap_size, window_size, dim_in, dim_embed, depths, stage_spec, n_groups,
                  use_pe, heads, stride, offset_range_factor, dwc_pe, no_off, fixed_pe, attn_drop,
                  proj_drop, expansion, drop, drop_path_rate, use_dwc_mlp, ksize, layer_scale_value,
-                 use_lpu, log_cpb, stage_i, use_checkpoint, attn_cls: Callable = DAttentionBaseline):
+                 use_lpu, log_cpb, stage_i, use_checkpoint, attn_cls: Callable = DAttentionBaseline,
+                 norm_cls: Callable = LayerNormProxy):
         super().__init__()
         fmap_size = _pair(fmap_size)
         self.depths, self.stage_spec = depths, list(stage_spec)
@@ -103,9 +105,9 @@ class TransformerStage(nn.Module):
         assert dim_embed == heads * hc
         self.proj = nn.Conv2d(dim_in, dim_embed, 1) if dim_in != dim_embed else nn.Identity()
         self.ln_cnvnxt = nn.ModuleDict(
-            {str(d): LayerNormProxy(dim_embed) for d in range(depths) if stage_spec[d] == "X"})
+            {str(d): norm_cls(dim_embed) for d in range(depths) if stage_spec[d] == "X"})
         self.layer_norms = nn.ModuleList(
-            [LayerNormProxy(dim_embed) if stage_spec[d // 2] != "X" else nn.Identity()
+            [norm_cls(dim_embed) if stage_spec[d // 2] != "X" else nn.Identity()
              for d in range(2 * depths)])
         mlp_cls = TransformerMLPWithConv if use_dwc_mlp else TransformerMLP
         self.mlps = nn.ModuleList([mlp_cls(dim_embed, expansion, drop) for _ in range(depths)])
@@ -168,7 +170,8 @@ class DAT(nn.Module):
                  qna_activation="exp", deform_groups=(0,) * 4, nat_ksizes=(3,) * 4,
                  layer_scale_values=(-1,) * 4, use_lpus=(False,) * 4, use_cmt_mlps=(False,) * 4,
                  log_cpb=(False,) * 4, out_indices=(0, 1, 2, 3), use_checkpoint=True,
-                 init_cfg=None, attn_cls: Callable = DAttentionBaseline, **kwargs):
+                 init_cfg=None, attn_cls: Callable = DAttentionBaseline,
+                 norm_cls: Callable = LayerNormProxy, **kwargs):
         super().__init__()
         if any(use_cmt_mlps):
             raise NotImplementedError("use_cmt_mlps (BatchNorm MLP variant) is not implemented")
@@ -176,11 +179,11 @@ class DAT(nn.Module):
         half = dim_stem // 2
         if use_conv_patches:
             self.patch_proj = nn.Sequential(
-                nn.Conv2d(3, half, 3, patch_size // 2, 1), LayerNormProxy(half), nn.GELU(),
-                nn.Conv2d(half, dim_stem, 3, patch_size // 2, 1), LayerNormProxy(dim_stem))
+                nn.Conv2d(3, half, 3, patch_size // 2, 1), norm_cls(half), nn.GELU(),
+                nn.Conv2d(half, dim_stem, 3, patch_size // 2, 1), norm_cls(dim_stem))
         else:
             self.patch_proj = nn.Sequential(nn.Conv2d(3, dim_stem, patch_size, patch_size, 0),
-                                            LayerNormProxy(dim_stem))
+                                            norm_cls(dim_stem))
         fmap = img_size // patch_size
         dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths))]
         self.stages = nn.ModuleList()
@@ -193,14 +196,14 @@ class DAT(nn.Module):
                 use_pes[i], heads[i], strides[i], offset_range_factor[i], dwc_pes[i], no_offs[i],
                 fixed_pes[i], attn_drop_rate, drop_rate, expansion, drop_rate, dpr[lo:hi],
                 use_dwc_mlps[i], ksizes[i], layer_scale_values[i], use_lpus[i], log_cpb[i], i,
-                use_checkpoint, attn_cls=attn_cls))
-            self.norms.append(LayerNormProxy(dims[i]) if i in out_indices else nn.Identity())
+                use_checkpoint, attn_cls=attn_cls, norm_cls=norm_cls))
+            self.norms.append(norm_cls(dims[i]) if i in out_indices else nn.Identity())
             fmap //= 2
         self.down_projs = nn.ModuleList()
         for i in range(3):
             conv = (nn.Conv2d(dims[i], dims[i + 1], 3, 2, 1, bias=False) if use_conv_patches
                     else nn.Conv2d(dims[i], dims[i + 1], 2, 2, 0, bias=False))
-            self.down_projs.append(nn.Sequential(conv, LayerNormProxy(dims[i + 1])))
+            self.down_projs.append(nn.Sequential(conv, norm_cls(dims[i + 1])))
 
     def forward(self, x):
         x = self.patch_proj(x)
@@ -213,10 +216,15 @@ class DAT(nn.Module):
         return outs
 
 
-def build_dat(cfg: dict = None, attn_cls: Callable = DAttentionBaseline, **override) -> DAT:
-    """DAT(**cfg) as `models/builder.py:93-102` does (init_cfg / type keys dropped)."""
+def build_dat(cfg: dict = None, attn_cls: Callable = DAttentionBaseline, norm_cls: Callable = None,
+              **override) -> DAT:
+    """DAT(**cfg) as `models/builder.py:93-102` does (init_cfg / type keys dropped).
+    `norm_cls` defaults to the dat_b200 LayerNorm kernels when the block is the dat_b200 block, and to
+    the library LayerNorm when another block implementation (reference / oracle, CPU) is plugged in."""
     kw = dict(DAT_TINY_PP if cfg is None else cfg)
     kw.update(override)
     kw.pop("type", None)
     kw.pop("init_cfg", None)
-    return DAT(attn_cls=attn_cls, **kw)
+    if norm_cls is None:
+        norm_cls = LayerNormProxy if attn_cls is DAttentionBaseline else TorchLayerNormProxy
+    return DAT(attn_cls=attn_cls, norm_cls=norm_cls, **kw)

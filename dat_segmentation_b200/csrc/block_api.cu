@@ -220,6 +220,24 @@ int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, con
   return attention_fwd_simt(s, q, k, v, pos, rpe_table, o, lse, (cudaStream_t)stream);
 }
 
+int dat_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, void* y,
+                      int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
+                      void* stream) {
+  DAT_REQUIRE(x && gamma && beta && y && mean && rstd, "layernorm_fwd: NULL pointer");
+  return layernorm_fwd(x, x_dtype, gamma, beta, y, y_dtype, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+}
+
+size_t dat_layernorm_bwd_workspace_bytes(int64_t rows, int32_t C) { return layernorm_bwd_workspace(rows, C); }
+
+int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype,
+                      const float* gamma, const float* mean, const float* rstd, void* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int32_t C, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "layernorm_bwd: NULL pointer");
+  return layernorm_bwd(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dx, dgamma, dbeta, rows, C, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table, float* bias,
                  void* stream) {
   Shape s;

@@ -116,3 +116,13 @@ size_t pointwise_wgrad_tc_workspace(long long M, int N, int K);
 int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, int N, int K, void* ws,
                        size_t ws_bytes, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// layernorm.cu
+size_t layernorm_bwd_workspace(long long rows, int C);
+int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
+                  float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st);
+int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
+                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                  long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace dat

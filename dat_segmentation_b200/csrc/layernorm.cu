@@ -1,0 +1,229 @@
+// Channel-last LayerNorm over C (the reference's LayerNormProxy, dat_blocks.py:229-240:
+// NCHW -> NHWC view -> nn.LayerNorm(C, eps=1e-5) -> back), forward and backward.
+// the LayerNorm that feeds every block (dat.py:147-151).
+//
+// HBM-bound streaming kernels: one warp per pixel row, lanes stride the channels with
+// 8-byte (fp32) / 4-byte (bf16) vector accesses, row statistics by warp shuffles, fp32 math.
+// Algorithmic bytes: forward R*C*(e_in + e_out) + 8R; backward R*C*(e_dy + e_x + e_dx) + 8R.
+// Backward: gamma / beta gradients are accumulated per lane over a grid-stride loop, reduced
+// per CTA in shared memory and across CTAs by a second tiny kernel in a fixed order
+// (deterministic, no atomics).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dat {
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAXV = 16;      // C <= 32 * 2 * 16 = 1024
+
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void st2(bf16* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+
+// NV = number of 64-channel groups (C = 64 * NV exactly, or C == 32 handled with NV = 1 and half
+// the lanes idle)
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TI* xr = x + row * C;
+  float2 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    v[i] = c < C ? ld2(xr + c) : make_float2(0.f, 0.f);
+    s += v[i].x + v[i].y;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    if (c < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean;
+      q += a * a + b * b;
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  TO* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    if (c < C) {
+      const float2 g = ld2(gamma + c), b = ld2(beta + c);
+      st2(yr + c, make_float2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y));
+    }
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+template <typename TI, typename TDY, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, TI* __restrict__ dx,
+                     float* __restrict__ partial, long long rows, int C) {
+  extern __shared__ float red[];     // [LN_WARPS][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2 gg[NV], gb[NV], gam[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    gg[i] = gb[i] = make_float2(0.f, 0.f);
+    gam[i] = c < C ? ld2(gamma + c) : make_float2(0.f, 0.f);
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows;
+       row += (long long)gridDim.x * LN_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const TI* xr = x + row * C;
+    const TDY* dr = dy + row * C;
+    float2 xh[NV], dg[NV];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 2;
+      xh[i] = dg[i] = make_float2(0.f, 0.f);
+      if (c < C) {
+        const float2 xv = ld2(xr + c), d = ld2(dr + c);
+        xh[i] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
+        gg[i].x = fmaf(d.x, xh[i].x, gg[i].x);
+        gg[i].y = fmaf(d.y, xh[i].y, gg[i].y);
+        gb[i].x += d.x;
+        gb[i].y += d.y;
+        dg[i] = make_float2(d.x * gam[i].x, d.y * gam[i].y);
+        m1 += dg[i].x + dg[i].y;
+        m2 += dg[i].x * xh[i].x + dg[i].y * xh[i].y;
+      }
+    }
+    m1 = warp_sum(m1) * inv_c;
+    m2 = warp_sum(m2) * inv_c;
+    TI* dxr = dx + row * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 2;
+      if (c < C)
+        st2(dxr + c, make_float2(rstd * (dg[i].x - m1 - xh[i].x * m2), rstd * (dg[i].y - m1 - xh[i].y * m2)));
+    }
+  }
+  float* mine = red + (size_t)warp * 2 * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    if (c < C) {
+      mine[c] = gg[i].x; mine[c + 1] = gg[i].y;
+      mine[C + c] = gb[i].x; mine[C + c + 1] = gb[i].y;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += red[(size_t)w * 2 * C + idx];
+    partial[(size_t)blockIdx.x * 2 * C + idx] = s;
+  }
+}
+
+__global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int idx = blockIdx.x * 32 + (threadIdx.x & 31), zl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (idx < 2 * C)
+    for (int z = zl; z < nblocks; z += 8) s += partial[(size_t)z * 2 * C + idx];
+  red[zl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (zl == 0 && idx < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][threadIdx.x & 31];
+    if (idx < C) dgamma[idx] = t; else dbeta[idx - C] = t;
+  }
+}
+
+int nv_of(int C) { return C <= 64 ? 1 : (C + 63) / 64; }
+
+int ln_bwd_blocks(long long rows) {
+  long long want = (rows + LN_WARPS - 1) / LN_WARPS;
+  return (int)(want < 592 ? want : 592);    // 4 CTAs per SM
+}
+
+}  // namespace
+
+size_t layernorm_bwd_workspace(long long rows, int C) {
+  return align_up((size_t)ln_bwd_blocks(rows) * 2 * C * sizeof(float), 256);
+}
+
+int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
+                  float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st) {
+  DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
+  const int grid = ceil_div(rows, LN_WARPS), nv = nv_of(C);
+#define LAUNCH(TI, TO, NVV)                                                                    \
+  layernorm_fwd_kernel<TI, TO, NVV><<<grid, LN_WARPS * 32, 0, st>>>((const TI*)x, gamma, beta, \
+                                                                     (TO*)y, mean, rstd, rows, C, eps)
+#define LAUNCH_NV(TI, TO)                                                      \
+  do {                                                                         \
+    if (nv == 1) LAUNCH(TI, TO, 1); else if (nv == 2) LAUNCH(TI, TO, 2);       \
+    else if (nv <= 4) LAUNCH(TI, TO, 4); else if (nv <= 8) LAUNCH(TI, TO, 8);  \
+    else LAUNCH(TI, TO, 16);                                                   \
+  } while (0)
+  if (x_dt == DAT_F32 && y_dt == DAT_F32) LAUNCH_NV(float, float);
+  else if (x_dt == DAT_F32) LAUNCH_NV(float, bf16);
+  else if (y_dt == DAT_F32) LAUNCH_NV(bf16, float);
+  else LAUNCH_NV(bf16, bf16);
+#undef LAUNCH_NV
+#undef LAUNCH
+  DAT_LAUNCH_OK("layernorm_fwd_kernel");
+  return DAT_OK;
+}
+
+int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
+                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                  long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
+  DAT_REQUIRE(ws_bytes >= layernorm_bwd_workspace(rows, C), "layernorm_bwd: workspace too small");
+  const int nblk = ln_bwd_blocks(rows), nv = nv_of(C);
+  const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
+  float* part = (float*)ws;
+#define LAUNCH(TI, TD, NVV)                                                                       \
+  do {                                                                                            \
+    auto kern = layernorm_bwd_kernel<TI, TD, NVV>;                                                \
+    if (smem > 48 * 1024)                                                                         \
+      DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<nblk, LN_WARPS * 32, smem, st>>>((const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
+                                            part, rows, C);                                       \
+  } while (0)
+#define LAUNCH_NV(TI, TD)                                                      \
+  do {                                                                         \
+    if (nv == 1) LAUNCH(TI, TD, 1); else if (nv == 2) LAUNCH(TI, TD, 2);       \
+    else if (nv <= 4) LAUNCH(TI, TD, 4); else if (nv <= 8) LAUNCH(TI, TD, 8);  \
+    else LAUNCH(TI, TD, 16);                                                   \
+  } while (0)
+  if (x_dt == DAT_F32 && dy_dt == DAT_F32) LAUNCH_NV(float, float);
+  else if (x_dt == DAT_F32) LAUNCH_NV(float, bf16);
+  else if (dy_dt == DAT_F32) LAUNCH_NV(bf16, float);
+  else LAUNCH_NV(bf16, bf16);
+#undef LAUNCH_NV
+#undef LAUNCH
+  DAT_LAUNCH_OK("layernorm_bwd_kernel");
+  layernorm_bwd_reduce_kernel<<<ceil_div(2 * C, 32), 256, 0, st>>>(part, nblk, C, dgamma, dbeta);
+  DAT_LAUNCH_OK("layernorm_bwd_reduce_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

@@ -1,0 +1,100 @@
+"""LayerNormProxy on the dat_b200 kernels (the LayerNorm that feeds every
+block, `models/utils/dat_blocks.py:229-240`, used at `models/backbones/dat.py:147,151`).
+
+Same module surface as the reference (`self.norm = nn.LayerNorm(dim)` → state-dict keys
+`norm.weight`, `norm.bias`; NCHW in, NCHW view of a channel-last buffer out).  CUDA only;
+`TorchLayerNormProxy` is the library-operator twin used by the CPU baseline / CPU tests.
+dtype semantics follow `torch.autocast`: LayerNorm computes and returns fp32 under autocast.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+
+__all__ = ["LayerNormProxy", "TorchLayerNormProxy"]
+
+_CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """x_l (..., C) contiguous → y_l (..., C) of `out_dtype`."""
+
+    @staticmethod
+    def forward(ctx, x_l, weight, bias, eps, out_dtype):
+        lib = _cabi.lib()
+        Cc = x_l.shape[-1]
+        rows = x_l.numel() // Cc
+        dev = x_l.device
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            y = torch.empty(x_l.shape, device=dev, dtype=out_dtype)
+            mean = torch.empty(rows, device=dev, dtype=torch.float32)
+            rstd = torch.empty(rows, device=dev, dtype=torch.float32)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(lib.dat_layernorm_fwd(_ptr(x_l), _CODE[x_l.dtype], _ptr(w32), _ptr(b32), _ptr(y),
+                                              _CODE[out_dtype], _ptr(mean), _ptr(rstd), rows, Cc,
+                                              float(eps), st), "dat_layernorm_fwd")
+        ctx.save_for_backward(x_l, w32, mean, rstd)
+        ctx.param_dtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.lib()
+        x_l, w32, mean, rstd = ctx.saved_tensors
+        Cc = x_l.shape[-1]
+        rows = x_l.numel() // Cc
+        dev = x_l.device
+        if dy.dtype not in _CODE:
+            dy = dy.float()
+        dy = dy.contiguous()
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x_l)
+            dg = torch.empty(Cc, device=dev, dtype=torch.float32)
+            db = torch.empty(Cc, device=dev, dtype=torch.float32)
+            nbytes = lib.dat_layernorm_bwd_workspace_bytes(rows, Cc)
+            ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(lib.dat_layernorm_bwd(_ptr(dy), _CODE[dy.dtype], _ptr(x_l), _CODE[x_l.dtype],
+                                              _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dg),
+                                              _ptr(db), rows, Cc, _ptr(ws), nbytes, st),
+                        "dat_layernorm_bwd")
+        return dx, dg.to(ctx.param_dtype), db.to(ctx.param_dtype), None, None
+
+
+class LayerNormProxy(nn.Module):
+    """LayerNorm over the channels of an NCHW tensor on the dat_b200 kernels."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("LayerNormProxy (dat_b200) runs on CUDA only; use TorchLayerNormProxy on CPU")
+        if x.dtype not in _CODE:
+            raise NotImplementedError(f"dtype {x.dtype} unsupported (float32 / bfloat16)")
+        out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype
+        x_l = x.permute(0, 2, 3, 1)
+        if not x_l.is_contiguous():
+            x_l = x_l.contiguous()
+        y_l = _LayerNormFn.apply(x_l, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
+        return y_l.permute(0, 3, 1, 2)
+
+
+class TorchLayerNormProxy(nn.Module):
+    """Library-operator twin (CPU baseline / CPU tests); identical parameters."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        return self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)

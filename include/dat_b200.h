@@ -164,6 +164,21 @@ int dat_attention_fwd(const dat_block_desc* d, const void* q, const void* k, con
                       const float* pos, const float* rpe_table, void* o, float* lse,
                       void* workspace, size_t workspace_bytes, int32_t impl, void* stream);
 
+/* ---- "next" row: the LayerNorm that feeds the block ------------ */
+
+/* Channel-last LayerNorm over C, eps inside the sqrt, affine (LayerNormProxy,
+ * dat_blocks.py:229-240; used at dat.py:147,151).  x (rows, C) -> y (rows, C); mean / rstd
+ * (rows) fp32 are saved for the backward.  C even, <= 1024. */
+int dat_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta,
+                      void* y, int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t C,
+                      float eps, void* stream);
+size_t dat_layernorm_bwd_workspace_bytes(int64_t rows, int32_t C);
+/* dx has x's dtype; dgamma / dbeta (C) fp32 are overwritten (deterministic reduction). */
+int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype,
+                      const float* gamma, const float* mean, const float* rstd, void* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int32_t C, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* The rpe bias alone, (B, n_heads, HW, Ns) fp32 (dat_blocks.py:198-212); test hook. */
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table,
                  float* bias, void* stream);
