@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .dattention import DAttentionBaseline, _pair
+from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
 
 __all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
@@ -71,19 +72,22 @@ class TransformerMLP(nn.Module):
 class TransformerMLPWithConv(nn.Module):
     """1x1 -> (+ depthwise 3x3) -> GELU -> 1x1 (dat_blocks.py:316-348)."""
 
-    def __init__(self, channels, expansion, drop):
+    def __init__(self, channels, expansion, drop, b200_ops=False):
         super().__init__()
         hidden = channels * expansion
+        self.b200_ops = b200_ops
         self.linear1 = nn.Sequential(nn.Conv2d(channels, hidden, 1))
         self.drop1 = nn.Dropout(drop)
         self.act = nn.GELU()
         self.linear2 = nn.Sequential(nn.Conv2d(hidden, channels, 1))
         self.drop2 = nn.Dropout(drop)
-        self.dwc = nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden)
+        # b200_ops: gelu(x + dwconv(x) + b) is one fused channel-last kernel
+        self.dwc = (DepthwiseConvCL(hidden, 3, MODE_RESIDUAL_GELU) if b200_ops
+                    else nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden))
 
     def forward(self, x):
         x = self.drop1(self.linear1(x))
-        x = self.act(x + self.dwc(x))
+        x = self.dwc(x) if self.b200_ops else self.act(x + self.dwc(x))
         return self.drop2(self.linear2(x))
 
 
@@ -96,8 +100,9 @@ class TransformerStage(nn.Module):
                  use_pe, heads, stride, offset_range_factor, dwc_pe, no_off, fixed_pe, attn_drop,
                  proj_drop, expansion, drop, drop_path_rate, use_dwc_mlp, ksize, layer_scale_value,
                  use_lpu, log_cpb, stage_i, use_checkpoint, attn_cls: Callable = DAttentionBaseline,
-                 norm_cls: Callable = LayerNormProxy):
+                 norm_cls: Callable = LayerNormProxy, b200_ops: bool = False):
         super().__init__()
+        self.b200_ops = b200_ops
         fmap_size = _pair(fmap_size)
         self.depths, self.stage_spec = depths, list(stage_spec)
         self.use_lpu, self.use_checkpoint = use_lpu, use_checkpoint
@@ -110,14 +115,16 @@ class TransformerStage(nn.Module):
             [norm_cls(dim_embed) if stage_spec[d // 2] != "X" else nn.Identity()
              for d in range(2 * depths)])
         mlp_cls = TransformerMLPWithConv if use_dwc_mlp else TransformerMLP
-        self.mlps = nn.ModuleList([mlp_cls(dim_embed, expansion, drop) for _ in range(depths)])
+        mlp_kw = dict(b200_ops=b200_ops) if use_dwc_mlp else {}
+        self.mlps = nn.ModuleList([mlp_cls(dim_embed, expansion, drop, **mlp_kw) for _ in range(depths)])
         self.attns = nn.ModuleList()
         self.drop_path = nn.ModuleList()
         self.layer_scales = nn.ModuleList(
             [LayerScale(dim_embed, layer_scale_value) if layer_scale_value > 0.0 else nn.Identity()
              for _ in range(2 * depths)])
         self.local_perception_units = nn.ModuleList(
-            [nn.Conv2d(dim_embed, dim_embed, 3, 1, 1, groups=dim_embed) if use_lpu else nn.Identity()
+            [(DepthwiseConvCL(dim_embed, 3, MODE_RESIDUAL, keep_input_dtype=True) if b200_ops
+              else nn.Conv2d(dim_embed, dim_embed, 3, 1, 1, groups=dim_embed)) if use_lpu else nn.Identity()
              for _ in range(depths)])
         for d in range(depths):
             if stage_spec[d] == "D":
@@ -125,7 +132,8 @@ class TransformerStage(nn.Module):
                                            proj_drop, stride, offset_range_factor, use_pe, dwc_pe,
                                            no_off, fixed_pe, ksize, log_cpb, stage_i))
             elif stage_spec[d] == "X":
-                self.attns.append(nn.Conv2d(dim_embed, dim_embed, window_size, padding=window_size // 2,
+                self.attns.append(DepthwiseConvCL(dim_embed, window_size, MODE_PLAIN) if b200_ops else
+                                  nn.Conv2d(dim_embed, dim_embed, window_size, padding=window_size // 2,
                                             groups=dim_embed))
             else:
                 raise NotImplementedError(f"Spec: {stage_spec[d]} is not supported.")
@@ -134,8 +142,9 @@ class TransformerStage(nn.Module):
     def _inner_forward(self, x):
         x = self.proj(x)
         for d in range(self.depths):
-            if self.use_lpu:
-                x = self.local_perception_units[d](x.contiguous()) + x
+            if self.use_lpu:   # b200: conv + bias + residual in one channel-last kernel
+                x = (self.local_perception_units[d](x) if self.b200_ops
+                     else self.local_perception_units[d](x.contiguous()) + x)
             if self.stage_spec[d] == "X":   # note: no residual around mixer+MLP (dat.py:140-144)
                 x = self.attns[d](self.layer_norms[2 * d](x))
                 x = self.drop_path[d](self.mlps[d](self.ln_cnvnxt[str(d)](x)))
@@ -171,7 +180,7 @@ class DAT(nn.Module):
                  layer_scale_values=(-1,) * 4, use_lpus=(False,) * 4, use_cmt_mlps=(False,) * 4,
                  log_cpb=(False,) * 4, out_indices=(0, 1, 2, 3), use_checkpoint=True,
                  init_cfg=None, attn_cls: Callable = DAttentionBaseline,
-                 norm_cls: Callable = LayerNormProxy, **kwargs):
+                 norm_cls: Callable = LayerNormProxy, b200_ops: bool = False, **kwargs):
         super().__init__()
         if any(use_cmt_mlps):
             raise NotImplementedError("use_cmt_mlps (BatchNorm MLP variant) is not implemented")
@@ -196,7 +205,7 @@ class DAT(nn.Module):
                 use_pes[i], heads[i], strides[i], offset_range_factor[i], dwc_pes[i], no_offs[i],
                 fixed_pes[i], attn_drop_rate, drop_rate, expansion, drop_rate, dpr[lo:hi],
                 use_dwc_mlps[i], ksizes[i], layer_scale_values[i], use_lpus[i], log_cpb[i], i,
-                use_checkpoint, attn_cls=attn_cls, norm_cls=norm_cls))
+                use_checkpoint, attn_cls=attn_cls, norm_cls=norm_cls, b200_ops=b200_ops))
             self.norms.append(norm_cls(dims[i]) if i in out_indices else nn.Identity())
             fmap //= 2
         self.down_projs = nn.ModuleList()
@@ -217,7 +226,7 @@ class DAT(nn.Module):
 
 
 def build_dat(cfg: dict = None, attn_cls: Callable = DAttentionBaseline, norm_cls: Callable = None,
-              **override) -> DAT:
+              b200_ops: bool = None, **override) -> DAT:
     """DAT(**cfg) as `models/builder.py:93-102` does (init_cfg / type keys dropped).
     `norm_cls` defaults to the dat_b200 LayerNorm kernels when the block is the dat_b200 block, and to
     the library LayerNorm when another block implementation (reference / oracle, CPU) is plugged in."""
@@ -227,4 +236,6 @@ def build_dat(cfg: dict = None, attn_cls: Callable = DAttentionBaseline, norm_cl
     kw.pop("init_cfg", None)
     if norm_cls is None:
         norm_cls = LayerNormProxy if attn_cls is DAttentionBaseline else TorchLayerNormProxy
-    return DAT(attn_cls=attn_cls, norm_cls=norm_cls, **kw)
+    if b200_ops is None:   # fused channel-last depthwise convs (LPU, MLP middle, 'X' mixer)
+        b200_ops = attn_cls is DAttentionBaseline
+    return DAT(attn_cls=attn_cls, norm_cls=norm_cls, b200_ops=b200_ops, **kw)

@@ -238,6 +238,31 @@ int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x
                        workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t dat_dwconv_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t C, int32_t k) {
+  return dwconv_workspace(B, H, W, C, k);
+}
+
+int dat_dwconv_fwd(const void* x, int32_t x_dtype, const float* w, const float* bias, void* y, void* z_out,
+                   int32_t y_dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, int32_t mode,
+                   int32_t flip, void* workspace, size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(x && w && y && workspace, "dwconv_fwd: NULL pointer");
+  return dwconv_fwd(x, x_dtype, w, bias, y, z_out, y_dtype, B, H, W, C, k, mode, flip, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
+}
+
+int dat_gelu_bwd(const void* dy, const void* z, void* dz, int32_t dtype, int64_t n, void* stream) {
+  DAT_REQUIRE(dy && z && dz, "gelu_bwd: NULL pointer");
+  return gelu_bwd(dy, z, dz, dtype, n, (cudaStream_t)stream);
+}
+
+int dat_dwconv_wgrad(const void* x, int32_t x_dtype, const void* dz, int32_t dz_dtype, float* dw,
+                     float* db, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(x && dz && dw && workspace, "dwconv_wgrad: NULL pointer");
+  return dwconv_wgrad(x, x_dtype, dz, dz_dtype, dw, db, B, H, W, C, k, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table, float* bias,
                  void* stream) {
   Shape s;

@@ -1,0 +1,226 @@
+// Channel-last depthwise k x k convolution (stride 1, "same" padding) with the fusions the DAT
+// backbone needs around the deformable-attention block:
+//   mode 0:  y = dwconv(x) + b                 'X' mixer, dat.py:118-121 (k = 7)
+//   mode 1:  y = dwconv(x) + b + x             local perception unit, dat.py:135-138 (k = 3)
+//   mode 2:  z = dwconv(x) + b + x; y = gelu(z) MLP middle, dat_blocks.py:338-343 (k = 3); z is saved
+// plus the gradients.  The data gradient is the same kernel run on dz with the flipped filter
+// (no bias); `gelu_bwd` forms dz = dy * gelu'(z) for mode 2.
+//
+// All kernels are HBM-bound streaming kernels: a thread owns 4 consecutive channels of one pixel,
+// every tap is a 16-byte (fp32) / 8-byte (bf16) vector read of a channel-last neighbour row, the
+// (k*k, C)-transposed filter is read through the read-only cache.  Algorithmic bytes:
+// forward R*C*(e_in + e_out) [+ R*C*e_z], data gradient R*C*(e_dz + e_dx), weight gradient
+// R*C*(e_dz + e_x).  The k*k-fold spatial reuse is served by L1/L2.
+// Weight gradient: per-CTA partial sums over a slice of the pixels, reduced in a fixed order
+// (deterministic, no atomics).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dat {
+
+namespace {
+
+__device__ __forceinline__ float gelu_f(float z) {
+  return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_df(float z) {
+  const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+  const float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
+  return cdf + z * pdf;
+}
+
+// (C, k*k) -> (k*k, C), optionally spatially flipped (for the data gradient)
+__global__ void dw_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int C, int kk,
+                                    int flip) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * kk) return;
+  const int c = idx % C, uv = idx / C;
+  wT[idx] = w[c * kk + (flip ? kk - 1 - uv : uv)];
+}
+
+template <typename TI, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+dwconv_cl_kernel(const TI* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
+                 TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int k,
+                 long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4n = C >> 2;
+  const int c = (int)(idx % c4n) * 4;
+  const long long pix = idx / c4n;
+  const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
+  const long long b = pix / ((long long)W * H);
+  const int p = k >> 1;
+  float4 acc = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int u_lo = max(0, p - yy), u_hi = min(k, H + p - yy);
+  const int v_lo = max(0, p - xx), v_hi = min(k, W + p - xx);
+  const TI* base = x + ((b * H + (yy - p)) * W + (xx - p)) * C + c;
+  for (int u = u_lo; u < u_hi; ++u) {
+    const TI* row = base + ((long long)u * W + v_lo) * C;
+    const float* wr = wT + (u * k + v_lo) * C + c;
+    for (int v = v_lo; v < v_hi; ++v) {
+      const float4 xv = load4(row);
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr));
+      acc.x = fmaf(xv.x, wv.x, acc.x);
+      acc.y = fmaf(xv.y, wv.y, acc.y);
+      acc.z = fmaf(xv.z, wv.z, acc.z);
+      acc.w = fmaf(xv.w, wv.w, acc.w);
+      row += C;
+      wr += C;
+    }
+  }
+  if (MODE >= 1) {
+    const float4 xc = load4(x + pix * C + c);
+    acc.x += xc.x; acc.y += xc.y; acc.z += xc.z; acc.w += xc.w;
+  }
+  if (MODE == 2) {
+    store4(z_out + pix * C + c, acc);
+    acc = make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w));
+  }
+  store4(y + pix * C + c, acc);
+}
+
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
+                                long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 d = load4(dy + 4 * i), zz = load4(z + 4 * i);
+  store4(dz + 4 * i, make_float4(d.x * gelu_df(zz.x), d.y * gelu_df(zz.y), d.z * gelu_df(zz.z), d.w * gelu_df(zz.w)));
+}
+
+// dw[c][uv] = sum_pix dz[pix][c] * x[pix + off(uv)][c];  db[c] = sum_pix dz[pix][c]
+// grid = (ceil(C / 128), nsplit); thread = one channel; partial[split][kk + 1][C]
+template <typename TX, typename TD, int KK>
+__global__ void __launch_bounds__(128)
+dwconv_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* __restrict__ partial,
+                    int B, int H, int W, int C, int k, long long pix_per_split) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const long long npix = (long long)B * H * W;
+  const long long p0 = (long long)blockIdx.y * pix_per_split;
+  const long long p1 = min(npix, p0 + pix_per_split);
+  const int p = k >> 1;
+  float acc[KK + 1];
+#pragma unroll
+  for (int i = 0; i <= KK; ++i) acc[i] = 0.f;
+  for (long long pix = p0; pix < p1; ++pix) {
+    const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
+    const float d = to_f32(dz[pix * C + c]);
+    acc[KK] += d;
+    const TX* base = x + (pix - (long long)p * W - p) * C + c;
+#pragma unroll
+    for (int uv = 0; uv < KK; ++uv) {
+      const int u = uv / k, v = uv - u * k;
+      const int y2 = yy + u - p, x2 = xx + v - p;
+      if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+        acc[uv] = fmaf(d, to_f32(base[((long long)u * W + v) * C]), acc[uv]);
+    }
+  }
+  float* out = partial + (size_t)blockIdx.y * (KK + 1) * C + c;
+#pragma unroll
+  for (int i = 0; i <= KK; ++i) out[(size_t)i * C] = acc[i];
+}
+
+// block (32, 32): fixed-order reduction over the splits; writes dw (C, kk) and db (C)
+__global__ void dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int kk, int C,
+                                           float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[32][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x;    // row * C + c, row in [0, kk]
+  const int n_out = (kk + 1) * C;
+  float s = 0.f;
+  if (idx < n_out)
+    for (int zz = threadIdx.y; zz < nsplit; zz += 32) s += partial[(size_t)zz * n_out + idx];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < n_out) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
+    const int row = idx / C, c = idx % C;
+    if (row < kk) dw[c * kk + row] = t;
+    else if (db != nullptr) db[c] = t;
+  }
+}
+
+int wgrad_splits(long long npix) {
+  long long s = (npix + 127) / 128;
+  return (int)(s < 1 ? 1 : (s > 1024 ? 1024 : s));
+}
+
+}  // namespace
+
+size_t dwconv_workspace(int B, int H, int W, int C, int k) {
+  const size_t wt = align_up((size_t)k * k * C * 4, 256);
+  const size_t part = align_up((size_t)wgrad_splits((long long)B * H * W) * (k * k + 1) * C * 4, 256);
+  return wt + part;
+}
+
+// mode 0/1/2 as above; z_out only for mode 2.  ws >= k*k*C*4 bytes (transposed filter).
+int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, void* z_out, int y_dt,
+               int B, int H, int W, int C, int k, int mode, int flip, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+  DAT_REQUIRE(C % 4 == 0 && (k & 1) == 1 && k >= 1 && k <= 15, "dwconv: C %% 4 == 0 and odd k <= 15 required");
+  DAT_REQUIRE(ws_bytes >= (size_t)k * k * C * 4, "dwconv: workspace too small");
+  DAT_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || z_out != nullptr), "dwconv: bad mode");
+  float* wT = (float*)ws;
+  dw_transpose_kernel<<<ceil_div(C * k * k, 256), 256, 0, st>>>(w, wT, C, k * k, flip);
+  DAT_LAUNCH_OK("dw_transpose_kernel");
+  const long long total = (long long)B * H * W * (C / 4);
+  const int grid = ceil_div(total, 256);
+#define LAUNCH(TI, TO, MD)                                                                      \
+  dwconv_cl_kernel<TI, TO, MD><<<grid, 256, 0, st>>>((const TI*)x, wT, bias, (TO*)y, (TO*)z_out, B, H, \
+                                                     W, C, k, total)
+#define LAUNCH_M(TI, TO)                                                   \
+  do {                                                                     \
+    if (mode == 0) LAUNCH(TI, TO, 0); else if (mode == 1) LAUNCH(TI, TO, 1); \
+    else LAUNCH(TI, TO, 2);                                                \
+  } while (0)
+  if (x_dt == DAT_F32 && y_dt == DAT_F32) LAUNCH_M(float, float);
+  else if (x_dt == DAT_F32) LAUNCH_M(float, bf16);
+  else if (y_dt == DAT_F32) LAUNCH_M(bf16, float);
+  else LAUNCH_M(bf16, bf16);
+#undef LAUNCH_M
+#undef LAUNCH
+  DAT_LAUNCH_OK("dwconv_cl_kernel");
+  return DAT_OK;
+}
+
+int gelu_bwd(const void* dy, const void* z, void* dz, int dt, long long n, cudaStream_t st) {
+  DAT_REQUIRE(n % 4 == 0, "gelu_bwd: n %% 4 != 0");
+  const long long n4 = n / 4;
+  if (dt == DAT_F32) gelu_bwd_kernel<float><<<ceil_div(n4, 256), 256, 0, st>>>((const float*)dy, (const float*)z, (float*)dz, n4);
+  else gelu_bwd_kernel<bf16><<<ceil_div(n4, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)z, (bf16*)dz, n4);
+  DAT_LAUNCH_OK("gelu_bwd_kernel");
+  return DAT_OK;
+}
+
+// dw (C, 1, k, k) and db (C) (db may be NULL), fp32, overwritten.
+int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, float* db, int B, int H,
+                 int W, int C, int k, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DAT_REQUIRE(k == 3 || k == 5 || k == 7, "dwconv_wgrad: k must be 3, 5 or 7");
+  DAT_REQUIRE(ws_bytes >= dwconv_workspace(B, H, W, C, k), "dwconv_wgrad: workspace too small");
+  const long long npix = (long long)B * H * W;
+  const int nsplit = wgrad_splits(npix);
+  const long long pps = (npix + nsplit - 1) / nsplit;
+  float* part = (float*)((char*)ws + align_up((size_t)k * k * C * 4, 256));
+  dim3 grid(ceil_div(C, 128), nsplit);
+#define LAUNCH(TX, TD, KKV)                                                                         \
+  dwconv_wgrad_kernel<TX, TD, KKV><<<grid, 128, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
+#define LAUNCH_K(TX, TD)                                  \
+  do {                                                    \
+    if (k == 3) LAUNCH(TX, TD, 9); else if (k == 5) LAUNCH(TX, TD, 25); else LAUNCH(TX, TD, 49); \
+  } while (0)
+  if (x_dt == DAT_F32 && dz_dt == DAT_F32) LAUNCH_K(float, float);
+  else if (x_dt == DAT_F32) LAUNCH_K(float, bf16);
+  else if (dz_dt == DAT_F32) LAUNCH_K(bf16, float);
+  else LAUNCH_K(bf16, bf16);
+#undef LAUNCH_K
+#undef LAUNCH
+  DAT_LAUNCH_OK("dwconv_wgrad_kernel");
+  dwconv_wgrad_reduce_kernel<<<ceil_div((k * k + 1) * C, 32), dim3(32, 32), 0, st>>>(part, nsplit, k * k, C, dw, db);
+  DAT_LAUNCH_OK("dwconv_wgrad_reduce_kernel");
+  return DAT_OK;
+}
+
+}  // namespace dat

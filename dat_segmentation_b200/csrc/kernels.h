@@ -126,3 +126,14 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
                   const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
                   long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// dwconv.cu
+size_t dwconv_workspace(int B, int H, int W, int C, int k);
+int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, void* z_out, int y_dt,
+               int B, int H, int W, int C, int k, int mode, int flip, void* ws, size_t ws_bytes,
+               cudaStream_t st);
+int gelu_bwd(const void* dy, const void* z, void* dz, int dt, long long n, cudaStream_t st);
+int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, float* db, int B, int H,
+                 int W, int C, int k, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace dat

@@ -179,6 +179,24 @@ int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x
                       float* dgamma, float* dbeta, int64_t rows, int32_t C, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- "next" rows: channel-last depthwise convolutions ---------- */
+
+/* Depthwise k x k conv, stride 1, padding k/2, x (B,H,W,C) channel-last, w (C,1,k,k) fp32.
+ * mode 0: y = conv(x)+b ('X' mixer, dat.py:118-121); mode 1: y = conv(x)+b+x (LPU, dat.py:135-138);
+ * mode 2: z = conv(x)+b+x, y = gelu(z), z stored to z_out (MLP middle, dat_blocks.py:338-343).
+ * flip = 1 applies the spatially flipped filter (data gradient: dx = dwconv(dz, flip=1, mode 0/1)).
+ * workspace >= dat_dwconv_workspace_bytes. */
+size_t dat_dwconv_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t C, int32_t k);
+int dat_dwconv_fwd(const void* x, int32_t x_dtype, const float* w, const float* bias, void* y, void* z_out,
+                   int32_t y_dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, int32_t mode,
+                   int32_t flip, void* workspace, size_t workspace_bytes, void* stream);
+/* dz = dy * gelu'(z), n elements (n % 4 == 0), all of dtype `dtype`. */
+int dat_gelu_bwd(const void* dy, const void* z, void* dz, int32_t dtype, int64_t n, void* stream);
+/* dw (C,1,k,k), db (C; may be NULL) fp32, overwritten; k in {3,5,7}; deterministic. */
+int dat_dwconv_wgrad(const void* x, int32_t x_dtype, const void* dz, int32_t dz_dtype, float* dw,
+                     float* db, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* The rpe bias alone, (B, n_heads, HW, Ns) fp32 (dat_blocks.py:198-212); test hook. */
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table,
                  float* bias, void* stream);

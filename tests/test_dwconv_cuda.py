@@ -1,0 +1,48 @@
+"""dat_b200 channel-last depthwise conv kernels against
+torch.nn.functional.conv2d: forward and all gradients, the three fusion modes."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def _ref(x, w, b, mode, k):
+    y = F.conv2d(x, w, b, 1, k // 2, groups=x.shape[1])
+    if mode >= 1:
+        y = y + x
+    if mode == 2:
+        y = F.gelu(y)
+    return y
+
+
+@pytest.mark.parametrize("C,k,mode", [(64, 3, 1), (256, 3, 2), (1024, 3, 2), (64, 7, 0), (128, 7, 0), (96, 5, 1), (512, 3, 1)])
+@pytest.mark.parametrize("dt", ["fp32", "bf16"])
+def test_dwconv_matches_conv2d(C, k, mode, dt):
+    from dat_segmentation_b200.dwconv import dwconv_cl
+    torch.manual_seed(C + k)
+    B, H, W = 2, 11, 14
+    dtype = torch.float32 if dt == "fp32" else torch.bfloat16
+    torch.backends.cudnn.allow_tf32 = False
+    x = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2).to(dtype)
+    w = (torch.randn(C, 1, k, k, device="cuda") / k).requires_grad_(True)
+    b = torch.randn(C, device="cuda").requires_grad_(True)
+    dy = torch.randn(B, C, H, W, device="cuda").to(dtype)
+    xa = x.clone().requires_grad_(True)
+    ya = dwconv_cl(xa, w, b, mode, dtype)
+    ya.backward(dy)
+    got = (ya.detach(), xa.grad.clone(), w.grad.clone(), b.grad.clone())
+    w.grad = b.grad = None
+    xb = x.float().clone().requires_grad_(True)          # fp32 reference of the same (rounded) inputs
+    yb = _ref(xb, w, b, mode, k)
+    yb.backward(dy.float())
+    ref = (yb.detach(), xb.grad, w.grad, b.grad)
+    tol = 2e-5 if dt == "fp32" else 1.5e-2
+    names = ("y", "dx", "dw", "db")
+    errs = {n: _rel(a.float(), r) for n, a, r in zip(names, got, ref)}
+    print(C, k, mode, dt, {n: f"{e:.2e}" for n, e in errs.items()})
+    assert all(e < tol for e in errs.values()), errs
