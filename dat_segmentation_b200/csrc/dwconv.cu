@@ -38,46 +38,97 @@ __global__ void dw_transpose_kernel(const float* __restrict__ w, float* __restri
   wT[idx] = w[c * kk + (flip ? kk - 1 - uv : uv)];
 }
 
-template <typename TI, typename TO, int MODE>
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int N = 4; };
+template <> struct VecOf<bf16> { static constexpr int N = 8; };
+
+template <int N> __device__ __forceinline__ void ldv(const float* p, float* o) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p + i);
+    o[i] = v.x; o[i + 1] = v.y; o[i + 2] = v.z; o[i + 3] = v.w;
+  }
+}
+template <int N> __device__ __forceinline__ void ldv(const bf16* p, float* o) {
+  static_assert(N == 8, "bf16 vectors are 8 wide");
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+template <int N> __device__ __forceinline__ void stv(float* p, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <int N> __device__ __forceinline__ void stv(bf16* p, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; i += 8) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+    *reinterpret_cast<uint4*>(p + i) = raw;
+  }
+}
+// 4-wide bf16 store (8 bytes) for the fp32-in / bf16-out combination
+__device__ __forceinline__ void stv4(bf16* p, const float* v) { store4(p, make_float4(v[0], v[1], v[2], v[3])); }
+__device__ __forceinline__ void stv4(float* p, const float* v) { store4(p, make_float4(v[0], v[1], v[2], v[3])); }
+
+// CTA = 8 x 8 pixel tile x 4 channel vectors (16 bytes of input each): every tap after the first
+// touch of the 10 x 10 (k = 3) halo is an L1 hit, so L2/HBM see x about once.
+// grid = (tiles_x * tiles_y * B, C / (4 * VEC)); K = 0 means a runtime k.
+template <typename TI, typename TO, int MODE, int K>
 __global__ void __launch_bounds__(256)
 dwconv_cl_kernel(const TI* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
-                 TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int k,
-                 long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c4n = C >> 2;
-  const int c = (int)(idx % c4n) * 4;
-  const long long pix = idx / c4n;
-  const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
-  const long long b = pix / ((long long)W * H);
+                 TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int k_rt,
+                 int tiles_x, int tiles_y) {
+  constexpr int VEC = VecOf<TI>::N;
+  const int k = K > 0 ? K : k_rt;
   const int p = k >> 1;
-  float4 acc = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const int u_lo = max(0, p - yy), u_hi = min(k, H + p - yy);
-  const int v_lo = max(0, p - xx), v_hi = min(k, W + p - xx);
-  const TI* base = x + ((b * H + (yy - p)) * W + (xx - p)) * C + c;
-  for (int u = u_lo; u < u_hi; ++u) {
-    const TI* row = base + ((long long)u * W + v_lo) * C;
-    const float* wr = wT + (u * k + v_lo) * C + c;
-    for (int v = v_lo; v < v_hi; ++v) {
-      const float4 xv = load4(row);
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr));
-      acc.x = fmaf(xv.x, wv.x, acc.x);
-      acc.y = fmaf(xv.y, wv.y, acc.y);
-      acc.z = fmaf(xv.z, wv.z, acc.z);
-      acc.w = fmaf(xv.w, wv.w, acc.w);
-      row += C;
-      wr += C;
+  const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
+  const int vec = threadIdx.x & 3, pix_l = threadIdx.x >> 2;
+  const int yy = (tile / tiles_x) * 8 + (pix_l >> 3), xx = (tile % tiles_x) * 8 + (pix_l & 7);
+  const int c = (blockIdx.y * 4 + vec) * VEC;
+  if (yy >= H || xx >= W || c >= C) return;
+  float acc[VEC];
+  if (bias != nullptr) ldv<VEC>(bias + c, acc);
+  else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  }
+  const long long img = (long long)b * H * W;
+#pragma unroll
+  for (int u = 0; u < (K > 0 ? K : 15); ++u) {
+    if (u >= k) break;
+    const int y2 = yy + u - p;
+    if (y2 < 0 || y2 >= H) continue;
+#pragma unroll
+    for (int v = 0; v < (K > 0 ? K : 15); ++v) {
+      if (v >= k) break;
+      const int x2 = xx + v - p;
+      if (x2 < 0 || x2 >= W) continue;
+      float xv[VEC], wv[VEC];
+      ldv<VEC>(x + (img + (long long)y2 * W + x2) * C + c, xv);
+      ldv<VEC>(wT + (u * k + v) * C + c, wv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(xv[i], wv[i], acc[i]);
     }
   }
+  const long long off = (img + (long long)yy * W + xx) * C + c;
   if (MODE >= 1) {
-    const float4 xc = load4(x + pix * C + c);
-    acc.x += xc.x; acc.y += xc.y; acc.z += xc.z; acc.w += xc.w;
+    float xc[VEC];
+    ldv<VEC>(x + off, xc);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += xc[i];
   }
   if (MODE == 2) {
-    store4(z_out + pix * C + c, acc);
-    acc = make_float4(gelu_f(acc.x), gelu_f(acc.y), gelu_f(acc.z), gelu_f(acc.w));
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) stv4(z_out + off + i, acc + i);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = gelu_f(acc[i]);
   }
-  store4(y + pix * C + c, acc);
+#pragma unroll
+  for (int i = 0; i < VEC; i += 4) stv4(y + off + i, acc + i);
 }
 
 template <typename T>
@@ -90,36 +141,60 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
 }
 
 // dw[c][uv] = sum_pix dz[pix][c] * x[pix + off(uv)][c];  db[c] = sum_pix dz[pix][c]
-// grid = (ceil(C / 128), nsplit); thread = one channel; partial[split][kk + 1][C]
-template <typename TX, typename TD, int KK>
+// grid = (ceil(C / (128 * CV)), nsplit); thread = CV consecutive channels (vector loads);
+// partial[split][kk + 1][C]
+template <int CV> __device__ __forceinline__ void ldc(const float* p, float* o) {
+  if (CV == 4) { const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  else if (CV == 2) { const float2 v = *reinterpret_cast<const float2*>(p); o[0] = v.x; o[1] = v.y; }
+  else o[0] = *p;
+}
+template <int CV> __device__ __forceinline__ void ldc(const bf16* p, float* o) {
+  if (CV == 4) { const float4 v = load4(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  else if (CV == 2) { const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); o[0] = v.x; o[1] = v.y; }
+  else o[0] = __bfloat162float(*p);
+}
+
+template <typename TX, typename TD, int KK, int CV>
 __global__ void __launch_bounds__(128)
 dwconv_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* __restrict__ partial,
                     int B, int H, int W, int C, int k, long long pix_per_split) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int c = (blockIdx.x * 128 + threadIdx.x) * CV;
   if (c >= C) return;
   const long long npix = (long long)B * H * W;
   const long long p0 = (long long)blockIdx.y * pix_per_split;
   const long long p1 = min(npix, p0 + pix_per_split);
-  const int p = k >> 1;
-  float acc[KK + 1];
+  constexpr int KS = KK == 9 ? 3 : (KK == 25 ? 5 : 7);   // compile-time filter size: constant tap offsets
+  (void)k;
+  constexpr int p = KS >> 1;
+  float acc[KK + 1][CV];
 #pragma unroll
-  for (int i = 0; i <= KK; ++i) acc[i] = 0.f;
+  for (int i = 0; i <= KK; ++i)
+#pragma unroll
+    for (int j = 0; j < CV; ++j) acc[i][j] = 0.f;
   for (long long pix = p0; pix < p1; ++pix) {
     const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
-    const float d = to_f32(dz[pix * C + c]);
-    acc[KK] += d;
+    float d[CV];
+    ldc<CV>(dz + pix * C + c, d);
+#pragma unroll
+    for (int j = 0; j < CV; ++j) acc[KK][j] += d[j];
     const TX* base = x + (pix - (long long)p * W - p) * C + c;
 #pragma unroll
     for (int uv = 0; uv < KK; ++uv) {
-      const int u = uv / k, v = uv - u * k;
+      const int u = uv / KS, v = uv - u * KS;
       const int y2 = yy + u - p, x2 = xx + v - p;
-      if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
-        acc[uv] = fmaf(d, to_f32(base[((long long)u * W + v) * C]), acc[uv]);
+      if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+        float xv[CV];
+        ldc<CV>(base + ((long long)u * W + v) * C, xv);
+#pragma unroll
+        for (int j = 0; j < CV; ++j) acc[uv][j] = fmaf(d[j], xv[j], acc[uv][j]);
+      }
     }
   }
   float* out = partial + (size_t)blockIdx.y * (KK + 1) * C + c;
 #pragma unroll
-  for (int i = 0; i <= KK; ++i) out[(size_t)i * C] = acc[i];
+  for (int i = 0; i <= KK; ++i)
+#pragma unroll
+    for (int j = 0; j < CV; ++j) out[(size_t)i * C + j] = acc[i][j];
 }
 
 // block (32, 32): fixed-order reduction over the splits; writes dw (C, kk) and db (C)
@@ -161,26 +236,35 @@ int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void*
                int B, int H, int W, int C, int k, int mode, int flip, void* ws, size_t ws_bytes,
                cudaStream_t st) {
   DAT_REQUIRE(C % 4 == 0 && (k & 1) == 1 && k >= 1 && k <= 15, "dwconv: C %% 4 == 0 and odd k <= 15 required");
+  DAT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "dwconv: 16-byte aligned tensors required");
   DAT_REQUIRE(ws_bytes >= (size_t)k * k * C * 4, "dwconv: workspace too small");
   DAT_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || z_out != nullptr), "dwconv: bad mode");
   float* wT = (float*)ws;
   dw_transpose_kernel<<<ceil_div(C * k * k, 256), 256, 0, st>>>(w, wT, C, k * k, flip);
   DAT_LAUNCH_OK("dw_transpose_kernel");
-  const long long total = (long long)B * H * W * (C / 4);
-  const int grid = ceil_div(total, 256);
-#define LAUNCH(TI, TO, MD)                                                                      \
-  dwconv_cl_kernel<TI, TO, MD><<<grid, 256, 0, st>>>((const TI*)x, wT, bias, (TO*)y, (TO*)z_out, B, H, \
-                                                     W, C, k, total)
+  const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 8);
+  const int vec = x_dt == DAT_F32 ? 4 : 8;
+  DAT_REQUIRE(C % vec == 0, "dwconv: C must be a multiple of %d for this dtype", vec);
+  dim3 grid(tiles_x * tiles_y * B, ceil_div(C, 4 * vec));
+#define LAUNCH(TI, TO, MD, KV)                                                                  \
+  dwconv_cl_kernel<TI, TO, MD, KV><<<grid, 256, 0, st>>>((const TI*)x, wT, bias, (TO*)y, (TO*)z_out, B, \
+                                                         H, W, C, k, tiles_x, tiles_y)
+#define LAUNCH_K(TI, TO, MD)                                                  \
+  do {                                                                        \
+    if (k == 3) LAUNCH(TI, TO, MD, 3); else if (k == 7) LAUNCH(TI, TO, MD, 7); \
+    else LAUNCH(TI, TO, MD, 0);                                               \
+  } while (0)
 #define LAUNCH_M(TI, TO)                                                   \
   do {                                                                     \
-    if (mode == 0) LAUNCH(TI, TO, 0); else if (mode == 1) LAUNCH(TI, TO, 1); \
-    else LAUNCH(TI, TO, 2);                                                \
+    if (mode == 0) LAUNCH_K(TI, TO, 0); else if (mode == 1) LAUNCH_K(TI, TO, 1); \
+    else LAUNCH_K(TI, TO, 2);                                              \
   } while (0)
   if (x_dt == DAT_F32 && y_dt == DAT_F32) LAUNCH_M(float, float);
   else if (x_dt == DAT_F32) LAUNCH_M(float, bf16);
   else if (y_dt == DAT_F32) LAUNCH_M(bf16, float);
   else LAUNCH_M(bf16, bf16);
 #undef LAUNCH_M
+#undef LAUNCH_K
 #undef LAUNCH
   DAT_LAUNCH_OK("dwconv_cl_kernel");
   return DAT_OK;
@@ -204,12 +288,14 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
   const int nsplit = wgrad_splits(npix);
   const long long pps = (npix + nsplit - 1) / nsplit;
   float* part = (float*)((char*)ws + align_up((size_t)k * k * C * 4, 256));
-  dim3 grid(ceil_div(C, 128), nsplit);
-#define LAUNCH(TX, TD, KKV)                                                                         \
-  dwconv_wgrad_kernel<TX, TD, KKV><<<grid, 128, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
+  const int cv = k == 3 ? 4 : (k == 5 ? 2 : 2);      // channels per thread (register budget (k*k+1)*cv)
+  DAT_REQUIRE(C % cv == 0, "dwconv_wgrad: C must be a multiple of %d", cv);
+  dim3 grid(ceil_div(C, 128 * cv), nsplit);
+#define LAUNCH(TX, TD, KKV, CVV)                                                                    \
+  dwconv_wgrad_kernel<TX, TD, KKV, CVV><<<grid, 128, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
 #define LAUNCH_K(TX, TD)                                  \
   do {                                                    \
-    if (k == 3) LAUNCH(TX, TD, 9); else if (k == 5) LAUNCH(TX, TD, 25); else LAUNCH(TX, TD, 49); \
+    if (k == 3) LAUNCH(TX, TD, 9, 4); else if (k == 5) LAUNCH(TX, TD, 25, 2); else LAUNCH(TX, TD, 49, 2); \
   } while (0)
   if (x_dt == DAT_F32 && dz_dt == DAT_F32) LAUNCH_K(float, float);
   else if (x_dt == DAT_F32) LAUNCH_K(float, bf16);
