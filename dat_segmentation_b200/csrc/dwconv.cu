@@ -154,47 +154,77 @@ template <int CV> __device__ __forceinline__ void ldc(const bf16* p, float* o) {
   else o[0] = __bfloat162float(*p);
 }
 
+// block = 32 channel vectors x 4 pixel lanes: the 4 lanes stride the CTA's pixel slice (4x shorter
+// serial chains than one thread per channel vector), then are summed in shared memory in a
+// fixed order.  32-bit index arithmetic, interior pixels skip the per-tap bounds checks.
 template <typename TX, typename TD, int KK, int CV>
 __global__ void __launch_bounds__(128)
 dwconv_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* __restrict__ partial,
                     int B, int H, int W, int C, int k, long long pix_per_split) {
-  const int c = (blockIdx.x * 128 + threadIdx.x) * CV;
-  if (c >= C) return;
-  const long long npix = (long long)B * H * W;
-  const long long p0 = (long long)blockIdx.y * pix_per_split;
-  const long long p1 = min(npix, p0 + pix_per_split);
   constexpr int KS = KK == 9 ? 3 : (KK == 25 ? 5 : 7);   // compile-time filter size: constant tap offsets
   (void)k;
   constexpr int p = KS >> 1;
+  __shared__ float red[3][32][(KK + 1) * CV + 1];
+  const int cvec = threadIdx.x & 31, plane = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cvec) * CV;
+  const bool active = c < C;
+  const int npix = B * H * W;
+  const int p0 = (int)(blockIdx.y * pix_per_split);
+  const int p1 = min(npix, p0 + (int)pix_per_split);
   float acc[KK + 1][CV];
 #pragma unroll
   for (int i = 0; i <= KK; ++i)
 #pragma unroll
     for (int j = 0; j < CV; ++j) acc[i][j] = 0.f;
-  for (long long pix = p0; pix < p1; ++pix) {
-    const int xx = (int)(pix % W), yy = (int)((pix / W) % H);
-    float d[CV];
-    ldc<CV>(dz + pix * C + c, d);
+  if (active) {
+    for (int pix = p0 + plane; pix < p1; pix += 4) {
+      const int rem = pix % (H * W);
+      const int yy = rem / W, xx = rem - yy * W;
+      float d[CV];
+      ldc<CV>(dz + (long long)pix * C + c, d);
 #pragma unroll
-    for (int j = 0; j < CV; ++j) acc[KK][j] += d[j];
-    const TX* base = x + (pix - (long long)p * W - p) * C + c;
+      for (int j = 0; j < CV; ++j) acc[KK][j] += d[j];
+      const TX* base = x + ((long long)pix - p * W - p) * C + c;
+      const bool interior = yy >= p && yy < H - p && xx >= p && xx < W - p;
+      if (interior) {
 #pragma unroll
-    for (int uv = 0; uv < KK; ++uv) {
-      const int u = uv / KS, v = uv - u * KS;
-      const int y2 = yy + u - p, x2 = xx + v - p;
-      if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
-        float xv[CV];
-        ldc<CV>(base + ((long long)u * W + v) * C, xv);
+        for (int uv = 0; uv < KK; ++uv) {
+          const int u = uv / KS, v = uv - u * KS;
+          float xv[CV];
+          ldc<CV>(base + ((long long)u * W + v) * C, xv);
 #pragma unroll
-        for (int j = 0; j < CV; ++j) acc[uv][j] = fmaf(d[j], xv[j], acc[uv][j]);
+          for (int j = 0; j < CV; ++j) acc[uv][j] = fmaf(d[j], xv[j], acc[uv][j]);
+        }
+      } else {
+#pragma unroll
+        for (int uv = 0; uv < KK; ++uv) {
+          const int u = uv / KS, v = uv - u * KS;
+          const int y2 = yy + u - p, x2 = xx + v - p;
+          if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            float xv[CV];
+            ldc<CV>(base + ((long long)u * W + v) * C, xv);
+#pragma unroll
+            for (int j = 0; j < CV; ++j) acc[uv][j] = fmaf(d[j], xv[j], acc[uv][j]);
+          }
+        }
       }
     }
   }
-  float* out = partial + (size_t)blockIdx.y * (KK + 1) * C + c;
+  if (plane > 0) {
 #pragma unroll
-  for (int i = 0; i <= KK; ++i)
+    for (int i = 0; i <= KK; ++i)
 #pragma unroll
-    for (int j = 0; j < CV; ++j) out[(size_t)i * C + j] = acc[i][j];
+      for (int j = 0; j < CV; ++j) red[plane - 1][cvec][i * CV + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (plane == 0 && active) {
+    float* out = partial + (size_t)blockIdx.y * (KK + 1) * C + c;
+#pragma unroll
+    for (int i = 0; i <= KK; ++i)
+#pragma unroll
+      for (int j = 0; j < CV; ++j)
+        out[(size_t)i * C + j] = ((acc[i][j] + red[0][cvec][i * CV + j]) + red[1][cvec][i * CV + j]) + red[2][cvec][i * CV + j];
+  }
 }
 
 // block (32, 32): fixed-order reduction over the splits; writes dw (C, kk) and db (C)
@@ -290,7 +320,7 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
   float* part = (float*)((char*)ws + align_up((size_t)k * k * C * 4, 256));
   const int cv = k == 3 ? 4 : (k == 5 ? 2 : 2);      // channels per thread (register budget (k*k+1)*cv)
   DAT_REQUIRE(C % cv == 0, "dwconv_wgrad: C must be a multiple of %d", cv);
-  dim3 grid(ceil_div(C, 128 * cv), nsplit);
+  dim3 grid(ceil_div(C, 32 * cv), nsplit);
 #define LAUNCH(TX, TD, KKV, CVV)                                                                    \
   dwconv_wgrad_kernel<TX, TD, KKV, CVV><<<grid, 128, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
 #define LAUNCH_K(TX, TD)                                  \
