@@ -10,8 +10,8 @@ images/s with inputs resident in HBM; `e2e` = the same step fed from pinned host
 device->host read of the loss every step.  `roofline` = the dominant hand-written kernel timed
 alone with CUDA events (L2 flushed between launches).  `cpu_baseline` / `--impl reference` =
 the oracle port of the reference (library-operator form) on the host cores, bounded sample.
-Under torchrun (N > 1): one process per GPU, batch-sharded, gradients all-reduced by NCCL
-(DistributedDataParallel), max-over-ranks timing.
+Under torchrun (N > 1): one process per GPU, batch-sharded, the flat gradient buffer all-reduced
+by one NCCL call per step, max-over-ranks timing.  The fwd+bwd of a step is a CUDA-graph replay.
 """
 import argparse
 import ctypes as C
@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dat_b200", choices=["dat_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -217,20 +218,50 @@ def main():
 
     torch.manual_seed(0)
     model = build_dat().to(dev).train()          # drop_path_rate 0.3 as in the shipped config
-    step_model = model
-    if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    # gradients live in one flat fp32 buffer: zeroed inside the step, all-reduced with ONE NCCL call
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev, generator=gen)
+    imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev, generator=gen)   # static step input
     host = torch.randn(PER_GPU_BATCH, 3, IMG, IMG).pin_memory()
-    dev_in = torch.empty_like(imgs)
 
-    def step(x):
-        model.zero_grad(set_to_none=True)
+    def fwd_bwd():
+        flat.zero_()
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            outs = step_model(x)
+            outs = model(imgs)
         loss = loss_of(outs)
         loss.backward()
+        return loss
+
+    # The whole fwd+bwd is captured once in a CUDA graph (shapes are static) and replayed: the
+    # ~2000 launches of a step cost one graph launch.  --no-graph runs the same function eagerly.
+    graph, static_loss = None, None
+    n0 = lib.dat_launch_count()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fwd_bwd()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    launches_per_step = (lib.dat_launch_count() - n0) // warmup
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = fwd_bwd()
+
+    def step():
+        loss = static_loss
+        if graph is not None:
+            graph.replay()
+        else:
+            loss = fwd_bwd()
+        if world > 1:      # the one exchange step of data-parallel training (new_train.py:116)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
         return loss
 
     def sync_all():
@@ -239,27 +270,26 @@ def main():
         torch.cuda.synchronize(dev)
 
     for _ in range(warmup):
-        step(imgs)
+        step()
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = lib.dat_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(imgs)
+        step()
     e1.record()
     sync_all()
-    launches = lib.dat_launch_count() - n0
+    launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1) / args.steps
 
     # end-to-end: pinned host -> device every step, loss read back every step
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dev_in.copy_(host, non_blocking=True)
-        _ = step(dev_in).item()
+        imgs.copy_(host, non_blocking=True)
+        _ = step().item()
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.summary() if sampler else None
@@ -277,11 +307,12 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "DAT-T++ backbone fwd+bwd, 512x512, batch 16 per GPU, bf16 autocast "
-                                   "(BASELINE.json configs[1]); 14 deformable-attention blocks in dat_b200 kernels, "
-                                   "rest of the backbone in PyTorch library ops",
+                                   "(BASELINE.json configs[1]); deformable-attention blocks, LayerNorms and depthwise "
+                                   "convs in dat_b200 kernels, stem / 1x1 MLP convs / down-projections in library ops",
                        "per_gpu_batch": PER_GPU_BATCH, "global_batch": total,
                        "parallelism": f"dp{world} (batch-sharded, NCCL gradient all-reduce)" if world > 1 else "single GPU",
                        "l2": "working set per step >> 126 MB L2 (no flush needed); roofline leg flushes L2 per launch",
+                       "cuda_graph": graph is not None,
                        "drop_path_rate": 0.3},
             "e2e": {"value": round(total / (e2e_ms * 1e-3), 2), "unit": UNIT,
                     "h2d_bytes_per_step": host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world},
