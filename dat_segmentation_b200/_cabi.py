@@ -77,6 +77,12 @@ def lib():
     L.dat_pointwise_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_pointwise_fwd_tc.argtypes = [vp, i32, vp, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_cast_bf16.argtypes = [f32p, vp, i64, vp]
+    L.dat_cast_transpose_bf16.argtypes = [f32p, vp, i32, i32, vp]
+    L.dat_pointwise_wgrad_tc_workspace_bytes.argtypes = [i64, i32, i32]
+    L.dat_pointwise_wgrad_tc_workspace_bytes.restype = C.c_size_t
+    L.dat_pointwise_wgrad_tc.argtypes = [vp, vp, f32p, i64, i32, i32, vp, C.c_size_t, vp]
+    L.dat_bias_grad.argtypes = [vp, i32, f32p, i64, i32, vp, C.c_size_t, vp]
+    L.dat_cast_transpose_bf16.restype = L.dat_pointwise_wgrad_tc.restype = L.dat_bias_grad.restype = C.c_int
     L.dat_debug_gemm_timing.argtypes = [C.POINTER(C.c_uint64)]
     L.dat_debug_gemm_timing.restype = C.c_int
     L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
@@ -120,6 +126,8 @@ def exported_symbols():
     return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
             "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing",
+            "dat_cast_transpose_bf16", "dat_pointwise_wgrad_tc_workspace_bytes", "dat_pointwise_wgrad_tc",
+            "dat_bias_grad",
             "dat_offset_pos_fwd",
             "dat_ref_points", "dat_sample_fwd",
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",

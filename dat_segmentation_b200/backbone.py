@@ -16,6 +16,7 @@ import torch.nn as nn
 from .dattention import DAttentionBaseline, _pair
 from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
+from .pointwise import PointwiseConvCL
 
 __all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
 
@@ -76,10 +77,11 @@ class TransformerMLPWithConv(nn.Module):
         super().__init__()
         hidden = channels * expansion
         self.b200_ops = b200_ops
-        self.linear1 = nn.Sequential(nn.Conv2d(channels, hidden, 1))
+        pw = PointwiseConvCL if b200_ops else (lambda cin, cout: nn.Conv2d(cin, cout, 1))
+        self.linear1 = nn.Sequential(pw(channels, hidden))
         self.drop1 = nn.Dropout(drop)
         self.act = nn.GELU()
-        self.linear2 = nn.Sequential(nn.Conv2d(hidden, channels, 1))
+        self.linear2 = nn.Sequential(pw(hidden, channels))
         self.drop2 = nn.Dropout(drop)
         # b200_ops: gelu(x + dwconv(x) + b) is one fused channel-last kernel
         self.dwc = (DepthwiseConvCL(hidden, 3, MODE_RESIDUAL_GELU) if b200_ops

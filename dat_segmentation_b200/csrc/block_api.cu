@@ -164,6 +164,31 @@ int dat_debug_gemm_timing(uint64_t* out8) {
   return debug_gemm_timing((unsigned long long*)out8);
 }
 
+int dat_cast_transpose_bf16(const float* w, void* out, int32_t N, int32_t K, void* stream) {
+  DAT_REQUIRE(w && out && N > 0 && K > 0, "cast_transpose_bf16: bad arguments");
+  return cast_transpose_bf16(w, out, N, K, (cudaStream_t)stream);
+}
+
+size_t dat_pointwise_wgrad_tc_workspace_bytes(int64_t M, int32_t N, int32_t K) {
+  return pointwise_wgrad_tc_supported(M, N, K) ? pointwise_wgrad_tc_workspace(M, N, K) : 0;
+}
+
+int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, int64_t M, int32_t N, int32_t K,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(dY && X && dW, "pointwise_wgrad_tc: NULL pointer");
+  if (!pointwise_wgrad_tc_supported(M, N, K)) {
+    set_error("pointwise_wgrad_tc: shape M=%lld N=%d K=%d not tileable", (long long)M, N, K);
+    return DAT_ERR_UNSUPPORTED;
+  }
+  return pointwise_wgrad_tc(dY, X, dW, M, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_t N, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(dY && db && workspace, "bias_grad: NULL pointer");
+  return bias_grad(dY, dy_dtype, db, M, N, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   DAT_REQUIRE(src && dst && n > 0, "cast_bf16: bad arguments");
   return cast_weights_bf16(src, nullptr, nullptr, dst, n, (cudaStream_t)stream);

@@ -224,20 +224,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The data-gradient GEMMs dX = dY W are then plain K-major products with "weight" W^T.
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                            const float* __restrict__ w2, const float* __restrict__ w3,
-                                           bf16* __restrict__ out, int C) {
-  __shared__ float tile[32][33];
+                                           bf16* __restrict__ out, int N, int K) {
+  __shared__ float tile[32][33];          // w_z is (N, K) row-major, out[z] is (K, N)
   const float* src = blockIdx.z == 0 ? w0 : (blockIdx.z == 1 ? w1 : (blockIdx.z == 2 ? w2 : w3));
   if (src == nullptr) return;
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     int n = n0 + r, k = k0 + threadIdx.x;
-    tile[r][threadIdx.x] = (n < C && k < C) ? src[(long long)n * C + k] : 0.f;
+    tile[r][threadIdx.x] = (n < N && k < K) ? src[(long long)n * K + k] : 0.f;
   }
   __syncthreads();
-  bf16* dst = out + (long long)blockIdx.z * C * C;
+  bf16* dst = out + (long long)blockIdx.z * N * K;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     int k = k0 + r, n = n0 + threadIdx.x;
-    if (k < C && n < C) dst[(long long)k * C + n] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    if (k < K && n < N) dst[(long long)k * N + n] = __float2bfloat16_rn(tile[threadIdx.x][r]);
   }
 }
 
@@ -281,7 +281,15 @@ int cast_weights_bf16(const float* a, const float* b, const float* c, void* out,
 int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w2, const float* w3,
                                 void* out, int C, cudaStream_t st) {
   dim3 grid(ceil_div(C, 32), ceil_div(C, 32), 4), block(32, 8);
-  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w0, w1, w2, w3, (bf16*)out, C);
+  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w0, w1, w2, w3, (bf16*)out, C, C);
+  DAT_LAUNCH_OK("cast_transpose_bf16_kernel");
+  return DAT_OK;
+}
+
+// one (N, K) fp32 matrix -> (K, N) bf16
+int cast_transpose_bf16(const float* w, void* out, int N, int K, cudaStream_t st) {
+  dim3 grid(ceil_div(K, 32), ceil_div(N, 32), 1), block(32, 8);
+  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w, nullptr, nullptr, nullptr, (bf16*)out, N, K);
   DAT_LAUNCH_OK("cast_transpose_bf16_kernel");
   return DAT_OK;
 }

@@ -65,11 +65,14 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         const int s = kc % stages;
         const uint32_t ph = (uint32_t)(kc / stages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
+        // a 64-channel tail tile loads one dY box only: rows 64-127 of the accumulator then hold
+        // products of stale shared memory, stay in their own rows and are never stored
+        const int a_boxes = (N - n0 >= WG_BM) ? 2 : 1;
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(a_boxes * BOX_BYTES + b_bytes));
         // rows past m_end belong to the next slice: they are loaded but must not count, so the
         // last chunk of a slice is clipped by construction (rows_per_split is a multiple of 64)
         const int mrow = (int)(m_begin + (long long)kc * WG_CHUNK);
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < a_boxes; ++i)
           tma_load_2d(sA + s * a_bytes + i * BOX_BYTES, &tmDY, &full[s], n0 + 64 * i, mrow);
         for (int i = 0; i < BNK / 64; ++i)
           tma_load_2d(sB + s * b_bytes + i * BOX_BYTES, &tmX, &full[s], k0 + 64 * i, mrow);
@@ -136,11 +139,12 @@ int wg_bnk(int C) { return C >= 256 ? 256 : C; }
 }  // namespace
 
 bool pointwise_wgrad_tc_supported(long long M, int N, int K) {
-  return M >= 64 && N % 128 == 0 && K % 128 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
+  // N = 64 runs as half-empty 128-row tiles (the out-of-range box is zero-filled by TMA)
+  return M >= 64 && N % 64 == 0 && K % 64 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
 }
 
 int pointwise_wgrad_tc_splits(long long M, int N, int K) {
-  const int tiles = (N / WG_BM) * (K / wg_bnk(K));
+  const int tiles = ((N + WG_BM - 1) / WG_BM) * (K / wg_bnk(K));
   long long want = (148 + tiles - 1) / tiles;
   long long cap = (M + 127) / 128;            // at least 2 chunks per slice
   long long s = want < cap ? want : cap;
@@ -173,7 +177,7 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, in
   int tmem_cols = 32;
   while (tmem_cols < BNK) tmem_cols <<= 1;
   float* part = splits > 1 ? (float*)ws : dW;
-  dim3 grid(N / WG_BM, K / BNK, splits);
+  dim3 grid((N + WG_BM - 1) / WG_BM, K / BNK, splits);
   DAT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gemm_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, part, N, K, BNK, (int)rps, M, stages, tmem_cols);
   DAT_LAUNCH_OK("gemm_tc_wgrad_kernel");

@@ -137,3 +137,7 @@ int gelu_bwd(const void* dy, const void* z, void* dz, int dt, long long n, cudaS
 int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, float* db, int B, int H,
                  int W, int C, int k, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+int cast_transpose_bf16(const float* w, void* out, int N, int K, cudaStream_t st);
+}

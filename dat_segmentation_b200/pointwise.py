@@ -1,0 +1,120 @@
+"""1x1 convolutions of the DAT MLP blocks (`TransformerMLPWithConv.linear1/linear2`,
+`models/utils/dat_blocks.py:316-348`) on the dat_b200 tcgen05 GEMMs.
+
+`PointwiseConvCL` keeps an `nn.Conv2d(cin, cout, 1)`'s parameters (same state-dict keys) and runs
+under bf16 autocast:
+  forward   Y = X W^T + b      tf32 MMA straight on an fp32 X (LayerNorm output), bf16 MMA otherwise
+  dX = dY W                    the same kernel against a transposed bf16 copy of W
+  dW = dY^T X, db = colsum dY  MN-major tensor-core weight gradient, deterministic reductions
+Shapes the kernels cannot tile, fp32 (non-autocast) execution and CPU tensors use the library
+convolution (`F.conv2d`) — this module is a "next row" outside the parity-critical block.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _cabi
+
+__all__ = ["PointwiseConvCL"]
+
+_CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _tileable(n):
+    tiles = (n + 255) // 256
+    return n % tiles == 0 and (n // tiles) % 32 == 0
+
+
+def _supported(M, N, K):
+    # forward / data-gradient tiling (gemm_tc.cu pick_bn) and the weight-gradient boxes (64 x 64)
+    return M >= 64 and _tileable(N) and _tileable(K) and N % 64 == 0 and K % 64 == 0
+
+
+class _PointwiseFn(torch.autograd.Function):
+    """x_l (M, K) contiguous (fp32 or bf16) -> y (M, N) bf16."""
+
+    @staticmethod
+    def forward(ctx, x_l, weight, bias):
+        lib = _cabi.lib()
+        M, K = x_l.shape
+        N = weight.shape[0]
+        dev = x_l.device
+        w32 = weight.detach().float().reshape(N, K).contiguous()
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        with torch.cuda.device(dev):
+            y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            if x_l.dtype == torch.float32:
+                w_op = w32                                   # tf32 MMA on the fp32 operands
+            else:
+                w_op = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+                _cabi.check(lib.dat_cast_bf16(_ptr(w32), _ptr(w_op), N * K, _stream(dev)), "dat_cast_bf16")
+            _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(x_l), _CODE[x_l.dtype], _ptr(w_op), _ptr(b32), _ptr(y),
+                                                 _cabi.DAT_BF16, M, N, K, _stream(dev)), "dat_pointwise_fwd_tc")
+        ctx.save_for_backward(x_l, w32)
+        ctx.has_bias, ctx.wdtype, ctx.wshape = bias is not None, weight.dtype, weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.lib()
+        x_l, w32 = ctx.saved_tensors
+        M, K = x_l.shape
+        N = w32.shape[0]
+        dev = x_l.device
+        dy = dy.to(torch.bfloat16).contiguous()
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            # dX = dY W: K-major GEMM against W^T (K, N) in bf16
+            wT = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
+            _cabi.check(lib.dat_cast_transpose_bf16(_ptr(w32), _ptr(wT), N, K, st), "dat_cast_transpose_bf16")
+            dx = torch.empty_like(x_l)
+            _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(dy), _cabi.DAT_BF16, _ptr(wT), None, _ptr(dx),
+                                                 _CODE[dx.dtype], M, K, N, st), "dat_pointwise_fwd_tc(dgrad)")
+            # dW = dY^T X (bf16 operands)
+            if x_l.dtype == torch.float32:
+                xb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+                _cabi.check(lib.dat_cast_bf16(_ptr(x_l), _ptr(xb), M * K, st), "dat_cast_bf16")
+            else:
+                xb = x_l
+            nbytes = lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K)
+            ws = torch.empty(max(nbytes, 64 * N * 4), device=dev, dtype=torch.uint8)
+            dw = torch.empty(N, K, device=dev, dtype=torch.float32)
+            _cabi.check(lib.dat_pointwise_wgrad_tc(_ptr(dy), _ptr(xb), _ptr(dw), M, N, K, _ptr(ws), ws.numel(), st),
+                        "dat_pointwise_wgrad_tc")
+            db = None
+            if ctx.has_bias:
+                db = torch.empty(N, device=dev, dtype=torch.float32)
+                _cabi.check(lib.dat_bias_grad(_ptr(dy), _cabi.DAT_BF16, _ptr(db), M, N, _ptr(ws), ws.numel(), st),
+                            "dat_bias_grad")
+        return dx, dw.reshape(ctx.wshape).to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None)
+
+
+class PointwiseConvCL(nn.Conv2d):
+    """nn.Conv2d(cin, cout, 1) parameters; tcgen05 GEMMs under bf16 autocast on CUDA."""
+
+    def __init__(self, cin, cout):
+        super().__init__(cin, cout, 1)
+
+    def forward(self, x):
+        B, K, H, W = x.shape
+        N = self.out_channels
+        use_tc = (x.is_cuda and torch.is_autocast_enabled("cuda")
+                  and torch.get_autocast_dtype("cuda") == torch.bfloat16 and x.dtype in _CODE
+                  and _supported(B * H * W, N, K))
+        if not use_tc:
+            return F.conv2d(x, self.weight, self.bias)
+        x_l = x.permute(0, 2, 3, 1)
+        if not x_l.is_contiguous():
+            x_l = x_l.contiguous()
+        y = _PointwiseFn.apply(x_l.reshape(B * H * W, K), self.weight, self.bias)
+        return y.reshape(B, H, W, N).permute(0, 3, 1, 2)

@@ -135,6 +135,18 @@ int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const fl
  * launch: entry, setup done, first TMA stage landed, MMAs issued, accumulator ready,
  * epilogue done (6 of 8 slots used).  Synchronises the device. */
 int dat_debug_gemm_timing(uint64_t* out8);
+/* Tensor-core gradients of the 1x1 convolution (bf16 operands, fp32 accumulation):
+ *   data gradient  dX[M,K] = dY[M,N] W[N,K]  ==  dat_pointwise_fwd_tc(dY, W^T) with the (K,N) bf16
+ *                  transposed weight from dat_cast_transpose_bf16;
+ *   weight gradient dW[N,K] = dY^T X (both bf16, read MN-major; N, K multiples of 128; deterministic
+ *                  split reduction) and bias gradient db[N] = column sums of dY. */
+int dat_cast_transpose_bf16(const float* w, void* out, int32_t N, int32_t K, void* stream);
+size_t dat_pointwise_wgrad_tc_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, int64_t M, int32_t N, int32_t K,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* workspace >= 64 * N * 4 bytes */
+int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_t N, void* workspace,
+                  size_t workspace_bytes, void* stream);
 /* fp32 -> bf16 copy of n elements (n % 4 == 0), used for the weight operands above. */
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -1,0 +1,61 @@
+"""dat_b200 tensor-core 1x1 convolutions of the MLP blocks against
+torch.nn.functional.conv2d in fp32: forward, data, weight and bias gradients.  The kernels run
+bf16 / tf32 MMAs with fp32 accumulation, so the bar is the bf16 one of the block (2e-2 relative
+to the tensor's max)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+# (cin, cout, B, H, W): the four DAT-T++ stage widths in both directions + ragged pixel counts
+SHAPES = [(64, 256, 2, 32, 32), (256, 64, 2, 32, 32), (128, 512, 2, 16, 16), (512, 128, 2, 16, 16),
+          (256, 1024, 2, 9, 7), (1024, 256, 2, 9, 7), (512, 2048, 1, 8, 8), (2048, 512, 1, 8, 8),
+          (128, 512, 3, 5, 5)]
+
+
+@pytest.mark.parametrize("cin,cout,B,H,W", SHAPES)
+@pytest.mark.parametrize("xdt", ["fp32", "bf16"])
+def test_pointwise_matches_conv2d(cin, cout, B, H, W, xdt):
+    from dat_segmentation_b200.pointwise import PointwiseConvCL, _supported
+    assert _supported(B * H * W, cout, cin)
+    torch.manual_seed(cin + cout)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = PointwiseConvCL(cin, cout).cuda()
+    dtype = torch.float32 if xdt == "fp32" else torch.bfloat16
+    x = torch.randn(B, H, W, cin, device="cuda").permute(0, 3, 1, 2).to(dtype)
+    dy = torch.randn(B, cout, H, W, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = m(xa)
+    assert ya.dtype == torch.bfloat16 and ya.shape == (B, cout, H, W)
+    ya.backward(dy.to(ya.dtype))
+    got = (ya.detach().float(), xa.grad.float().clone(), m.weight.grad.clone(), m.bias.grad.clone())
+    assert xa.grad.dtype == x.dtype
+    m.weight.grad = m.bias.grad = None
+    xb = x.float().clone().requires_grad_(True)
+    yb = F.conv2d(xb, m.weight, m.bias)
+    yb.backward(dy.to(torch.bfloat16).float())
+    ref = (yb.detach(), xb.grad, m.weight.grad, m.bias.grad)
+    errs = {n: _rel(a, r) for n, a, r in zip(("y", "dx", "dw", "db"), got, ref)}
+    print(cin, cout, xdt, {n: f"{e:.2e}" for n, e in errs.items()})
+    assert all(e < 2e-2 for e in errs.values()), errs
+
+
+def test_pointwise_fallbacks_match_library():
+    """fp32 (no autocast) execution and untileable widths go through F.conv2d unchanged."""
+    from dat_segmentation_b200.pointwise import PointwiseConvCL
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False
+    m = PointwiseConvCL(96, 200).cuda()
+    x = torch.randn(2, 96, 6, 6, device="cuda")
+    assert torch.equal(m(x), F.conv2d(x, m.weight, m.bias))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x)
+        assert torch.equal(y, F.conv2d(x, m.weight, m.bias))
