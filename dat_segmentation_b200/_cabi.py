@@ -104,6 +104,9 @@ def lib():
     L.dat_gelu_bwd.argtypes = [vp, vp, vp, i32, i64, vp]
     L.dat_dwconv_wgrad.argtypes = [vp, i32, vp, i32, f32p, f32p, i32, i32, i32, i32, i32, vp, C.c_size_t, vp]
     L.dat_dwconv_fwd.restype = L.dat_gelu_bwd.restype = L.dat_dwconv_wgrad.restype = C.c_int
+    L.dat_dwconv_bwd.argtypes = [vp, i32, vp, vp, i32, f32p, vp, f32p, f32p, i32, i32, i32, i32, i32, i32, vp,
+                                 C.c_size_t, vp]
+    L.dat_dwconv_bwd.restype = C.c_int
     L.dat_layernorm_fwd.restype = C.c_int
     L.dat_layernorm_bwd.restype = C.c_int
     for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
@@ -132,4 +135,5 @@ def exported_symbols():
             "dat_ref_points", "dat_sample_fwd",
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
             "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd",
-            "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad"]
+            "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad",
+            "dat_dwconv_bwd"]

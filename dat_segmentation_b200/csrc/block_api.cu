@@ -288,6 +288,16 @@ int dat_dwconv_wgrad(const void* x, int32_t x_dtype, const void* dz, int32_t dz_
                       (cudaStream_t)stream);
 }
 
+int dat_dwconv_bwd(const void* x, int32_t x_dtype, const void* dy, const void* z, int32_t d_dtype,
+                   const float* w, void* dx, float* dw, float* db, int32_t B, int32_t H, int32_t W,
+                   int32_t C, int32_t k, int32_t mode, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  DAT_REQUIRE(x && dy && w && dx && dw && workspace, "dwconv_bwd: NULL pointer");
+  DAT_REQUIRE(dwconv3_supported(C, k), "dwconv_bwd: the fused backward needs k == 3 and an even C");
+  return dwconv3_bwd(x, x_dtype, dy, z, d_dtype, w, dx, dw, db, B, H, W, C, mode, workspace,
+                     workspace_bytes, (cudaStream_t)stream);
+}
+
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table, float* bias,
                  void* stream) {
   Shape s;

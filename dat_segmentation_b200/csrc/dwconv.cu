@@ -13,6 +13,8 @@
 // R*C*(e_dz + e_x).  The k*k-fold spatial reuse is served by L1/L2.
 // Weight gradient: per-CTA partial sums over a slice of the pixels, reduced in a fixed order
 // (deterministic, no atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -258,13 +260,22 @@ int wgrad_splits(long long npix) {
 size_t dwconv_workspace(int B, int H, int W, int C, int k) {
   const size_t wt = align_up((size_t)k * k * C * 4, 256);
   const size_t part = align_up((size_t)wgrad_splits((long long)B * H * W) * (k * k + 1) * C * 4, 256);
-  return wt + part;
+  const size_t fused = dwconv3_supported(C, k) ? dwconv3_partial_bytes(B, H, W, C) : 0;
+  return wt + part > fused ? wt + part : fused;
+}
+
+int dwconv_wgrad_reduce(const float* partial, int nsplit, int kk, int C, float* dw, float* db, cudaStream_t st) {
+  dwconv_wgrad_reduce_kernel<<<ceil_div((kk + 1) * C, 32), dim3(32, 32), 0, st>>>(partial, nsplit, kk, C, dw, db);
+  DAT_LAUNCH_OK("dwconv_wgrad_reduce_kernel");
+  return DAT_OK;
 }
 
 // mode 0/1/2 as above; z_out only for mode 2.  ws >= k*k*C*4 bytes (transposed filter).
 int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, void* z_out, int y_dt,
                int B, int H, int W, int C, int k, int mode, int flip, void* ws, size_t ws_bytes,
                cudaStream_t st) {
+  if (dwconv3_supported(C, k) && std::getenv("DAT_B200_DWCONV_GENERIC") == nullptr)
+    return dwconv3_fwd(x, x_dt, w, bias, y, z_out, y_dt, B, H, W, C, mode, flip, st);
   DAT_REQUIRE(C % 4 == 0 && (k & 1) == 1 && k >= 1 && k <= 15, "dwconv: C %% 4 == 0 and odd k <= 15 required");
   DAT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "dwconv: 16-byte aligned tensors required");
   DAT_REQUIRE(ws_bytes >= (size_t)k * k * C * 4, "dwconv: workspace too small");

@@ -141,3 +141,15 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
 namespace dat {
 int cast_transpose_bf16(const float* w, void* out, int N, int K, cudaStream_t st);
 }
+
+namespace dat {
+// dwconv3.cu - register-window depthwise 3x3 (forward + fused backward)
+bool dwconv3_supported(int C, int k);
+size_t dwconv3_partial_bytes(int B, int H, int W, int C);
+int dwconv3_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, void* z_out, int y_dt,
+                int B, int H, int W, int C, int mode, int flip, cudaStream_t st);
+int dwconv3_bwd(const void* x, int x_dt, const void* dy, const void* z, int d_dt, const float* w, void* dx,
+                float* dw, float* db, int B, int H, int W, int C, int mode, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+int dwconv_wgrad_reduce(const float* partial, int nsplit, int kk, int C, float* dw, float* db, cudaStream_t st);
+}  // namespace dat

@@ -9,6 +9,7 @@ dtype semantics follow autocast: the convolution result is bf16 under autocast, 
 whose residual add promotes to the dtype of x (fp32 residual stream).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -60,6 +61,19 @@ class _DwConvFn(torch.autograd.Function):
         mode = ctx.mode
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if k == 3 and Cc % 2 == 0 and not os.environ.get("DAT_B200_DWCONV_GENERIC"):
+                # fused: dz = dy * gelu'(z), dx, dw, db in one pass over dy, z, x
+                d_dt = z.dtype if z is not None else (dy.dtype if dy.dtype in _CODE else torch.float32)
+                dy = dy.to(d_dt).contiguous()
+                nbytes = lib.dat_dwconv_workspace_bytes(B, H, W, Cc, k)
+                ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                dx = torch.empty_like(x_l)
+                dw = torch.empty_like(w32)
+                db = torch.empty(Cc, device=dev, dtype=torch.float32) if ctx.has_bias else None
+                _cabi.check(lib.dat_dwconv_bwd(_ptr(x_l), _CODE[x_l.dtype], _ptr(dy), _ptr(z), _CODE[d_dt],
+                                               _ptr(w32), _ptr(dx), _ptr(dw), _ptr(db), B, H, W, Cc, k, mode,
+                                               _ptr(ws), nbytes, st), "dat_dwconv_bwd")
+                return dx, dw.to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None), None, None
             if mode == MODE_RESIDUAL_GELU:
                 dy = dy.to(z.dtype).contiguous()
                 dz = torch.empty_like(z)

@@ -209,6 +209,15 @@ int dat_dwconv_wgrad(const void* x, int32_t x_dtype, const void* dz, int32_t dz_
                      float* db, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Fused backward of the 3 x 3 case (k must be 3, C even): one pass over dy, z (mode 2 only), x forms
+ * dz = dy * gelu'(z) on the fly and produces dx (dtype of x), dw (C,1,3,3), db (C; may be NULL);
+ * all overwritten, deterministic.  dy / z have dtype d_dtype.  Autograd of dat.py:135-138 and
+ * dat_blocks.py:338-343.  workspace >= dat_dwconv_workspace_bytes(B, H, W, C, 3). */
+int dat_dwconv_bwd(const void* x, int32_t x_dtype, const void* dy, const void* z, int32_t d_dtype,
+                   const float* w, void* dx, float* dw, float* db, int32_t B, int32_t H, int32_t W,
+                   int32_t C, int32_t k, int32_t mode, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* The rpe bias alone, (B, n_heads, HW, Ns) fp32 (dat_blocks.py:198-212); test hook. */
 int dat_rpe_bias(const dat_block_desc* d, const float* pos, const float* rpe_table,
                  float* bias, void* stream);

@@ -46,3 +46,32 @@ def test_dwconv_matches_conv2d(C, k, mode, dt):
     errs = {n: _rel(a.float(), r) for n, a, r in zip(names, got, ref)}
     print(C, k, mode, dt, {n: f"{e:.2e}" for n, e in errs.items()})
     assert all(e < tol for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("C,mode,H,W", [(64, 2, 40, 37), (128, 1, 33, 18), (256, 0, 19, 50), (66, 2, 9, 9)])
+@pytest.mark.parametrize("dt", ["fp32", "bf16"])
+def test_dwconv3_strips_and_fused_backward(C, mode, H, W, dt):
+    """3x3 register-window kernels: several row strips per column, ragged right / bottom edges,
+    per-CTA merged partial sums (C = 64) and per-strip ones (C = 66, 256)."""
+    from dat_segmentation_b200.dwconv import dwconv_cl
+    torch.manual_seed(C + H)
+    torch.backends.cudnn.allow_tf32 = False
+    B, k = 3, 3
+    dtype = torch.float32 if dt == "fp32" else torch.bfloat16
+    x = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2).to(dtype)
+    w = (torch.randn(C, 1, k, k, device="cuda") / k).requires_grad_(True)
+    b = torch.randn(C, device="cuda").requires_grad_(True)
+    dy = torch.randn(B, C, H, W, device="cuda").to(dtype)
+    xa = x.clone().requires_grad_(True)
+    ya = dwconv_cl(xa, w, b, mode, dtype)
+    ya.backward(dy)
+    got = (ya.detach(), xa.grad.clone(), w.grad.clone(), b.grad.clone())
+    w.grad = b.grad = None
+    xb = x.float().clone().requires_grad_(True)
+    yb = _ref(xb, w, b, mode, k)
+    yb.backward(dy.float())
+    ref = (yb.detach(), xb.grad, w.grad, b.grad)
+    tol = 2e-5 if dt == "fp32" else 1.5e-2
+    errs = {n: _rel(a.float(), r) for n, a, r in zip(("y", "dx", "dw", "db"), got, ref)}
+    print(C, mode, H, W, dt, {n: f"{e:.2e}" for n, e in errs.items()})
+    assert all(e < tol for e in errs.values()), errs
