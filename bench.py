@@ -219,22 +219,29 @@ def main():
     torch.manual_seed(0)
     model = build_dat().to(dev).train()          # drop_path_rate 0.3 as in the shipped config
     params = [p for p in model.parameters() if p.requires_grad]
-    # gradients live in one flat fp32 buffer: zeroed inside the step, all-reduced with ONE NCCL call
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    # N > 1: the step's gradients are packed into one flat fp32 buffer (multi-tensor copy) and
+    # all-reduced with ONE NCCL call.  Autograd assigns fresh gradients every step (no accumulation
+    # pass into pre-zeroed buffers).
+    flat, views = None, []
+    if world > 1:
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        off = 0
+        for p in params:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev, generator=gen)   # static step input
     host = torch.randn(PER_GPU_BATCH, 3, IMG, IMG).pin_memory()
 
     def fwd_bwd():
-        flat.zero_()
+        for p in params:
+            p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outs = model(imgs)
         loss = loss_of(outs)
         loss.backward()
+        if world > 1:
+            torch._foreach_copy_(views, [p.grad for p in params])
         return loss
 
     # The whole fwd+bwd is captured once in a CUDA graph (shapes are static) and replayed: the

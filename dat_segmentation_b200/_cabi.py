@@ -95,8 +95,10 @@ def lib():
     L.dat_layernorm_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, f32p, f32p, i64, i32, C.c_float, vp]
     L.dat_layernorm_bwd_workspace_bytes.argtypes = [i64, i32]
     L.dat_layernorm_bwd_workspace_bytes.restype = C.c_size_t
-    L.dat_layernorm_bwd.argtypes = [vp, i32, vp, i32, f32p, f32p, f32p, vp, f32p, f32p, i64, i32, vp,
+    L.dat_layernorm_bwd.argtypes = [vp, i32, vp, i32, f32p, f32p, f32p, vp, vp, f32p, f32p, i64, i32, vp,
                                     C.c_size_t, vp]
+    L.dat_scale_residual.argtypes = [vp, i32, vp, i32, f32p, vp, i32, i64, i64, vp]
+    L.dat_scale_residual.restype = C.c_int
     L.dat_dwconv_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.dat_dwconv_workspace_bytes.restype = C.c_size_t
     L.dat_dwconv_fwd.argtypes = [vp, i32, f32p, f32p, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp,
@@ -136,4 +138,4 @@ def exported_symbols():
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
             "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd",
             "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad",
-            "dat_dwconv_bwd"]
+            "dat_dwconv_bwd", "dat_scale_residual"]

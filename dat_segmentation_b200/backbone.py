@@ -17,6 +17,7 @@ from .dattention import DAttentionBaseline, _pair
 from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
 from .pointwise import PointwiseConvCL
+from .residual import drop_path_scale, scale_residual
 
 __all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
 
@@ -105,6 +106,7 @@ class TransformerStage(nn.Module):
                  norm_cls: Callable = LayerNormProxy, b200_ops: bool = False):
         super().__init__()
         self.b200_ops = b200_ops
+        self.fused_residual = b200_ops and hasattr(norm_cls, "forward_fork")
         fmap_size = _pair(fmap_size)
         self.depths, self.stage_spec = depths, list(stage_spec)
         self.use_lpu, self.use_checkpoint = use_lpu, use_checkpoint
@@ -141,7 +143,33 @@ class TransformerStage(nn.Module):
                 raise NotImplementedError(f"Spec: {stage_spec[d]} is not supported.")
             self.drop_path.append(DropPath(drop_path_rate[d]) if drop_path_rate[d] > 0.0 else nn.Identity())
 
+    def _inner_forward_b200(self, x):
+        """Same dataflow as `_inner_forward` with the dat_b200 fusions: LayerNorm + residual fork in
+        one autograd node, `drop_path(branch) + x` in one kernel.  (layer_scale > 0 is applied by
+        the library multiply before the fused add.)"""
+        x = self.proj(x)
+        for d in range(self.depths):
+            p = getattr(self.drop_path[d], "p", 0.0)
+            if self.use_lpu:
+                x = self.local_perception_units[d](x)
+            if self.stage_spec[d] == "X":   # note: no residual around mixer+MLP (dat.py:140-144)
+                x = self.attns[d](self.layer_norms[2 * d](x))
+                m = self.mlps[d](self.ln_cnvnxt[str(d)](x))
+                x = scale_residual(m, None, drop_path_scale(m.shape[0], p, self.training, m.device)) if p > 0.0 and self.training else m
+            else:
+                x, ln = self.layer_norms[2 * d].forward_fork(x)
+                a, _, _ = self.attns[d](ln)
+                x = scale_residual(self.layer_scales[2 * d](a), x,
+                                   drop_path_scale(a.shape[0], p, self.training, a.device))
+                x, ln = self.layer_norms[2 * d + 1].forward_fork(x)
+                m = self.mlps[d](ln)
+                x = scale_residual(self.layer_scales[2 * d + 1](m), x,
+                                   drop_path_scale(m.shape[0], p, self.training, m.device))
+        return x
+
     def _inner_forward(self, x):
+        if self.fused_residual and x.is_cuda:
+            return self._inner_forward_b200(x)
         x = self.proj(x)
         for d in range(self.depths):
             if self.use_lpu:   # b200: conv + bias + residual in one channel-last kernel

@@ -256,11 +256,17 @@ size_t dat_layernorm_bwd_workspace_bytes(int64_t rows, int32_t C) { return layer
 
 int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype,
                       const float* gamma, const float* mean, const float* rstd, void* dx,
-                      float* dgamma, float* dbeta, int64_t rows, int32_t C, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      const void* dres, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   DAT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "layernorm_bwd: NULL pointer");
-  return layernorm_bwd(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dx, dgamma, dbeta, rows, C, workspace,
+  return layernorm_bwd(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dx, dres, dgamma, dbeta, rows, C, workspace,
                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int dat_scale_residual(const void* a, int32_t a_dtype, const void* x, int32_t x_dtype, const float* scale,
+                       void* y, int32_t y_dtype, int64_t B, int64_t per_sample, void* stream) {
+  DAT_REQUIRE(a && scale && y && B >= 0 && per_sample >= 0, "scale_residual: NULL pointer / bad size");
+  return scale_residual(a, a_dtype, x, x_dtype, scale, y, y_dtype, B, per_sample, (cudaStream_t)stream);
 }
 
 size_t dat_dwconv_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t C, int32_t k) {

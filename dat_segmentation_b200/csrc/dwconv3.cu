@@ -19,7 +19,9 @@
 //             gelu_bwd + data gradient + weight gradient).  Per-strip partial dw/db are reduced in
 //             a fixed order by dwconv_wgrad_reduce_kernel (deterministic, no atomics).
 // GELU and its derivative use erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), which shares
-// exp(-z^2/2) between the cdf and the pdf: the kernels stay HBM-bound.
+// exp(-z^2/2) between the cdf and the pdf (13-14 instructions per element).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,27 +52,30 @@ template <> struct Raw2<bf16> {
   }
 };
 
-// erf(|z| / sqrt 2) pieces (Abramowitz-Stegun 7.1.26): returns q = poly(t) * exp(-z^2 / 2), so that
-// Phi(z) = z >= 0 ? 1 - q / 2 : q / 2, and e = exp(-z^2 / 2).
-__device__ __forceinline__ float as_q(float z, float& e) {
-  const float a = fabsf(z) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
-  e = __expf(-a * a);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return p * t * e;
+// GELU pieces from erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7):
+//   r(z) = 1/2 - Phi(-|z|) = 1/2 - (1/2) poly(t) exp(-z^2/2),  t = 1 / (1 + p |z| / sqrt 2)
+//   Phi(z) = 1/2 + sgn(z) r,   gelu(z) = z / 2 + |z| r,   gelu'(z) = Phi(z) + z exp(-z^2/2) / sqrt(2 pi)
+// MUFU.RCP / MUFU.EX2 in their flush-to-zero forms (no denormal fix-up code around them).
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gelu_r(float z, float& e) {
+  const float t = rcp_ftz(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(z), 1.0f));
+  e = ex2_ftz(z * z * -0.72134752044448170368f);          // exp(-z^2 / 2)
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return fmaf(-(p * t), e, 0.5f);
 }
 __device__ __forceinline__ float gelu_fast(float z) {
   float e;
-  const float q = 0.5f * as_q(z, e);
-  return z * (z >= 0.f ? 1.0f - q : q);
+  const float r = gelu_r(z, e);
+  return fmaf(fabsf(z), r, 0.5f * z);
 }
 __device__ __forceinline__ float gelu_grad_fast(float z) {
   float e;
-  const float q = 0.5f * as_q(z, e);
-  return (z >= 0.f ? 1.0f - q : q) + z * e * 0.39894228040143267794f;
+  const float r = gelu_r(z, e);
+  return fmaf(z * 0.39894228040143267794f, e, copysignf(r, z)) + 0.5f;
 }
 
 struct Strip {
@@ -92,20 +97,27 @@ __device__ __forceinline__ Strip strip_of(int B, int C, int th, int strips_x, in
   return s;
 }
 
-// raw loads of window row yy (columns x0-1 .. x0+TW), zeros outside the image
-template <typename T>
-__device__ __forceinline__ void load_row(const T* __restrict__ img, int yy, int x0, int H, int W, int C,
-                                         typename Raw2<T>::type (&raw)[TW + 2]) {
-  const bool row_ok = yy >= 0 && yy < H;
-  const T* rowp = img + ((long long)yy * W + (x0 - 1)) * C;
+// raw loads of one window row (columns x0-1 .. x0+TW); rp points at column x0 of that row, zeros
+// outside the image.  ALIGNED (W % TW == 0): only the two halo columns need a column predicate,
+// and those predicates (lval / rval) are per-thread constants.
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void load_row(const T* __restrict__ rp, bool row_ok, bool lval, bool rval, int C,
+                                         int x0, int W, typename Raw2<T>::type (&raw)[TW + 2]) {
+  if (ALIGNED) {
+    raw[0] = (row_ok && lval) ? Raw2<T>::load(rp - C) : Raw2<T>::zero();
 #pragma unroll
-  for (int j = 0; j < TW + 2; ++j) {
-    const int xx = x0 - 1 + j;
-    raw[j] = (row_ok && xx >= 0 && xx < W) ? Raw2<T>::load(rowp + (long long)j * C) : Raw2<T>::zero();
+    for (int j = 1; j <= TW; ++j) raw[j] = row_ok ? Raw2<T>::load(rp + (j - 1) * C) : Raw2<T>::zero();
+    raw[TW + 1] = (row_ok && rval) ? Raw2<T>::load(rp + TW * C) : Raw2<T>::zero();
+  } else {
+#pragma unroll
+    for (int j = 0; j < TW + 2; ++j) {
+      const int xx = x0 - 1 + j;
+      raw[j] = (row_ok && xx >= 0 && xx < W) ? Raw2<T>::load(rp + (j - 1) * C) : Raw2<T>::zero();
+    }
   }
 }
 
-template <typename TI, typename TO, int MODE>
+template <typename TI, typename TO, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(D3_THREADS, 5)
 dwconv3_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int th,
@@ -120,17 +132,23 @@ dwconv3_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
     wr[uv][1] = w[(s.c + 1) * 9 + (flip ? 8 - uv : uv)];
   }
   const float b0 = bias != nullptr ? bias[s.c] : 0.f, b1 = bias != nullptr ? bias[s.c + 1] : 0.f;
-  const long long img_off = (long long)s.b * H * W * C + s.c;
-  const TI* img = x + img_off;
+  const bool lval = s.x0 > 0, rval = s.x0 + TW < W;
+  const int rstride = W * C;                               // < 2^31 elements per image
+  const long long pix0 = (long long)s.b * H * rstride + (long long)s.y0 * rstride + s.x0 * C + s.c;
+  const TI* rp = x + pix0 - rstride;                       // row being loaded: starts at y0 - 1
+  TO* yp = y + pix0;
+  TO* zp = MODE == 2 ? z_out + pix0 : nullptr;
   float win[3][TW + 2][2];
   typename RI::type raw[TW + 2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {            // rows y0-1, y0 -> slots 0, 1
-    load_row<TI>(img, s.y0 - 1 + r, s.x0, H, W, C, raw);
+    load_row<TI, ALIGNED>(rp, s.y0 - 1 + r >= 0, lval, rval, C, s.x0, W, raw);
+    rp += rstride;
 #pragma unroll
     for (int j = 0; j < TW + 2; ++j) { const float2 f = RI::cvt(raw[j]); win[r][j][0] = f.x; win[r][j][1] = f.y; }
   }
-  load_row<TI>(img, s.y0 + 1, s.x0, H, W, C, raw);      // row y0+1, converted inside the loop
+  load_row<TI, ALIGNED>(rp, s.y0 + 1 < H, lval, rval, C, s.x0, W, raw);      // row y0+1, converted in the loop
+  rp += rstride;
   const int y_end = min(s.y0 + th, H);
   for (int yb = s.y0; yb < y_end; yb += 3) {
 #pragma unroll
@@ -142,12 +160,11 @@ dwconv3_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
         float (&next)[TW + 2][2] = win[(k + 2) % 3];
 #pragma unroll
         for (int j = 0; j < TW + 2; ++j) { const float2 f = RI::cvt(raw[j]); next[j][0] = f.x; next[j][1] = f.y; }
-        load_row<TI>(img, yy + 2, s.x0, H, W, C, raw);   // prefetch: consumed by the next iteration
-        TO* yrow = y + img_off + ((long long)yy * W + s.x0) * C;
-        TO* zrow = MODE == 2 ? z_out + img_off + ((long long)yy * W + s.x0) * C : nullptr;
+        load_row<TI, ALIGNED>(rp, yy + 2 < H, lval, rval, C, s.x0, W, raw);   // prefetch for the next iteration
+        rp += rstride;
 #pragma unroll
         for (int i = 0; i < TW; ++i) {
-          if (s.x0 + i < W) {
+          if (ALIGNED || s.x0 + i < W) {
             float a0 = b0, a1 = b1;
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
@@ -157,20 +174,22 @@ dwconv3_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
             }
             if (MODE >= 1) { a0 += cur[i + 1][0]; a1 += cur[i + 1][1]; }
             if (MODE == 2) {
-              Raw2<TO>::store(zrow + (long long)i * C, a0, a1);
+              Raw2<TO>::store(zp + i * C, a0, a1);
               a0 = gelu_fast(a0);
               a1 = gelu_fast(a1);
             }
-            Raw2<TO>::store(yrow + (long long)i * C, a0, a1);
+            Raw2<TO>::store(yp + i * C, a0, a1);
           }
         }
+        yp += rstride;
+        if (MODE == 2) zp += rstride;
       }
     }
   }
 }
 
-// fused backward; partial[strip][10][C] (rows 0-8 = dw taps, row 9 = db)
-template <typename TX, typename TD, int MODE>
+// fused backward; partial[strip or CTA][10][C] (rows 0-8 = dw taps, row 9 = db)
+template <typename TX, typename TD, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(D3_THREADS, 4)
 dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD* __restrict__ z,
                    const float* __restrict__ w, TX* __restrict__ dx, float* __restrict__ partial, int B,
@@ -186,9 +205,14 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
   }
 #pragma unroll
   for (int uv = 0; uv < 10; ++uv) dwa[uv][0] = dwa[uv][1] = 0.f;
-  const long long img_off = (long long)s.b * H * W * C + s.c;
-  const TD* dimg = dy + img_off;
-  const TD* zimg = MODE == 2 ? z + img_off : nullptr;
+  if (!s.ok) H = 0;                       // every load of an idle thread is masked off
+  const bool lval = s.x0 > 0, rval = s.x0 + TW < W;
+  const int rstride = W * C;
+  const long long pix0 = s.ok ? (long long)s.b * H * rstride + (long long)s.y0 * rstride + s.x0 * C + s.c : 0;
+  const TD* dp = dy + pix0 - rstride;     // window row being loaded: starts at y0 - 1
+  const TD* zp = MODE == 2 ? z + pix0 - rstride : nullptr;
+  const TX* xp = x + pix0;                // centre row being loaded: starts at y0
+  TX* dxp = dx + pix0;
   float win[3][TW + 2][2];
   typename RD::type rawd[TW + 2], rawz[TW + 2];
   typename RX::type rawx[TW];
@@ -205,23 +229,29 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
       row[j][1] = d.y;
     }
   };
-  if (!s.ok) H = 0;                       // every load of an idle thread is masked off
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    load_row<TD>(dimg, s.y0 - 1 + r, s.x0, H, W, C, rawd);
-    if (MODE == 2) load_row<TD>(zimg, s.y0 - 1 + r, s.x0, H, W, C, rawz);
-    fill(win[r]);
-  }
-  load_row<TD>(dimg, s.y0 + 1, s.x0, H, W, C, rawd);
-  if (MODE == 2) load_row<TD>(zimg, s.y0 + 1, s.x0, H, W, C, rawz);
-  const int y_end = s.ok ? min(s.y0 + th, H) : s.y0;     // threads past the last strip do no rows
+  auto load_win = [&](int yy) {
+    const bool ok = yy >= 0 && yy < H;
+    load_row<TD, ALIGNED>(dp, ok, lval, rval, C, s.x0, W, rawd);
+    dp += rstride;
+    if (MODE == 2) {
+      load_row<TD, ALIGNED>(zp, ok, lval, rval, C, s.x0, W, rawz);
+      zp += rstride;
+    }
+  };
   auto load_x = [&](int yy) {
-    const TX* xrow = x + img_off + ((long long)yy * W + s.x0) * C;
 #pragma unroll
     for (int i = 0; i < TW; ++i)
-      rawx[i] = (yy < H && s.x0 + i < W) ? RX::load(xrow + (long long)i * C) : RX::zero();
+      rawx[i] = (yy < H && (ALIGNED || s.x0 + i < W)) ? RX::load(xp + i * C) : RX::zero();
+    xp += rstride;
   };
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    load_win(s.y0 - 1 + r);
+    fill(win[r]);
+  }
+  load_win(s.y0 + 1);
   load_x(s.y0);
+  const int y_end = s.ok ? min(s.y0 + th, H) : s.y0;     // threads past the last strip do no rows
   for (int yb = s.y0; yb < y_end; yb += 3) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -234,13 +264,11 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
         float xq[TW][2];
 #pragma unroll
         for (int i = 0; i < TW; ++i) { const float2 f = RX::cvt(rawx[i]); xq[i][0] = f.x; xq[i][1] = f.y; }
-        load_row<TD>(dimg, yy + 2, s.x0, H, W, C, rawd);   // prefetch for the next iteration
-        if (MODE == 2) load_row<TD>(zimg, yy + 2, s.x0, H, W, C, rawz);
+        load_win(yy + 2);                                  // prefetch for the next iteration
         load_x(yy + 1);
-        TX* dxrow = dx + img_off + ((long long)yy * W + s.x0) * C;
 #pragma unroll
         for (int i = 0; i < TW; ++i) {
-          if (s.x0 + i < W) {
+          if (ALIGNED || s.x0 + i < W) {
             float a0 = MODE >= 1 ? cur[i + 1][0] : 0.f, a1 = MODE >= 1 ? cur[i + 1][1] : 0.f;
             dwa[9][0] += cur[i + 1][0];
             dwa[9][1] += cur[i + 1][1];
@@ -255,9 +283,10 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
               dwa[3 + v][0] = fmaf(xq[i][0], cur[col][0], dwa[3 + v][0]);  dwa[3 + v][1] = fmaf(xq[i][1], cur[col][1], dwa[3 + v][1]);
               dwa[6 + v][0] = fmaf(xq[i][0], prev[col][0], dwa[6 + v][0]); dwa[6 + v][1] = fmaf(xq[i][1], prev[col][1], dwa[6 + v][1]);
             }
-            RX::store(dxrow + (long long)i * C, a0, a1);
+            RX::store(dxp + i * C, a0, a1);
           }
         }
+        dxp += rstride;
       }
     }
   }
@@ -288,12 +317,14 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
 
 }  // namespace
 
-// rows per strip: whole columns when that already fills the GPU, else halved until ~1300
-// threads per SM are in flight (never below 8 rows: the 2-row halo is re-read per strip)
+// rows per strip: whole columns when that already fills the GPU, else halved until ~1.5 waves
+// of threads exist (measured optimum; never below 8 rows: the 2-row halo is re-read and, in the
+// backward, its gelu' recomputed per strip)
 int dwconv3_rows_per_strip(int B, int H, int W, int C) {
   const long long per_row_block = (long long)B * ceil_div(W, TW) * (C / 2);
+  if (const char* e = std::getenv("DAT_B200_DW3_TH")) { const int v = std::atoi(e); if (v > 0) return v < H ? v : H; }
   int th = H;
-  while (th > 8 && per_row_block * ceil_div(H, th) < 148ll * 1300) th = (th + 1) / 2;
+  while (th > 8 && per_row_block * ceil_div(H, th) < 148ll * 700) th = (th + 1) / 2;
   return th;
 }
 
@@ -322,9 +353,13 @@ int dwconv3_fwd(const void* x, int x_dt, const float* w, const float* bias, void
   const int sx = ceil_div(W, TW), sy = ceil_div(H, th);
   const long long threads = (long long)B * sx * sy * (C / 2);
   const unsigned grid = (unsigned)ceil_div(threads, (long long)D3_THREADS);
-#define LAUNCH(TI, TO, MD)                                                                              \
-  dwconv3_fwd_kernel<TI, TO, MD><<<grid, D3_THREADS, 0, st>>>((const TI*)x, w, bias, (TO*)y, (TO*)z_out, B, H, \
-                                                               W, C, th, sx, sy, flip)
+#define LAUNCH_A(TI, TO, MD, AL)                                                                        \
+  dwconv3_fwd_kernel<TI, TO, MD, AL><<<grid, D3_THREADS, 0, st>>>((const TI*)x, w, bias, (TO*)y, (TO*)z_out, B, \
+                                                                   H, W, C, th, sx, sy, flip)
+#define LAUNCH(TI, TO, MD)                                                    \
+  do {                                                                        \
+    if (W % TW == 0) LAUNCH_A(TI, TO, MD, true); else LAUNCH_A(TI, TO, MD, false); \
+  } while (0)
 #define LAUNCH_M(TI, TO)                                                                  \
   do {                                                                                    \
     if (mode == 0) LAUNCH(TI, TO, 0); else if (mode == 1) LAUNCH(TI, TO, 1); else LAUNCH(TI, TO, 2); \
@@ -335,6 +370,7 @@ int dwconv3_fwd(const void* x, int x_dt, const float* w, const float* bias, void
   else LAUNCH_M(bf16, bf16);
 #undef LAUNCH_M
 #undef LAUNCH
+#undef LAUNCH_A
   DAT_LAUNCH_OK("dwconv3_fwd_kernel");
   return DAT_OK;
 }
@@ -353,9 +389,13 @@ int dwconv3_bwd(const void* x, int x_dt, const void* dy, const void* z, int d_dt
   const unsigned grid = (unsigned)ceil_div(nstrips * (C / 2), (long long)D3_THREADS);
   float* part = (float*)ws;
   const int spc = strips_per_cta(C);
-#define LAUNCH(TX, TD, MD)                                                                                \
-  dwconv3_bwd_kernel<TX, TD, MD><<<grid, D3_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (const TD*)z, w, \
-                                                               (TX*)dx, part, B, H, W, C, th, sx, sy, spc)
+#define LAUNCH_A(TX, TD, MD, AL)                                                                              \
+  dwconv3_bwd_kernel<TX, TD, MD, AL><<<grid, D3_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (const TD*)z, w, \
+                                                                   (TX*)dx, part, B, H, W, C, th, sx, sy, spc)
+#define LAUNCH(TX, TD, MD)                                                    \
+  do {                                                                        \
+    if (W % TW == 0) LAUNCH_A(TX, TD, MD, true); else LAUNCH_A(TX, TD, MD, false); \
+  } while (0)
 #define LAUNCH_M(TX, TD)                                                                  \
   do {                                                                                    \
     if (mode == 0) LAUNCH(TX, TD, 0); else if (mode == 1) LAUNCH(TX, TD, 1); else LAUNCH(TX, TD, 2); \
@@ -366,6 +406,7 @@ int dwconv3_bwd(const void* x, int x_dt, const void* dy, const void* z, int d_dt
   else LAUNCH_M(bf16, bf16);
 #undef LAUNCH_M
 #undef LAUNCH
+#undef LAUNCH_A
   DAT_LAUNCH_OK("dwconv3_bwd_kernel");
   return dwconv_wgrad_reduce(part, (int)n_partials(B, H, W, C), 9, C, dw, db, st);
 }

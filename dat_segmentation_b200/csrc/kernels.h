@@ -123,8 +123,8 @@ size_t layernorm_bwd_workspace(long long rows, int C);
 int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st);
 int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
-                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                  long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+                  const float* mean, const float* rstd, void* dx, const void* dres, float* dgamma,
+                  float* dbeta, long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace dat
 
 namespace dat {
@@ -152,4 +152,10 @@ int dwconv3_bwd(const void* x, int x_dt, const void* dy, const void* z, int d_dt
                 float* dw, float* db, int B, int H, int W, int C, int mode, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 int dwconv_wgrad_reduce(const float* partial, int nsplit, int kk, int C, float* dw, float* db, cudaStream_t st);
+}  // namespace dat
+
+namespace dat {
+// residual.cu - y = x + a * s[b] (residual + stochastic depth), also the branch gradient
+int scale_residual(const void* a, int a_dt, const void* x, int x_dt, const float* s, void* y, int y_dt,
+                   long long B, long long per_sample, cudaStream_t st);
 }  // namespace dat

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, TI* __restrict__ dx,
-                     float* __restrict__ partial, long long rows, int C) {
+                     const TI* __restrict__ dres, float* __restrict__ partial, long long rows, int C) {
   extern __shared__ float red[];     // [LN_WARPS][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2 gg[NV], gb[NV], gam[NV];
@@ -114,11 +114,15 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
     m1 = warp_sum(m1) * inv_c;
     m2 = warp_sum(m2) * inv_c;
     TI* dxr = dx + row * C;
+    const TI* rr = dres != nullptr ? dres + row * C : nullptr;   // gradient of the residual path through x
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 2;
-      if (c < C)
-        st2(dxr + c, make_float2(rstd * (dg[i].x - m1 - xh[i].x * m2), rstd * (dg[i].y - m1 - xh[i].y * m2)));
+      if (c < C) {
+        float2 o = make_float2(rstd * (dg[i].x - m1 - xh[i].x * m2), rstd * (dg[i].y - m1 - xh[i].y * m2));
+        if (rr != nullptr) { const float2 r = ld2(rr + c); o.x += r.x; o.y += r.y; }
+        st2(dxr + c, o);
+      }
     }
   }
   float* mine = red + (size_t)warp * 2 * C;
@@ -193,8 +197,8 @@ int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta
 }
 
 int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
-                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                  long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  const float* mean, const float* rstd, void* dx, const void* dres, float* dgamma,
+                  float* dbeta, long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
   DAT_REQUIRE(ws_bytes >= layernorm_bwd_workspace(rows, C), "layernorm_bwd: workspace too small");
   const int nblk = ln_bwd_blocks(rows), nv = nv_of(C);
@@ -206,7 +210,7 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
     if (smem > 48 * 1024)                                                                         \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<nblk, LN_WARPS * 32, smem, st>>>((const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
-                                            part, rows, C);                                       \
+                                            (const TI*)dres, part, rows, C);                                    \
   } while (0)
 #define LAUNCH_NV(TI, TD)                                                      \
   do {                                                                         \

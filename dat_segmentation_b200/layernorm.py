@@ -20,7 +20,7 @@ _CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.data_ptr() if t is not None else 0)
 
 
 class _LayerNormFn(torch.autograd.Function):
@@ -46,7 +46,7 @@ class _LayerNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         lib = _cabi.lib()
         x_l, w32, mean, rstd = ctx.saved_tensors
         Cc = x_l.shape[-1]
@@ -55,6 +55,8 @@ class _LayerNormFn(torch.autograd.Function):
         if dy.dtype not in _CODE:
             dy = dy.float()
         dy = dy.contiguous()
+        if dres is not None:      # gradient of the residual path around the norm: added in the same pass
+            dres = dres.to(x_l.dtype).contiguous()
         with torch.cuda.device(dev):
             dx = torch.empty_like(x_l)
             dg = torch.empty(Cc, device=dev, dtype=torch.float32)
@@ -63,10 +65,27 @@ class _LayerNormFn(torch.autograd.Function):
             ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _cabi.check(lib.dat_layernorm_bwd(_ptr(dy), _CODE[dy.dtype], _ptr(x_l), _CODE[x_l.dtype],
-                                              _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dg),
-                                              _ptr(db), rows, Cc, _ptr(ws), nbytes, st),
+                                              _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dres),
+                                              _ptr(dg), _ptr(db), rows, Cc, _ptr(ws), nbytes, st),
                         "dat_layernorm_bwd")
         return dx, dg.to(ctx.param_dtype), db.to(ctx.param_dtype), None, None
+
+
+class _LayerNormForkFn(torch.autograd.Function):
+    """x_l -> (x_l, LayerNorm(x_l)): the residual stream and the normed branch input leave one node,
+    so the backward adds the residual-path gradient inside the LayerNorm kernel instead of autograd
+    running a separate accumulation pass over the stream (dat.py:147-156)."""
+
+    @staticmethod
+    def forward(ctx, x_l, weight, bias, eps, out_dtype):
+        y = _LayerNormFn.forward(ctx, x_l, weight, bias, eps, out_dtype)
+        return x_l, y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        if dy is None:
+            return dres, None, None, None, None
+        return _LayerNormFn.backward(ctx, dy, dres)
 
 
 class LayerNormProxy(nn.Module):
@@ -76,7 +95,7 @@ class LayerNormProxy(nn.Module):
         super().__init__()
         self.norm = nn.LayerNorm(dim)
 
-    def forward(self, x):
+    def _prep(self, x):
         if not x.is_cuda:
             raise RuntimeError("LayerNormProxy (dat_b200) runs on CUDA only; use TorchLayerNormProxy on CPU")
         if x.dtype not in _CODE:
@@ -85,8 +104,18 @@ class LayerNormProxy(nn.Module):
         x_l = x.permute(0, 2, 3, 1)
         if not x_l.is_contiguous():
             x_l = x_l.contiguous()
+        return x_l, out_dtype
+
+    def forward(self, x):
+        x_l, out_dtype = self._prep(x)
         y_l = _LayerNormFn.apply(x_l, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
         return y_l.permute(0, 3, 1, 2)
+
+    def forward_fork(self, x):
+        """(x, LayerNorm(x)) for `branch(LN(x)) + x` call sites: use the returned x for the residual."""
+        x_l, out_dtype = self._prep(x)
+        x_p, y_l = _LayerNormForkFn.apply(x_l, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
+        return x_p.permute(0, 3, 1, 2), y_l.permute(0, 3, 1, 2)
 
 
 class TorchLayerNormProxy(nn.Module):
@@ -98,3 +127,6 @@ class TorchLayerNormProxy(nn.Module):
 
     def forward(self, x):
         return self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+    def forward_fork(self, x):
+        return x, self.forward(x)

@@ -185,11 +185,21 @@ int dat_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const 
                       void* y, int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t C,
                       float eps, void* stream);
 size_t dat_layernorm_bwd_workspace_bytes(int64_t rows, int32_t C);
-/* dx has x's dtype; dgamma / dbeta (C) fp32 are overwritten (deterministic reduction). */
+/* dx has x's dtype; dgamma / dbeta (C) fp32 are overwritten (deterministic reduction).
+ * dres (may be NULL; x's dtype, (rows, C)): the gradient that reaches x through the residual path
+ * around the norm (dat.py:147-156) - it is added into dx in the same pass. */
 int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype,
                       const float* gamma, const float* mean, const float* rstd, void* dx,
-                      float* dgamma, float* dbeta, int64_t rows, int32_t C, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      const void* dres, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Residual add with stochastic depth (dat.py:147-156, `x = drop_path(branch) + x`):
+ * y[b, :] = x[b, :] + a[b, :] * scale[b]; x may be NULL ('X' blocks, dat.py:140-144).  a, x, y are
+ * dense tensors of one layout whose outermost dimension is the sample (per_sample elements each,
+ * a multiple of 4); scale is a device array of B floats (mask / keep_prob).  The branch gradient is
+ * the same call: da = dy * scale[b] (a = dy, x = NULL). */
+int dat_scale_residual(const void* a, int32_t a_dtype, const void* x, int32_t x_dtype, const float* scale,
+                       void* y, int32_t y_dtype, int64_t B, int64_t per_sample, void* stream);
 
 /* ---- "next" rows: channel-last depthwise convolutions ---------- */
 
