@@ -260,7 +260,8 @@ int wgrad_splits(long long npix) {
 size_t dwconv_workspace(int B, int H, int W, int C, int k) {
   const size_t wt = align_up((size_t)k * k * C * 4, 256);
   const size_t part = align_up((size_t)wgrad_splits((long long)B * H * W) * (k * k + 1) * C * 4, 256);
-  const size_t fused = dwconv3_supported(C, k) ? dwconv3_partial_bytes(B, H, W, C) : 0;
+  size_t fused = dwconv3_supported(C, k) ? dwconv3_partial_bytes(B, H, W, C) : 0;
+  if (dwconv7_supported(C, k)) fused = dwconv7_partial_bytes(B, H, W, C);
   return wt + part > fused ? wt + part : fused;
 }
 
@@ -276,6 +277,8 @@ int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void*
                cudaStream_t st) {
   if (dwconv3_supported(C, k) && std::getenv("DAT_B200_DWCONV_GENERIC") == nullptr)
     return dwconv3_fwd(x, x_dt, w, bias, y, z_out, y_dt, B, H, W, C, mode, flip, st);
+  if (dwconv7_supported(C, k) && mode == 0 && std::getenv("DAT_B200_DWCONV_GENERIC") == nullptr)
+    return dwconv7_fwd(x, x_dt, w, bias, y, y_dt, B, H, W, C, flip, st);
   DAT_REQUIRE(C % 4 == 0 && (k & 1) == 1 && k >= 1 && k <= 15, "dwconv: C %% 4 == 0 and odd k <= 15 required");
   DAT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "dwconv: 16-byte aligned tensors required");
   DAT_REQUIRE(ws_bytes >= (size_t)k * k * C * 4, "dwconv: workspace too small");
@@ -325,6 +328,8 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
                  int W, int C, int k, void* ws, size_t ws_bytes, cudaStream_t st) {
   DAT_REQUIRE(k == 3 || k == 5 || k == 7, "dwconv_wgrad: k must be 3, 5 or 7");
   DAT_REQUIRE(ws_bytes >= dwconv_workspace(B, H, W, C, k), "dwconv_wgrad: workspace too small");
+  if (dwconv7_supported(C, k) && std::getenv("DAT_B200_DWCONV_GENERIC") == nullptr)
+    return dwconv7_wgrad(x, x_dt, dz, dz_dt, dw, db, B, H, W, C, ws, ws_bytes, st);
   const long long npix = (long long)B * H * W;
   const int nsplit = wgrad_splits(npix);
   const long long pps = (npix + nsplit - 1) / nsplit;

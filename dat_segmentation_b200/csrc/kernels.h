@@ -159,3 +159,13 @@ namespace dat {
 int scale_residual(const void* a, int a_dt, const void* x, int x_dt, const float* s, void* y, int y_dt,
                    long long B, long long per_sample, cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// dwconv7.cu - input-row-stationary depthwise 7x7 (forward / data gradient, weight gradient)
+bool dwconv7_supported(int C, int k);
+size_t dwconv7_partial_bytes(int B, int H, int W, int C);
+int dwconv7_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, int y_dt, int B, int H,
+                int W, int C, int flip, cudaStream_t st);
+int dwconv7_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, float* db, int B, int H,
+                  int W, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace dat

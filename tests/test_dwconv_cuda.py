@@ -75,3 +75,34 @@ def test_dwconv3_strips_and_fused_backward(C, mode, H, W, dt):
     errs = {n: _rel(a.float(), r) for n, a, r in zip(("y", "dx", "dw", "db"), got, ref)}
     print(C, mode, H, W, dt, {n: f"{e:.2e}" for n, e in errs.items()})
     assert all(e < tol for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 40, 36), (256, 19, 48), (66, 9, 8), (128, 33, 18)])
+@pytest.mark.parametrize("dt", ["fp32", "bf16", "fp32_bf16"])
+def test_dwconv7_row_stationary_kernels(C, H, W, dt):
+    """7x7 'X' mixer kernels: several row strips, aligned (W % 4 == 0) and ragged widths, merged /
+    per-strip partial sums, the fp32-in / bf16-out combination of the autocast backbone."""
+    from dat_segmentation_b200.dwconv import dwconv_cl
+    torch.manual_seed(C + H)
+    torch.backends.cudnn.allow_tf32 = False
+    B, k, mode = 3, 7, 0
+    xdt = torch.bfloat16 if dt == "bf16" else torch.float32
+    ydt = torch.float32 if dt == "fp32" else torch.bfloat16
+    x = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2).to(xdt)
+    w = (torch.randn(C, 1, k, k, device="cuda") / k).requires_grad_(True)
+    b = torch.randn(C, device="cuda").requires_grad_(True)
+    dy = torch.randn(B, C, H, W, device="cuda").to(ydt)
+    xa = x.clone().requires_grad_(True)
+    ya = dwconv_cl(xa, w, b, mode, ydt)
+    ya.backward(dy)
+    got = (ya.detach(), xa.grad.clone(), w.grad.clone(), b.grad.clone())
+    assert got[1].dtype == xdt
+    w.grad = b.grad = None
+    xb = x.float().clone().requires_grad_(True)
+    yb = _ref(xb, w, b, mode, k)
+    yb.backward(dy.float())
+    ref = (yb.detach(), xb.grad, w.grad, b.grad)
+    tol = 2e-5 if dt == "fp32" else 1.5e-2
+    errs = {n: _rel(a.float(), r) for n, a, r in zip(("y", "dx", "dw", "db"), got, ref)}
+    print(C, H, W, dt, {n: f"{e:.2e}" for n, e in errs.items()})
+    assert all(e < tol for e in errs.values()), errs
