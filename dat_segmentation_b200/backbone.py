@@ -148,20 +148,22 @@ class TransformerStage(nn.Module):
         one autograd node, `drop_path(branch) + x` in one kernel.  (layer_scale > 0 is applied by
         the library multiply before the fused add.)"""
         x = self.proj(x)
+        # the MLP's first 1x1 conv casts its input to the autocast dtype: let the LayerNorm write it
+        mlp_in = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
         for d in range(self.depths):
             p = getattr(self.drop_path[d], "p", 0.0)
             if self.use_lpu:
                 x = self.local_perception_units[d](x)
             if self.stage_spec[d] == "X":   # note: no residual around mixer+MLP (dat.py:140-144)
                 x = self.attns[d](self.layer_norms[2 * d](x))
-                m = self.mlps[d](self.ln_cnvnxt[str(d)](x))
+                m = self.mlps[d](self.ln_cnvnxt[str(d)](x, out_dtype=mlp_in))
                 x = scale_residual(m, None, drop_path_scale(m.shape[0], p, self.training, m.device)) if p > 0.0 and self.training else m
             else:
                 x, ln = self.layer_norms[2 * d].forward_fork(x)
                 a, _, _ = self.attns[d](ln)
                 x = scale_residual(self.layer_scales[2 * d](a), x,
                                    drop_path_scale(a.shape[0], p, self.training, a.device))
-                x, ln = self.layer_norms[2 * d + 1].forward_fork(x)
+                x, ln = self.layer_norms[2 * d + 1].forward_fork(x, out_dtype=mlp_in)
                 m = self.mlps[d](ln)
                 x = scale_residual(self.layer_scales[2 * d + 1](m), x,
                                    drop_path_scale(m.shape[0], p, self.training, m.device))

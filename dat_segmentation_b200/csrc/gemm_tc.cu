@@ -89,9 +89,11 @@ constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;
 constexpr int CHUNK_BYTES = 128;          // K bytes per pipeline stage row (one swizzle atom)
 constexpr int A_STAGE_BYTES = TC_BM * CHUNK_BYTES;
+constexpr int EPI_COLS = 128;            // epilogue column group (staging area per warp: 32 x 128 outputs)
+constexpr int SMEM_BUDGET = 108 * 1024;   // per CTA: two CTAs share an SM
 
 template <bool TF32, typename TOut>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
@@ -182,36 +184,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full, 0);
     tc_fence_after_sync();
     if (warp == 2 && lane == 0) TSTAMP(4);
-    // TMEM -> registers (+bias, convert) -> this warp's 32 x BN staging tile in shared
-    // memory (row pitch padded by 16 B: conflict-free 16-byte accesses) -> global memory
-    // one whole output row per store instruction (fully coalesced 512 B+ segments; the
-    // per-thread row-strided 8-byte stores this replaces cost 5.5 us per tile).
-    const int row_bytes = BN * (int)sizeof(TOut);
-    const int pitch = row_bytes + 16;
+    // TMEM -> registers (+bias, convert) -> this warp's 32-row staging tile in shared memory (row
+    // pitch padded by 16 B: conflict-free 16-byte accesses) -> global memory one row segment per
+    // store instruction (coalesced 256-512 B runs).  Column groups of EPI_COLS keep the staging
+    // area small enough for two CTAs per SM, whose load / MMA / store phases then overlap.
+    const int gcols = BN < EPI_COLS ? BN : EPI_COLS;
+    const int seg_bytes = gcols * (int)sizeof(TOut);
+    const int pitch = seg_bytes + 16;
     uint8_t* stage = sA + (warp - 2) * 32 * pitch;
     (void)row;
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_wait_ld();
-      const float* bp = sBias + c * 32;
-      TOut* dst = reinterpret_cast<TOut*>(stage + lane * pitch) + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        const float4 bb = *reinterpret_cast<const float4*>(bp + j);
-        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-        store4(dst + j, v);
-      }
-    }
-    __syncwarp();
     const int rows_here = min(32, M - (m0 + quad * 32));
-    for (int rr = 0; rr < rows_here; ++rr) {
-      uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0);
-      const uint8_t* srow = stage + rr * pitch;
-      for (int off = lane * 16; off < row_bytes; off += 512)
-        *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
+    for (int cg = 0; cg < BN; cg += gcols) {
+      for (int c = 0; c < gcols / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg + c * 32), r);
+        tmem_wait_ld();
+        const float* bp = sBias + cg + c * 32;
+        TOut* dst = reinterpret_cast<TOut*>(stage + lane * pitch) + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          const float4 bb = *reinterpret_cast<const float4*>(bp + j);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          store4(dst + j, v);
+        }
+      }
+      __syncwarp();
+      for (int rr = 0; rr < rows_here; ++rr) {
+        uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0 + cg);
+        const uint8_t* srow = stage + rr * pitch;
+        for (int off = lane * 16; off < seg_bytes; off += 512)
+          *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
+      }
+      __syncwarp();
     }
   }
   tc_fence_before_sync();
@@ -320,11 +326,11 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     DAT_FWD(tc::make_tmap_2d(&tmB2, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
   }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
-  int stages = 200 * 1024 / stage_bytes;
+  int stages = (SMEM_BUDGET - 3072) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages > k_chunks) stages = k_chunks;
   if (stages < 1) stages = 1;
-  const size_t out_stage = (size_t)4 * 32 * (BN * dtype_size(y_dt) + 16);
+  const size_t out_stage = (size_t)4 * 32 * ((BN < EPI_COLS ? BN : EPI_COLS) * dtype_size(y_dt) + 16);
   size_t buf = (size_t)stages * stage_bytes;
   if (out_stage > buf) buf = out_stage;
   size_t smem = 1024 /*alignment slack*/ + 2048 /*barriers + bias*/ + buf;

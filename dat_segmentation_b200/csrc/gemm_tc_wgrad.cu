@@ -21,7 +21,7 @@ constexpr int WG_BM = 128;           // out-channel rows of dW per CTA (UMMA M)
 constexpr int WG_CHUNK = 64;         // pixels per pipeline stage
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column bf16 box
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      float* __restrict__ partial, int N, int K, int BNK, int rows_per_split,
                      long long M, int stages, int tmem_cols) {
@@ -100,33 +100,38 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   } else {
     const int quad = warp & 3;
     float* out = partial + ((long long)split * N + n0 + quad * 32) * K + k0;
-    const int row_bytes = BNK * 4, pitch = row_bytes + 16;
+    // column groups of 128 keep the staging area at 66 KB: two CTAs per SM overlap their phases
+    const int gcols = BNK < 128 ? BNK : 128;
+    const int seg_bytes = gcols * 4, pitch = seg_bytes + 16;
     uint8_t* stage = sA + (warp - 2) * 32 * pitch;
     if (chunks > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after_sync();
     }
-    for (int c = 0; c < BNK / 32; ++c) {
-      uint32_t r[32];
-      if (chunks > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
-        tmem_wait_ld();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      float* dst = reinterpret_cast<float*>(stage + lane * pitch) + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    }
-    __syncwarp();
     const int rows_here = min(32, N - (n0 + quad * 32));
-    for (int rr = 0; rr < rows_here; ++rr) {
-      uint8_t* grow = reinterpret_cast<uint8_t*>(out + (long long)rr * K);
-      const uint8_t* srow = stage + rr * pitch;
-      for (int off = lane * 16; off < row_bytes; off += 512)
-        *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
+    for (int cg = 0; cg < BNK; cg += gcols) {
+      for (int c = 0; c < gcols / 32; ++c) {
+        uint32_t r[32];
+        if (chunks > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg + c * 32), r);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        float* dst = reinterpret_cast<float*>(stage + lane * pitch) + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      __syncwarp();
+      for (int rr = 0; rr < rows_here; ++rr) {
+        uint8_t* grow = reinterpret_cast<uint8_t*>(out + (long long)rr * K + cg);
+        const uint8_t* srow = stage + rr * pitch;
+        for (int off = lane * 16; off < seg_bytes; off += 512)
+          *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
+      }
+      __syncwarp();
     }
   }
   tc_fence_before_sync();
@@ -145,7 +150,7 @@ bool pointwise_wgrad_tc_supported(long long M, int N, int K) {
 
 int pointwise_wgrad_tc_splits(long long M, int N, int K) {
   const int tiles = ((N + WG_BM - 1) / WG_BM) * (K / wg_bnk(K));
-  long long want = (148 + tiles - 1) / tiles;
+  long long want = (2 * 148 + tiles - 1) / tiles;   // two CTAs per SM
   long long cap = (M + 127) / 128;            // at least 2 chunks per slice
   long long s = want < cap ? want : cap;
   return (int)(s < 1 ? 1 : s);
@@ -168,10 +173,10 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, in
   DAT_FWD(tc::make_tmap_2d(&tmDY, dY, 2, false, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 64, 64, 128));
   DAT_FWD(tc::make_tmap_2d(&tmX, X, 2, false, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, 64, 64, 128));
   const int stage_bytes = 2 * BOX_BYTES + (BNK / 64) * BOX_BYTES;
-  int stages = 192 * 1024 / stage_bytes;
+  int stages = 104 * 1024 / stage_bytes;      // two CTAs per SM
   if (stages > 6) stages = 6;
   size_t buf = (size_t)stages * stage_bytes;
-  const size_t out_stage = (size_t)4 * 32 * (BNK * 4 + 16);
+  const size_t out_stage = (size_t)4 * 32 * ((BNK < 128 ? BNK : 128) * 4 + 16);
   if (out_stage > buf) buf = out_stage;
   const size_t smem = 1024 + 1024 + buf;
   int tmem_cols = 32;

@@ -95,25 +95,29 @@ class LayerNormProxy(nn.Module):
         super().__init__()
         self.norm = nn.LayerNorm(dim)
 
-    def _prep(self, x):
+    def _prep(self, x, out_dtype=None):
         if not x.is_cuda:
             raise RuntimeError("LayerNormProxy (dat_b200) runs on CUDA only; use TorchLayerNormProxy on CPU")
         if x.dtype not in _CODE:
             raise NotImplementedError(f"dtype {x.dtype} unsupported (float32 / bfloat16)")
-        out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype
+        if out_dtype is None:
+            out_dtype = torch.float32 if torch.is_autocast_enabled("cuda") else x.dtype
         x_l = x.permute(0, 2, 3, 1)
         if not x_l.is_contiguous():
             x_l = x_l.contiguous()
         return x_l, out_dtype
 
-    def forward(self, x):
-        x_l, out_dtype = self._prep(x)
+    def forward(self, x, out_dtype=None):
+        """`out_dtype`: dtype of the result; default fp32 under autocast (library semantics).  A caller
+        whose only consumer is an autocast convolution may ask for bf16 directly - the same rounding
+        the convolution's input cast would apply, without the fp32 round trip through HBM."""
+        x_l, out_dtype = self._prep(x, out_dtype)
         y_l = _LayerNormFn.apply(x_l, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
         return y_l.permute(0, 3, 1, 2)
 
-    def forward_fork(self, x):
+    def forward_fork(self, x, out_dtype=None):
         """(x, LayerNorm(x)) for `branch(LN(x)) + x` call sites: use the returned x for the residual."""
-        x_l, out_dtype = self._prep(x)
+        x_l, out_dtype = self._prep(x, out_dtype)
         x_p, y_l = _LayerNormForkFn.apply(x_l, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
         return x_p.permute(0, 3, 1, 2), y_l.permute(0, 3, 1, 2)
 
@@ -125,8 +129,9 @@ class TorchLayerNormProxy(nn.Module):
         super().__init__()
         self.norm = nn.LayerNorm(dim)
 
-    def forward(self, x):
-        return self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    def forward(self, x, out_dtype=None):
+        y = self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return y if out_dtype is None else y.to(out_dtype)
 
-    def forward_fork(self, x):
-        return x, self.forward(x)
+    def forward_fork(self, x, out_dtype=None):
+        return x, self.forward(x, out_dtype)
