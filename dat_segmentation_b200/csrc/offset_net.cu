@@ -359,6 +359,126 @@ __global__ void offset_bwd_dgrad_kernel(const float* __restrict__ dt,
   dq[idx] = from_f32<TQ>(to_f32(dq[idx]) + s);
 }
 
+// ---- compile-time-k versions for Cg % 64 == 0 (every DAT / DAT++ configuration: Cg = 64) ------
+// A lane owns 2 consecutive channels of a 64-channel chunk, so each q / dt / dq access of a warp
+// is one contiguous 128-256 byte run, and all the window index arithmetic is warp-uniform with
+// the divisions by k folded at compile time.
+
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void st_pair(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void st_pair(bf16* p, float2 v) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+}
+
+constexpr int WGR_PG = 2;     // point groups per CTA (their sums are merged in shared memory)
+
+// Weight gradient: warp (u, pg) owns tap row u for the points p0 + pg, p0 + pg + PG, ...:
+// per point one dt load and K contiguous-pixel q loads, 2K FMAs into registers.
+// partial[split][u * K + v][Cg]
+template <typename TQ, int K>
+__global__ void __launch_bounds__(K * WGR_PG * 32)
+offset_bwd_wgrad_rows_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
+                             float* __restrict__ partial, int pts_per_split, OffsetArgs a) {
+  __shared__ float2 red[(WGR_PG - 1) * K * K][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = warp % K, pg = warp / K;
+  const int npts = (int)a.n_points;
+  const int p0 = blockIdx.x * pts_per_split;
+  const int p1 = min(npts, p0 + pts_per_split);
+  for (int cc = 0; cc < a.Cg; cc += 64) {
+    const int c = cc + lane * 2;
+    float2 acc[K];
+#pragma unroll
+    for (int v = 0; v < K; ++v) acc[v] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int sp = p0 + pg; sp < p1; sp += WGR_PG) {
+      const int n = sp % a.Ns, bg = sp / a.Ns;
+      const int g = bg % a.G, b = bg / a.G;
+      const int y = (n / a.Wk) * a.stride - a.pad + u, xb = (n % a.Wk) * a.stride - a.pad;
+      if (y < 0 || y >= a.H) continue;
+      const float2 d = ld_pair(dt + (long long)sp * a.Cg + c);
+      const TQ* qrow = q + ((long long)(b * a.H + y) * a.W + xb) * a.C + g * a.Cg + c;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        const int x = xb + v;
+        if (x >= 0 && x < a.W) {
+          const float2 qv = ld_pair(qrow + (long long)v * a.C);
+          acc[v].x = fmaf(d.x, qv.x, acc[v].x);
+          acc[v].y = fmaf(d.y, qv.y, acc[v].y);
+        }
+      }
+    }
+    if (pg > 0) {
+#pragma unroll
+      for (int v = 0; v < K; ++v) red[((pg - 1) * K + u) * K + v][lane] = acc[v];
+    }
+    __syncthreads();
+    if (pg == 0) {
+      float* out = partial + ((size_t)blockIdx.x * K * K + u * K) * a.Cg + c;
+#pragma unroll
+      for (int v = 0; v < K; ++v) {
+        float2 t = acc[v];
+#pragma unroll
+        for (int m = 1; m < WGR_PG; ++m) { const float2 o = red[((m - 1) * K + u) * K + v][lane]; t.x += o.x; t.y += o.y; }
+        *reinterpret_cast<float2*>(out + (size_t)v * a.Cg) = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Data gradient, gather form: warp = one pixel x one 64-channel chunk; the <= ceil(k/s)^2 sample
+// points whose window covers the pixel are enumerated once per warp; transposed weights in smem.
+template <typename TQ, int K>
+__global__ void __launch_bounds__(256)
+offset_bwd_dgrad_warp_kernel(const float* __restrict__ dt, const float* __restrict__ w_dw,
+                             TQ* __restrict__ dq, int n_items, OffsetArgs a) {
+  extern __shared__ float wT[];          // [K * K][Cg]
+  for (int i = threadIdx.x; i < K * K * a.Cg; i += blockDim.x) {
+    const int uv = i / a.Cg, c = i - uv * a.Cg;
+    wT[i] = w_dw[c * K * K + uv];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int chunks = a.C >> 6;
+  const int pix = item / chunks, cf = (item - pix * chunks) * 64 + lane * 2;
+  const int x = pix % a.W, yy = pix / a.W;
+  const int y = yy % a.H, b = yy / a.H;
+  const int g = cf / a.Cg, c = cf - g * a.Cg;
+  // i*s - p + u = y, 0 <= u < k  ->  (y + p - k + 1)/s <= i <= (y + p)/s
+  int i_lo = y + a.pad - K + 1;
+  i_lo = i_lo <= 0 ? 0 : (i_lo + a.stride - 1) / a.stride;
+  const int i_hi = min(a.Hk - 1, (y + a.pad) / a.stride);
+  int j_lo = x + a.pad - K + 1;
+  j_lo = j_lo <= 0 ? 0 : (j_lo + a.stride - 1) / a.stride;
+  const int j_hi = min(a.Wk - 1, (x + a.pad) / a.stride);
+  float2 s = make_float2(0.f, 0.f);
+  const float* dtb = dt + ((long long)(b * a.G + g) * a.Ns) * a.Cg + c;
+  for (int i = i_lo; i <= i_hi; ++i) {
+    const int u = y + a.pad - i * a.stride;
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const int v = x + a.pad - j * a.stride;
+      const float2 d = ld_pair(dtb + (long long)(i * a.Wk + j) * a.Cg);
+      const float2 w = *reinterpret_cast<const float2*>(wT + (u * K + v) * a.Cg + c);
+      s.x = fmaf(w.x, d.x, s.x);
+      s.y = fmaf(w.y, d.y, s.y);
+    }
+  }
+  TQ* dst = dq + (long long)pix * a.C + cf;
+  const float2 old = ld_pair(dst);
+  st_pair(dst, make_float2(old.x + s.x, old.y + s.y));
+}
+
+bool offset_bwd_fast_supported(const Shape& s) {
+  return s.Cg % 64 == 0 && s.Cg <= 128 && (s.ksize == 3 || s.ksize == 5 || s.ksize == 7 || s.ksize == 9) &&
+         (long long)s.B * s.G * s.Ns < (1ll << 30) && (long long)s.B * s.HW * (s.C / 64) < (1ll << 31);
+}
+
 OffsetArgs make_args(const Shape& s) {
   OffsetArgs a;
   a.B = s.B; a.H = s.H; a.W = s.W; a.C = s.C; a.G = s.G; a.Cg = s.Cg;
@@ -429,6 +549,11 @@ static int offset_bwd_blocks(const Shape& s) {
 }
 static int offset_wgrad_splits(const Shape& s) {
   long long pts = (long long)s.B * s.G * s.Ns;
+  if (offset_bwd_fast_supported(s)) {   // ~2.5 CTAs per SM; at least 8 points each
+    long long per = (pts + 383) / 384;
+    if (per < 8) per = 8;
+    return (int)((pts + per - 1) / per);
+  }
   long long sp = (pts + 7) / 8;      // ~8 points per CTA: latency-bound loop, so go wide
   return (int)(sp < 1 ? 1 : (sp > 4096 ? 4096 : sp));
 }
@@ -472,7 +597,19 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
 
   int nsplit = offset_wgrad_splits(s);
   long long pps = (a.n_points + nsplit - 1) / nsplit;
-  if (s.act_dtype == DAT_F32)
+  const bool fast = offset_bwd_fast_supported(s);
+  if (fast) {
+#define LAUNCH_WG(TQ, KV) \
+    offset_bwd_wgrad_rows_kernel<TQ, KV><<<nsplit, KV * WGR_PG * 32, 0, st>>>((const TQ*)q, dt, part2, (int)pps, a)
+#define LAUNCH_WG_K(TQ)                                                             \
+    do {                                                                            \
+      if (s.ksize == 3) LAUNCH_WG(TQ, 3); else if (s.ksize == 5) LAUNCH_WG(TQ, 5);  \
+      else if (s.ksize == 7) LAUNCH_WG(TQ, 7); else LAUNCH_WG(TQ, 9);               \
+    } while (0)
+    if (s.act_dtype == DAT_F32) LAUNCH_WG_K(float); else LAUNCH_WG_K(bf16);
+#undef LAUNCH_WG_K
+#undef LAUNCH_WG
+  } else if (s.act_dtype == DAT_F32)
     offset_bwd_wgrad_kernel<float><<<nsplit, 256, 0, st>>>((const float*)q, dt, part2, pps, a);
   else
     offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, st>>>((const bf16*)q, dt, part2, pps, a);
@@ -482,6 +619,23 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   DAT_LAUNCH_OK("offset_bwd_wgrad_reduce_kernel");
 
   long long total = (long long)s.B * s.HW * s.C;
+  if (fast) {
+    const int n_items = (int)((long long)s.B * s.HW * (s.C / 64));
+    const size_t wsm = (size_t)kk * s.Cg * sizeof(float);
+#define LAUNCH_DG(TQ, KV)                                                                             \
+    offset_bwd_dgrad_warp_kernel<TQ, KV><<<ceil_div(n_items, 8), 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, \
+                                                                                 n_items, a)
+#define LAUNCH_DG_K(TQ)                                                             \
+    do {                                                                            \
+      if (s.ksize == 3) LAUNCH_DG(TQ, 3); else if (s.ksize == 5) LAUNCH_DG(TQ, 5);  \
+      else if (s.ksize == 7) LAUNCH_DG(TQ, 7); else LAUNCH_DG(TQ, 9);               \
+    } while (0)
+    if (s.act_dtype == DAT_F32) LAUNCH_DG_K(float); else LAUNCH_DG_K(bf16);
+#undef LAUNCH_DG_K
+#undef LAUNCH_DG
+    DAT_LAUNCH_OK("offset_bwd_dgrad_warp_kernel");
+    return DAT_OK;
+  }
   if (s.act_dtype == DAT_F32)
     offset_bwd_dgrad_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>(dt, p->off_dw_w, (float*)dq, total, a);
   else
