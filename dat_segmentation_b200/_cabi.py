@@ -80,7 +80,7 @@ def lib():
     L.dat_cast_transpose_bf16.argtypes = [f32p, vp, i32, i32, vp]
     L.dat_pointwise_wgrad_tc_workspace_bytes.argtypes = [i64, i32, i32]
     L.dat_pointwise_wgrad_tc_workspace_bytes.restype = C.c_size_t
-    L.dat_pointwise_wgrad_tc.argtypes = [vp, vp, f32p, i64, i32, i32, vp, C.c_size_t, vp]
+    L.dat_pointwise_wgrad_tc.argtypes = [vp, vp, f32p, f32p, i64, i32, i32, vp, C.c_size_t, vp]
     L.dat_bias_grad.argtypes = [vp, i32, f32p, i64, i32, vp, C.c_size_t, vp]
     L.dat_cast_transpose_bf16.restype = L.dat_pointwise_wgrad_tc.restype = L.dat_bias_grad.restype = C.c_int
     L.dat_debug_gemm_timing.argtypes = [C.POINTER(C.c_uint64)]

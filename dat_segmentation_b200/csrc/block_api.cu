@@ -173,14 +173,14 @@ size_t dat_pointwise_wgrad_tc_workspace_bytes(int64_t M, int32_t N, int32_t K) {
   return pointwise_wgrad_tc_supported(M, N, K) ? pointwise_wgrad_tc_workspace(M, N, K) : 0;
 }
 
-int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, int64_t M, int32_t N, int32_t K,
+int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, int64_t M, int32_t N, int32_t K,
                            void* workspace, size_t workspace_bytes, void* stream) {
   DAT_REQUIRE(dY && X && dW, "pointwise_wgrad_tc: NULL pointer");
   if (!pointwise_wgrad_tc_supported(M, N, K)) {
     set_error("pointwise_wgrad_tc: shape M=%lld N=%d K=%d not tileable", (long long)M, N, K);
     return DAT_ERR_UNSUPPORTED;
   }
-  return pointwise_wgrad_tc(dY, X, dW, M, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
+  return pointwise_wgrad_tc(dY, X, dW, db, M, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_t N, void* workspace,
@@ -384,8 +384,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   auto wgrad = [&](const void* dY, const void* X, int x_dt, float* dW, float* db, long long rows) -> int {
     if (!tcw) return pointwise_wgrad_simt(dY, adt, X, x_dt, dW, db, rows, C, C, w.sub, w.sub_bytes, st);
     const size_t wsz_tc = pointwise_wgrad_tc_workspace(rows, C, C);
-    DAT_FWD(pointwise_wgrad_tc(dY, X, dW, rows, C, C, w.sub, wsz_tc, st));
-    return bias_grad(dY, adt, db, rows, C, (char*)w.sub + wsz_tc, w.sub_bytes - wsz_tc, st);
+    return pointwise_wgrad_tc(dY, X, dW, db, rows, C, C, w.sub, wsz_tc, st);
   };
   // proj_out
   DAT_FWD(wgrad(dy, sv->o, adt, g->wo, g->bo, M));

@@ -6,6 +6,9 @@
 // blocks 8 KB apart) - no transposed copy of either activation is ever made.
 // One CTA = one 128 (out-channel) x BNK (in-channel, <= 256) tile of dW over one slice of the
 // pixels; fp32 partial tiles per slice are reduced in a fixed order afterwards (deterministic).
+// The bias gradient db[n] = sum_m dY[m, n] rides along: the CTAs of the first in-channel tile issue
+// one extra N = 16 MMA per step against a shared-memory tile of ones (accumulated in 16 spare
+// TMEM columns), so dY is not read a second time by a column-sum kernel.
 // Warp roles as in gemm_tc.cu: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -20,11 +23,12 @@ constexpr int WG_THREADS = 192;
 constexpr int WG_BM = 128;           // out-channel rows of dW per CTA (UMMA M)
 constexpr int WG_CHUNK = 64;         // pixels per pipeline stage
 constexpr int BOX_BYTES = 64 * 128;  // one 64-row x 64-column bf16 box
+constexpr int ONES_BYTES = 2048;     // bf16 ones read by the N = 16 bias-gradient MMA
 
 __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                     float* __restrict__ partial, int N, int K, int BNK, int rows_per_split,
-                     long long M, int stages, int tmem_cols) {
+                     float* __restrict__ partial, float* __restrict__ db_partial, int N, int K, int BNK,
+                     int rows_per_split, long long M, int stages, int tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -33,8 +37,10 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  uint8_t* sA = smem + 1024;
+  uint8_t* sOnes = smem + 1024;
+  uint8_t* sA = sOnes + ONES_BYTES;
   uint8_t* sB = sA + stages * a_bytes;
+  const bool with_db = db_partial != nullptr && blockIdx.y == 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * WG_BM, k0 = blockIdx.y * BNK, split = blockIdx.z;
@@ -54,6 +60,10 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (with_db) {
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += WG_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor-core (async) proxy
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -81,6 +91,8 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_instr_desc(FMT_BF16, WG_BM, (uint32_t)BNK, 1, 1);   // A, B MN-major
+      const uint32_t idesc1 = make_instr_desc(FMT_BF16, WG_BM, 16u, 1, 1);
+      const uint64_t onesd = make_smem_desc(smem_u32(sOnes), BOX_BYTES, 1024, LAYOUT_SW128);
       for (int kc = 0; kc < chunks; ++kc) {
         const int s = kc % stages;
         const uint32_t ph = (uint32_t)(kc / stages) & 1u;
@@ -92,6 +104,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
           const uint64_t ad = make_smem_desc(a_addr + j * 2048, BOX_BYTES, 1024, LAYOUT_SW128);
           const uint64_t bd = make_smem_desc(b_addr + j * 2048, BOX_BYTES, 1024, LAYOUT_SW128);
           mma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)((kc | j) != 0));
+          if (with_db) mma_bf16_ss(tmem_base + (uint32_t)BNK, ad, onesd, idesc1, (uint32_t)((kc | j) != 0));
         }
         tc_commit(&empty[s]);
       }
@@ -109,6 +122,16 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       tc_fence_after_sync();
     }
     const int rows_here = min(32, N - (n0 + quad * 32));
+    if (with_db) {                       // column BNK of this lane's row = sum over the slice's pixels
+      uint32_t r[32];
+      if (chunks > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)BNK, r);
+        tmem_wait_ld();
+      } else {
+        r[0] = 0u;
+      }
+      if (lane < rows_here) db_partial[(long long)split * N + n0 + quad * 32 + lane] = __uint_as_float(r[0]);
+    }
     for (int cg = 0; cg < BNK; cg += gcols) {
       for (int c = 0; c < gcols / 32; ++c) {
         uint32_t r[32];
@@ -139,7 +162,9 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
-int wg_bnk(int C) { return C >= 256 ? 256 : C; }
+// in-channel tile: <= 128 so that accumulator + 16 bias-gradient columns fit 256 TMEM columns
+// (two CTAs per SM share the 512)
+int wg_bnk(int C) { return C >= 128 ? 128 : C; }
 
 }  // namespace
 
@@ -157,11 +182,32 @@ int pointwise_wgrad_tc_splits(long long M, int N, int K) {
 }
 
 size_t pointwise_wgrad_tc_workspace(long long M, int N, int K) {
-  return align_up((size_t)pointwise_wgrad_tc_splits(M, N, K) * N * K * 4, 256);
+  const size_t splits = (size_t)pointwise_wgrad_tc_splits(M, N, K);
+  return align_up(splits * N * K * 4, 256) + align_up(splits * N * 4, 256);
 }
 
-// dW[N,K] (fp32, overwritten) = dY[M,N]^T X[M,K]; dY, X bf16 channel-last.
-int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, int N, int K,
+namespace {
+// fixed-order sum over the splits of dW and db partials in one launch
+__global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, const float* __restrict__ bpart,
+                                    int splits, long long nk, int n, float* __restrict__ dW,
+                                    float* __restrict__ db) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nk) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += wpart[(long long)z * nk + i];
+    dW[i] = s;
+  } else if (i < nk + n && db != nullptr) {
+    const int c = (int)(i - nk);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += bpart[(long long)z * n + c];
+    db[c] = s;
+  }
+}
+}  // namespace
+
+// dW[N,K] (fp32, overwritten) = dY[M,N]^T X[M,K] and, when db != NULL, db[N] = column sums of dY;
+// dY, X bf16 channel-last.
+int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long long M, int N, int K,
                        void* ws, size_t ws_bytes, cudaStream_t st) {
   DAT_REQUIRE(pointwise_wgrad_tc_supported(M, N, K), "pointwise_wgrad_tc: unsupported shape");
   DAT_REQUIRE(ws_bytes >= pointwise_wgrad_tc_workspace(M, N, K), "pointwise_wgrad_tc: workspace too small");
@@ -173,20 +219,28 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, in
   DAT_FWD(tc::make_tmap_2d(&tmDY, dY, 2, false, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 64, 64, 128));
   DAT_FWD(tc::make_tmap_2d(&tmX, X, 2, false, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, 64, 64, 128));
   const int stage_bytes = 2 * BOX_BYTES + (BNK / 64) * BOX_BYTES;
-  int stages = 104 * 1024 / stage_bytes;      // two CTAs per SM
+  int stages = 100 * 1024 / stage_bytes;      // two CTAs per SM
   if (stages > 6) stages = 6;
   size_t buf = (size_t)stages * stage_bytes;
   const size_t out_stage = (size_t)4 * 32 * ((BNK < 128 ? BNK : 128) * 4 + 16);
   if (out_stage > buf) buf = out_stage;
-  const size_t smem = 1024 + 1024 + buf;
+  const size_t smem = 1024 + 1024 + ONES_BYTES + buf;
   int tmem_cols = 32;
-  while (tmem_cols < BNK) tmem_cols <<= 1;
+  while (tmem_cols < BNK + 32) tmem_cols <<= 1;      // + the bias-gradient columns (read 32 wide)
   float* part = splits > 1 ? (float*)ws : dW;
+  float* bpart = nullptr;
+  if (db != nullptr)
+    bpart = splits > 1 ? (float*)((char*)ws + align_up((size_t)splits * N * K * 4, 256)) : db;
   dim3 grid((N + WG_BM - 1) / WG_BM, K / BNK, splits);
   DAT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, part, N, K, BNK, (int)rps, M, stages, tmem_cols);
+  gemm_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, part, bpart, N, K, BNK, (int)rps, M, stages,
+                                                       tmem_cols);
   DAT_LAUNCH_OK("gemm_tc_wgrad_kernel");
-  if (splits > 1) DAT_FWD(reduce_partials((const float*)ws, splits, (long long)N * K, dW, DAT_F32, st));
+  if (splits > 1) {
+    const long long nk = (long long)N * K;
+    wgrad_reduce_kernel<<<(unsigned)ceil_div(nk + N, 256ll), 256, 0, st>>>(part, bpart, splits, nk, N, dW, db);
+    DAT_LAUNCH_OK("wgrad_reduce_kernel");
+  }
   return DAT_OK;
 }
 

@@ -113,8 +113,8 @@ int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws
               cudaStream_t st);
 bool pointwise_wgrad_tc_supported(long long M, int N, int K);
 size_t pointwise_wgrad_tc_workspace(long long M, int N, int K);
-int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, long long M, int N, int K, void* ws,
-                       size_t ws_bytes, cudaStream_t st);
+int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long long M, int N, int K,
+                       void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace dat
 
 namespace dat {

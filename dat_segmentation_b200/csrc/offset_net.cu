@@ -443,9 +443,10 @@ offset_bwd_dgrad_warp_kernel(const float* __restrict__ dt, const float* __restri
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (item >= n_items) return;
   const int chunks = a.C >> 6;
+  // grid-stride over the (pixel, chunk) items: the shared-memory filter is staged once per CTA
+  for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items;
+       item += gridDim.x * (blockDim.x >> 5)) {
   const int pix = item / chunks, cf = (item - pix * chunks) * 64 + lane * 2;
   const int x = pix % a.W, yy = pix / a.W;
   const int y = yy % a.H, b = yy / a.H;
@@ -472,6 +473,7 @@ offset_bwd_dgrad_warp_kernel(const float* __restrict__ dt, const float* __restri
   TQ* dst = dq + (long long)pix * a.C + cf;
   const float2 old = ld_pair(dst);
   st_pair(dst, make_float2(old.x + s.x, old.y + s.y));
+  }
 }
 
 bool offset_bwd_fast_supported(const Shape& s) {
@@ -622,8 +624,9 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   if (fast) {
     const int n_items = (int)((long long)s.B * s.HW * (s.C / 64));
     const size_t wsm = (size_t)kk * s.Cg * sizeof(float);
+    const int dg_grid = ceil_div(n_items, 8) < 148 * 8 ? ceil_div(n_items, 8) : 148 * 8;
 #define LAUNCH_DG(TQ, KV)                                                                             \
-    offset_bwd_dgrad_warp_kernel<TQ, KV><<<ceil_div(n_items, 8), 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, \
+    offset_bwd_dgrad_warp_kernel<TQ, KV><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, \
                                                                                  n_items, a)
 #define LAUNCH_DG_K(TQ)                                                             \
     do {                                                                            \

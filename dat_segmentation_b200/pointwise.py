@@ -5,7 +5,7 @@
 under bf16 autocast:
   forward   Y = X W^T + b      tf32 MMA straight on an fp32 X (LayerNorm output), bf16 MMA otherwise
   dX = dY W                    the same kernel against a transposed bf16 copy of W
-  dW = dY^T X, db = colsum dY  MN-major tensor-core weight gradient, deterministic reductions
+  dW = dY^T X, db = colsum dY  one MN-major tensor-core pass over dY and X, deterministic reductions
 Shapes the kernels cannot tile, fp32 (non-autocast) execution and CPU tensors use the library
 convolution (`F.conv2d`) — this module is a "next row" outside the parity-critical block.
 """
@@ -87,15 +87,12 @@ class _PointwiseFn(torch.autograd.Function):
             else:
                 xb = x_l
             nbytes = lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K)
-            ws = torch.empty(max(nbytes, 64 * N * 4), device=dev, dtype=torch.uint8)
+            ws = torch.empty(max(nbytes, 64), device=dev, dtype=torch.uint8)
             dw = torch.empty(N, K, device=dev, dtype=torch.float32)
-            _cabi.check(lib.dat_pointwise_wgrad_tc(_ptr(dy), _ptr(xb), _ptr(dw), M, N, K, _ptr(ws), ws.numel(), st),
-                        "dat_pointwise_wgrad_tc")
-            db = None
-            if ctx.has_bias:
-                db = torch.empty(N, device=dev, dtype=torch.float32)
-                _cabi.check(lib.dat_bias_grad(_ptr(dy), _cabi.DAT_BF16, _ptr(db), M, N, _ptr(ws), ws.numel(), st),
-                            "dat_bias_grad")
+            db = torch.empty(N, device=dev, dtype=torch.float32) if ctx.has_bias else None
+            # db = column sums of dY ride along in the same tensor-core pass
+            _cabi.check(lib.dat_pointwise_wgrad_tc(_ptr(dy), _ptr(xb), _ptr(dw), _ptr(db), M, N, K, _ptr(ws),
+                                                   ws.numel(), st), "dat_pointwise_wgrad_tc")
         return dx, dw.reshape(ctx.wshape).to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None)
 
 

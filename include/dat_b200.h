@@ -138,12 +138,14 @@ int dat_debug_gemm_timing(uint64_t* out8);
 /* Tensor-core gradients of the 1x1 convolution (bf16 operands, fp32 accumulation):
  *   data gradient  dX[M,K] = dY[M,N] W[N,K]  ==  dat_pointwise_fwd_tc(dY, W^T) with the (K,N) bf16
  *                  transposed weight from dat_cast_transpose_bf16;
- *   weight gradient dW[N,K] = dY^T X (both bf16, read MN-major; N, K multiples of 128; deterministic
- *                  split reduction) and bias gradient db[N] = column sums of dY. */
+ *   weight gradient dW[N,K] = dY^T X (both bf16, read MN-major; N, K multiples of 64; deterministic
+ *                  split reduction); the bias gradient db[N] = column sums of dY comes out of the
+ *                  same pass over dY when db != NULL (an extra N = 16 MMA against a tile of ones).
+ *                  dat_bias_grad is the stand-alone column sum. */
 int dat_cast_transpose_bf16(const float* w, void* out, int32_t N, int32_t K, void* stream);
 size_t dat_pointwise_wgrad_tc_workspace_bytes(int64_t M, int32_t N, int32_t K);
-int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, int64_t M, int32_t N, int32_t K,
-                           void* workspace, size_t workspace_bytes, void* stream);
+int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, int64_t M, int32_t N,
+                           int32_t K, void* workspace, size_t workspace_bytes, void* stream);
 /* workspace >= 64 * N * 4 bytes */
 int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_t N, void* workspace,
                   size_t workspace_bytes, void* stream);

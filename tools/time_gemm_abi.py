@@ -56,9 +56,10 @@ for name, M, N, K, xdt, ydt in CASES:
         nb = lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K)
         ws = torch.empty(max(nb, 64), device="cuda", dtype=torch.uint8)
         dw = torch.empty(N, K, device="cuda")
+        dbias = torch.empty(N, device="cuda")
 
         def wg(i):
-            _cabi.check(lib.dat_pointwise_wgrad_tc(p(dy[i % NSET]), p(sets[i % NSET][0]), p(dw), M, N, K, p(ws), nb, st), "wgrad")
+            _cabi.check(lib.dat_pointwise_wgrad_tc(p(dy[i % NSET]), p(sets[i % NSET][0]), p(dw), p(dbias), M, N, K, p(ws), nb, st), "wgrad")
 
         t = timeit(wg)
         print(f"{'   wgrad':14s} M={M:6d} N={N:5d} K={K:5d} {'':18s} {t*1e3:7.1f} us {2*M*N*K/t/1e9:7.1f} TF/s "
