@@ -12,6 +12,8 @@
 //          parameter — no cast pass at all; x is read exactly once at 4 B/element, which
 //          is what bounds proj_q (HBM-bound: 4 B in + 2 B out per element, ~64 FLOP/B).
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -93,7 +95,7 @@ constexpr int EPI_COLS = 128;            // epilogue column group (staging area 
 constexpr int SMEM_BUDGET = 108 * 1024;   // per CTA: two CTAs share an SM
 
 template <bool TF32, typename TOut>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 4)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
@@ -256,7 +258,14 @@ __global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __res
   store4(out + (long long)blockIdx.y * n + i, load4(src + i));
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e != nullptr && std::atoi(e) > 0 ? std::atoi(e) : dflt;
+}
+
 int pick_bn(int N) {
+  const int cap = env_int("DAT_B200_GEMM_BN", 256);     // tuning knob: widest output tile
+  if (cap < 256 && N % cap == 0) return cap;
   int tiles = (N + 255) / 256;
   if (N % tiles != 0) return 0;
   int bn = N / tiles;
@@ -326,7 +335,8 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     DAT_FWD(tc::make_tmap_2d(&tmB2, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
   }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
-  int stages = (SMEM_BUDGET - 3072) / stage_bytes;
+  const int budget = env_int("DAT_B200_GEMM_SMEM_KB", SMEM_BUDGET / 1024) * 1024;   // tuning knob: CTAs per SM
+  int stages = (budget - 3072) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages > k_chunks) stages = k_chunks;
   if (stages < 1) stages = 1;
