@@ -180,7 +180,10 @@ def kernel_roofline(dev, pk):
     achieved = flops / (ms * 1e-3) / 1e12
     return {"kernel": "dat_attention_fwd (stage-2 shape, B=16, bf16)", "bound": "tensor",
             "achieved": round(achieved, 3), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": round(achieved / pk["bf16_tflops"], 5), "traffic": None, "ms": round(ms, 4),
+            "frac": round(achieved / pk["bf16_tflops"], 5),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
+            # (profiles/r01_ncu_kernels.md): 12.82 MB + 9 KB
+            "traffic": 12834048, "ms": round(ms, 4),
             "algorithmic_bytes": byts, "hbm_gbs_at_this_time": round(byts / (ms * 1e-3) / 1e9, 1),
             "peak_source": pk["source"]}
 
