@@ -228,6 +228,161 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// Persistent version: one CTA per SM walks the output tiles (m fastest, so neighbouring CTAs share
+// the weight tile in L2).  The TMA producer never drains its ring between tiles, the fp32
+// accumulator is double-buffered in TMEM (2 x BN columns), and the four epilogue warps store tile
+// i while the MMA warp accumulates tile i + 1: loads, MMAs and stores of a CTA overlap instead of
+// alternating (the one-tile kernel idles its loads ~60 % of a CTA's lifetime, profiles/r01_ncu_kernels.md).
+//   barriers: full/empty per ring stage, acc_full/acc_empty per TMEM buffer.
+template <bool TF32, typename TOut>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                          const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
+                          int k_chunks1, int BN, int stages, int tmem_cols, int m_tiles, int total_tiles,
+                          int stage_pitch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int b_stage_bytes = BN * CHUNK_BYTES;
+  // [barriers 1 KB][bias 2 x 256 floats][ring: A stages | B stages (1 KB aligned)][epilogue staging]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sBias = reinterpret_cast<float*>(smem + 1024);
+  uint8_t* sA = smem + 3072;
+  uint8_t* sB = sA + stages * A_STAGE_BYTES;
+  uint8_t* sStage = sB + stages * b_stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CHUNK_ELEMS = TF32 ? 32 : 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (k_chunks1 < k_chunks) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);       // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * TC_BM, n0 = (t / m_tiles) * BN;
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+          const bool second = kc >= k_chunks1;
+          const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
+          tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
+          tma_load_2d(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TC_BM, (uint32_t)BN);
+      int it = 0, li = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+        const int buf = li & 1;
+        mbar_wait(&acc_empty[buf], (uint32_t)((li >> 1) & 1) ^ 1u);   // epilogue has drained this buffer
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < CHUNK_BYTES / 32; ++k4) {
+            const uint64_t ad = make_smem_desc(a_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t bd = make_smem_desc(b_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+            if (TF32) mma_tf32_ss(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+            else mma_bf16_ss(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int epi_tid = threadIdx.x - 64;
+    const int gcols = BN < EPI_COLS ? BN : EPI_COLS;
+    const int seg_bytes = gcols * (int)sizeof(TOut);
+    uint8_t* stage = sStage + (warp - 2) * 32 * stage_pitch;
+    int li = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+      const int buf = li & 1;
+      const int m0 = (t % m_tiles) * TC_BM, n0 = (t / m_tiles) * BN;
+      float* bvec = sBias + buf * 256;
+      for (int i = epi_tid; i < BN; i += 128) bvec[i] = bias != nullptr ? bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps
+      mbar_wait(&acc_full[buf], (uint32_t)((li >> 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      const int rows_here = min(32, M - (m0 + quad * 32));
+      for (int cg = 0; cg < BN; cg += gcols) {
+        for (int c = 0; c < gcols / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + (uint32_t)(cg + c * 32), r);
+          tmem_wait_ld();
+          const float* bp = bvec + cg + c * 32;
+          TOut* dst = reinterpret_cast<TOut*>(stage + lane * stage_pitch) + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            const float4 bb = *reinterpret_cast<const float4*>(bp + j);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            store4(dst + j, v);
+          }
+        }
+        if (cg + gcols >= BN) {          // accumulator fully read: hand the TMEM buffer back early
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();
+        // 512 bytes per store instruction: 512 / seg_bytes rows at a time
+        const int lanes_per_row = seg_bytes / 16;
+        const int rows_per_it = 32 / lanes_per_row;
+        const int rsub = lane / lanes_per_row, off = (lane % lanes_per_row) * 16;
+        for (int rr = rsub; rr < rows_here; rr += rows_per_it) {
+          uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0 + cg);
+          *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(stage + rr * stage_pitch + off);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 // fp32 (C x C) -> transposed bf16 for up to 4 matrices in one launch: out[z][k][n] = w_z[n][k].
 // The data-gradient GEMMs dX = dY W are then plain K-major products with "weight" W^T.
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
@@ -335,6 +490,34 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     DAT_FWD(tc::make_tmap_2d(&tmB2, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
   }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
+  if (std::getenv("DAT_B200_GEMM_LEGACY") == nullptr) {
+    // persistent kernel: ring + separate epilogue staging in up to 224 KB, one CTA per SM
+    const int gcols = BN < EPI_COLS ? BN : EPI_COLS;
+    const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
+    const int staging = 4 * 32 * stage_pitch;
+    int stages = (224 * 1024 - 1024 - 3072 - staging) / stage_bytes;
+    if (stages > 8) stages = 8;
+    DAT_REQUIRE(stages >= 2, "pointwise_fwd_tc: tile does not fit shared memory");
+    const size_t smem = 1024 + 3072 + (size_t)stages * stage_bytes + staging;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+    const int m_tiles = (int)ceil_div(M, (long long)TC_BM), total = m_tiles * (N / BN);
+    const int grid = total < 148 ? total : 148;
+#define LAUNCH_P(TF, TO)                                                                          \
+  do {                                                                                            \
+    auto kern = gemm_tc_persistent_kernel<TF, TO>;                                                \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,      \
+                                         k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch); \
+  } while (0)
+    if (tf32 && y_dt == DAT_F32) LAUNCH_P(true, float);
+    else if (tf32) LAUNCH_P(true, bf16);
+    else if (y_dt == DAT_F32) LAUNCH_P(false, float);
+    else LAUNCH_P(false, bf16);
+#undef LAUNCH_P
+    DAT_LAUNCH_OK("gemm_tc_persistent_kernel");
+    return DAT_OK;
+  }
   const int budget = env_int("DAT_B200_GEMM_SMEM_KB", SMEM_BUDGET / 1024) * 1024;   // tuning knob: CTAs per SM
   int stages = (budget - 3072) / stage_bytes;
   if (stages > 6) stages = 6;
