@@ -228,6 +228,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+__device__ __forceinline__ void store8(float* p, float4 a, float4 b) {
+  *reinterpret_cast<float4*>(p) = a;
+  *reinterpret_cast<float4*>(p + 4) = b;
+}
+__device__ __forceinline__ void store8(bf16* p, float4 a, float4 b) {
+  uint4 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+  h[0] = __floats2bfloat162_rn(a.x, a.y); h[1] = __floats2bfloat162_rn(a.z, a.w);
+  h[2] = __floats2bfloat162_rn(b.x, b.y); h[3] = __floats2bfloat162_rn(b.z, b.w);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
 // Persistent version: one CTA per SM walks the output tiles (m fastest, so neighbouring CTAs share
 // the weight tile in L2).  The TMA producer never drains its ring between tiles, the fp32
 // accumulator is double-buffered in TMEM (2 x BN columns), and the four epilogue warps store tile
@@ -344,26 +356,36 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
       const int rows_here = min(32, M - (m0 + quad * 32));
+      const int nch = gcols / 32;
       for (int cg = 0; cg < BN; cg += gcols) {
-        for (int c = 0; c < gcols / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + (uint32_t)(cg + c * 32), r);
-          tmem_wait_ld();
-          const float* bp = bvec + cg + c * 32;
-          TOut* dst = reinterpret_cast<TOut*>(stage + lane * stage_pitch) + c * 32;
+        // the whole column group (<= 128 columns) is fetched with back-to-back tcgen05.ld and one
+        // wait: one TMEM round trip per group instead of one per 32 columns
+        uint32_t r[4][32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            const float4 bb = *reinterpret_cast<const float4*>(bp + j);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-            store4(dst + j, v);
-          }
-        }
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) tmem_ld_32x32(t_addr + (uint32_t)(cg + c * 32), r[c]);
+        tmem_wait_ld();
         if (cg + gcols >= BN) {          // accumulator fully read: hand the TMEM buffer back early
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {
+            const float* bp = bvec + cg + c * 32;
+            TOut* dst = reinterpret_cast<TOut*>(stage + lane * stage_pitch) + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bp + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bp + j + 4);
+              const float4 v0 = make_float4(__uint_as_float(r[c][j]) + b0.x, __uint_as_float(r[c][j + 1]) + b0.y,
+                                            __uint_as_float(r[c][j + 2]) + b0.z, __uint_as_float(r[c][j + 3]) + b0.w);
+              const float4 v1 = make_float4(__uint_as_float(r[c][j + 4]) + b1.x, __uint_as_float(r[c][j + 5]) + b1.y,
+                                            __uint_as_float(r[c][j + 6]) + b1.z, __uint_as_float(r[c][j + 7]) + b1.w);
+              store8(dst + j, v0, v1);    // 16-byte shared stores: conflict-free with the +16 B row pitch
+            }
+          }
         }
         __syncwarp();
         // 512 bytes per store instruction: 512 / seg_bytes rows at a time
