@@ -28,47 +28,67 @@ __device__ __forceinline__ void st2(bf16* p, float2 v) {
 }
 
 // NV = number of 64-channel groups (C = 64 * NV exactly, or C == 32 handled with NV = 1 and half
-// the lanes idle)
+// the lanes idle).  ROWS = rows a warp handles at once: all their loads are issued before the
+// first reduction, so narrow rows (C = 64: 8 bytes per lane) still keep enough bytes in flight.
+template <int NV> struct RowsOf { static constexpr int R = NV == 1 ? 4 : (NV == 2 ? 2 : 1); };
+
 template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  constexpr int R = RowsOf<NV>::R;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const TI* xr = x + row * C;
-  float2 v[NV];
-  float s = 0.f;
+  const long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  float2 v[R][NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 2;
-    v[i] = c < C ? ld2(xr + c) : make_float2(0.f, 0.f);
-    s += v[i].x + v[i].y;
-  }
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const TI* xr = x + (row0 + r) * C;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 2;
-    if (c < C) {
-      const float a = v[i].x - mean, b = v[i].y - mean;
-      q += a * a + b * b;
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 2;
+      v[r][i] = (c < C && row0 + r < rows) ? ld2(xr + c) : make_float2(0.f, 0.f);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-  TO* yr = y + row * C;
+  float2 g[NV], b[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 2;
-    if (c < C) {
-      const float2 g = ld2(gamma + c), b = ld2(beta + c);
-      st2(yr + c, make_float2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y));
-    }
+    g[i] = c < C ? ld2(gamma + c) : make_float2(0.f, 0.f);
+    b[i] = c < C ? ld2(beta + c) : make_float2(0.f, 0.f);
   }
-  if (lane == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[r][i].x + v[r][i].y;
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 2;
+      if (c < C) {
+        const float a0 = v[r][i].x - mean, a1 = v[r][i].y - mean;
+        q += a0 * a0 + a1 * a1;
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+    if (row < rows) {
+      TO* yr = y + row * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 2;
+        if (c < C)
+          st2(yr + c, make_float2((v[r][i].x - mean) * rstd * g[i].x + b[i].x,
+                                  (v[r][i].y - mean) * rstd * g[i].y + b[i].y));
+      }
+      if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+    }
   }
 }
 
@@ -78,6 +98,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, TI* __restrict__ dx,
                      const TI* __restrict__ dres, float* __restrict__ partial, long long rows, int C) {
+  constexpr int R = NV == 1 ? 2 : 1;   // 4 rows / iteration measured slower: registers -> occupancy
   extern __shared__ float red[];     // [LN_WARPS][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2 gg[NV], gb[NV], gam[NV];
@@ -88,40 +109,59 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
     gam[i] = c < C ? ld2(gamma + c) : make_float2(0.f, 0.f);
   }
   const float inv_c = 1.0f / (float)C;
-  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows;
-       row += (long long)gridDim.x * LN_WARPS) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const TI* xr = x + row * C;
-    const TDY* dr = dy + row * C;
-    float2 xh[NV], dg[NV];
-    float m1 = 0.f, m2 = 0.f;
+  for (long long row0 = ((long long)blockIdx.x * LN_WARPS + warp) * R; row0 < rows;
+       row0 += (long long)gridDim.x * LN_WARPS * R) {
+    float2 xv[R][NV], dv[R][NV], rv[R][NV];
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 2;
-      xh[i] = dg[i] = make_float2(0.f, 0.f);
-      if (c < C) {
-        const float2 xv = ld2(xr + c), d = ld2(dr + c);
-        xh[i] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
-        gg[i].x = fmaf(d.x, xh[i].x, gg[i].x);
-        gg[i].y = fmaf(d.y, xh[i].y, gg[i].y);
-        gb[i].x += d.x;
-        gb[i].y += d.y;
-        dg[i] = make_float2(d.x * gam[i].x, d.y * gam[i].y);
-        m1 += dg[i].x + dg[i].y;
-        m2 += dg[i].x * xh[i].x + dg[i].y * xh[i].y;
+    for (int r = 0; r < R; ++r) {          // every load of the R rows is in flight before the first use
+      const long long row = row0 + r;
+      const bool ok = row < rows;
+      mean[r] = ok ? mean_in[row] : 0.f;
+      rstd[r] = ok ? rstd_in[row] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 2;
+        const bool in = ok && c < C;
+        xv[r][i] = in ? ld2(x + row * C + c) : make_float2(0.f, 0.f);
+        dv[r][i] = in ? ld2(dy + row * C + c) : make_float2(0.f, 0.f);
+        rv[r][i] = (in && dres != nullptr) ? ld2(dres + row * C + c) : make_float2(0.f, 0.f);
       }
     }
-    m1 = warp_sum(m1) * inv_c;
-    m2 = warp_sum(m2) * inv_c;
-    TI* dxr = dx + row * C;
-    const TI* rr = dres != nullptr ? dres + row * C : nullptr;   // gradient of the residual path through x
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 2;
-      if (c < C) {
-        float2 o = make_float2(rstd * (dg[i].x - m1 - xh[i].x * m2), rstd * (dg[i].y - m1 - xh[i].y * m2));
-        if (rr != nullptr) { const float2 r = ld2(rr + c); o.x += r.x; o.y += r.y; }
-        st2(dxr + c, o);
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      float2 xh[NV], dg[NV];
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 2;
+        xh[i] = dg[i] = make_float2(0.f, 0.f);
+        if (c < C && row < rows) {
+          const float2 d = dv[r][i];
+          xh[i] = make_float2((xv[r][i].x - mean[r]) * rstd[r], (xv[r][i].y - mean[r]) * rstd[r]);
+          gg[i].x = fmaf(d.x, xh[i].x, gg[i].x);
+          gg[i].y = fmaf(d.y, xh[i].y, gg[i].y);
+          gb[i].x += d.x;
+          gb[i].y += d.y;
+          dg[i] = make_float2(d.x * gam[i].x, d.y * gam[i].y);
+          m1 += dg[i].x + dg[i].y;
+          m2 += dg[i].x * xh[i].x + dg[i].y * xh[i].y;
+        }
+      }
+      m1 = warp_sum(m1) * inv_c;
+      m2 = warp_sum(m2) * inv_c;
+      if (row < rows) {
+        TI* dxr = dx + row * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 2;
+          if (c < C) {
+            // + gradient of the residual path through x (dat.py:147-156)
+            st2(dxr + c, make_float2(rstd[r] * (dg[i].x - m1 - xh[i].x * m2) + rv[r][i].x,
+                                     rstd[r] * (dg[i].y - m1 - xh[i].y * m2) + rv[r][i].y));
+          }
+        }
       }
     }
   }
@@ -143,19 +183,21 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
   }
 }
 
+// block (32, 32): threadIdx.x = output within a 32-wide slice, threadIdx.y = partial lane; fixed
+// summation order (lane-strided partial sums, then lanes 0..31): deterministic.
 __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int C,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red[8][33];
-  const int idx = blockIdx.x * 32 + (threadIdx.x & 31), zl = threadIdx.x >> 5;
+  __shared__ float red[32][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x, zl = threadIdx.y;
   float s = 0.f;
   if (idx < 2 * C)
-    for (int z = zl; z < nblocks; z += 8) s += partial[(size_t)z * 2 * C + idx];
-  red[zl][threadIdx.x & 31] = s;
+    for (int z = zl; z < nblocks; z += 32) s += partial[(size_t)z * 2 * C + idx];
+  red[zl][threadIdx.x] = s;
   __syncthreads();
   if (zl == 0 && idx < 2 * C) {
     float t = 0.f;
 #pragma unroll
-    for (int l = 0; l < 8; ++l) t += red[l][threadIdx.x & 31];
+    for (int l = 0; l < 32; ++l) t += red[l][threadIdx.x];
     if (idx < C) dgamma[idx] = t; else dbeta[idx - C] = t;
   }
 }
@@ -176,7 +218,9 @@ size_t layernorm_bwd_workspace(long long rows, int C) {
 int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st) {
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
-  const int grid = ceil_div(rows, LN_WARPS), nv = nv_of(C);
+  const int nv = nv_of(C);
+  const int rows_per_warp = nv == 1 ? 4 : (nv == 2 ? 2 : 1);      // RowsOf<NV>::R
+  const int grid = (int)ceil_div(rows, (long long)LN_WARPS * rows_per_warp);
 #define LAUNCH(TI, TO, NVV)                                                                    \
   layernorm_fwd_kernel<TI, TO, NVV><<<grid, LN_WARPS * 32, 0, st>>>((const TI*)x, gamma, beta, \
                                                                      (TO*)y, mean, rstd, rows, C, eps)
@@ -201,7 +245,8 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
                   float* dbeta, long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
   DAT_REQUIRE(ws_bytes >= layernorm_bwd_workspace(rows, C), "layernorm_bwd: workspace too small");
-  const int nblk = ln_bwd_blocks(rows), nv = nv_of(C);
+  int nblk = ln_bwd_blocks(rows);
+  const int nv = nv_of(C);
   const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
   float* part = (float*)ws;
 #define LAUNCH(TI, TD, NVV)                                                                       \
@@ -209,6 +254,11 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
     auto kern = layernorm_bwd_kernel<TI, TD, NVV>;                                                \
     if (smem > 48 * 1024)                                                                         \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    /* persistent grid = exactly the CTAs that are resident at once (one wave) */                 \
+    int occ = 1;                                                                                  \
+    DAT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LN_WARPS * 32, smem));  \
+    if (occ < 1) occ = 1;                                                                         \
+    if (nblk > 148 * occ) nblk = 148 * occ;                                                       \
     kern<<<nblk, LN_WARPS * 32, smem, st>>>((const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
                                             (const TI*)dres, part, rows, C);                                    \
   } while (0)
@@ -225,7 +275,7 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
 #undef LAUNCH_NV
 #undef LAUNCH
   DAT_LAUNCH_OK("layernorm_bwd_kernel");
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * C, 32), 256, 0, st>>>(part, nblk, C, dgamma, dbeta);
+  layernorm_bwd_reduce_kernel<<<ceil_div(2 * C, 32), dim3(32, 32), 0, st>>>(part, nblk, C, dgamma, dbeta);
   DAT_LAUNCH_OK("layernorm_bwd_reduce_kernel");
   return DAT_OK;
 }
