@@ -10,6 +10,7 @@ Shapes the kernels cannot tile, fp32 (non-autocast) execution and CPU tensors us
 convolution (`F.conv2d`) — this module is a "next row" outside the parity-critical block.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -18,6 +19,35 @@ import torch.nn.functional as F
 from . import _cabi
 
 __all__ = ["PointwiseConvCL"]
+
+# The weight / bias gradients are off the critical path of the backward pass (nothing downstream
+# reads them), so they are enqueued on a side stream and run concurrently with the data-gradient
+# chain; the streams are joined once, by an autograd-engine callback at the end of the backward
+# pass.  Under CUDA-graph capture the fork / join become graph dependencies.  DAT_B200_SERIAL_WGRAD=1
+# keeps everything on the current stream.
+_SIDE = {}
+_PENDING = []
+_JOIN_QUEUED = [False]
+
+
+def _side_stream(dev):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev)
+    return _SIDE[key]
+
+
+def _join_side_streams():
+    _JOIN_QUEUED[0] = False
+    for idx, side in _SIDE.items():
+        torch.cuda.current_stream(idx).wait_stream(side)
+    _PENDING.clear()           # tensors the side stream was reading may be reused from here on
+
+
+def _queue_join():
+    if not _JOIN_QUEUED[0]:
+        _JOIN_QUEUED[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
 
 _CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
 
@@ -73,27 +103,39 @@ class _PointwiseFn(torch.autograd.Function):
         dev = x_l.device
         dy = dy.to(torch.bfloat16).contiguous()
         with torch.cuda.device(dev):
+            # dW = dY^T X (bf16 operands), on the side stream
+            serial = bool(os.environ.get("DAT_B200_SERIAL_WGRAD"))
+            cur = torch.cuda.current_stream(dev)
+            wst = cur if serial else _side_stream(dev)
+            if not serial:
+                wst.wait_stream(cur)         # dy (and x) are produced on the current stream
+            with torch.cuda.stream(wst):
+                sw = _stream(dev)
+                if x_l.dtype == torch.float32:
+                    xb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+                    _cabi.check(lib.dat_cast_bf16(_ptr(x_l), _ptr(xb), M * K, sw), "dat_cast_bf16")
+                else:
+                    xb = x_l
+                nbytes = lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K)
+                ws = torch.empty(max(nbytes, 64), device=dev, dtype=torch.uint8)
+                dw = torch.empty(N, K, device=dev, dtype=torch.float32)
+                db = torch.empty(N, device=dev, dtype=torch.float32) if ctx.has_bias else None
+                # db = column sums of dY ride along in the same tensor-core pass
+                _cabi.check(lib.dat_pointwise_wgrad_tc(_ptr(dy), _ptr(xb), _ptr(dw), _ptr(db), M, N, K, _ptr(ws),
+                                                       ws.numel(), sw), "dat_pointwise_wgrad_tc")
+                dw = dw.reshape(ctx.wshape).to(ctx.wdtype)
+                db = db.to(ctx.wdtype) if db is not None else None
+            if not serial:
+                _PENDING.append((dy, x_l, xb, ws))   # keep what the side stream reads alive until the join
+                _queue_join()
+            # dX = dY W: K-major GEMM against W^T (K, N) in bf16, on the current stream
             st = _stream(dev)
-            # dX = dY W: K-major GEMM against W^T (K, N) in bf16
             wT = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
             _cabi.check(lib.dat_cast_transpose_bf16(_ptr(w32), _ptr(wT), N, K, st), "dat_cast_transpose_bf16")
             dx = torch.empty_like(x_l)
             _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(dy), _cabi.DAT_BF16, _ptr(wT), None, _ptr(dx),
                                                  _CODE[dx.dtype], M, K, N, st), "dat_pointwise_fwd_tc(dgrad)")
-            # dW = dY^T X (bf16 operands)
-            if x_l.dtype == torch.float32:
-                xb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
-                _cabi.check(lib.dat_cast_bf16(_ptr(x_l), _ptr(xb), M * K, st), "dat_cast_bf16")
-            else:
-                xb = x_l
-            nbytes = lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K)
-            ws = torch.empty(max(nbytes, 64), device=dev, dtype=torch.uint8)
-            dw = torch.empty(N, K, device=dev, dtype=torch.float32)
-            db = torch.empty(N, device=dev, dtype=torch.float32) if ctx.has_bias else None
-            # db = column sums of dY ride along in the same tensor-core pass
-            _cabi.check(lib.dat_pointwise_wgrad_tc(_ptr(dy), _ptr(xb), _ptr(dw), _ptr(db), M, N, K, _ptr(ws),
-                                                   ws.numel(), st), "dat_pointwise_wgrad_tc")
-        return dx, dw.reshape(ctx.wshape).to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None)
+        return dx, dw, db
 
 
 class PointwiseConvCL(nn.Conv2d):
