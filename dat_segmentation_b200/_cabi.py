@@ -85,6 +85,8 @@ def lib():
     L.dat_cast_transpose_bf16.restype = L.dat_pointwise_wgrad_tc.restype = L.dat_bias_grad.restype = C.c_int
     L.dat_debug_gemm_timing.argtypes = [C.POINTER(C.c_uint64)]
     L.dat_debug_gemm_timing.restype = C.c_int
+    L.dat_debug_attn_bwd_timing.argtypes = [C.POINTER(C.c_uint64)]
+    L.dat_debug_attn_bwd_timing.restype = C.c_int
     L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
     L.dat_ref_points.argtypes = [i32, i32, f32p, f32p, vp]
     L.dat_sample_fwd.argtypes = [dp, vp, f32p, vp, vp, vp]
@@ -130,7 +132,7 @@ def exported_symbols():
     """Names declared in include/dat_b200.h (used by the CPU-side symbol test)."""
     return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
-            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing",
+            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing", "dat_debug_attn_bwd_timing",
             "dat_cast_transpose_bf16", "dat_pointwise_wgrad_tc_workspace_bytes", "dat_pointwise_wgrad_tc",
             "dat_bias_grad",
             "dat_offset_pos_fwd",

@@ -22,10 +22,17 @@
 //     in runs (table step per query < 1), so runs are pre-summed with a segmented shuffle
 //     reduction and only run leaders issue shared-memory atomics into a per-CTA padded fp32
 //     copy of the table, flushed with one global atomic per cell at the end.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
 namespace dat {
+
+// Phase cycle counters of compute warp 4, summed over the CTAs of every launch (debug aid, read by
+// dat_debug_attn_bwd_timing): [0] tile loop total, [1] wait for S / dP, [2] score loop (bias, P, dS,
+// table gradient), [3] d pos column sums, [4] dQ wait + store, [5] per-tile setup, [6] CTAs.
+__device__ unsigned long long g_attn_bwd_prof[8];
 
 namespace {
 
@@ -45,7 +52,7 @@ constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 288, TM_DV = 352;
 
 struct BtcArgs {
   int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
-  int n_tiles, rows_max, chunks, nslots;
+  int n_tiles, rows_max, chunks, nslots, light_table;
   float c1, scale, kx, ky, gsx, gsy;
 };
 
@@ -294,7 +301,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int i = 0; i < NHALF * 2; ++i) dpx_acc[i] = dpy_acc[i] = 0.f;
     int it = 0;
+    long long pf_total = clock64(), pf_wait = 0, pf_score = 0, pf_col = 0, pf_dq = 0, pf_setup = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      long long pf_t = clock64();
       const int m = tile * TQ + row;
       const bool valid = m < a.HW;
       const int mm = valid ? m : a.HW - 1;
@@ -320,19 +329,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float dl = delta[(long long)bh * a.HW + mm];
       const int r_up = __shfl_up_sync(FULL, r, 1);
       const bool row_head = lane == 0 || r_up != r;
+      const int r_up2 = __shfl_up_sync(FULL, r, 2), r_dn = __shfl_down_sync(FULL, r, 1);
+      const bool rs1 = lane >= 1 && r_up == r, rs2 = lane >= 2 && r_up2 == r;   // lane-1 / lane-2 in my image row
+      const bool row_end = lane == 31 || r_dn != r;
       float* mytab = sDTab + (PRIV ? (warp - 4) * a.Hp * a.Wp : 0);
       uint8_t* prow_p = sP + chalf * 16384 + row * 128;
       uint8_t* prow_d = sDS + chalf * 16384 + row * 128;
 
+      pf_setup += clock64() - pf_t;
 #pragma unroll 1
       for (int h = 0; h < NHALF; ++h) {
         const uint32_t e_idx = (uint32_t)(it * NHALF + h);
+        pf_t = clock64();
         mbar_wait(sdp_full, e_idx & 1u);
         tc_fence_after_sync();
+        pf_wait += clock64() - pf_t;
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
           const int col0 = chalf * 64 + sub * 32;          // column within the half
           uint32_t sv[32], dpv[32];
+          pf_t = clock64();
           tmem_ld_32x32(t_lane + TM_S + (uint32_t)col0, sv);
           tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
           tmem_wait_ld();
@@ -344,8 +360,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int2 ye = yt[j];
-            float u = ax - xk[j];
-            u = fminf(fmaxf(u, -1.5f), xhi);
+            const float ur = ax - xk[j];
+            const float u = fminf(fmaxf(ur, -1.5f), xhi);
             const float aa = u + MAGIC;
             const float fx = (u - (aa - MAGIC)) + 0.5f;
             const float fy = __int_as_float(ye.y);
@@ -393,54 +409,81 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // neighbour (same image row, cell x0-1, single window), so a run usually issues 2
             // updates (rows y0, y0+1 of one cell) instead of 4.
             {
-              const int pk = __shfl_up_sync(FULL, idx, 1);
-              const bool head = row_head || pk != idx;
-              const unsigned heads = __ballot_sync(FULL, head);
-              const int start = 31 - __clz((int)(heads & (FULL >> (31 - lane))));
-              float Qw = ds * fx, Pw = ds - Qw;
-#pragma unroll
-              for (int dsh = 1; dsh <= 4; dsh <<= 1) {
-                const float oP = __shfl_down_sync(FULL, Pw, dsh), oQ = __shfl_down_sync(FULL, Qw, dsh);
-                const int os = __shfl_down_sync(FULL, start, dsh);
-                const bool same = (lane + dsh < 32) && (os == start);
-                Pw += same ? oP : 0.f;
-                Qw += same ? oQ : 0.f;
-              }
-              const unsigned above = (heads >> lane) >> 1;              // heads strictly above my lane
-              const int nh = above ? lane + __ffs((int)above) : 32;    // next run head (32: none)
-              const int src_n = nh & 31;
-              const int idx_n = __shfl_sync(FULL, idx, src_n);
-              const int r_n = __shfl_sync(FULL, r, src_n);
-              const bool is_head = lane == start;
-              // my Q is absorbed by the next run's head
-              const bool absorbed = is_head && nh < 32 && (nh - lane) <= 8 && idx_n == idx + 1 && r_n == r;
-              // I (a run head) absorb the previous run's Q: previous head lane
-              const unsigned below = heads & ((1u << lane) - 1u);
-              const int ph = below ? 31 - __clz((int)below) : 0;
-              const float q_prev = __shfl_sync(FULL, Qw, ph);
-              const bool take = is_head && below != 0u && (lane - ph) <= 8 && pk + 1 == idx && r_up == r;
-              const float Uw = Pw + (take ? q_prev : 0.f);
-              const bool leader = ((lane - start) & 7) == 0;
               float* cell = mytab + idx;                  // padded index: no bounds checks
               const float wy1 = fy, wy0 = 1.0f - fy;
-              if (PRIV) {
-                if (leader) { cell[0] += Uw * wy0; cell[a.Wp] += Uw * wy1; }
+              // Light path (0.29 <= table step per query <= 1, nothing clamped: every shipped config):
+              // runs are at most 4 lanes and consecutive runs hit consecutive cells.  Two-level
+              // segmented prefix scans leave the run totals in the run's LAST lane, which sits next
+              // to the head of the following run: the fx part of run k moves to run k + 1 with one
+              // shuffle, so a run issues 2 updates (8 shuffles, no ballots / bit scans).
+              if (PRIV && a.light_table && !__any_sync(FULL, u != ur)) {   // (measured slower with atomics)
+                const int i_u1 = __shfl_up_sync(FULL, idx, 1), i_u2 = __shfl_up_sync(FULL, idx, 2);
+                const int i_d1 = __shfl_down_sync(FULL, idx, 1);
+                const bool s1 = rs1 && i_u1 == idx, s2 = rs2 && i_u2 == idx;
+                const bool tail = row_end || i_d1 != idx;
+                float Qs = ds * fx, Ps = ds - Qs, t;
+                t = __shfl_up_sync(FULL, Qs, 1); Qs += s1 ? t : 0.f;
+                t = __shfl_up_sync(FULL, Qs, 2); Qs += s2 ? t : 0.f;
+                const float qp = __shfl_up_sync(FULL, Qs, 1);          // previous run's total (from its last lane)
+                Ps += (!s1 && rs1 && i_u1 + 1 == idx) ? qp : 0.f;
+                t = __shfl_up_sync(FULL, Ps, 1); Ps += s1 ? t : 0.f;
+                t = __shfl_up_sync(FULL, Ps, 2); Ps += s2 ? t : 0.f;
+                const bool absorbed = !row_end && i_d1 == idx + 1;     // the next run's head took my fx part
+                if (tail) { cell[0] += Ps * wy0; cell[a.Wp] += Ps * wy1; }
                 __syncwarp();
-                if (leader && !absorbed) { cell[1] += Qw * wy0; cell[a.Wp + 1] += Qw * wy1; }
+                if (tail && !absorbed) { cell[1] += Qs * wy0; cell[a.Wp + 1] += Qs * wy1; }
                 __syncwarp();
-              } else if (leader) {
-                atomicAdd(cell, Uw * wy0);
-                atomicAdd(cell + a.Wp, Uw * wy1);
-                if (!absorbed) {
-                  atomicAdd(cell + 1, Qw * wy0);
-                  atomicAdd(cell + a.Wp + 1, Qw * wy1);
+              } else {
+                const int pk = __shfl_up_sync(FULL, idx, 1);
+                const bool head = row_head || pk != idx;
+                const unsigned heads = __ballot_sync(FULL, head);
+                const int start = 31 - __clz((int)(heads & (FULL >> (31 - lane))));
+                float Qw = ds * fx, Pw = ds - Qw;
+#pragma unroll
+                for (int dsh = 1; dsh <= 4; dsh <<= 1) {
+                  const float oP = __shfl_down_sync(FULL, Pw, dsh), oQ = __shfl_down_sync(FULL, Qw, dsh);
+                  const int os = __shfl_down_sync(FULL, start, dsh);
+                  const bool same = (lane + dsh < 32) && (os == start);
+                  Pw += same ? oP : 0.f;
+                  Qw += same ? oQ : 0.f;
+                }
+                const unsigned above = (heads >> lane) >> 1;              // heads strictly above my lane
+                const int nh = above ? lane + __ffs((int)above) : 32;    // next run head (32: none)
+                const int src_n = nh & 31;
+                const int idx_n = __shfl_sync(FULL, idx, src_n);
+                const int r_n = __shfl_sync(FULL, r, src_n);
+                const bool is_head = lane == start;
+                // my Q is absorbed by the next run's head
+                const bool absorbed = is_head && nh < 32 && (nh - lane) <= 8 && idx_n == idx + 1 && r_n == r;
+                // I (a run head) absorb the previous run's Q: previous head lane
+                const unsigned below = heads & ((1u << lane) - 1u);
+                const int ph = below ? 31 - __clz((int)below) : 0;
+                const float q_prev = __shfl_sync(FULL, Qw, ph);
+                const bool take = is_head && below != 0u && (lane - ph) <= 8 && pk + 1 == idx && r_up == r;
+                const float Uw = Pw + (take ? q_prev : 0.f);
+                const bool leader = ((lane - start) & 7) == 0;
+                if (PRIV) {
+                  if (leader) { cell[0] += Uw * wy0; cell[a.Wp] += Uw * wy1; }
+                  __syncwarp();
+                  if (leader && !absorbed) { cell[1] += Qw * wy0; cell[a.Wp + 1] += Qw * wy1; }
+                  __syncwarp();
+                } else if (leader) {
+                  atomicAdd(cell, Uw * wy0);
+                  atomicAdd(cell + a.Wp, Uw * wy1);
+                  if (!absorbed) {
+                    atomicAdd(cell + 1, Qw * wy0);
+                    atomicAdd(cell + a.Wp + 1, Qw * wy1);
+                  }
                 }
               }
             }
           }
           // d pos: column sums over this warp's 32 rows (lane L ends up with column L)
+          const long long pf_m = clock64();
+          pf_score += pf_m - pf_t;
           dpx_acc[h * 2 + sub] += column_sums32(gxs, lane);
           dpy_acc[h * 2 + sub] += column_sums32(gys, lane);
+          pf_col += clock64() - pf_m;
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
@@ -448,6 +491,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
 
       // dQ tile: TMEM -> * scale -> bf16 -> global (each compute warp writes 16 channels)
+      pf_t = clock64();
       mbar_wait(dq_full, (uint32_t)it & 1u);
       tc_fence_after_sync();
       uint32_t qv[16];
@@ -464,6 +508,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         dst[0] = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
         dst[1] = make_uint4(pk8[4], pk8[5], pk8[6], pk8[7]);
       }
+      pf_dq += clock64() - pf_t;
+    }
+    if (warp == 4 && lane == 0) {
+      atomicAdd(&g_attn_bwd_prof[0], (unsigned long long)(clock64() - pf_total));
+      atomicAdd(&g_attn_bwd_prof[1], (unsigned long long)pf_wait);
+      atomicAdd(&g_attn_bwd_prof[2], (unsigned long long)pf_score);
+      atomicAdd(&g_attn_bwd_prof[3], (unsigned long long)pf_col);
+      atomicAdd(&g_attn_bwd_prof[4], (unsigned long long)pf_dq);
+      atomicAdd(&g_attn_bwd_prof[5], (unsigned long long)pf_setup);
+      atomicAdd(&g_attn_bwd_prof[6], 1ull);
     }
 
     // ---- end of CTA: dK / dV accumulators, d pos, d table --------------------------------------
@@ -581,6 +635,13 @@ BtcVariant pick_variant(const Shape& s) {
   return v;
 }
 
+int debug_attn_bwd_timing(unsigned long long* out8) {
+  DAT_CUDA_OK(cudaMemcpyFromSymbol(out8, g_attn_bwd_prof, sizeof(unsigned long long) * 8));
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  DAT_CUDA_OK(cudaMemcpyToSymbol(g_attn_bwd_prof, zero, sizeof(zero)));
+  return DAT_OK;
+}
+
 bool attention_bwd_tc_supported(const Shape& s) { return pick_variant(s).ok != 0; }
 bool attention_bwd_tc_compact_table(const Shape& s) { return pick_variant(s).compact != 0; }
 
@@ -601,6 +662,10 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
   DAT_REQUIRE(var.ok, "attention_bwd_tc: unsupported shape");
   BtcArgs a;
   a.nslots = var.nslots;
+  {   // light table-gradient path: 0.29 <= table cells per query step <= 1 (runs of <= 3.5 lanes)
+    const float step = 0.5f * (float)(s.Tw - 1) / (float)(s.W - 1);
+    a.light_table = step >= 0.2857f && step <= 1.0f && std::getenv("DAT_B200_ATTN_BWD_GENERIC_TABLE") == nullptr;
+  }
   a.B = s.B; a.H = s.H; a.W = s.W; a.HW = s.HW; a.C = s.C; a.heads = s.heads; a.G = s.G; a.hg = s.hg;
   a.Th = s.Th; a.Tw = s.Tw; a.Wp = s.Tw + 3; a.Hp = s.Th + 3;
   a.n_tiles = (s.HW + TQ - 1) / TQ;

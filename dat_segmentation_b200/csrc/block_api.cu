@@ -158,6 +158,11 @@ int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const fl
   return pointwise_fwd_tc(X, x_dtype, W, b, Y, y_dtype, M, N, K, (cudaStream_t)stream);
 }
 
+int dat_debug_attn_bwd_timing(uint64_t* out8) {
+  DAT_REQUIRE(out8 != nullptr, "debug_attn_bwd_timing: NULL pointer");
+  return debug_attn_bwd_timing((unsigned long long*)out8);
+}
+
 int dat_debug_gemm_timing(uint64_t* out8) {
   DAT_REQUIRE(out8 != nullptr, "debug_gemm_timing: NULL pointer");
   DAT_CUDA_OK(cudaDeviceSynchronize());

@@ -73,6 +73,7 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
 
 namespace dat {
 int debug_gemm_timing(unsigned long long* out8);
+int debug_attn_bwd_timing(unsigned long long* out8);
 }
 
 namespace dat {

@@ -135,6 +135,10 @@ int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const fl
  * launch: entry, setup done, first TMA stage landed, MMAs issued, accumulator ready,
  * epilogue done (6 of 8 slots used).  Synchronises the device. */
 int dat_debug_gemm_timing(uint64_t* out8);
+/* Debug aid: SM-cycle phase counters of the tensor-core attention backward since the last call
+ * (summed over CTAs): [0] tile loop, [1] wait for S/dP, [2] score loop, [3] d pos column sums,
+ * [4] dQ wait + store, [5] per-tile setup, [6] number of CTAs.  Synchronises the device. */
+int dat_debug_attn_bwd_timing(uint64_t* out8);
 /* Tensor-core gradients of the 1x1 convolution (bf16 operands, fp32 accumulation):
  *   data gradient  dX[M,K] = dY[M,N] W[N,K]  ==  dat_pointwise_fwd_tc(dY, W^T) with the (K,N) bf16
  *                  transposed weight from dat_cast_transpose_bf16;
