@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = "DAT-T++ backbone fwd+bwd images/sec @512x512"
 UNIT = "images/s"
 IMG = 512
+WORKLOAD = ("DAT-T++ backbone fwd+bwd, 512x512, batch 16 per GPU, bf16 autocast "
+            "(BASELINE.json configs[1])")
 PER_GPU_BATCH = 16
 STAGES = [  # DAT-T++ @512²: (H=W, C, heads, groups, stride, ksize, q_size, n_blocks)
     (128, 64, 2, 1, 8, 9, 56, 1), (64, 128, 4, 2, 4, 7, 28, 2),
@@ -120,8 +122,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(r["ms_per_step"], 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "DAT-T++ backbone fwd+bwd 512x512 (configs[1]), CPU sample batch 2",
-                   "per_gpu_batch": PER_GPU_BATCH},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH,
+                   "implementation": "oracle port of the backbone (library operators) on the host cores; each step "
+                                     "is a bounded sample of the workload: batch 2 instead of 16",
+                   "drop_path_rate": 0.3},
         "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -316,9 +320,9 @@ def main():
             "metric": METRIC, "value": round(total / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "DAT-T++ backbone fwd+bwd, 512x512, batch 16 per GPU, bf16 autocast "
-                                   "(BASELINE.json configs[1]); deformable-attention blocks, LayerNorms and depthwise "
-                                   "convs in dat_b200 kernels, stem / 1x1 MLP convs / down-projections in library ops",
+            "config": {"workload": WORKLOAD,
+                       "implementation": "deformable-attention blocks, LayerNorms, residual/drop-path, MLP 1x1 convs and "
+                                         "depthwise convs in dat_b200 kernels; conv stem / down-projections in library ops",
                        "per_gpu_batch": PER_GPU_BATCH, "global_batch": total,
                        "parallelism": f"dp{world} (batch-sharded, NCCL gradient all-reduce)" if world > 1 else "single GPU",
                        "l2": "working set per step >> 126 MB L2 (no flush needed); roofline leg flushes L2 per launch",
