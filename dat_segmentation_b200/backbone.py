@@ -17,7 +17,7 @@ from .dattention import DAttentionBaseline, _pair
 from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
 from .pointwise import PointwiseConvCL
-from .residual import drop_path_scale, scale_residual
+from .residual import scale_residual
 
 __all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
 
@@ -150,6 +150,18 @@ class TransformerStage(nn.Module):
         x = self.proj(x)
         # the MLP's first 1x1 conv casts its input to the autocast dtype: let the LayerNorm write it
         mlp_in = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+        # stochastic-depth scales of the whole stage in one draw: row i = i-th drop_path call
+        # (independent per call and per sample, as in the reference), mask / keep_prob
+        B = x.shape[0]
+        ps = []
+        for d in range(self.depths):
+            ps += [getattr(self.drop_path[d], "p", 0.0)] * (1 if self.stage_spec[d] == "X" else 2)
+        if self.training and any(q > 0.0 for q in ps):
+            keep = self._keep_probs(ps, x.device)
+            scales = (torch.rand(len(ps), B, device=x.device) < keep).float() / keep
+        else:
+            scales = torch.ones(len(ps), B, device=x.device)
+        si = 0
         for d in range(self.depths):
             p = getattr(self.drop_path[d], "p", 0.0)
             if self.use_lpu:
@@ -157,17 +169,23 @@ class TransformerStage(nn.Module):
             if self.stage_spec[d] == "X":   # note: no residual around mixer+MLP (dat.py:140-144)
                 x = self.attns[d](self.layer_norms[2 * d](x))
                 m = self.mlps[d](self.ln_cnvnxt[str(d)](x, out_dtype=mlp_in))
-                x = scale_residual(m, None, drop_path_scale(m.shape[0], p, self.training, m.device)) if p > 0.0 and self.training else m
+                x = scale_residual(m, None, scales[si]) if p > 0.0 and self.training else m
+                si += 1
             else:
                 x, ln = self.layer_norms[2 * d].forward_fork(x)
                 a, _, _ = self.attns[d](ln)
-                x = scale_residual(self.layer_scales[2 * d](a), x,
-                                   drop_path_scale(a.shape[0], p, self.training, a.device))
+                x = scale_residual(self.layer_scales[2 * d](a), x, scales[si])
                 x, ln = self.layer_norms[2 * d + 1].forward_fork(x, out_dtype=mlp_in)
                 m = self.mlps[d](ln)
-                x = scale_residual(self.layer_scales[2 * d + 1](m), x,
-                                   drop_path_scale(m.shape[0], p, self.training, m.device))
+                x = scale_residual(self.layer_scales[2 * d + 1](m), x, scales[si + 1])
+                si += 2
         return x
+
+    def _keep_probs(self, ps, device):
+        key = (tuple(ps), str(device))
+        if getattr(self, "_keep_cache", (None, None))[0] != key:
+            self._keep_cache = (key, torch.tensor([1.0 - q for q in ps], device=device).view(-1, 1))
+        return self._keep_cache[1]
 
     def _inner_forward(self, x):
         if self.fused_residual and x.is_cuda:
