@@ -1,6 +1,7 @@
 // C ABI (include/dat_b200.h): argument validation, workspace planning and the host-side
 // sequencing of the kernels of one deformable-attention block.  No allocation, no host
 // synchronisation: everything is enqueued on the caller's stream.
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -74,8 +75,41 @@ struct BwdPlan {
   void* wT;         // bf16 transposed copies of (wo, wk, wv, wq) for the tensor-core data gradients
   void* x_bf;       // bf16 copy of an fp32 x for the tensor-core weight gradient of proj_q
   void* sub;        // shared scratch of the individual stages (used one at a time)
-  size_t sub_bytes, total;
+  void* wg;         // scratch of the tensor-core weight gradients (they run on a side stream)
+  size_t sub_bytes, wg_bytes, total;
 };
+
+// The weight / bias gradients of the four projections are off the critical path (nothing later in
+// the backward reads them).  They are enqueued on a library-owned side stream, forked from the
+// caller's stream when their inputs are ready and joined before dat_block_backward returns, so they
+// run next to the attention backward (which leaves SMs idle) and the data-gradient chain.  Under
+// CUDA-graph capture the fork / join become graph edges.  DAT_B200_SERIAL_WGRAD=1 disables this.
+struct SideStreams {
+  cudaStream_t s;
+  cudaEvent_t ev[5];
+};
+SideStreams* side_streams() {
+  static SideStreams ctx[64];
+  static bool made[64];
+  static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  if (getenv("DAT_B200_SERIAL_WGRAD") != nullptr) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  pthread_mutex_lock(&mu);
+  if (!made[dev]) {
+    bool ok = cudaStreamCreateWithFlags(&ctx[dev].s, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 5 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&ctx[dev].ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      pthread_mutex_unlock(&mu);
+      return nullptr;
+    }
+    made[dev] = true;
+  }
+  pthread_mutex_unlock(&mu);
+  return &ctx[dev];
+}
 
 bool use_tc_attn_bwd(const Shape& s) { return tc_enabled() && attention_bwd_tc_supported(s); }
 // number of query splits whose partial dK / dV / dpos the backward produces
@@ -115,6 +149,14 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   if (w3 > sub) sub = w3;
   p.sub_bytes = sub;
   p.sub = c.take(sub);
+  p.wg_bytes = 0;
+  if (s.act_dtype == DAT_BF16 && pointwise_wgrad_tc_supported((long long)s.B * s.HW, s.C, s.C) &&
+      pointwise_wgrad_tc_supported((long long)s.B * s.Ns, s.C, s.C)) {
+    const size_t a = pointwise_wgrad_tc_workspace((long long)s.B * s.HW, s.C, s.C);
+    const size_t b = pointwise_wgrad_tc_workspace((long long)s.B * s.Ns, s.C, s.C);
+    p.wg_bytes = a > b ? a : b;
+  }
+  p.wg = c.take(p.wg_bytes);
   p.total = c.off;
   return p;
 }
@@ -386,12 +428,21 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   // weight gradients dW = dY^T X on the tensor cores (both operands read MN-major), bias
   // gradients as column sums
   const bool tcw = tc && pointwise_wgrad_tc_supported(M, C, C) && pointwise_wgrad_tc_supported(Mk, C, C);
+  SideStreams* ss = tcw && w.wg_bytes > 0 ? side_streams() : nullptr;
+  cudaStream_t wst = ss != nullptr ? ss->s : st;       // stream of the tensor-core weight gradients
+  auto fork = [&](int i) -> int {                       // side stream waits for the work enqueued so far
+    if (ss != nullptr) {
+      DAT_CUDA_OK(cudaEventRecord(ss->ev[i], st));
+      DAT_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->ev[i], 0));
+    }
+    return DAT_OK;
+  };
   auto wgrad = [&](const void* dY, const void* X, int x_dt, float* dW, float* db, long long rows) -> int {
     if (!tcw) return pointwise_wgrad_simt(dY, adt, X, x_dt, dW, db, rows, C, C, w.sub, w.sub_bytes, st);
-    const size_t wsz_tc = pointwise_wgrad_tc_workspace(rows, C, C);
-    return pointwise_wgrad_tc(dY, X, dW, db, rows, C, C, w.sub, wsz_tc, st);
+    return pointwise_wgrad_tc(dY, X, dW, db, rows, C, C, w.wg, w.wg_bytes, wst);
   };
   // proj_out
+  DAT_FWD(fork(0));
   DAT_FWD(wgrad(dy, sv->o, adt, g->wo, g->bo, M));
   if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
@@ -416,6 +467,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
                                w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
   }
   // proj_k / proj_v
+  DAT_FWD(fork(1));
   DAT_FWD(wgrad(w.dk, sv->xs, adt, g->wk, g->bk, Mk));
   DAT_FWD(wgrad(w.dv, sv->xs, adt, g->wv, g->bv, Mk));
   if (tc) {
@@ -428,8 +480,9 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
   DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
   // proj_q, then the sampling scatter on top of its data gradient
+  DAT_FWD(fork(2));
   if (tcw && s.x_dtype == DAT_F32) {
-    DAT_FWD(cast_weights_bf16((const float*)x, nullptr, nullptr, w.x_bf, M * C, st));
+    DAT_FWD(cast_weights_bf16((const float*)x, nullptr, nullptr, w.x_bf, M * C, wst));
     DAT_FWD(wgrad(w.dq, w.x_bf, DAT_BF16, g->wq, g->bq, M));
   } else {
     DAT_FWD(wgrad(w.dq, x, s.x_dtype, g->wq, g->bq, M));
@@ -437,6 +490,10 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   if (tc) DAT_FWD(pointwise_fwd_tc(w.dq, adt, wT + 3 * wsz, nullptr, dx, DAT_F32, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
   DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
+  if (ss != nullptr) {                                  // join: the caller's stream owns every result again
+    DAT_CUDA_OK(cudaEventRecord(ss->ev[4], ss->s));
+    DAT_CUDA_OK(cudaStreamWaitEvent(st, ss->ev[4], 0));
+  }
   return DAT_OK;
 }
 
