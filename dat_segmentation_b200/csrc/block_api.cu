@@ -478,7 +478,8 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   }
   // sampling -> d pos; offset network -> dq
   DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
-  DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st));
+  DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st,
+                     ss != nullptr ? ss->s : st, ss != nullptr ? ss->ev[3] : nullptr));
   // proj_q, then the sampling scatter on top of its data gradient
   DAT_FWD(fork(2));
   if (tcw && s.x_dtype == DAT_F32) {

@@ -30,7 +30,7 @@ int ref_points(int Hk, int Wk, float* ry, float* rx, cudaStream_t st);
 size_t offset_bwd_workspace(const Shape& s);
 int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const float* t_dw,
                const float* off_raw, const float* dpos, void* dq, const dat_block_grads* g,
-               void* ws, size_t ws_bytes, cudaStream_t st);
+               void* ws, size_t ws_bytes, cudaStream_t st, cudaStream_t pst, cudaEvent_t fork_ev);
 
 // gather.cu
 int sample_fwd(const Shape& s, const void* x, const float* pos, void* xs, int32_t* taps,

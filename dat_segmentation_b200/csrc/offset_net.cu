@@ -570,7 +570,7 @@ size_t offset_bwd_workspace(const Shape& s) {
 // dpos (B,G,Ns,2) -> parameter grads of the offset net, and dq += depthwise data gradient.
 int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const float* t_dw,
                const float* off_raw, const float* dpos, void* dq, const dat_block_grads* g,
-               void* ws, size_t ws_bytes, cudaStream_t st) {
+               void* ws, size_t ws_bytes, cudaStream_t st, cudaStream_t pst, cudaEvent_t fork_ev) {
   DAT_REQUIRE(s.Cg <= 512, "offset net: Cg=%d > 512 unsupported", s.Cg);
   DAT_REQUIRE(ws_bytes >= offset_bwd_workspace(s), "offset_bwd: workspace too small");
   OffsetArgs a = make_args(s);
@@ -593,7 +593,13 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   if (cpl == 2) LAUNCH(2); else if (cpl == 4) LAUNCH(4); else if (cpl == 8) LAUNCH(8); else LAUNCH(16);
 #undef LAUNCH
   DAT_LAUNCH_OK("offset_bwd_point_kernel");
-  offset_bwd_reduce_kernel<<<ceil_div(5 * s.Cg, 128), 128, 0, st>>>(
+  // the parameter gradients (reductions, depthwise weight gradient) are off the critical path: they
+  // go to the side stream `pst` (== st: no fork); only the data gradient below stays on `st`
+  if (pst != st) {
+    DAT_CUDA_OK(cudaEventRecord(fork_ev, st));
+    DAT_CUDA_OK(cudaStreamWaitEvent(pst, fork_ev, 0));
+  }
+  offset_bwd_reduce_kernel<<<ceil_div(5 * s.Cg, 128), 128, 0, pst>>>(
       part1, nblk, s.Cg, g->off_pw_w, g->off_ln_g, g->off_ln_b, g->off_dw_b);
   DAT_LAUNCH_OK("offset_bwd_reduce_kernel");
 
@@ -602,7 +608,7 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   const bool fast = offset_bwd_fast_supported(s);
   if (fast) {
 #define LAUNCH_WG(TQ, KV) \
-    offset_bwd_wgrad_rows_kernel<TQ, KV><<<nsplit, KV * WGR_PG * 32, 0, st>>>((const TQ*)q, dt, part2, (int)pps, a)
+    offset_bwd_wgrad_rows_kernel<TQ, KV><<<nsplit, KV * WGR_PG * 32, 0, pst>>>((const TQ*)q, dt, part2, (int)pps, a)
 #define LAUNCH_WG_K(TQ)                                                             \
     do {                                                                            \
       if (s.ksize == 3) LAUNCH_WG(TQ, 3); else if (s.ksize == 5) LAUNCH_WG(TQ, 5);  \
@@ -612,11 +618,11 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
 #undef LAUNCH_WG_K
 #undef LAUNCH_WG
   } else if (s.act_dtype == DAT_F32)
-    offset_bwd_wgrad_kernel<float><<<nsplit, 256, 0, st>>>((const float*)q, dt, part2, pps, a);
+    offset_bwd_wgrad_kernel<float><<<nsplit, 256, 0, pst>>>((const float*)q, dt, part2, pps, a);
   else
-    offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, st>>>((const bf16*)q, dt, part2, pps, a);
+    offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, pst>>>((const bf16*)q, dt, part2, pps, a);
   DAT_LAUNCH_OK("offset_bwd_wgrad_kernel");
-  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 32), dim3(32, 32), 0, st>>>(part2, nsplit, kk, s.Cg,
+  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 32), dim3(32, 32), 0, pst>>>(part2, nsplit, kk, s.Cg,
                                                                                     g->off_dw_w);
   DAT_LAUNCH_OK("offset_bwd_wgrad_reduce_kernel");
 

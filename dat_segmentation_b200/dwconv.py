@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from ._streams import hold_until_join, serial as _serial, side_stream
 
 __all__ = ["dwconv_cl", "DepthwiseConvCL"]
 
@@ -84,17 +85,29 @@ class _DwConvFn(torch.autograd.Function):
                 dz = dz.contiguous()
             nbytes = lib.dat_dwconv_workspace_bytes(B, H, W, Cc, k)
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            # weight / bias gradient: off the critical path, on the side stream (own workspace)
+            cur = torch.cuda.current_stream(dev)
+            wst = cur if _serial() else side_stream(dev)
+            if wst is not cur:
+                wst.wait_stream(cur)         # dz was produced on the current stream
+            with torch.cuda.stream(wst):
+                sw = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                ws2 = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                dw = torch.empty_like(w32)
+                db = torch.empty(Cc, device=dev, dtype=torch.float32) if ctx.has_bias else None
+                _cabi.check(lib.dat_dwconv_wgrad(_ptr(x_l), _CODE[x_l.dtype], _ptr(dz), _CODE[dz.dtype], _ptr(dw),
+                                                 _ptr(db), B, H, W, Cc, k, _ptr(ws2), nbytes, sw), "dat_dwconv_wgrad")
+                dw = dw.to(ctx.wdtype)
+                db = db.to(ctx.wdtype) if db is not None else None
+            if wst is not cur:
+                hold_until_join(x_l, dz, ws2)
             dx = torch.empty_like(x_l)
             # data gradient: the same kernel with the flipped filter, + dz for the residual modes
             _cabi.check(lib.dat_dwconv_fwd(_ptr(dz), _CODE[dz.dtype], _ptr(w32), None, _ptr(dx), None,
                                            _CODE[dx.dtype], B, H, W, Cc, k,
                                            MODE_PLAIN if mode == MODE_PLAIN else MODE_RESIDUAL, 1, _ptr(ws),
                                            nbytes, st), "dat_dwconv_fwd(dgrad)")
-            dw = torch.empty_like(w32)
-            db = torch.empty(Cc, device=dev, dtype=torch.float32) if ctx.has_bias else None
-            _cabi.check(lib.dat_dwconv_wgrad(_ptr(x_l), _CODE[x_l.dtype], _ptr(dz), _CODE[dz.dtype], _ptr(dw),
-                                             _ptr(db), B, H, W, Cc, k, _ptr(ws), nbytes, st), "dat_dwconv_wgrad")
-        return dx, dw.to(ctx.wdtype), (db.to(ctx.wdtype) if db is not None else None), None, None
+        return dx, dw, db, None, None
 
 
 def dwconv_cl(x, weight, bias, mode, out_dtype=None):

@@ -10,44 +10,15 @@ Shapes the kernels cannot tile, fp32 (non-autocast) execution and CPU tensors us
 convolution (`F.conv2d`) — this module is a "next row" outside the parity-critical block.
 """
 import ctypes as C
-import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
+from ._streams import hold_until_join, serial as _serial, side_stream
 
 __all__ = ["PointwiseConvCL"]
-
-# The weight / bias gradients are off the critical path of the backward pass (nothing downstream
-# reads them), so they are enqueued on a side stream and run concurrently with the data-gradient
-# chain; the streams are joined once, by an autograd-engine callback at the end of the backward
-# pass.  Under CUDA-graph capture the fork / join become graph dependencies.  DAT_B200_SERIAL_WGRAD=1
-# keeps everything on the current stream.
-_SIDE = {}
-_PENDING = []
-_JOIN_QUEUED = [False]
-
-
-def _side_stream(dev):
-    key = (dev.index if dev.index is not None else torch.cuda.current_device())
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(dev)
-    return _SIDE[key]
-
-
-def _join_side_streams():
-    _JOIN_QUEUED[0] = False
-    for idx, side in _SIDE.items():
-        torch.cuda.current_stream(idx).wait_stream(side)
-    _PENDING.clear()           # tensors the side stream was reading may be reused from here on
-
-
-def _queue_join():
-    if not _JOIN_QUEUED[0]:
-        _JOIN_QUEUED[0] = True
-        torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
 
 _CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
 
@@ -104,9 +75,9 @@ class _PointwiseFn(torch.autograd.Function):
         dy = dy.to(torch.bfloat16).contiguous()
         with torch.cuda.device(dev):
             # dW = dY^T X (bf16 operands), on the side stream
-            serial = bool(os.environ.get("DAT_B200_SERIAL_WGRAD"))
+            serial = _serial()
             cur = torch.cuda.current_stream(dev)
-            wst = cur if serial else _side_stream(dev)
+            wst = cur if serial else side_stream(dev)
             if not serial:
                 wst.wait_stream(cur)         # dy (and x) are produced on the current stream
             with torch.cuda.stream(wst):
@@ -126,8 +97,7 @@ class _PointwiseFn(torch.autograd.Function):
                 dw = dw.reshape(ctx.wshape).to(ctx.wdtype)
                 db = db.to(ctx.wdtype) if db is not None else None
             if not serial:
-                _PENDING.append((dy, x_l, xb, ws))   # keep what the side stream reads alive until the join
-                _queue_join()
+                hold_until_join(dy, x_l, xb, ws)   # what the side stream reads stays alive until the join
             # dX = dY W: K-major GEMM against W^T (K, N) in bf16, on the current stream
             st = _stream(dev)
             wT = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
