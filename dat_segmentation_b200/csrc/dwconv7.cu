@@ -103,11 +103,13 @@ dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
   const TI* rp = x + pix0 - (long long)RAD * rstride;      // input row being loaded: starts at y0 - 3
   TO* yp = y + pix0;
   const int th_eff = min(th, H - s.y0);
-  float acc[7][TW][2];
+  // channel pairs are kept as float2 and updated with the packed fp32 FMA (FFMA2): one issue slot per
+  // two multiply-adds in this issue-bound kernel
+  float2 acc[7][TW];
 #pragma unroll
   for (int q = 0; q < 7; ++q)
 #pragma unroll
-    for (int i = 0; i < TW; ++i) acc[q][i][0] = acc[q][i][1] = 0.f;
+    for (int i = 0; i < TW; ++i) acc[q][i] = make_float2(0.f, 0.f);
   typename RI::type raw[WIN];
   load_row<TI, ALIGNED>(rp, s.y0 - RAD >= 0, lval, rval, C, s.x0, W, raw);
   rp += rstride;
@@ -118,9 +120,9 @@ dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
       const int n = nb + k;
       if (n < steps) {
         const int r = s.y0 - RAD + n;
-        float in[WIN][2];
+        float2 in[WIN];
 #pragma unroll
-        for (int j = 0; j < WIN; ++j) { const float2 f = RI::cvt(raw[j]); in[j][0] = f.x; in[j][1] = f.y; }
+        for (int j = 0; j < WIN; ++j) in[j] = RI::cvt(raw[j]);
         load_row<TI, ALIGNED>(rp, r + 1 >= 0 && r + 1 < H && n + 1 < steps, lval, rval, C, s.x0, W, raw);   // prefetch
         rp += rstride;
         if (r >= 0 && r < H) {
@@ -128,25 +130,22 @@ dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
           for (int u = 0; u < 7; ++u) {
             const int m = n - u;                             // output row (relative) fed through tap row u
             if (m >= 0 && m < th_eff) {
-              float (&a)[TW][2] = acc[(k - u + 7) % 7];
+              float2 (&a)[TW] = acc[(k - u + 7) % 7];
 #pragma unroll
               for (int v = 0; v < 7; ++v) {
                 const float2 wv = w_s[u * 7 + v][threadIdx.x];
 #pragma unroll
-                for (int i = 0; i < TW; ++i) {
-                  a[i][0] = fmaf(wv.x, in[i + v][0], a[i][0]);
-                  a[i][1] = fmaf(wv.y, in[i + v][1], a[i][1]);
-                }
+                for (int i = 0; i < TW; ++i) a[i] = __ffma2_rn(wv, in[i + v], a[i]);
               }
             }
           }
         }
         if (n >= 2 * RAD) {                                  // output row n - 6 has seen its last input row
-          float (&a)[TW][2] = acc[(k + 1) % 7];
+          float2 (&a)[TW] = acc[(k + 1) % 7];
 #pragma unroll
           for (int i = 0; i < TW; ++i) {
-            if (ALIGNED || s.x0 + i < W) Raw2<TO>::store(yp + i * C, a[i][0] + b0, a[i][1] + b1);
-            a[i][0] = a[i][1] = 0.f;
+            if (ALIGNED || s.x0 + i < W) Raw2<TO>::store(yp + i * C, a[i].x + b0, a[i].y + b1);
+            a[i] = make_float2(0.f, 0.f);
           }
           yp += rstride;
         }
