@@ -80,7 +80,8 @@ class ClockSampler(threading.Thread):
 
 
 def loss_of(outs):
-    return sum(o.float().square().mean() for o in outs)
+    # loss = sum of the means of the 4 backbone outputs
+    return sum(o.float().mean() for o in outs)
 
 
 # --------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ x = torch.randn(B, 3, 512, 512, device="cuda")
 def step():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         outs = model(x)
-    loss = sum(o.float().square().mean() for o in outs)
+    loss = sum(o.float().mean() for o in outs)
     loss.backward()
     return loss
 
