@@ -299,11 +299,32 @@ def main():
     launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1) / args.steps
 
-    # end-to-end: pinned host -> device every step, loss read back every step
+    # end-to-end: every step copies its batch from pinned host memory and reads the loss back.  The
+    # input pipeline is the usual prefetching loader: the H2D copy of batch i + 1 runs on a copy
+    # stream into a staging buffer while step i computes; a device-side copy moves it into the
+    # graph's static input at the start of the step.  (All copies are inside the timed region.)
+    copy_stream = torch.cuda.Stream(dev)
+    staging = torch.empty_like(imgs)
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            staging.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        imgs.copy_(host, non_blocking=True)
+    ready = prefetch()
+    for i in range(args.steps):
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready)
+        imgs.copy_(staging, non_blocking=True)
+        consumed = torch.cuda.Event()
+        consumed.record(cur)
+        copy_stream.wait_event(consumed)          # staging may be overwritten once it has been consumed
+        if i + 1 < args.steps:
+            ready = prefetch()
         _ = step().item()
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
