@@ -116,6 +116,82 @@ for s, (Cc, HW) in enumerate(STAGES):
             del dxa
         del xa, ya, za
 
+# ---- the deformable-attention block itself (K1 offset net, K2 gather, K3 attention, whole block) ----
+BLOCK_STAGES = [  # DAT-T++ @512^2: (H=W, C, heads, groups, stride, ksize, q_size)
+    (128, 64, 2, 1, 8, 9, 56), (64, 128, 4, 2, 4, 7, 28), (32, 256, 8, 4, 2, 5, 14), (16, 512, 16, 8, 1, 3, 7)]
+for s, (Hh, Cc, heads, G, stride, ksize, qs) in enumerate(BLOCK_STAGES):
+    HWn, Cg = Hh * Hh, Cc // G
+    Th = 2 * qs - 1
+    d = _cabi.BlockDesc(B, Hh, Hh, heads, G, stride, ksize, Th, Th, -1.0, _cabi.DAT_F32, _cabi.DAT_BF16)
+    hk, wk = C.c_int32(), C.c_int32()
+    _cabi.check(lib.dat_sample_grid(C.byref(d), C.byref(hk), C.byref(wk)), "grid")
+    Ns = hk.value * wk.value
+    gen = torch.Generator(device="cuda").manual_seed(s)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    prm = [rn(Cg, 1, ksize, ksize) / ksize, rn(Cg) * 0.1, torch.ones(Cg, device="cuda"), torch.zeros(Cg, device="cuda"),
+           rn(2, Cg, 1, 1) / Cg ** 0.5] + [t for _ in range(4) for t in (rn(Cc, Cc, 1, 1) / Cc ** 0.5, rn(Cc) * 0.1)] + \
+          [rn(heads, Th, Th) * 0.1]
+    ps = _cabi.BlockParams()
+    for n_, t_ in zip(_cabi.PARAM_FIELDS, prm):
+        setattr(ps, n_, t_.data_ptr())
+    xa = [rn(B, HWn, Cc) for _ in range(NSET)]                       # block input, fp32 (LayerNorm output)
+    qa = [rn(B, HWn, Cc).to(b16) for _ in range(NSET)]
+    ka = [rn(B, Ns, Cc).to(b16) for _ in range(NSET)]
+    va = [rn(B, Ns, Cc).to(b16) for _ in range(NSET)]
+    oa = [torch.empty(B, HWn, Cc, device="cuda", dtype=b16) for _ in range(NSET)]
+    xsa = [torch.empty(B, Ns, Cc, device="cuda", dtype=b16) for _ in range(NSET)]
+    tdw = torch.empty(B, G, Ns, Cg, device="cuda")
+    offr = torch.empty(B, G, Ns, 2, device="cuda")
+    posa = [torch.empty(B, G, Ns, 2, device="cuda") for _ in range(NSET)]
+    lse = torch.empty(B, heads, HWn, device="cuda")
+    # K1: offset network -> pos
+    t = timeit(lambda i: _cabi.check(lib.dat_offset_pos_fwd(C.byref(d), C.byref(ps), p(qa[i % NSET]), p(tdw), p(offr),
+                                                             p(posa[i % NSET]), st), "k1"))
+    add("K1 offset_pos_fwd (dw conv, LN, GELU, 1x1, ref, clamp)", f"s{s} q {B}x{HWn}x{Cc} k{ksize}/s{stride} -> {B}x{G}x{Ns}", t,
+        nbytes=B * HWn * Cc * 2 + B * G * Ns * (4 * Cg + 16))
+    # K2: bilinear gather
+    t = timeit(lambda i: _cabi.check(lib.dat_sample_fwd(C.byref(d), p(xa[i % NSET]), p(posa[i % NSET]), p(xsa[i % NSET]), None,
+                                                         st), "k2"))
+    add("K2 sample_fwd (4-tap gather, fp32 x)", f"s{s} x {B}x{HWn}x{Cc} -> {B}x{Ns}x{Cc}", t,
+        nbytes=4 * B * Ns * Cc * 4 + B * G * Ns * 8 + B * Ns * Cc * 2)
+    # K3: attention core
+    nws = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
+    wsa = torch.empty(max(nws, 64), device="cuda", dtype=torch.uint8)
+    t = timeit(lambda i: _cabi.check(lib.dat_attention_fwd(C.byref(d), p(qa[i % NSET]), p(ka[i % NSET]), p(va[i % NSET]),
+                                                            p(posa[i % NSET]), p(prm[13]), p(oa[i % NSET]), p(lse), p(wsa), nws, 0,
+                                                            st), "k3"))
+    add("K3 attention_fwd (QK^T + rpe bias + softmax + PV)", f"s{s} {B}x{heads} heads, {HWn}x{Ns} scores", t,
+        nbytes=(2 * B * HWn * Cc + 2 * B * Ns * Cc) * 2 + B * G * Ns * 8 + heads * Th * Th * 4 + B * heads * HWn * 4,
+        flops=4.0 * HWn * Ns * Cc * B)
+    # whole block forward / backward through dat_block_forward / dat_block_backward
+    e_ = lambda *sh, dt=b16: torch.empty(*sh, device="cuda", dtype=dt)
+    saved = [e_(B, HWn, Cc), e_(B, G, Ns, Cg, dt=f32), e_(B, G, Ns, 2, dt=f32), e_(B, G, Ns, 2, dt=f32), e_(B, Ns, Cc),
+             e_(B, Ns, Cc), e_(B, Ns, Cc), e_(B, HWn, Cc), e_(B, heads, HWn, dt=f32)]
+    ss = _cabi.BlockSaved()
+    for n_, t_ in zip(_cabi.SAVED_FIELDS, saved):
+        setattr(ss, n_, t_.data_ptr())
+    nf = lib.dat_block_fwd_workspace_bytes(C.byref(d))
+    nbk = lib.dat_block_bwd_workspace_bytes(C.byref(d))
+    wsf = torch.empty(max(nf, nbk, 64), device="cuda", dtype=torch.uint8)
+    ya = [e_(B, HWn, Cc) for _ in range(NSET)]
+    t = timeit(lambda i: _cabi.check(lib.dat_block_forward(C.byref(d), C.byref(ps), p(xa[i % NSET]), p(ya[i % NSET]), C.byref(ss),
+                                                            p(wsf), nf, st), "blockf"))
+    dense_f = (4.0 * HWn * Cc * Cc + 4.0 * Ns * Cc * Cc + 4.0 * HWn * Ns * Cc) * B
+    add("block forward (8 launches)", f"s{s} x {B}x{HWn}x{Cc} f32 -> y bf16", t, nbytes=B * HWn * Cc * (4 + 2) + 4 * Cc * Cc * 4,
+        flops=dense_f)
+    grads = [torch.empty_like(t_) for t_ in prm]
+    gs = _cabi.BlockGrads()
+    for n_, t_ in zip(_cabi.PARAM_FIELDS, grads):
+        setattr(gs, n_, t_.data_ptr())
+    dya = [rn(B, HWn, Cc).to(b16) for _ in range(NSET)]
+    dxa = [torch.empty(B, HWn, Cc, device="cuda") for _ in range(NSET)]
+    t = timeit(lambda i: _cabi.check(lib.dat_block_backward(C.byref(d), C.byref(ps), p(xa[NSET - 1]), p(dya[i % NSET]),
+                                                             C.byref(ss), p(dxa[i % NSET]), C.byref(gs), p(wsf), nbk, st), "blockb"))
+    saved_bytes = B * HWn * Cc * 2 * 2 + 3 * B * Ns * Cc * 2 + B * G * Ns * (4 * Cg + 16) + B * heads * HWn * 4
+    add("block backward (all gradients)", f"s{s} dy bf16 -> dx f32 + 14 parameter grads", t,
+        nbytes=B * HWn * Cc * (2 + 4 + 4) + saved_bytes + 8 * Cc * Cc * 4, flops=2.0 * dense_f + 2.0 * HWn * Ns * Cc * B)
+    del xa, qa, ka, va, oa, xsa, saved, ya, dya, dxa
+
 print("# dat_b200 kernels against the measured B200 peaks (round 1)\n")
 print(f"HBM peak {HBM:.0f} GB/s, dense bf16 peak {TF:.1f} TFLOP/s (MEASURED_PEAKS.json).  Each kernel launched alone through the C ABI, "
       f"batch {B}, 3 rotating buffer sets, {REP} launches between CUDA events (tools/kernel_rooflines.py).  "
