@@ -19,11 +19,15 @@ class BlockDesc(C.Structure):
                 ("n_groups", C.c_int32), ("stride", C.c_int32), ("ksize", C.c_int32),
                 ("table_h", C.c_int32), ("table_w", C.c_int32),
                 ("offset_range_factor", C.c_float), ("x_dtype", C.c_int32),
-                ("act_dtype", C.c_int32)]
+                ("act_dtype", C.c_int32), ("pe_mode", C.c_int32), ("no_off", C.c_int32)]
+
+
+# dat_block_desc.pe_mode (include/dat_b200.h)
+PE_RPE, PE_NONE, PE_DWC, PE_FIXED, PE_LOGCPB = 0, 1, 2, 3, 4
 
 
 PARAM_FIELDS = ("off_dw_w", "off_dw_b", "off_ln_g", "off_ln_b", "off_pw_w", "wq", "bq", "wk", "bk",
-                "wv", "bv", "wo", "bo", "rpe_table")
+                "wv", "bv", "wo", "bo", "rpe_table", "pe_b", "pe_w2")
 # state-dict key of every field (reference names, dat_blocks.py:51-104)
 PARAM_KEYS = ("conv_offset.0.weight", "conv_offset.0.bias", "conv_offset.1.norm.weight",
               "conv_offset.1.norm.bias", "conv_offset.3.weight", "proj_q.weight", "proj_q.bias",

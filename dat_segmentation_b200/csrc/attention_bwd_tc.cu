@@ -642,7 +642,7 @@ int debug_attn_bwd_timing(unsigned long long* out8) {
   return DAT_OK;
 }
 
-bool attention_bwd_tc_supported(const Shape& s) { return pick_variant(s).ok != 0; }
+bool attention_bwd_tc_supported(const Shape& s) { return s.pe_mode == DAT_PE_RPE && pick_variant(s).ok != 0; }
 bool attention_bwd_tc_compact_table(const Shape& s) { return pick_variant(s).compact != 0; }
 
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st) {

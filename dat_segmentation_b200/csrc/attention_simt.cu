@@ -8,6 +8,8 @@
 // image at stage 2) are never materialised: each thread owns one query, streams the
 // sampled keys/values of its head through shared memory and evaluates the 4-tap bias
 // on the fly from a shared-memory copy of the head's table (online softmax).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,7 +26,16 @@ struct AttnArgs {
   int B, H, W, HW, C, heads, G, hg, Ns, Th, Tw;
   float scale;
   int table_in_smem;
+  // bias modes other than the rpe table (BM_DENSE): bias (Bb, heads, HW, Ns) fp32 added to the scaled
+  // scores, batch stride 0 when shared by the batch; dbias (B, heads, HW, Ns) receives dS.
+  const float* bias;
+  long long bias_bstride;
+  float* dbias;
 };
+
+// bias source of the score: BM_RPE bilinear rpe table (shipped configs), BM_NONE (use_pe False, dwc_pe,
+// no_off), BM_DENSE a materialised bias tensor (fixed_pe, log_cpb — the reference materialises it too)
+constexpr int BM_RPE = 0, BM_NONE = 1, BM_DENSE = 2;
 
 struct BiasEval {
   float val, d_dix, d_diy;  // value, d/d(ix), d/d(iy) of the bilinear interpolant
@@ -124,7 +135,7 @@ __device__ __forceinline__ void stage_rows(const T* __restrict__ src, long long 
 }
 
 // smem layout: [table Th*Tw | ks KV_CHUNK*32 | vs KV_CHUNK*32 | ps KV_CHUNK*2]
-template <typename T>
+template <typename T, int BM>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                      const float* __restrict__ pos, const float* __restrict__ table,
@@ -136,8 +147,8 @@ attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
   float* vs = ks + KV_CHUNK * HC;
   float* ps = vs + KV_CHUNK * HC;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
-  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
-  if (a.table_in_smem)
+  const float* tab_g = BM == BM_RPE ? table + (long long)eta * a.Th * a.Tw : nullptr;
+  if (BM == BM_RPE && a.table_in_smem)
     for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) tab_s[i] = tab_g[i];
   const float* tab = a.table_in_smem ? tab_s : tab_g;
 
@@ -145,6 +156,7 @@ attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
   const bool valid = m_raw < a.HW;
   const int m = valid ? m_raw : a.HW - 1;
   const float gy = query_point(m / a.W, a.H), gx = query_point(m % a.W, a.W);
+  const float* brow = BM == BM_DENSE ? a.bias + (long long)b * a.bias_bstride + ((long long)eta * a.HW + m) * a.Ns : nullptr;
   float qr[HC], acc[HC];
   load_row32(q + ((long long)b * a.HW + m) * a.C + eta * HC, qr);
 #pragma unroll
@@ -166,7 +178,9 @@ attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < HC; ++c) s = fmaf(qr[c], kr[c], s);
-      s = s * a.scale + rpe_bias_eval<false>(tab, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]).val;
+      s = s * a.scale;
+      if (BM == BM_RPE) s += rpe_bias_eval<false>(tab, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]).val;
+      if (BM == BM_DENSE) s += brow[n0 + n];
       if (s > mx) {
         const float corr = expf(mx - s);  // exp(-inf) = 0 on the first key
         l *= corr;
@@ -230,7 +244,7 @@ __global__ void attn_delta_kernel(const T* __restrict__ d_o, const T* __restrict
 // Query-parallel backward: dQ and the rpe-table gradient.
 // The table gradient is accumulated in a per-CTA shared-memory copy (shared atomics) and
 // flushed with one global atomicAdd per touched cell; d_table must be zeroed beforehand.
-template <typename T>
+template <typename T, int BM>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                    const T* __restrict__ d_o, const float* __restrict__ lse,
@@ -245,15 +259,20 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
   float* vs = ks + KV_CHUNK * HC;
   float* ps = vs + KV_CHUNK * HC;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
-  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
-  for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
-    tab_s[i] = tab_g[i];
-    dtab_s[i] = 0.f;
+  if (BM == BM_RPE) {
+    const float* tab_g = table + (long long)eta * a.Th * a.Tw;
+    for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
+      tab_s[i] = tab_g[i];
+      dtab_s[i] = 0.f;
+    }
   }
   const int m_raw = blockIdx.x * ATT_THREADS + threadIdx.x;
   const bool valid = m_raw < a.HW;
   const int m = valid ? m_raw : a.HW - 1;
   const float gy = query_point(m / a.W, a.H), gx = query_point(m % a.W, a.W);
+  const long long brow_off = ((long long)eta * a.HW + m) * a.Ns;
+  const float* brow = BM == BM_DENSE ? a.bias + (long long)b * a.bias_bstride + brow_off : nullptr;
+  float* dbrow = BM == BM_DENSE ? a.dbias + (long long)b * a.heads * a.HW * a.Ns + brow_off : nullptr;
   float qr[HC], dor[HC], acc[HC];
   load_row32(q + ((long long)b * a.HW + m) * a.C + eta * HC, qr);
   load_row32(d_o + ((long long)b * a.HW + m) * a.C + eta * HC, dor);
@@ -281,12 +300,19 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
         s = fmaf(qr[c], kr[c], s);
         dp = fmaf(dor[c], vr[c], dp);
       }
-      const BiasEval be = rpe_bias_eval<false>(tab_s, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]);
-      const float p = expf(s * a.scale + be.val - lse_m);
+      BiasEval be;
+      float bval = 0.f;
+      if (BM == BM_RPE) {
+        be = rpe_bias_eval<false>(tab_s, a.Th, a.Tw, gy, gx, ps[2 * n], ps[2 * n + 1]);
+        bval = be.val;
+      }
+      if (BM == BM_DENSE) bval = brow[n0 + n];
+      const float p = expf(s * a.scale + bval - lse_m);
       const float ds = valid ? p * (dp - dl_m) : 0.f;
 #pragma unroll
       for (int c = 0; c < HC; ++c) acc[c] = fmaf(ds, kr[c], acc[c]);
-      table_grad_scatter(dtab_s, a.Tw, be, ds, m / a.W);
+      if (BM == BM_RPE) table_grad_scatter(dtab_s, a.Tw, be, ds, m / a.W);
+      if (BM == BM_DENSE && valid) dbrow[n0 + n] = ds;
     }
   }
   if (valid) {
@@ -294,11 +320,13 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
     for (int c = 0; c < HC; ++c) acc[c] *= a.scale;
     store_row32(dq + ((long long)b * a.HW + m) * a.C + eta * HC, acc);
   }
-  __syncthreads();
-  float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
-  for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
-    float vv = dtab_s[i];
-    if (vv != 0.f) atomicAdd(dt_g + i, vv);
+  if (BM == BM_RPE) {
+    __syncthreads();
+    float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
+    for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) {
+      float vv = dtab_s[i];
+      if (vv != 0.f) atomicAdd(dt_g + i, vv);
+    }
   }
 }
 
@@ -306,7 +334,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
 // sampled key; queries of the CTA's q-split stream through shared memory.  Outputs are
 // per-split partials (fixed-order reduction afterwards): no atomics.
 //   dk_part/dv_part: (qsplit, B, Ns, C) fp32;  dpos_part: (B, heads, qsplit, Ns, 2) fp32
-template <typename T>
+template <typename T, int BM>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                     const T* __restrict__ d_o, const float* __restrict__ lse,
@@ -323,10 +351,11 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
   float* dls = ls + Q_CHUNK;          // delta
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
   const int z = blockIdx.z, qsplit = gridDim.z;
-  const float* tab_g = table + (long long)eta * a.Th * a.Tw;
-  if (a.table_in_smem)
+  const float* tab_g = BM == BM_RPE ? table + (long long)eta * a.Th * a.Tw : nullptr;
+  if (BM == BM_RPE && a.table_in_smem)
     for (int i = threadIdx.x; i < a.Th * a.Tw; i += blockDim.x) tab_s[i] = tab_g[i];
   const float* tab = a.table_in_smem ? tab_s : tab_g;
+  const float* bcol = BM == BM_DENSE ? a.bias + (long long)b * a.bias_bstride + (long long)eta * a.HW * a.Ns : nullptr;
 
   const int n_raw = blockIdx.x * ATT_THREADS + threadIdx.x;
   const bool valid = n_raw < a.Ns;
@@ -363,17 +392,22 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
         s = fmaf(qr[c], kr[c], s);
         dp = fmaf(dor[c], vr[c], dp);
       }
-      const BiasEval be = rpe_bias_eval<true>(tab, a.Th, a.Tw, query_point(m / a.W, a.H),
-                                              query_point(m % a.W, a.W), py, px);
-      const float p = expf(s * a.scale + be.val - ls[mi]);
+      float bval = 0.f, d_dix = 0.f, d_diy = 0.f;
+      if (BM == BM_RPE) {
+        const BiasEval be = rpe_bias_eval<true>(tab, a.Th, a.Tw, query_point(m / a.W, a.H),
+                                                query_point(m % a.W, a.W), py, px);
+        bval = be.val; d_dix = be.d_dix; d_diy = be.d_diy;
+      }
+      if (BM == BM_DENSE) bval = bcol[(long long)m * a.Ns + n];
+      const float p = expf(s * a.scale + bval - ls[mi]);
       const float ds = p * (dp - dls[mi]);
 #pragma unroll
       for (int c = 0; c < HC; ++c) {
         dv[c] = fmaf(p, dor[c], dv[c]);
         dk[c] = fmaf(ds, qr[c], dk[c]);
       }
-      dpx = fmaf(ds, be.d_dix, dpx);
-      dpy = fmaf(ds, be.d_diy, dpy);
+      dpx = fmaf(ds, d_dix, dpx);
+      dpy = fmaf(ds, d_diy, dpy);
     }
   }
   if (valid) {
@@ -395,7 +429,13 @@ AttnArgs make_args(const Shape& s) {
   a.hg = s.hg; a.Ns = s.Ns; a.Th = s.Th; a.Tw = s.Tw;
   a.scale = 1.0f / sqrtf((float)HC);
   a.table_in_smem = ((size_t)s.Th * s.Tw * sizeof(float) <= 96 * 1024) ? 1 : 0;
+  a.bias = nullptr; a.bias_bstride = 0; a.dbias = nullptr;
+  if (s.pe_mode != DAT_PE_RPE) { a.Th = a.Tw = 0; a.table_in_smem = 1; }   // no table: no shared-memory copy
   return a;
+}
+
+int bias_mode(const Shape& s) {
+  return s.pe_mode == DAT_PE_RPE ? BM_RPE : (s.pe_mode == DAT_PE_FIXED || s.pe_mode == DAT_PE_LOGCPB) ? BM_DENSE : BM_NONE;
 }
 
 template <typename K>
@@ -405,24 +445,40 @@ int set_smem(K kern, size_t smem) {
   return DAT_OK;
 }
 
+// dtype x bias-mode dispatch: F is a generic lambda called with (T value, integral_constant<int, BM>)
+template <typename F>
+int dispatch(int act_dtype, int bm, F&& f) {
+#define DAT_BM_CASE(T)                                                         \
+  switch (bm) {                                                                \
+    case BM_RPE: return f(T(), std::integral_constant<int, BM_RPE>());        \
+    case BM_NONE: return f(T(), std::integral_constant<int, BM_NONE>());      \
+    default: return f(T(), std::integral_constant<int, BM_DENSE>());          \
+  }
+  if (act_dtype == DAT_F32) { DAT_BM_CASE(float) }
+  DAT_BM_CASE(bf16)
+#undef DAT_BM_CASE
+}
+
 }  // namespace
 
 int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void* v,
                        const float* pos, const float* table, void* o, float* lse,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* bias, long long bias_bstride) {
   AttnArgs a = make_args(s);
-  const size_t tsz = a.table_in_smem ? (size_t)((s.Th * s.Tw + 3) & ~3) : 0;
+  a.bias = bias; a.bias_bstride = bias_bstride;
+  const int bm = bias_mode(s);
+  DAT_REQUIRE(bm != BM_DENSE || bias != nullptr, "attention_fwd: dense bias mode without a bias tensor");
+  const size_t tsz = a.table_in_smem ? (size_t)((a.Th * a.Tw + 3) & ~3) : 0;
   size_t smem = (tsz + 2 * KV_CHUNK * HC + 2 * KV_CHUNK) * sizeof(float);
   dim3 grid(ceil_div(s.HW, ATT_THREADS), s.B * s.heads);
-  if (s.act_dtype == DAT_F32) {
-    DAT_FWD(set_smem(attn_fwd_simt_kernel<float>, smem));
-    attn_fwd_simt_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
-        (const float*)q, (const float*)k, (const float*)v, pos, table, (float*)o, lse, a);
-  } else {
-    DAT_FWD(set_smem(attn_fwd_simt_kernel<bf16>, smem));
-    attn_fwd_simt_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
-        (const bf16*)q, (const bf16*)k, (const bf16*)v, pos, table, (bf16*)o, lse, a);
-  }
+  DAT_FWD(dispatch(s.act_dtype, bm, [&](auto tv, auto bmc) -> int {
+    using T = decltype(tv);
+    constexpr int BM = decltype(bmc)::value;
+    DAT_FWD(set_smem(attn_fwd_simt_kernel<T, BM>, smem));
+    attn_fwd_simt_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, pos, table,
+                                                                   (T*)o, lse, a);
+    return DAT_OK;
+  }));
   DAT_LAUNCH_OK("attn_fwd_simt_kernel");
   return DAT_OK;
 }
@@ -461,60 +517,54 @@ size_t attention_bwd_workspace(const Shape& s) {
   return delta + 2 * part;
 }
 
-// dq, dk, dv (act dtype), d_table (fp32, overwritten), dpos_part (B,heads,qsplit,Ns,2).
+// dq, dk, dv (act dtype), d_table (fp32, overwritten; rpe mode only), dpos_part (B,heads,qsplit,Ns,2; zeros
+// unless rpe mode).  Dense-bias mode: `bias` as in the forward, `dbias` (B, heads, HW, Ns) receives dS.
 int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void* v, const void* o,
                        const void* d_o, const float* lse, const float* pos, const float* table,
                        void* dq, void* dk, void* dv, float* d_table, float* dpos_part,
-                       void* ws, size_t ws_bytes, cudaStream_t st) {
+                       void* ws, size_t ws_bytes, cudaStream_t st, const float* bias, long long bias_bstride,
+                       float* dbias) {
   DAT_REQUIRE(ws_bytes >= attention_bwd_workspace(s), "attention_bwd: workspace too small");
-  DAT_REQUIRE((size_t)s.Th * s.Tw * 4 <= 48 * 1024 + 32 * 1024,
-              "attention_bwd: rpe table %dx%d too large for the shared-memory gradient copy", s.Th, s.Tw);
   AttnArgs a = make_args(s);
+  a.bias = bias; a.bias_bstride = bias_bstride; a.dbias = dbias;
+  const int bm = bias_mode(s);
+  DAT_REQUIRE(bm != BM_DENSE || (bias != nullptr && dbias != nullptr), "attention_bwd: dense bias mode without bias / dbias");
+  DAT_REQUIRE((size_t)a.Th * a.Tw * 4 <= 48 * 1024 + 32 * 1024,
+              "attention_bwd: rpe table %dx%d too large for the shared-memory gradient copy", s.Th, s.Tw);
   const int qsplit = attention_bwd_qsplit(s);
   float* delta = (float*)ws;
   float* dk_part = (float*)((char*)ws + align_up((size_t)s.B * s.heads * s.HW * 4, 256));
   float* dv_part = (float*)((char*)dk_part + align_up((size_t)qsplit * s.B * s.Ns * s.C * 4, 256));
-  const bool f32 = s.act_dtype == DAT_F32;
 
-  long long tot = (long long)s.B * s.HW * s.heads;
-  if (f32) attn_delta_kernel<float><<<ceil_div(tot, 256), 256, 0, st>>>((const float*)d_o, (const float*)o, delta, s.HW, s.C, s.heads, tot);
-  else attn_delta_kernel<bf16><<<ceil_div(tot, 256), 256, 0, st>>>((const bf16*)d_o, (const bf16*)o, delta, s.HW, s.C, s.heads, tot);
-  DAT_LAUNCH_OK("attn_delta_kernel");
-
-  DAT_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
+  DAT_FWD(attention_delta(s, d_o, o, delta, st));
+  if (bm == BM_RPE) DAT_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
   {
-    const size_t tsz = (size_t)((s.Th * s.Tw + 3) & ~3);
+    const size_t tsz = (size_t)((a.Th * a.Tw + 3) & ~3);
     size_t smem = (2 * tsz + 2 * KV_CHUNK * HC + 2 * KV_CHUNK) * sizeof(float);
     dim3 grid(ceil_div(s.HW, ATT_THREADS), s.B * s.heads);
-    if (f32) {
-      DAT_FWD(set_smem(attn_bwd_dq_kernel<float>, smem));
-      attn_bwd_dq_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
-          (const float*)q, (const float*)k, (const float*)v, (const float*)d_o, lse, delta, pos,
-          table, (float*)dq, d_table, a);
-    } else {
-      DAT_FWD(set_smem(attn_bwd_dq_kernel<bf16>, smem));
-      attn_bwd_dq_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
-          (const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta, pos,
-          table, (bf16*)dq, d_table, a);
-    }
+    DAT_FWD(dispatch(s.act_dtype, bm, [&](auto tv, auto bmc) -> int {
+      using T = decltype(tv);
+      constexpr int BM = decltype(bmc)::value;
+      DAT_FWD(set_smem(attn_bwd_dq_kernel<T, BM>, smem));
+      attn_bwd_dq_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
+                                                                   delta, pos, table, (T*)dq, d_table, a);
+      return DAT_OK;
+    }));
     DAT_LAUNCH_OK("attn_bwd_dq_kernel");
   }
   {
-    const size_t tsz = a.table_in_smem ? (size_t)((s.Th * s.Tw + 3) & ~3) : 0;
+    const size_t tsz = a.table_in_smem ? (size_t)((a.Th * a.Tw + 3) & ~3) : 0;
     size_t smem = (tsz + 2 * Q_CHUNK * HC + 2 * Q_CHUNK) * sizeof(float);
     dim3 grid(ceil_div(s.Ns, ATT_THREADS), s.B * s.heads, qsplit);
     int qps = ceil_div(ceil_div(s.HW, qsplit), Q_CHUNK) * Q_CHUNK;
-    if (f32) {
-      DAT_FWD(set_smem(attn_bwd_dkv_kernel<float>, smem));
-      attn_bwd_dkv_kernel<float><<<grid, ATT_THREADS, smem, st>>>(
-          (const float*)q, (const float*)k, (const float*)v, (const float*)d_o, lse, delta, pos,
-          table, dk_part, dv_part, dpos_part, qps, a);
-    } else {
-      DAT_FWD(set_smem(attn_bwd_dkv_kernel<bf16>, smem));
-      attn_bwd_dkv_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>(
-          (const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta, pos,
-          table, dk_part, dv_part, dpos_part, qps, a);
-    }
+    DAT_FWD(dispatch(s.act_dtype, bm, [&](auto tv, auto bmc) -> int {
+      using T = decltype(tv);
+      constexpr int BM = decltype(bmc)::value;
+      DAT_FWD(set_smem(attn_bwd_dkv_kernel<T, BM>, smem));
+      attn_bwd_dkv_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
+                                                                    delta, pos, table, dk_part, dv_part, dpos_part, qps, a);
+      return DAT_OK;
+    }));
     DAT_LAUNCH_OK("attn_bwd_dkv_kernel");
   }
   long long cnt = (long long)s.B * s.Ns * s.C;

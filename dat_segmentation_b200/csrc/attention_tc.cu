@@ -395,7 +395,7 @@ int attention_pack_table(const Shape& s, const float* table, void* out, cudaStre
 }
 
 bool attention_fwd_tc_supported(const Shape& s) {
-  if (s.act_dtype != DAT_BF16) return false;
+  if (s.act_dtype != DAT_BF16 || s.pe_mode != DAT_PE_RPE) return false;
   if (!(s.Ns == 64 || s.Ns == 128 || s.Ns == 256)) return false;
   if (s.C % 8 != 0) return false;
   SmemPlan sp = plan_smem(s.Ns, s.Th + 3, s.Tw + 3, rows_spanned_max(s.HW, s.W));

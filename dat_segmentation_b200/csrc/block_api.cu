@@ -29,7 +29,11 @@ int make_shape(const dat_block_desc* d, Shape* s) {
   DAT_REQUIRE(d->n_heads > 0 && d->n_groups > 0 && d->n_heads % d->n_groups == 0,
               "n_heads=%d must be a positive multiple of n_groups=%d", d->n_heads, d->n_groups);
   DAT_REQUIRE(d->stride > 0 && d->ksize > 0, "bad stride/ksize");
-  DAT_REQUIRE(d->table_h > 0 && d->table_w > 0, "bad rpe table size");
+  DAT_REQUIRE(d->pe_mode >= DAT_PE_RPE && d->pe_mode <= DAT_PE_LOGCPB, "bad pe_mode %d", d->pe_mode);
+  s->no_off = d->no_off != 0;
+  s->pe_mode = s->no_off ? DAT_PE_NONE : d->pe_mode;
+  const bool has_table = s->pe_mode == DAT_PE_RPE || s->pe_mode == DAT_PE_FIXED;
+  DAT_REQUIRE(!has_table || (d->table_h > 0 && d->table_w > 0), "bad rpe table size");
   DAT_REQUIRE((d->x_dtype == DAT_F32 || d->x_dtype == DAT_BF16) &&
                   (d->act_dtype == DAT_F32 || d->act_dtype == DAT_BF16), "bad dtype code");
   s->B = d->B; s->H = d->H; s->W = d->W; s->HW = d->H * d->W;
@@ -42,8 +46,13 @@ int make_shape(const dat_block_desc* d, Shape* s) {
   s->Hk = (d->H + 2 * s->pad - d->ksize) / d->stride + 1;
   s->Wk = (d->W + 2 * s->pad - d->ksize) / d->stride + 1;
   DAT_REQUIRE(s->Hk > 1 && s->Wk > 1, "sample grid %dx%d: the reference divides by (Hk-1), (Wk-1)", s->Hk, s->Wk);
+  if (s->no_off) {   // F.avg_pool2d(x, stride, stride): floor division, no padding (dat_blocks.py:165-167)
+    s->Hk = d->H / d->stride;
+    s->Wk = d->W / d->stride;
+    DAT_REQUIRE(s->Hk > 0 && s->Wk > 0, "no_off: map smaller than the pooling window");
+  }
   s->Ns = s->Hk * s->Wk;
-  s->Th = d->table_h; s->Tw = d->table_w;
+  s->Th = has_table ? d->table_h : 1; s->Tw = has_table ? d->table_w : 1;
   s->orf = d->offset_range_factor;
   s->x_dtype = d->x_dtype; s->act_dtype = d->act_dtype;
   DAT_REQUIRE((long long)s->B * s->HW * s->C < (1ll << 40), "tensor too large");
@@ -76,8 +85,43 @@ struct BwdPlan {
   void* x_bf;       // bf16 copy of an fp32 x for the tensor-core weight gradient of proj_q
   void* sub;        // shared scratch of the individual stages (used one at a time)
   void* wg;         // scratch of the tensor-core weight gradients (they run on a side stream)
+  // variant branches: dense bias + its gradient (fixed_pe, log_cpb); LePE, o + LePE, dq of the LePE conv and
+  // the depthwise kernels' scratch (dwc_pe)
+  float *bias, *dbias;
+  void *lepe, *o2, *dq_lepe, *dw_ws;
+  size_t dw_ws_bytes;
   size_t sub_bytes, wg_bytes, total;
 };
+
+// scratch of the variant branches in the forward pass, placed after the bf16 weights / packed table
+struct FwdVar {
+  float* bias;
+  void *lepe, *o2, *dw_ws;
+  size_t dw_ws_bytes, total;
+};
+size_t dense_bias_bytes(const Shape& s) {
+  if (s.pe_mode == DAT_PE_FIXED) return (size_t)s.heads * s.HW * s.Ns * 4;
+  if (s.pe_mode == DAT_PE_LOGCPB) return (size_t)s.B * s.heads * s.HW * s.Ns * 4;
+  return 0;
+}
+FwdVar plan_fwd_var(const Shape& s, void* base) {
+  FwdVar f;
+  Carver c(base);
+  const size_t act = (size_t)s.B * s.HW * s.C * dtype_size(s.act_dtype);
+  const bool dwc = s.pe_mode == DAT_PE_DWC;
+  f.bias = (float*)c.take(dense_bias_bytes(s));
+  f.lepe = c.take(dwc ? act : 0);
+  f.o2 = c.take(dwc ? act : 0);
+  f.dw_ws_bytes = dwc ? dwconv_workspace(s.B, s.H, s.W, s.C, 3) : 0;
+  f.dw_ws = c.take(f.dw_ws_bytes);
+  f.total = c.off;
+  return f;
+}
+size_t fwd_fixed_bytes(const Shape& s) {   // bf16 weight copies + packed table of the tensor-core attention
+  if (s.act_dtype != DAT_BF16) return 0;
+  return align_up((size_t)4 * s.C * s.C * 2, 256) +
+         align_up(attention_fwd_tc_supported(s) ? attention_fwd_tc_workspace(s) : 0, 256);
+}
 
 // The weight / bias gradients of the four projections are off the critical path (nothing later in
 // the backward reads them).  They are enqueued on a library-owned side stream, forked from the
@@ -157,6 +201,15 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
     p.wg_bytes = a > b ? a : b;
   }
   p.wg = c.take(p.wg_bytes);
+  const bool dwc = s.pe_mode == DAT_PE_DWC;
+  const size_t act = (size_t)s.B * s.HW * s.C * e;
+  p.bias = (float*)c.take(dense_bias_bytes(s));
+  p.dbias = (float*)c.take(dense_bias_bytes(s) ? (size_t)s.B * s.heads * s.HW * s.Ns * 4 : 0);
+  p.lepe = c.take(dwc ? act : 0);
+  p.o2 = c.take(dwc ? act : 0);
+  p.dq_lepe = c.take(dwc ? act : 0);
+  p.dw_ws_bytes = dwc ? dwconv_workspace(s.B, s.H, s.W, s.C, 3) : 0;
+  p.dw_ws = c.take(p.dw_ws_bytes);
   p.total = c.off;
   return p;
 }
@@ -183,11 +236,9 @@ int dat_sample_grid(const dat_block_desc* d, int32_t* Hk, int32_t* Wk) {
 size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d) {
   Shape s;
   if (make_shape(d, &s) != DAT_OK) return 0;
-  // bf16 copies of (wk, wv, wo) and of wq for the tensor-core projections, then the packed
-  // rpe table of the tensor-core attention kernel
-  if (s.act_dtype != DAT_BF16) return 0;
-  return align_up((size_t)4 * s.C * s.C * 2, 256) +
-         (attention_fwd_tc_supported(s) ? attention_fwd_tc_workspace(s) : 0);
+  // bf16 copies of (wk, wv, wo) and of wq for the tensor-core projections, the packed rpe table of the
+  // tensor-core attention kernel, then the scratch of the variant branches
+  return fwd_fixed_bytes(s) + plan_fwd_var(s, nullptr).total;
 }
 
 int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b, void* Y,
@@ -385,8 +436,13 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
   } else {
     DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, adt, M, C, C, st));
   }
-  DAT_FWD(offset_pos_fwd(s, p, sv->q, sv->t_dw, sv->off_raw, sv->pos, st));
-  DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
+  if (s.no_off) {   // dat_blocks.py:156-157,164-167: offsets zeroed, keys / values from the average-pooled map
+    DAT_CUDA_OK(cudaMemsetAsync(sv->pos, 0, (size_t)s.B * s.G * s.Ns * 2 * 4, st));
+    DAT_FWD(avgpool_fwd(s, x, sv->xs, st));
+  } else {
+    DAT_FWD(offset_pos_fwd(s, p, sv->q, sv->t_dw, sv->off_raw, sv->pos, st));
+    DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
+  }
   if (tc) {
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf, p->bk, sv->k, adt, Mk, C, C, st));
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf + wsz, p->bv, sv->v, adt, Mk, C, C, st));
@@ -395,14 +451,41 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
     DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wv, p->bv, sv->v, adt, Mk, C, C, st));
   }
   const size_t w_bytes = align_up((size_t)4 * C * C * 2, 256);
+  // variant branches: scratch behind the fixed part of the workspace
+  FwdVar fv = plan_fwd_var(s, nullptr);
+  if (fv.total > 0) {
+    DAT_REQUIRE(workspace != nullptr && workspace_bytes >= fwd_fixed_bytes(s) + fv.total,
+                "block_forward: workspace %zu < %zu bytes", workspace_bytes, fwd_fixed_bytes(s) + fv.total);
+    fv = plan_fwd_var(s, (char*)workspace + fwd_fixed_bytes(s));
+  }
+  long long bias_bstride = 0;
+  if (s.pe_mode == DAT_PE_FIXED) {
+    DAT_REQUIRE(p->rpe_table, "block_forward: fixed_pe needs rpe_table");
+    DAT_FWD(fixed_bias_fwd(s, p->rpe_table, fv.bias, st));
+  } else if (s.pe_mode == DAT_PE_LOGCPB) {
+    DAT_REQUIRE(p->rpe_table && p->pe_b && p->pe_w2, "block_forward: log_cpb needs rpe_table.0.weight / .0.bias / .2.weight");
+    DAT_FWD(logcpb_bias_fwd(s, sv->pos, p->rpe_table, p->pe_b, p->pe_w2, fv.bias, st));
+    bias_bstride = (long long)s.heads * s.HW * s.Ns;
+  }
   if (adt == DAT_BF16 && tc_enabled() && attention_fwd_tc_supported(s) && workspace != nullptr &&
-      workspace_bytes >= w_bytes + attention_fwd_tc_workspace(s))
+      workspace_bytes >= w_bytes + attention_fwd_tc_workspace(s)) {
+    DAT_REQUIRE(p->rpe_table, "block_forward: rpe_table is NULL");
     DAT_FWD(attention_fwd_tc(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse,
-                             (char*)workspace + w_bytes, workspace_bytes - w_bytes, st));
-  else
-    DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st));
-  if (tc) DAT_FWD(pointwise_fwd_tc(sv->o, adt, wbf + 2 * wsz, p->bo, y, adt, M, C, C, st));
-  else DAT_FWD(pointwise_fwd_simt(sv->o, adt, p->wo, p->bo, y, adt, M, C, C, st));
+                             (char*)workspace + w_bytes, attention_fwd_tc_workspace(s), st));
+  } else {
+    DAT_REQUIRE(s.pe_mode != DAT_PE_RPE || p->rpe_table, "block_forward: rpe_table is NULL");
+    DAT_FWD(attention_fwd_simt(s, sv->q, sv->k, sv->v, sv->pos, p->rpe_table, sv->o, sv->lse, st, fv.bias, bias_bstride));
+  }
+  const void* o_in = sv->o;
+  if (s.pe_mode == DAT_PE_DWC) {   // out = out + rpe_table(q), a depthwise 3x3 conv (dat_blocks.py:185-186,221-222)
+    DAT_REQUIRE(p->rpe_table && p->pe_b, "block_forward: dwc_pe needs rpe_table.weight / rpe_table.bias");
+    DAT_FWD(dwconv_fwd(sv->q, adt, p->rpe_table, p->pe_b, fv.lepe, nullptr, adt, s.B, s.H, s.W, C, 3, 0, 0, fv.dw_ws,
+                       fv.dw_ws_bytes, st));
+    DAT_FWD(add2(sv->o, fv.lepe, fv.o2, adt, M * C, st));
+    o_in = fv.o2;
+  }
+  if (tc) DAT_FWD(pointwise_fwd_tc(o_in, adt, wbf + 2 * wsz, p->bo, y, adt, M, C, C, st));
+  else DAT_FWD(pointwise_fwd_simt(o_in, adt, p->wo, p->bo, y, adt, M, C, C, st));
   return DAT_OK;
 }
 
@@ -441,9 +524,18 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     if (!tcw) return pointwise_wgrad_simt(dY, adt, X, x_dt, dW, db, rows, C, C, w.sub, w.sub_bytes, st);
     return pointwise_wgrad_tc(dY, X, dW, db, rows, C, C, w.wg, w.wg_bytes, wst);
   };
+  // dwc_pe: the input of proj_out was o + LePE(q); recompute it (two launches) instead of saving it
+  const void* o_in = sv->o;
+  if (s.pe_mode == DAT_PE_DWC) {
+    DAT_REQUIRE(p->rpe_table && p->pe_b && g->rpe_table && g->pe_b, "block_backward: dwc_pe needs rpe_table.weight / .bias");
+    DAT_FWD(dwconv_fwd(sv->q, adt, p->rpe_table, p->pe_b, w.lepe, nullptr, adt, s.B, s.H, s.W, C, 3, 0, 0, w.dw_ws,
+                       w.dw_ws_bytes, st));
+    DAT_FWD(add2(sv->o, w.lepe, w.o2, adt, M * C, st));
+    o_in = w.o2;
+  }
   // proj_out
   DAT_FWD(fork(0));
-  DAT_FWD(wgrad(dy, sv->o, adt, g->wo, g->bo, M));
+  DAT_FWD(wgrad(dy, o_in, adt, g->wo, g->bo, M));
   if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
   // attention core
@@ -463,8 +555,25 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     DAT_FWD(reduce_partials(dk_part, chunks, (long long)s.B * s.Ns * C, w.dk, adt, st));
     DAT_FWD(reduce_partials(dv_part, chunks, (long long)s.B * s.Ns * C, w.dv, adt, st));
   } else {
+    long long bias_bstride = 0;
+    if (s.pe_mode == DAT_PE_FIXED) {
+      DAT_REQUIRE(p->rpe_table && g->rpe_table, "block_backward: fixed_pe needs rpe_table");
+      DAT_FWD(fixed_bias_fwd(s, p->rpe_table, w.bias, st));
+    } else if (s.pe_mode == DAT_PE_LOGCPB) {
+      DAT_REQUIRE(p->rpe_table && p->pe_b && p->pe_w2 && g->rpe_table && g->pe_b && g->pe_w2,
+                  "block_backward: log_cpb needs rpe_table.0.weight / .0.bias / .2.weight and their gradients");
+      DAT_FWD(logcpb_bias_fwd(s, sv->pos, p->rpe_table, p->pe_b, p->pe_w2, w.bias, st));
+      bias_bstride = (long long)s.heads * s.HW * s.Ns;
+    }
+    if (s.pe_mode == DAT_PE_DWC)   // gradient of the LePE conv: dq_lepe, d weight, d bias from dO (= d(o + LePE))
+      DAT_FWD(dwconv3_bwd(sv->q, adt, w.d_o, nullptr, adt, p->rpe_table, w.dq_lepe, g->rpe_table, g->pe_b, s.B, s.H,
+                          s.W, C, 0, w.dw_ws, w.dw_ws_bytes, st));
+    DAT_REQUIRE(s.pe_mode != DAT_PE_RPE || (p->rpe_table && g->rpe_table), "block_backward: rpe_table is NULL");
     DAT_FWD(attention_bwd_simt(s, sv->q, sv->k, sv->v, sv->o, w.d_o, sv->lse, sv->pos, p->rpe_table,
-                               w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st));
+                               w.dq, w.dk, w.dv, g->rpe_table, w.dpos_part, w.sub, w.sub_bytes, st, w.bias,
+                               bias_bstride, w.dbias));
+    if (s.pe_mode == DAT_PE_FIXED) DAT_FWD(fixed_bias_bwd(s, w.dbias, g->rpe_table, st));
+    if (s.pe_mode == DAT_PE_DWC) DAT_FWD(add2(w.dq, w.dq_lepe, w.dq, adt, M * C, st));
   }
   // proj_k / proj_v
   DAT_FWD(fork(1));
@@ -476,10 +585,15 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     DAT_FWD(pointwise_dgrad_simt(w.dk, adt, p->wk, w.dxs, adt, Mk, C, C, 0, st));
     DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
   }
-  // sampling -> d pos; offset network -> dq
-  DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
-  DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st,
-                     ss != nullptr ? ss->s : st, ss != nullptr ? ss->ev[3] : nullptr));
+  // sampling -> d pos; offset network -> dq  (no_off: the offset network is unused, its gradients are not written)
+  if (!s.no_off) {
+    DAT_FWD(sample_bwd_dpos(s, x, sv->pos, w.dxs, w.dpos_part, bwd_qsplit(s), w.dpos, st));
+    if (s.pe_mode == DAT_PE_LOGCPB)   // the bias MLP's parameter gradients and its part of d pos
+      DAT_FWD(logcpb_bias_bwd(s, w.dbias, sv->pos, p->rpe_table, p->pe_b, p->pe_w2, g->rpe_table, g->pe_b, g->pe_w2,
+                              w.dpos, st));
+    DAT_FWD(offset_bwd(s, p, sv->q, sv->t_dw, sv->off_raw, w.dpos, w.dq, g, w.sub, w.sub_bytes, st,
+                       ss != nullptr ? ss->s : st, ss != nullptr ? ss->ev[3] : nullptr));
+  }
   // proj_q, then the sampling scatter on top of its data gradient
   DAT_FWD(fork(2));
   if (tcw && s.x_dtype == DAT_F32) {
@@ -490,7 +604,8 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   }
   if (tc) DAT_FWD(pointwise_fwd_tc(w.dq, adt, wT + 3 * wsz, nullptr, dx, DAT_F32, M, C, C, st));
   else DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
-  DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
+  if (s.no_off) DAT_FWD(avgpool_bwd(s, w.dxs, dx, st));
+  else DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
   if (ss != nullptr) {                                  // join: the caller's stream owns every result again
     DAT_CUDA_OK(cudaEventRecord(ss->ev[4], ss->s));
     DAT_CUDA_OK(cudaStreamWaitEvent(st, ss->ev[4], 0));

@@ -53,6 +53,7 @@ struct Shape {
   int B, H, W, HW, C, heads, G, Cg, hg, stride, ksize, pad, Hk, Wk, Ns, Th, Tw;
   float orf;
   int x_dtype, act_dtype;
+  int pe_mode, no_off;       // DAT_PE_*; no_off forces DAT_PE_NONE and the avg-pool sample grid
 };
 
 // Validates a descriptor and fills the derived sizes; DAT_OK or DAT_ERR_ARG.

@@ -42,14 +42,15 @@ int sample_bwd_dx(const Shape& s, const float* pos, const void* dxs, float* dx, 
 // attention_simt.cu
 int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void* v,
                        const float* pos, const float* table, void* o, float* lse,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* bias = nullptr, long long bias_bstride = 0);
 int rpe_bias(const Shape& s, const float* pos, const float* table, float* bias, cudaStream_t st);
 int attention_bwd_qsplit(const Shape& s);
 size_t attention_bwd_workspace(const Shape& s);
 int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void* v, const void* o,
                        const void* d_o, const float* lse, const float* pos, const float* table,
                        void* dq, void* dk, void* dv, float* d_table, float* dpos_part, void* ws,
-                       size_t ws_bytes, cudaStream_t st);
+                       size_t ws_bytes, cudaStream_t st, const float* bias = nullptr, long long bias_bstride = 0,
+                       float* dbias = nullptr);
 
 }  // namespace dat
 
@@ -169,4 +170,18 @@ int dwconv7_fwd(const void* x, int x_dt, const float* w, const float* bias, void
                 int W, int C, int flip, cudaStream_t st);
 int dwconv7_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, float* db, int B, int H,
                   int W, int C, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace dat
+
+namespace dat {
+// variants.cu - the block's variant branches (no_off, dwc_pe, fixed_pe, log_cpb)
+int avgpool_fwd(const Shape& s, const void* x, void* xs, cudaStream_t st);
+int avgpool_bwd(const Shape& s, const void* dxs, float* dx, cudaStream_t st);
+int add2(const void* a, const void* b, void* y, int dt, long long n, cudaStream_t st);
+int fixed_bias_fwd(const Shape& s, const float* table, float* bias, cudaStream_t st);
+int fixed_bias_bwd(const Shape& s, const float* dbias, float* dtable, cudaStream_t st);
+bool logcpb_supported(const Shape& s);
+int logcpb_bias_fwd(const Shape& s, const float* pos, const float* w1, const float* b1, const float* w2, float* bias,
+                    cudaStream_t st);
+int logcpb_bias_bwd(const Shape& s, const float* dbias, const float* pos, const float* w1, const float* b1,
+                    const float* w2, float* dw1, float* db1, float* dw2, float* dpos, cudaStream_t st);
 }  // namespace dat

@@ -7,7 +7,9 @@ checkpoints load with `strict=True`), same `forward(x) -> (y, None, None)` contr
 (`:138,227`).  All arithmetic runs in the hand-written sm_100a kernels behind the C
 ABI of `include/dat_b200.h`; this file only owns parameters, dtype / layout plumbing
 and autograd wiring.  There is no PyTorch or CPU fallback: a CPU tensor, a missing
-`libdat_b200.so` or an unsupported variant flag raises.
+`libdat_b200.so` or an unsupported configuration raises.  The variant branches of the
+reference (`use_pe=False`, `no_off`, `dwc_pe`, `fixed_pe`, `log_cpb`; `:57-59,84-99,
+156-157,164-167,185-197,221-222`) are implemented with the reference's parameter names.
 """
 import ctypes as C
 
@@ -49,8 +51,11 @@ def _f32c(t):
 
 def _fill_struct(struct, names, tensors):
     for n, t in zip(names, tensors):
-        setattr(struct, n, t.data_ptr())
+        setattr(struct, n, t.data_ptr() if t is not None else 0)
     return struct
+
+
+N_PARAMS = len(_cabi.PARAM_FIELDS)   # 13 common tensors + up to 3 of the position-encoding branch
 
 
 class _BlockFn(torch.autograd.Function):
@@ -65,12 +70,14 @@ class _BlockFn(torch.autograd.Function):
                                meta["ksize"], meta["table_h"], meta["table_w"],
                                float(meta["orf"]),
                                _cabi.DAT_BF16 if x_l.dtype == torch.bfloat16 else _cabi.DAT_F32,
-                               _cabi.DAT_BF16 if act == torch.bfloat16 else _cabi.DAT_F32)
+                               _cabi.DAT_BF16 if act == torch.bfloat16 else _cabi.DAT_F32,
+                               meta["pe_mode"], int(meta["no_off"]))
         hk, wk = C.c_int32(), C.c_int32()
         _cabi.check(lib.dat_sample_grid(C.byref(desc), C.byref(hk), C.byref(wk)), "dat_sample_grid")
         Ns, G = hk.value * wk.value, meta["n_groups"]
         dev = x_l.device
-        p32 = [_f32c(p) for p in params]
+        assert len(params) == N_PARAMS
+        p32 = [_f32c(p) if p is not None else None for p in params]
         with torch.cuda.device(dev):
             e = lambda *s, dt=act: torch.empty(s, device=dev, dtype=dt)
             f32 = torch.float32
@@ -88,8 +95,9 @@ class _BlockFn(torch.autograd.Function):
                         "dat_block_forward")
         ctx.meta = meta
         ctx.desc = desc
-        ctx.param_dtypes = [p.dtype for p in params]
-        ctx.save_for_backward(x_l, *p32, *saved)
+        ctx.param_dtypes = [p.dtype if p is not None else None for p in params]
+        ctx.present = [p is not None for p in params]
+        ctx.save_for_backward(x_l, *[p for p in p32 if p is not None], *saved)
         pos = saved[3]
         ctx.mark_non_differentiable(pos)
         return y_l, pos
@@ -98,12 +106,17 @@ class _BlockFn(torch.autograd.Function):
     def backward(ctx, dy_l, _dpos):
         lib = _cabi.lib()
         tensors = ctx.saved_tensors
-        x_l, p32, saved = tensors[0], list(tensors[1:15]), list(tensors[15:])
+        n_present = sum(ctx.present)
+        it = iter(tensors[1:1 + n_present])
+        x_l, saved = tensors[0], list(tensors[1 + n_present:])
+        p32 = [next(it) if here else None for here in ctx.present]
         desc, act = ctx.desc, ctx.meta["act_dtype"]
         dev = x_l.device
         dy_l = dy_l.to(act).contiguous()
         with torch.cuda.device(dev):
-            grads = [torch.empty_like(p) for p in p32]
+            # no_off: the offset network is unused and frozen (dat_blocks.py:57-59) - its gradients stay None
+            skip = range(5) if ctx.meta["no_off"] else ()
+            grads = [torch.empty_like(p) if p is not None and i not in skip else None for i, p in enumerate(p32)]
             dx = torch.empty(x_l.shape, device=dev, dtype=torch.float32)
             nbytes = lib.dat_block_bwd_workspace_bytes(C.byref(desc))
             ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
@@ -116,7 +129,7 @@ class _BlockFn(torch.autograd.Function):
                                                nbytes, stream), "dat_block_backward")
         if dx.dtype != x_l.dtype:
             dx = dx.to(x_l.dtype)
-        grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, ctx.param_dtypes)]
+        grads = [g if g is None or g.dtype == dt else g.to(dt) for g, dt in zip(grads, ctx.param_dtypes)]
         return (dx, None, *grads)
 
 
@@ -130,10 +143,6 @@ class DAttentionBaseline(nn.Module):
         if n_head_channels != _cabi.HEAD_DIM:
             raise NotImplementedError(f"n_head_channels={n_head_channels}: kernels are built for 32 "
                                       "(every DAT++ variant, dat.py:57)")
-        if dwc_pe or fixed_pe or log_cpb or no_off or not use_pe:
-            raise NotImplementedError(
-                "only the rpe_table (bilinear relative-position bias) variant is implemented: "
-                "use_pe=True, dwc_pe=fixed_pe=log_cpb=no_off=False (dat_blocks.py:198-214)")
         if n_heads % n_groups != 0:
             raise ValueError("n_heads must be a multiple of n_groups")
         self.fp16_enabled = False
@@ -161,15 +170,47 @@ class DAttentionBaseline(nn.Module):
         self.proj_k = nn.Conv2d(self.nc, self.nc, 1, 1, 0)
         self.proj_v = nn.Conv2d(self.nc, self.nc, 1, 1, 0)
         self.proj_out = nn.Conv2d(self.nc, self.nc, 1, 1, 0)
-        self.rpe_table = nn.Parameter(torch.zeros(n_heads, self.q_h * 2 - 1, self.q_w * 2 - 1))
-        nn.init.trunc_normal_(self.rpe_table, std=0.01)
+        if no_off:   # dat_blocks.py:57-59
+            for prm in self.conv_offset.parameters():
+                prm.requires_grad_(False)
+        # position-encoding branch, in the reference's precedence order (dat_blocks.py:84-104)
+        if self.use_pe and not self.no_off:
+            if self.dwc_pe:
+                self.pe_mode = _cabi.PE_DWC
+                self.rpe_table = nn.Conv2d(self.nc, self.nc, kernel_size=3, stride=1, padding=1, groups=self.nc)
+            elif self.fixed_pe:
+                self.pe_mode = _cabi.PE_FIXED
+                self.rpe_table = nn.Parameter(torch.zeros(n_heads, self.q_h * self.q_w, self.kv_h * self.kv_w))
+                nn.init.trunc_normal_(self.rpe_table, std=0.01)
+            elif self.log_cpb:
+                if self.n_group_heads > 16:
+                    raise NotImplementedError("log_cpb: at most 16 heads per group")
+                self.pe_mode = _cabi.PE_LOGCPB
+                self.rpe_table = nn.Sequential(nn.Linear(2, 32, bias=True), nn.ReLU(inplace=True),
+                                               nn.Linear(32, self.n_group_heads, bias=False))
+            else:
+                self.pe_mode = _cabi.PE_RPE
+                self.rpe_table = nn.Parameter(torch.zeros(n_heads, self.q_h * 2 - 1, self.q_w * 2 - 1))
+                nn.init.trunc_normal_(self.rpe_table, std=0.01)
+        else:
+            self.pe_mode = _cabi.PE_NONE
+            self.rpe_table = None
 
     def _params(self):
+        """The 16 slots of dat_block_params: 13 common tensors, then rpe_table / pe_b / pe_w2 (None = unused)."""
         co = self.conv_offset
+        t = self.rpe_table
+        if self.pe_mode == _cabi.PE_DWC:
+            pe = (t.weight, t.bias, None)
+        elif self.pe_mode == _cabi.PE_LOGCPB:
+            pe = (t[0].weight, t[0].bias, t[2].weight)
+        elif self.pe_mode == _cabi.PE_NONE:
+            pe = (None, None, None)
+        else:
+            pe = (t, None, None)
         return (co[0].weight, co[0].bias, co[1].norm.weight, co[1].norm.bias, co[3].weight,
                 self.proj_q.weight, self.proj_q.bias, self.proj_k.weight, self.proj_k.bias,
-                self.proj_v.weight, self.proj_v.bias, self.proj_out.weight, self.proj_out.bias,
-                self.rpe_table)
+                self.proj_v.weight, self.proj_v.bias, self.proj_out.weight, self.proj_out.bias, *pe)
 
     def forward(self, x):
         if not x.is_cuda:
@@ -190,14 +231,16 @@ class DAttentionBaseline(nn.Module):
         x_l = x.permute(0, 2, 3, 1)
         if not x_l.is_contiguous():   # in situ x is already physically NHWC (dat.py:147)
             x_l = x_l.contiguous()
+        has_table = self.pe_mode in (_cabi.PE_RPE, _cabi.PE_FIXED)
         meta = dict(n_heads=self.n_heads, n_groups=self.n_groups, stride=self.stride,
-                    ksize=self.ksize, table_h=self.rpe_table.shape[1], table_w=self.rpe_table.shape[2],
-                    orf=self.offset_range_factor, act_dtype=act)
+                    ksize=self.ksize, table_h=self.rpe_table.shape[1] if has_table else 1,
+                    table_w=self.rpe_table.shape[2] if has_table else 1,
+                    orf=self.offset_range_factor, act_dtype=act, pe_mode=self.pe_mode, no_off=bool(self.no_off))
         y_l, pos = _BlockFn.apply(x_l, meta, *self._params())
         y = y_l.permute(0, 3, 1, 2)
         if not self.return_pos_ref:
             return y, None, None
-        hk = (H + 2 * self.conv_offset[0].padding[0] - self.ksize) // self.stride + 1
+        hk = H // self.stride if self.no_off else (H + 2 * self.conv_offset[0].padding[0] - self.ksize) // self.stride + 1
         wk = pos.shape[2] // hk
         ry = torch.empty(hk, device=x.device)
         rx = torch.empty(wk, device=x.device)

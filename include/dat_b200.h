@@ -39,6 +39,16 @@ extern "C" {
 
 #define DAT_HEAD_DIM 32       /* n_head_channels; 32 in every DAT++ variant (dat.py:57) */
 
+/* Position-encoding branch of the block (dat_blocks.py:84-104 ctor, :183-214,221-222 forward), in the
+ * reference's precedence order: `use_pe and not no_off`, then dwc_pe / fixed_pe / log_cpb / rpe_table. */
+#define DAT_PE_RPE 0          /* bilinear sample of rpe_table (n_heads, 2q_h-1, 2q_w-1) at (q_grid - pos)/2 */
+#define DAT_PE_NONE 1         /* use_pe = False (or no_off): no bias                                        */
+#define DAT_PE_DWC 2          /* dwc_pe: depthwise 3x3 conv of q added to the attention output (:185,221)    */
+#define DAT_PE_FIXED 3        /* fixed_pe: dense table (n_heads, q_h*q_w, kv_h*kv_w), bilinearly resized
+                                 (align_corners) to (HW, Ns) (:187-191)                                      */
+#define DAT_PE_LOGCPB 4       /* log_cpb: Linear(2,32)-ReLU-Linear(32,hg) on sign(d)log2(|d|+1)/3,
+                                 d = 4 (q_grid - pos) (:192-197)                                             */
+
 /* Shape / hyper-parameters of one block call.  Mirrors the constructor arguments of
  * DAttentionBaseline (dat_blocks.py:21-50) plus the runtime (B, H, W). */
 typedef struct dat_block_desc {
@@ -50,6 +60,10 @@ typedef struct dat_block_desc {
   float offset_range_factor;  /* :45; < 0 selects the clamp(-1, 1) branch (:159-162)     */
   int32_t x_dtype;            /* dtype of x and of dx                                    */
   int32_t act_dtype;          /* dtype of q, xs, k, v, o, y, dy and of d{o,q,k,v,xs}     */
+  int32_t pe_mode;            /* DAT_PE_*; for DAT_PE_FIXED table_h = q_h*q_w, table_w = kv_h*kv_w;
+                                 table_h/table_w are ignored by NONE / DWC / LOGCPB        */
+  int32_t no_off;             /* :57-59,156-157,164-167: keys/values from avg_pool2d(x, stride), Hk = H/stride,
+                                 offset network unused (its gradients are not written), no bias */
 } dat_block_desc;
 
 /* The 14 reference parameters (state-dict names in comments), fp32. */
@@ -63,14 +77,17 @@ typedef struct dat_block_params {
   const float* wk; const float* bk;   /* proj_k.*                                     */
   const float* wv; const float* bv;   /* proj_v.*                                     */
   const float* wo; const float* bo;   /* proj_out.*                                   */
-  const float* rpe_table;  /* rpe_table (n_heads, table_h, table_w) */
+  const float* rpe_table;  /* RPE / FIXED: rpe_table (n_heads, table_h, table_w); DWC: rpe_table.weight (C,1,3,3);
+                              LOGCPB: rpe_table.0.weight (32, 2); NONE: ignored (may be NULL)               */
+  const float* pe_b;       /* DWC: rpe_table.bias (C); LOGCPB: rpe_table.0.bias (32); else ignored          */
+  const float* pe_w2;      /* LOGCPB: rpe_table.2.weight (hg, 32); else ignored                             */
 } dat_block_params;
 
 /* Gradients of the same 14 tensors (fp32, OVERWRITTEN, not accumulated). */
 typedef struct dat_block_grads {
   float* off_dw_w; float* off_dw_b; float* off_ln_g; float* off_ln_b; float* off_pw_w;
   float* wq; float* bq; float* wk; float* bk; float* wv; float* bv; float* wo; float* bo;
-  float* rpe_table;
+  float* rpe_table; float* pe_b; float* pe_w2;   /* as in dat_block_params; unused ones may be NULL */
 } dat_block_grads;
 
 /* Activations kept between forward and backward; caller allocates each buffer.

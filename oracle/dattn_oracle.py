@@ -56,6 +56,19 @@ class BlockCfg:
     stride: int
     ksize: int
     offset_range_factor: float
+    # variant branches (dat_blocks.py:57-59,84-99,156-157,164-167,185-197,221-222); defaults = shipped configs
+    use_pe: bool = True
+    dwc_pe: bool = False
+    no_off: bool = False
+    fixed_pe: bool = False
+    log_cpb: bool = False
+
+    @property
+    def pe_mode(self):
+        """'none' | 'dwc' | 'fixed' | 'log_cpb' | 'rpe' in the reference's precedence order (:84-104, :183-214)."""
+        if not self.use_pe or self.no_off:
+            return "none"
+        return "dwc" if self.dwc_pe else "fixed" if self.fixed_pe else "log_cpb" if self.log_cpb else "rpe"
 
     @property
     def nc(self):
@@ -465,19 +478,44 @@ def forward_libops(x_nchw: Tensor, p: Dict[str, Tensor], cfg: BlockCfg) -> Tenso
     pos = off + ref
     if orf < 0:
         pos = pos.clamp(-1.0, 1.0)
-    xs = F.grid_sample(x_nchw.reshape(B * G, Cg, H, W), pos.flip(-1), mode="bilinear",
-                       align_corners=True).reshape(B, C, 1, Ns)
+    if cfg.no_off:   # :164-167 — offsets ignored, keys/values from the average-pooled map
+        xs = F.avg_pool2d(x_nchw, kernel_size=cfg.stride, stride=cfg.stride)
+        hk, wk = xs.shape[2], xs.shape[3]
+        Ns = hk * wk
+        xs = xs.reshape(B, C, 1, Ns)
+    else:
+        xs = F.grid_sample(x_nchw.reshape(B * G, Cg, H, W), pos.flip(-1), mode="bilinear",
+                           align_corners=True).reshape(B, C, 1, Ns)
     k = F.conv2d(xs, p["proj_k.weight"], p["proj_k.bias"]).reshape(B * h, hc, Ns)
     v = F.conv2d(xs, p["proj_v.weight"], p["proj_v.bias"]).reshape(B * h, hc, Ns)
     attn = torch.einsum("bcm,bcn->bmn", q.reshape(B * h, hc, H * W), k).mul(hc ** -0.5)
-    qy, qx = query_grid(H, W, x_nchw.dtype)
-    qg = torch.stack(torch.meshgrid(qy, qx, indexing="ij"), -1).reshape(1, H * W, 1, 2)
-    disp = (qg - pos.reshape(B * G, 1, Ns, 2)).mul(0.5)
-    th, tw = p["rpe_table"].shape[1:]
-    tab = p["rpe_table"].reshape(1, G, hg, th, tw).expand(B, G, hg, th, tw).reshape(B * G, hg, th, tw)
-    bias = F.grid_sample(tab, disp.flip(-1), mode="bilinear", align_corners=True)
-    attn = F.softmax(attn + bias.reshape(B * h, H * W, Ns), dim=2)
+    mode = cfg.pe_mode
+    lepe = None
+    if mode in ("rpe", "log_cpb"):
+        qy, qx = query_grid(H, W, x_nchw.dtype)
+        qg = torch.stack(torch.meshgrid(qy, qx, indexing="ij"), -1).reshape(1, H * W, 1, 2)
+    if mode == "rpe":        # :198-214
+        disp = (qg - pos.reshape(B * G, 1, Ns, 2)).mul(0.5)
+        th, tw = p["rpe_table"].shape[1:]
+        tab = p["rpe_table"].reshape(1, G, hg, th, tw).expand(B, G, hg, th, tw).reshape(B * G, hg, th, tw)
+        bias = F.grid_sample(tab, disp.flip(-1), mode="bilinear", align_corners=True)
+        attn = attn + bias.reshape(B * h, H * W, Ns)
+    elif mode == "dwc":      # :185-186,221-222 — depthwise 3x3 on q, added to the attention output
+        lepe = F.conv2d(q, p["rpe_table.weight"], p["rpe_table.bias"], padding=1, groups=C)
+    elif mode == "fixed":    # :187-191 — dense table, bilinearly resized to (HW, Ns)
+        bias = F.interpolate(p["rpe_table"][None].expand(B, -1, -1, -1), size=(H * W, Ns), mode="bilinear",
+                             align_corners=True)
+        attn = attn + bias.reshape(B * h, H * W, Ns)
+    elif mode == "log_cpb":  # :192-197 — Swin-V2 style MLP on the log-scaled displacement
+        disp = (qg - pos.reshape(B * G, 1, Ns, 2)).mul(4.0)
+        disp = torch.sign(disp) * torch.log2(torch.abs(disp) + 1.0) / math.log2(8.0)
+        hid = F.relu(F.linear(disp, p["rpe_table.0.weight"], p["rpe_table.0.bias"]))
+        bias = F.linear(hid, p["rpe_table.2.weight"])                 # (B*G, HW, Ns, hg)
+        attn = attn + bias.permute(0, 3, 1, 2).reshape(B * h, H * W, Ns)
+    attn = F.softmax(attn, dim=2)
     out = torch.einsum("bmn,bcn->bcm", attn, v).reshape(B, C, H, W)
+    if lepe is not None:
+        out = out + lepe
     return F.conv2d(out, p["proj_out.weight"], p["proj_out.bias"])
 
 

@@ -38,3 +38,15 @@ def load_case(name):
 
 def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
+
+
+def load_variant(name):
+    """Golden case of a variant branch (tests/golden/make_golden_variants.py): (cfg, x, dy, record)."""
+    from make_golden_variants import VARIANTS, variant_inputs  # noqa: F401
+    rec = torch.load(os.path.join(HERE, "golden", "variants.pt"), weights_only=False)[name]
+    m = rec["meta"]
+    cfg = BlockCfg(m["q_size"][0], m["q_size"][1], m["n_heads"], HC, m["n_groups"], m["stride"], m["ksize"],
+                   m["orf"], **m["flags"])
+    x, dy = variant_inputs(name)
+    assert abs(x.double().sum().item() - rec["x_sum"]) < 1e-6, "seeded input drifted"
+    return cfg, x, dy, rec

@@ -89,14 +89,30 @@ def test_default_init_matches_reference_rng_stream():
         assert torch.equal(v, rec["params"][k]), k
 
 
-@pytest.mark.parametrize("flag", ["dwc_pe", "no_off", "fixed_pe", "log_cpb", "no_pe"])
-def test_unimplemented_variants_raise(flag):
+def _variant_module(name):
+    from golden_util import load_variant
     from dat_segmentation_b200.dattention import DAttentionBaseline
-    kw = dict(use_pe=True, dwc_pe=False, no_off=False, fixed_pe=False, log_cpb=False)
-    if flag == "no_pe":
-        kw["use_pe"] = False
-    else:
-        kw[flag] = True
-    with pytest.raises(NotImplementedError):
-        DAttentionBaseline((14, 14), (14, 14), 8, 32, 4, 0.0, 0.0, 2, -1, kw["use_pe"], kw["dwc_pe"],
-                           kw["no_off"], kw["fixed_pe"], 5, kw["log_cpb"], 2)
+    cfg, x, dy, rec = load_variant(name)
+    m, f = rec["meta"], rec["meta"]["flags"]
+    mod = DAttentionBaseline(m["q_size"], m["q_size"], m["n_heads"], 32, m["n_groups"], 0.0, 0.0, m["stride"], m["orf"],
+                             f["use_pe"], f["dwc_pe"], f["no_off"], f["fixed_pe"], m["ksize"], f["log_cpb"], 2)
+    return mod, cfg, x, dy, rec
+
+
+@pytest.mark.parametrize("name", ["no_pe", "no_off", "dwc_pe", "fixed_pe_resize", "log_cpb"])
+def test_variant_modules_share_the_reference_state_dict(name):
+    """Variant branches (dat_blocks.py:57-59,84-104): same parameter names / shapes / frozen set as the
+    reference module, same default initialisation under the same seed."""
+    torch.manual_seed(11)
+    mod, cfg, x, dy, rec = _variant_module(name)
+    sd = mod.state_dict()
+    assert list(sd.keys()) == list(rec["params"].keys())
+    assert all(sd[k].shape == rec["params"][k].shape for k in sd)
+    assert sorted(k for k, v in mod.named_parameters() if not v.requires_grad) == sorted(rec["frozen"])
+    with torch.no_grad():
+        mod.conv_offset[3].weight.mul_(2.0)
+        if isinstance(mod.rpe_table, torch.nn.Parameter):
+            mod.rpe_table.mul_(30.0)
+    for k, v in mod.state_dict().items():
+        assert torch.equal(v, rec["params"][k]), k
+    mod.load_state_dict(rec["params"], strict=True)

@@ -81,3 +81,25 @@ def test_backward_explicit_fp64_vs_autograd_of_port():
         if key == "proj_k.bias":
             continue
         assert rel_err(grads[key], leaves[key].grad) < 1e-9, key
+
+
+# ---- variant branches (dat_blocks.py:57-59,84-99,156-157,164-167,185-197,221-222) ----------------
+
+from golden_util import load_variant  # noqa: E402
+from make_golden_variants import VARIANTS  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_port_matches_reference(name):
+    """The library-op port with the variant flags == the unmodified reference: forward, dx and the
+    gradient of every trainable parameter (autograd of the port vs the reference's autograd)."""
+    cfg, x, dy, rec = load_variant(name)
+    leaves = {k: v.clone().requires_grad_(k not in rec["frozen"]) for k, v in rec["params"].items()}
+    xin = x.clone().requires_grad_(True)
+    y = orc.forward_libops(xin, leaves, cfg)
+    assert rel_err(y, rec["y"]) < 1e-6
+    y.backward(dy)
+    assert rel_err(xin.grad, rec["dx"]) < 1e-5
+    assert set(rec["grads"]) == {k for k, v in leaves.items() if v.grad is not None}
+    for k, g in rec["grads"].items():
+        assert rel_err(leaves[k].grad, g) < 1e-5, k

@@ -17,13 +17,18 @@ SWEEP = [(hw, g, orf) for hw, (h, _, _, _) in PRESETS.items() for g in (1, 2, 4,
 
 
 def _build(hw, groups, orf, seed):
+    """The module with its own (reference-identical) default initialisation under a seed, offsets and
+    bias table widened as in tests/golden/make_golden.py so OOB taps / tanh saturation are exercised."""
     from dat_segmentation_b200.dattention import DAttentionBaseline
     heads, stride, ksize, qs = PRESETS[hw]
     cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, orf)
-    params = orc.init_params(cfg, seed=seed)
+    torch.manual_seed(seed)
     m = DAttentionBaseline((qs, qs), (qs, qs), heads, 32, groups, 0.0, 0.0, stride, orf, True, False,
                            False, False, ksize, False, 0)
-    m.load_state_dict(params, strict=True)
+    with torch.no_grad():
+        m.conv_offset[3].weight.mul_(2.0)
+        m.rpe_table.mul_(10.0)
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
     return cfg, params, m.cuda()
 
 
@@ -38,7 +43,7 @@ def test_sweep_forward(hw, groups, orf):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yb, _, _ = m(x.cuda())
     assert rel_err(y.cpu(), y_ref) < 1e-5
-    assert (yb.float().cpu() - y_ref).abs().max().item() < 2e-2 * max(1.0, y_ref.abs().max().item())
+    assert (yb.float().cpu() - y_ref).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("hw,groups", sorted({(hw, g) for hw, g, _ in SWEEP}))
@@ -57,6 +62,9 @@ def test_sweep_backward_fp32(hw, groups):
     y.backward(dy.cuda())
     report = {"dx": rel_err(xd.grad.cpu(), xr.grad)}
     for k, p in m.named_parameters():
+        if k == "proj_k.bias":      # analytically zero (softmax shift invariance): absolute check
+            assert p.grad.abs().max().item() < 1e-4
+            continue
         report[k] = rel_err(p.grad.cpu(), pr[k].grad)
     bad = {k: v for k, v in report.items() if v > 5e-5}
     assert not bad, bad
