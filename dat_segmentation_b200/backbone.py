@@ -19,7 +19,8 @@ from .layernorm import LayerNormProxy, TorchLayerNormProxy
 from .pointwise import PointwiseConvCL
 from .residual import scale_residual
 
-__all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "build_dat", "LayerNormProxy", "TorchLayerNormProxy"]
+__all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "DAT_SMALL_PP", "DAT_BASE_PP", "build_dat", "LayerNormProxy",
+           "TorchLayerNormProxy"]
 
 # DAT-T++ backbone hyper-parameters (configs/dat/upn_tiny_160k_dp03_lr6.py:9-32)
 DAT_TINY_PP = dict(
@@ -29,6 +30,15 @@ DAT_TINY_PP = dict(
     offset_range_factor=[-1, -1, -1, -1], use_dwc_mlps=[True] * 4, use_lpus=[True] * 4,
     use_conv_patches=True, ksizes=[9, 7, 5, 3], nat_ksizes=[7, 7, 7, 7], drop_path_rate=0.3,
     use_checkpoint=False)
+
+
+# DAT-S++ / DAT-B++ (BASELINE.json configs[2], configs[3]).  Their config files are NOT in the reference tree
+# (only the tiny one is): these are the upstream DAT++ hyper-parameters, "assumed, unpinned by the reference"
+#  - same structure as the tiny config, wider / deeper.
+DAT_SMALL_PP = dict(DAT_TINY_PP, dim_stem=96, dims=[96, 192, 384, 768], depths=[2, 4, 18, 2],
+                    heads=[3, 6, 12, 24], groups=[1, 2, 3, 6], drop_path_rate=0.4)
+DAT_BASE_PP = dict(DAT_TINY_PP, dim_stem=128, dims=[128, 256, 512, 1024], depths=[2, 4, 18, 2],
+                   heads=[4, 8, 16, 32], groups=[2, 4, 8, 16], drop_path_rate=0.6)
 
 
 class DropPath(nn.Module):

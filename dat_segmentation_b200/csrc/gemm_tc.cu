@@ -443,10 +443,10 @@ int env_int(const char* name, int dflt) {
 int pick_bn(int N) {
   const int cap = env_int("DAT_B200_GEMM_BN", 256);     // tuning knob: widest output tile
   if (cap < 256 && N % cap == 0) return cap;
-  int tiles = (N + 255) / 256;
-  if (N % tiles != 0) return 0;
-  int bn = N / tiles;
-  return (bn % 32 == 0 && bn >= 32) ? bn : 0;
+  // widest tile that divides N; tiles wider than one epilogue column group (128) must be a multiple of it
+  for (int bn : {256, 128, 96, 64, 32})
+    if (N % bn == 0) return bn;
+  return 0;
 }
 
 }  // namespace

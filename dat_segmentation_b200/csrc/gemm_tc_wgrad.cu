@@ -164,7 +164,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 
 // in-channel tile: <= 128 so that accumulator + 16 bias-gradient columns fit 256 TMEM columns
 // (two CTAs per SM share the 512)
-int wg_bnk(int C) { return C >= 128 ? 128 : C; }
+int wg_bnk(int C) { return C % 128 == 0 ? 128 : 64; }
 
 }  // namespace
 

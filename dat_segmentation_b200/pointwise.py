@@ -31,14 +31,11 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _tileable(n):
-    tiles = (n + 255) // 256
-    return n % tiles == 0 and (n // tiles) % 32 == 0
-
-
 def _supported(M, N, K):
-    # forward / data-gradient tiling (gemm_tc.cu pick_bn) and the weight-gradient boxes (64 x 64)
-    return M >= 64 and _tileable(N) and _tileable(K) and N % 64 == 0 and K % 64 == 0
+    # forward / data-gradient tiling (gemm_tc.cu pick_bn: a tile of 32..256 columns must divide N, resp. K) and
+    # the weight-gradient kernel's own predicate (64 x 64 boxes), asked through the C ABI
+    return (M >= 64 and N % 32 == 0 and K % 32 == 0
+            and _cabi.lib().dat_pointwise_wgrad_tc_workspace_bytes(M, N, K) > 0)
 
 
 class _PointwiseFn(torch.autograd.Function):

@@ -78,3 +78,38 @@ def test_backbone_cuda_vs_oracle_port(size):
                 and cp[k].grad.abs().max() > 1e-6)
     print("worst param-grad rel err", worst)
     assert worst[0] < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["small", "base"])
+def test_backbone_family_cuda_vs_oracle_port(family):
+    """DAT-S++ / DAT-B++ widths (BASELINE.json configs[2], [3]; C = 96.. and 128..1024, 3 / 6 / 12 / 24 and up to
+    32 heads, groups 1..16) with the depths cut to one 'X' + 'D' pair per stage so the CPU port stays quick:
+    fp32 CUDA backbone vs the oracle-port backbone, then the bf16 autocast forward."""
+    from dat_segmentation_b200.backbone import DAT_BASE_PP, DAT_SMALL_PP
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(DAT_SMALL_PP if family == "small" else DAT_BASE_PP, depths=[2, 2, 2, 2],
+               stage_spec=[["X", "D"], ["X", "D"], ["X", "D"], ["D", "D"]], drop_path_rate=0.0)
+    torch.manual_seed(9)
+    gpu = build_dat(cfg).cuda()
+    with torch.no_grad():
+        for m in gpu.modules():
+            if type(m).__name__ == "DAttentionBaseline":
+                m.conv_offset[3].weight.mul_(2.0)
+                m.rpe_table.mul_(10.0)
+    cpu = build_dat(cfg, attn_cls=orc.OracleDAttention)
+    cpu.load_state_dict({k: v.cpu() for k, v in gpu.state_dict().items()}, strict=True)
+    x = torch.randn(1, 3, 128, 160)
+    xg = x.cuda().requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    og, oc = gpu(xg), cpu(xc)
+    for a, b in zip(og, oc):
+        assert _rel(a.detach().cpu(), b.detach()) < 2e-4
+    sum(o.square().mean() for o in og).backward()
+    sum(o.square().mean() for o in oc).backward()
+    assert _rel(xg.grad.cpu(), xc.grad) < 5e-3
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ob = gpu(x.cuda())
+    for a, b in zip(ob, oc):
+        assert _rel(a.float().cpu(), b.detach()) < 6e-2      # bf16 through 8 blocks; outputs are LayerNormed (O(1))

@@ -91,7 +91,8 @@ def test_pointwise_fwd(M, N, K, dt):
     assert err < (FP32_TOL if dt == "f32" else 8e-3), err
 
 
-@pytest.mark.parametrize("M,C", [(4096, 64), (1000, 128), (16384, 256), (300, 512), (513, 96), (256, 1024)])
+@pytest.mark.parametrize("M,C", [(4096, 64), (1000, 128), (16384, 256), (300, 512), (513, 96), (256, 1024),
+                                 (700, 192), (640, 384), (300, 768), (260, 160)])
 @pytest.mark.parametrize("kind", ["tf32", "bf16"])
 def test_pointwise_fwd_tensor_core(M, C, kind):
     """tcgen05 GEMM (TMA-fed, TMEM accumulator) against an fp64 product of the same

@@ -16,7 +16,10 @@ def _rel(a, b):
 # (cin, cout, B, H, W): the four DAT-T++ stage widths in both directions + ragged pixel counts
 SHAPES = [(64, 256, 2, 32, 32), (256, 64, 2, 32, 32), (128, 512, 2, 16, 16), (512, 128, 2, 16, 16),
           (256, 1024, 2, 9, 7), (1024, 256, 2, 9, 7), (512, 2048, 1, 8, 8), (2048, 512, 1, 8, 8),
-          (128, 512, 3, 5, 5)]
+          (128, 512, 3, 5, 5),
+          # DAT-S++ widths (C = 192, 384, 768; 96 x 4 = 384 columns out of a 96-wide input is not tileable)
+          (192, 768, 2, 12, 12), (768, 192, 2, 12, 12), (384, 1536, 1, 9, 9), (1536, 384, 1, 9, 9),
+          (768, 3072, 1, 8, 8), (3072, 768, 1, 8, 8)]
 
 
 @pytest.mark.parametrize("cin,cout,B,H,W", SHAPES)
