@@ -45,6 +45,11 @@ struct AtcArgs {
   float c1;        // hc^-0.5 * log2(e)
   float kx, ky;    // 0.25 * (Tw - 1), 0.25 * (Th - 1)
   float gsx, gsy;  // 2 / (W - 1), 2 / (H - 1): query grid step (no IEEE division in the kernel)
+  // split-KV launches (Ns > 256, e.g. the 512 x 2048 evaluation shape: 16 x 64 = 1024 samples): CTA z handles
+  // the samples [n_off0 + z * NS, + NS) of ns_total and writes its normalised partial output / log-sum-exp into
+  // slot z0 + z (strides o_zstride / lse_zstride elements); attn_combine_kernel merges the slots.
+  int ns_total, n_off0, z0;
+  long long o_zstride, lse_zstride;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -142,6 +147,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
   constexpr uint32_t TMEM_COLS = NS < 32 ? 32 : NS;   // NS is a power of two here
+  const int n_off = a.n_off0 + (int)blockIdx.z * NS;   // first sample of this CTA's KV chunk
+  o += (long long)(a.z0 + (int)blockIdx.z) * a.o_zstride;
+  lse += (long long)(a.z0 + (int)blockIdx.z) * a.lse_zstride;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -162,7 +170,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   {
     const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
     for (int i = threadIdx.x; i < a.Hp * a.Wp; i += ATC_THREADS) sTab[i] = src[i];
-    const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
+    const float* pp = pos + (((long long)b * a.G + g) * a.ns_total + n_off) * 2;
     for (int n = threadIdx.x; n < NS; n += ATC_THREADS) {
       sYk[n] = pp[2 * n] * a.ky;
       sXk[n] = pp[2 * n + 1] * a.kx;
@@ -177,8 +185,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0 && lane == 0) {
       // ---- TMA producer ------------------------------------------------------------
       mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
-      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * NS);
-      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * NS);
+      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * a.ns_total + n_off);
+      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * a.ns_total + n_off);
       int it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int slot = it & 1;
@@ -377,13 +385,60 @@ AtcArgs make_args(const Shape& s) {
   a.ky = 0.25f * (float)(s.Th - 1);
   a.gsx = 2.0f / (float)(s.W - 1);
   a.gsy = 2.0f / (float)(s.H - 1);
+  a.ns_total = s.Ns; a.n_off0 = 0; a.z0 = 0; a.o_zstride = 0; a.lse_zstride = 0;
   return a;
 }
+
+// Merge of the split-KV partials: slot c holds softmax(S_c) V_c and lse_c of its sample chunk;
+// O = sum_c w_c O_c / sum_c w_c, w_c = exp(lse_c - max lse), lse = max + log sum_c w_c.
+__global__ void attn_combine_kernel(const bf16* __restrict__ o_part, const float* __restrict__ lse_part,
+                                    bf16* __restrict__ o, float* __restrict__ lse, int nch, int HW, int C, int heads,
+                                    long long o_zstride, long long lse_zstride, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, m, eta, 8-channel group)
+  if (idx >= total) return;
+  const int c8 = (int)(idx & 3);
+  const int eta = (int)((idx >> 2) % heads);
+  const long long bm = (idx >> 2) / heads;
+  const int m = (int)(bm % HW);
+  const long long b = bm / HW;
+  const long long li = (b * heads + eta) * HW + m;
+  float mx = -INFINITY;
+  for (int c = 0; c < nch; ++c) mx = fmaxf(mx, lse_part[c * lse_zstride + li]);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float den = 0.f;
+  const long long oi = bm * C + eta * 32 + c8 * 8;
+  for (int c = 0; c < nch; ++c) {
+    const float w = __expf(lse_part[c * lse_zstride + li] - mx);
+    den += w;
+    const uint4 raw = *reinterpret_cast<const uint4*>(o_part + c * o_zstride + oi);
+    const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(w, __uint_as_float(rw[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(w, __uint_as_float(rw[i] & 0xffff0000u), acc[2 * i + 1]);
+    }
+  }
+  const float inv = 1.0f / den;
+  *reinterpret_cast<uint4*>(o + oi) = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                                                  pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  if (c8 == 0) lse[li] = mx + __logf(den);
+}
+
+constexpr int KV_MAX = 256;            // samples per CTA (one TMEM accumulator of 128 x 256 fp32)
+constexpr int KV_CHUNKS_MAX = 32;      // Ns <= 8192
+int kv_chunks(int Ns) { return Ns <= KV_MAX ? 1 : Ns / KV_MAX + ((Ns % KV_MAX) & 128 ? 1 : 0) + ((Ns % KV_MAX) & 64 ? 1 : 0); }
+size_t table_bytes(const Shape& s) { return align_up((size_t)s.heads * (s.Th + 3) * (s.Tw + 3) * 8, 256); }
 
 }  // namespace
 
 size_t attention_fwd_tc_workspace(const Shape& s) {
-  return align_up((size_t)s.heads * (s.Th + 3) * (s.Tw + 3) * 8, 256);
+  // packed table, then (Ns > 256 only) the split-KV partial outputs (bf16) and log-sum-exps
+  size_t n = table_bytes(s);
+  if (s.Ns > KV_MAX) {
+    const size_t nch = (size_t)kv_chunks(s.Ns);
+    n += align_up(nch * s.B * s.HW * s.C * 2, 256) + align_up(nch * s.B * s.heads * s.HW * 4, 256);
+  }
+  return n;
 }
 
 // packed table (see pack_table_kernel) into `out`, attention_fwd_tc_workspace(s) bytes
@@ -396,9 +451,10 @@ int attention_pack_table(const Shape& s, const float* table, void* out, cudaStre
 
 bool attention_fwd_tc_supported(const Shape& s) {
   if (s.act_dtype != DAT_BF16 || s.pe_mode != DAT_PE_RPE) return false;
-  if (!(s.Ns == 64 || s.Ns == 128 || s.Ns == 256)) return false;
+  // one CTA holds up to 256 samples; more are split into chunks of 256 (+ a 128 and / or a 64 remainder)
+  if (s.Ns % 64 != 0 || kv_chunks(s.Ns) > KV_CHUNKS_MAX) return false;
   if (s.C % 8 != 0) return false;
-  SmemPlan sp = plan_smem(s.Ns, s.Th + 3, s.Tw + 3, rows_spanned_max(s.HW, s.W));
+  SmemPlan sp = plan_smem(s.Ns < KV_MAX ? s.Ns : KV_MAX, s.Th + 3, s.Tw + 3, rows_spanned_max(s.HW, s.W));
   return sp.total <= 227 * 1024;
 }
 
@@ -411,23 +467,50 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   const int ntab = s.heads * a.Hp * a.Wp;
   pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table_kernel");
-  CUtensorMap tmQ, tmK, tmV;
+  const int nch = kv_chunks(s.Ns);
+  bf16* o_dst = (bf16*)o;
+  float* lse_dst = lse;
+  if (nch > 1) {   // partial slots behind the packed table
+    o_dst = (bf16*)((char*)ws + table_bytes(s));
+    lse_dst = (float*)((char*)o_dst + align_up((size_t)nch * s.B * s.HW * s.C * 2, 256));
+    a.o_zstride = (long long)s.B * s.HW * s.C;
+    a.lse_zstride = (long long)s.B * s.heads * s.HW;
+  }
+  CUtensorMap tmQ;
   DAT_FWD(tc::make_tmap_2d(&tmQ, q, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, (uint64_t)s.C * 2, TQ, 32, 64));
-  DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, s.Ns, 32, 64));
-  DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, s.Ns, 32, 64));
-  SmemPlan sp = plan_smem(s.Ns, a.Hp, a.Wp, a.rows_max);
-  dim3 grid(pick_chunks(s.B * s.heads, a.n_tiles), s.B * s.heads);
+  const int gx = pick_chunks(s.B * s.heads * nch, a.n_tiles);
+  // one launch per chunk size: all 256-sample chunks along grid.z, then the 128 / 64 remainders
+  int n_off = 0, z = 0;
+  for (int size : {256, 128, 64}) {
+    int count = s.Ns <= KV_MAX ? (s.Ns == size ? 1 : 0) : (size == 256 ? s.Ns / 256 : ((s.Ns % 256) & size ? 1 : 0));
+    if (count == 0) continue;
+    CUtensorMap tmK, tmV;
+    DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, size, 32, 64));
+    DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, (uint64_t)s.C * 2, size, 32, 64));
+    SmemPlan sp = plan_smem(size, a.Hp, a.Wp, a.rows_max);
+    dim3 grid(gx, s.B * s.heads, count);
+    a.n_off0 = n_off;
+    a.z0 = z;
 #define LAUNCH(NSV)                                                                              \
   do {                                                                                           \
     auto kern = attn_fwd_tc_kernel<NSV>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
-    kern<<<grid, ATC_THREADS, sp.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, (bf16*)o, lse, a); \
+    kern<<<grid, ATC_THREADS, sp.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
   } while (0)
-  if (s.Ns == 256) LAUNCH(256);
-  else if (s.Ns == 128) LAUNCH(128);
-  else LAUNCH(64);
+    if (size == 256) LAUNCH(256);
+    else if (size == 128) LAUNCH(128);
+    else LAUNCH(64);
 #undef LAUNCH
-  DAT_LAUNCH_OK("attn_fwd_tc_kernel");
+    DAT_LAUNCH_OK("attn_fwd_tc_kernel");
+    n_off += count * size;
+    z += count;
+  }
+  if (nch > 1) {
+    const long long total = (long long)s.B * s.HW * s.heads * 4;
+    attn_combine_kernel<<<ceil_div(total, 256), 256, 0, st>>>(o_dst, lse_dst, (bf16*)o, lse, nch, s.HW, s.C, s.heads,
+                                                               a.o_zstride, a.lse_zstride, total);
+    DAT_LAUNCH_OK("attn_combine_kernel");
+  }
   return DAT_OK;
 }
 

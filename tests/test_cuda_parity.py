@@ -255,6 +255,45 @@ def test_attention_core_fwd_tensor_core(stage):
         assert e_o < 2e-2 and e_l < 2e-2
 
 
+@pytest.mark.parametrize("H,W,heads,groups,stride,ksize,qs", [
+    (16, 64, 8, 4, 1, 3, 7),      # 16 x 64 = 1024 samples = 4 x 256 (the 512 x 2048 evaluation shape, stage 3)
+    (32, 128, 4, 2, 2, 5, 14),    # 1024 samples at the stage-2 stride
+    (24, 24, 2, 2, 1, 3, 7),      # 576 = 2 x 256 + 64
+    (16, 28, 4, 1, 1, 3, 7),      # 448 = 256 + 128 + 64
+    (48, 32, 2, 1, 2, 5, 14),     # 384 = 256 + 128
+])
+def test_attention_core_fwd_tensor_core_split_kv(H, W, heads, groups, stride, ksize, qs):
+    """More than 256 samples (BASELINE.json configs[3]: 512 x 2048 inputs give a 16 x 64 sample grid): the tcgen05
+    kernel runs one CTA per chunk of 256 / 128 / 64 samples and merges the partial softmaxes.  Checked against
+    the fp32 CUDA-core kernel on the same bf16 q / k / v."""
+    cab, lib = _lib()
+    B = 2
+    cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, -1)
+    d = _desc(cab, cfg, B, H, W, 0, 1)
+    hk, wk = cfg.sample_grid(H, W)
+    Ns, Cc = hk * wk, heads * 32
+    assert Ns > 256
+    g = torch.Generator().manual_seed(H * W + heads)
+    q = torch.randn(B, H * W, Cc, generator=g).bfloat16().cuda()
+    k = torch.randn(B, Ns, Cc, generator=g).bfloat16().cuda()
+    v = torch.randn(B, Ns, Cc, generator=g).bfloat16().cuda()
+    pos = (torch.rand(B, groups, Ns, 2, generator=g) * 2.2 - 1.1).cuda()
+    tab = (torch.randn(heads, 2 * qs - 1, 2 * qs - 1, generator=g) * 0.5).cuda()
+    nb = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
+    assert nb > 0
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    res = {}
+    for impl in (0, 1):
+        o = torch.zeros_like(q)
+        lse = torch.zeros(B, heads, H * W, device="cuda")
+        cab.check(lib.dat_attention_fwd(C.byref(d), _p(q), _p(k), _p(v), _p(pos), _p(tab), _p(o), _p(lse), _p(ws), nb,
+                                        impl, _stream()), "attn")
+        torch.cuda.synchronize()
+        res[impl] = (o.float().cpu(), lse.cpu())
+    assert (res[0][0] - res[1][0]).abs().max().item() < 2e-2
+    assert (res[0][1] - res[1][1]).abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("layout", ["nchw", "channels_last"])
 def test_block_forward_fp32_vs_reference(name, layout):
