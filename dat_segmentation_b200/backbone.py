@@ -10,6 +10,8 @@ dict loads with `strict=True`.
 """
 from typing import Callable, Sequence
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -273,6 +275,13 @@ class DAT(nn.Module):
             conv = (nn.Conv2d(dims[i], dims[i + 1], 3, 2, 1, bias=False) if use_conv_patches
                     else nn.Conv2d(dims[i], dims[i + 1], 2, 2, 0, bias=False))
             self.down_projs.append(nn.Sequential(conv, norm_cls(dims[i + 1])))
+        if b200_ops and os.environ.get("DAT_B200_NCHW_CONVS") is None:
+            # The dat_b200 kernels are channel-last; keep the (library) stem / down-projection convolutions in
+            # channels_last too, so their outputs feed the LayerNorm kernels without NCHW <-> NHWC copies.
+            # Shapes and state-dict contents are unchanged (only the parameters' strides differ).
+            for m in list(self.patch_proj) + [dp[0] for dp in self.down_projs]:
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
     def forward(self, x):
         x = self.patch_proj(x)
