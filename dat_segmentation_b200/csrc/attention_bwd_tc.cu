@@ -139,16 +139,21 @@ __host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int row
 // PRIV:    every compute warp owns a private padded copy of the table gradient and updates it
 //          with plain read-modify-writes (no atomics); needs W % 32 == 0 (a warp's 32 queries
 //          lie in one image row, so its run leaders hit distinct cells).
-template <int NS, bool COMPACT, bool PRIV>
+// TBL:     true = the table gradient is accumulated inside this kernel (shared-memory scatter, above);
+//          false = dS (bf16, [b*heads][m][n]) is streamed to `ds_out` instead and the table gradient is
+//          formed from it by rpe_table_grad_mma (rpe_table_grad.cu) as small tensor-core GEMMs - the
+//          per-score scatter is 50-75 % of this kernel's time, the 16-byte stores are ~2 %.
+template <int NS, bool COMPACT, bool PRIV, bool TBL>
 __global__ void __launch_bounds__(BTC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const float* __restrict__ pos, const void* __restrict__ tab_packed,
                    const float* __restrict__ lse, const float* __restrict__ delta,
                    bf16* __restrict__ dq, float* __restrict__ dk_part, float* __restrict__ dv_part,
-                   float* __restrict__ d_table, float* __restrict__ dpos_part, BtcArgs a) {
+                   float* __restrict__ d_table, float* __restrict__ dpos_part, bf16* __restrict__ ds_out,
+                   BtcArgs a) {
   constexpr int NHALF = NS / NHC;
-  constexpr int NDT = PRIV ? 8 : 1;          // copies of the table gradient
+  constexpr int NDT = !TBL ? 0 : (PRIV ? 8 : 1);          // copies of the table gradient
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -335,6 +340,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float* mytab = sDTab + (PRIV ? (warp - 4) * a.Hp * a.Wp : 0);
       uint8_t* prow_p = sP + chalf * 16384 + row * 128;
       uint8_t* prow_d = sDS + chalf * 16384 + row * 128;
+      bf16* ds_row = TBL ? nullptr : ds_out + ((long long)bh * a.HW + mm) * NS;
 
       pf_setup += clock64() - pf_t;
 #pragma unroll 1
@@ -400,6 +406,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
               *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
               *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+              if (!TBL && valid)      // the same 8 dS values, [m][n] layout, for the tensor-core table gradient
+                *reinterpret_cast<uint4*>(ds_row + nbase + j - 7) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
             }
             // ---- d rpe_table ----------------------------------------------------------------
             // Lanes = consecutive queries of an image row; the table step per query is < 1 cell,
@@ -408,7 +416,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // (2) a run head also takes the Q of the previous run when that run is its left
             // neighbour (same image row, cell x0-1, single window), so a run usually issues 2
             // updates (rows y0, y0+1 of one cell) instead of 4.
-            {
+            if (TBL) {
               float* cell = mytab + idx;                  // padded index: no bounds checks
               const float wy1 = fy, wy0 = 1.0f - fy;
               // Light path (0.29 <= table step per query <= 1, nothing clamped: every shipped config):
@@ -571,7 +579,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // padded shared-memory table gradient -> global (one atomic per touched in-range cell)
     float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
-    for (int i = ctid; i < a.Hp * a.Wp; i += COMP_THREADS) {
+    for (int i = ctid; TBL && i < a.Hp * a.Wp; i += COMP_THREADS) {
       const int y = i / a.Wp - 2, x = i - (i / a.Wp) * a.Wp - 2;
       float vv = 0.f;
 #pragma unroll
@@ -615,7 +623,7 @@ int attention_bwd_tc_chunks(const Shape& s) {
 // kernel variant for a shape: private table-gradient copies and 8-byte table entries when they
 // fit, else shared copy (atomics) / compact table / single Q,dO slot.  variant < 0: unsupported.
 struct BtcVariant { int ok, compact, priv, nslots; uint32_t smem; };
-BtcVariant pick_variant(const Shape& s) {
+BtcVariant pick_variant(const Shape& s, bool tbl = true) {
   BtcVariant v = {0, 0, 0, 2, 0};
   if (s.act_dtype != DAT_BF16 || !(s.Ns == 128 || s.Ns == 256) || s.C % 8 != 0) return v;
   const int rows = rows_spanned_max_b(s.HW, s.W);
@@ -625,8 +633,8 @@ BtcVariant pick_variant(const Shape& s) {
   const bool priv_ok = (s.W % 32) == 0 && (s.Tw - 1) * 5 >= (s.W - 1);
   const int tries[4][3] = {{0, 1, 2}, {0, 0, 2}, {1, 0, 2}, {1, 0, 1}};   // {compact, priv, nslots}
   for (int t = 0; t < 4; ++t) {
-    if (tries[t][1] && !priv_ok) continue;
-    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, tries[t][1] ? 8 : 1, tries[t][2]);
+    if (tries[t][1] && (!priv_ok || !tbl)) continue;
+    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, !tbl ? 0 : (tries[t][1] ? 8 : 1), tries[t][2]);
     if (sp.total <= lim) {
       v.ok = 1; v.compact = tries[t][0]; v.priv = tries[t][1]; v.nslots = tries[t][2]; v.smem = sp.total;
       return v;
@@ -643,7 +651,7 @@ int debug_attn_bwd_timing(unsigned long long* out8) {
 }
 
 bool attention_bwd_tc_supported(const Shape& s) { return s.pe_mode == DAT_PE_RPE && pick_variant(s).ok != 0; }
-bool attention_bwd_tc_compact_table(const Shape& s) { return pick_variant(s).compact != 0; }
+bool attention_bwd_tc_compact_table(const Shape& s, bool tbl) { return pick_variant(s, tbl).compact != 0; }
 
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st) {
   const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
@@ -657,8 +665,9 @@ int attention_pack_table_compact(const Shape& s, const float* table, void* out, 
 int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
                      const float* lse, const float* delta, const float* pos, const void* tab_packed,
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
-                     cudaStream_t st) {
-  const BtcVariant var = pick_variant(s);
+                     cudaStream_t st, void* ds_out) {
+  const bool tbl = ds_out == nullptr;      // dS streamed out: the table gradient is formed by rpe_table_grad_mma
+  const BtcVariant var = pick_variant(s, tbl);
   DAT_REQUIRE(var.ok, "attention_bwd_tc: unsupported shape");
   BtcArgs a;
   a.nslots = var.nslots;
@@ -684,18 +693,20 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
   DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
   DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
   dim3 grid(a.chunks, s.B * s.heads);
-#define LAUNCH(NSV, CP, PV)                                                                      \
+#define LAUNCH(NSV, CP, PV, TB)                                                                  \
   do {                                                                                           \
-    auto kern = attn_bwd_tc_kernel<NSV, CP, PV>;                                                 \
+    auto kern = attn_bwd_tc_kernel<NSV, CP, PV, TB>;                                             \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem)); \
     kern<<<grid, BTC_THREADS, var.smem, st>>>(tmQ, tmDO, tmK, tmV, pos, tab_packed, lse, delta,  \
-                                              (bf16*)dq, dk_part, dv_part, d_table, dpos_part, a); \
+                                              (bf16*)dq, dk_part, dv_part, d_table, dpos_part, (bf16*)ds_out, a); \
   } while (0)
 #define LAUNCH_NS(NSV)                                   \
   do {                                                   \
-    if (var.compact) LAUNCH(NSV, true, false);           \
-    else if (var.priv) LAUNCH(NSV, false, true);         \
-    else LAUNCH(NSV, false, false);                      \
+    if (!tbl && var.compact) LAUNCH(NSV, true, false, false);  \
+    else if (!tbl) LAUNCH(NSV, false, false, false);     \
+    else if (var.compact) LAUNCH(NSV, true, false, true); \
+    else if (var.priv) LAUNCH(NSV, false, true, true);   \
+    else LAUNCH(NSV, false, false, true);                \
   } while (0)
   if (s.Ns == 256) LAUNCH_NS(256); else LAUNCH_NS(128);
 #undef LAUNCH_NS

@@ -88,6 +88,7 @@ struct BwdPlan {
   // variant branches: dense bias + its gradient (fixed_pe, log_cpb); LePE, o + LePE, dq of the LePE conv and
   // the depthwise kernels' scratch (dwc_pe)
   float *bias, *dbias;
+  void* ds_tab;     // bf16 dS (B * heads, HW, Ns) streamed out of the attention backward for the table gradient
   void *lepe, *o2, *dq_lepe, *dw_ws;
   size_t dw_ws_bytes;
   size_t sub_bytes, wg_bytes, total;
@@ -156,6 +157,12 @@ SideStreams* side_streams() {
 }
 
 bool use_tc_attn_bwd(const Shape& s) { return tc_enabled() && attention_bwd_tc_supported(s); }
+// d rpe_table from the streamed dS as tensor-core GEMMs (rpe_table_grad.cu) instead of the in-kernel scatter;
+// DAT_B200_TABLE_SCATTER=1 keeps the scatter (A/B measurements)
+bool use_mma_table_grad(const Shape& s) {
+  static const int off = [] { const char* e = getenv("DAT_B200_TABLE_SCATTER"); return e && e[0] == '1' ? 1 : 0; }();
+  return off == 0 && use_tc_attn_bwd(s) && rpe_table_grad_mma_supported(s);
+}
 // number of query splits whose partial dK / dV / dpos the backward produces
 int bwd_qsplit(const Shape& s) {
   return use_tc_attn_bwd(s) ? attention_bwd_tc_chunks(s) : attention_bwd_qsplit(s);
@@ -205,6 +212,7 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   const size_t act = (size_t)s.B * s.HW * s.C * e;
   p.bias = (float*)c.take(dense_bias_bytes(s));
   p.dbias = (float*)c.take(dense_bias_bytes(s) ? (size_t)s.B * s.heads * s.HW * s.Ns * 4 : 0);
+  p.ds_tab = c.take(use_mma_table_grad(s) ? (size_t)s.B * s.heads * s.HW * s.Ns * 2 : 0);
   p.lepe = c.take(dwc ? act : 0);
   p.o2 = c.take(dwc ? act : 0);
   p.dq_lepe = c.take(dwc ? act : 0);
@@ -547,11 +555,12 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     float* dv_part = (float*)((char*)dk_part + part);
     void* tabp = (char*)dv_part + part;
     DAT_FWD(attention_delta(s, w.d_o, sv->o, delta, st));
-    DAT_CUDA_OK(cudaMemsetAsync(g->rpe_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
-    if (attention_bwd_tc_compact_table(s)) DAT_FWD(attention_pack_table_compact(s, p->rpe_table, tabp, st));
+    const bool mma_table = use_mma_table_grad(s);
+    if (!mma_table) DAT_CUDA_OK(cudaMemsetAsync(g->rpe_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
+    if (attention_bwd_tc_compact_table(s, !mma_table)) DAT_FWD(attention_pack_table_compact(s, p->rpe_table, tabp, st));
     else DAT_FWD(attention_pack_table(s, p->rpe_table, tabp, st));
     DAT_FWD(attention_bwd_tc(s, sv->q, sv->k, sv->v, w.d_o, sv->lse, delta, sv->pos, tabp, w.dq, dk_part,
-                             dv_part, g->rpe_table, w.dpos_part, st));
+                             dv_part, g->rpe_table, w.dpos_part, st, mma_table ? w.ds_tab : nullptr));
     DAT_FWD(reduce_partials(dk_part, chunks, (long long)s.B * s.Ns * C, w.dk, adt, st));
     DAT_FWD(reduce_partials(dv_part, chunks, (long long)s.B * s.Ns * C, w.dv, adt, st));
   } else {
@@ -577,6 +586,8 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   }
   // proj_k / proj_v
   DAT_FWD(fork(1));
+  if (use_mma_table_grad(s))   // d rpe_table: nothing later reads it - on the side stream when there is one
+    DAT_FWD(rpe_table_grad_mma(s, w.ds_tab, sv->pos, g->rpe_table, wst));
   DAT_FWD(wgrad(w.dk, sv->xs, adt, g->wk, g->bk, Mk));
   DAT_FWD(wgrad(w.dv, sv->xs, adt, g->wv, g->bv, Mk));
   if (tc) {

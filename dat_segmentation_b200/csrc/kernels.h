@@ -101,11 +101,11 @@ int attention_bwd_tc_chunks(const Shape& s);
 int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
                      const float* lse, const float* delta, const float* pos, const void* tab_packed,
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
-                     cudaStream_t st);
+                     cudaStream_t st, void* ds_out = nullptr);
 }  // namespace dat
 
 namespace dat {
-bool attention_bwd_tc_compact_table(const Shape& s);
+bool attention_bwd_tc_compact_table(const Shape& s, bool tbl = true);
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st);
 }  // namespace dat
 
@@ -184,4 +184,10 @@ int logcpb_bias_fwd(const Shape& s, const float* pos, const float* w1, const flo
                     cudaStream_t st);
 int logcpb_bias_bwd(const Shape& s, const float* dbias, const float* pos, const float* w1, const float* b1,
                     const float* w2, float* dw1, float* db1, float* dw2, float* dpos, cudaStream_t st);
+}  // namespace dat
+
+namespace dat {
+// rpe_table_grad.cu - d rpe_table from the streamed dS as per-sample tensor-core GEMMs (mma.sync)
+bool rpe_table_grad_mma_supported(const Shape& s);
+int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, cudaStream_t st);
 }  // namespace dat
