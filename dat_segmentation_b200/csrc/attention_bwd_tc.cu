@@ -140,7 +140,7 @@ __host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int row
 //          with plain read-modify-writes (no atomics); needs W % 32 == 0 (a warp's 32 queries
 //          lie in one image row, so its run leaders hit distinct cells).
 // TBL:     true = the table gradient is accumulated inside this kernel (shared-memory scatter, above);
-//          false = dS (bf16, [b*heads][m][n]) is streamed to `ds_out` instead and the table gradient is
+//          false = dS (bf16, [b*heads][NS/8][m][8]) is streamed to `ds_out` instead and the table gradient is
 //          formed from it by rpe_table_grad_mma (rpe_table_grad.cu) as small tensor-core GEMMs - the
 //          per-score scatter is 50-75 % of this kernel's time, the 16-byte stores are ~2 %.
 template <int NS, bool COMPACT, bool PRIV, bool TBL>
@@ -340,7 +340,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float* mytab = sDTab + (PRIV ? (warp - 4) * a.Hp * a.Wp : 0);
       uint8_t* prow_p = sP + chalf * 16384 + row * 128;
       uint8_t* prow_d = sDS + chalf * 16384 + row * 128;
-      bf16* ds_row = TBL ? nullptr : ds_out + ((long long)bh * a.HW + mm) * NS;
+      // dS for the table gradient: groups of 8 samples, [bh][NS / 8][m][8] - a warp's 32 rows write 512 contiguous bytes
+      bf16* ds_row = TBL ? nullptr : ds_out + (long long)bh * a.HW * NS + (long long)mm * 8;
 
       pf_setup += clock64() - pf_t;
 #pragma unroll 1
@@ -407,7 +408,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
               *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
               if (!TBL && valid)      // the same 8 dS values, [m][n] layout, for the tensor-core table gradient
-                *reinterpret_cast<uint4*>(ds_row + nbase + j - 7) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                *reinterpret_cast<uint4*>(ds_row + (long long)((nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
             }
             // ---- d rpe_table ----------------------------------------------------------------
             // Lanes = consecutive queries of an image row; the table step per query is < 1 cell,
