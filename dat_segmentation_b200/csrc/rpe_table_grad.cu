@@ -22,13 +22,14 @@ namespace dat {
 
 namespace {
 
-constexpr int TG_THREADS = 256;   // 8 warps
+constexpr int TG_MAXN = 64;       // samples per staging step (8 groups of 8) at most
 constexpr int TG_NB = 8;          // samples staged per step (one 16-byte load per query)
 constexpr int TG_TILE = 32;       // table tile edge per warp
 
 struct TgArgs {
   int H, W, HW, heads, G, hg, Ns, Th, Tw;
   int rows_chunk, n_per_cta, tiles_x, ntiles, pitch, ng;   // ng: 8-sample groups staged per step
+  int log2w;                                               // W is a power of two (no divisions in the staging loop)
   float ax, ay, kx, ky;
 };
 
@@ -45,11 +46,14 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// TPW: table tiles per warp (1: up to 8 tiles per table, warps share tiles and split the samples; 2: 9-16 tiles)
-template <int TPW>
-__global__ void __launch_bounds__(TG_THREADS)
+// NT threads = NW warps.  TPW: table tiles per warp (1: at most NW tiles, warps share tiles and split the
+// samples; 2: up to 2 NW tiles)
+template <int TPW, int NT>
+__global__ void __launch_bounds__(NT)
 rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos, float* __restrict__ d_table,
                       TgArgs a) {
+  constexpr int NW = NT / 32;
+  __shared__ float s_bx[TG_MAXN], s_by[TG_MAXN];                // (1 - pos) * k of the staged samples
   extern __shared__ __align__(16) uint8_t tg_smem[];
   bf16* tile = reinterpret_cast<bf16*>(tg_smem);                 // [8 ng][rows_chunk][pitch]
   float* sred = reinterpret_cast<float*>(tg_smem);               // [Th * Tw], after the sample loop
@@ -62,13 +66,13 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
   int my_tile[TPW];
   int n_phase = 0, n_step = 1;
   if (TPW == 1) {
-    const int share = a.ntiles >= 8 ? 1 : 8 / a.ntiles;          // warps per tile (ntiles in {1, 2, 4, 8})
-    my_tile[0] = a.ntiles >= 8 ? warp : warp % a.ntiles;
-    n_phase = a.ntiles >= 8 ? 0 : warp / a.ntiles;
+    const int share = a.ntiles >= NW ? 1 : NW / a.ntiles;        // warps per tile (ntiles divides NW)
+    my_tile[0] = a.ntiles >= NW ? warp : warp % a.ntiles;
+    n_phase = a.ntiles >= NW ? 0 : warp / a.ntiles;
     n_step = share;
   } else {
 #pragma unroll
-    for (int i = 0; i < TPW; ++i) my_tile[i] = warp + 8 * i;     // may be >= ntiles: idle slot
+    for (int i = 0; i < TPW; ++i) my_tile[i] = warp + NW * i;    // may be >= ntiles: idle slot
   }
   float acc[TPW][2][4][4];
 #pragma unroll
@@ -90,16 +94,36 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
     __syncthreads();
     // stage dS[rows x W queries][n0 .. n0 + 8 ng) transposed into tile[nl][r][c]
     const int groups = min(a.ng, (n_end - n0) / TG_NB);
-    for (int i = threadIdx.x; i < n_rows_px * groups; i += TG_THREADS) {
-      const int gi = i / n_rows_px, m = i - gi * n_rows_px;
-      const uint4 v = *reinterpret_cast<const uint4*>(dsb + ((long long)(n0 / TG_NB + gi) * a.HW + m) * TG_NB);
-      const int r = m / a.W, c = m - r * a.W;
-      bf16* dst = tile + ((long long)gi * TG_NB * a.rows_chunk + r) * a.pitch + c;
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if ((int)threadIdx.x < nstage && n0 + (int)threadIdx.x < n_end) {
+      s_bx[threadIdx.x] = (1.0f - pbase[2 * (n0 + threadIdx.x) + 1]) * a.kx;
+      s_by[threadIdx.x] = (1.0f - pbase[2 * (n0 + threadIdx.x)]) * a.ky;
+    }
+    // 4 independent 16-byte loads in flight per thread, then their 32 two-byte transposing stores
+    // (n_rows_px is a multiple of 256, so a group never straddles a thread's batch unevenly)
+    const int plane = a.rows_chunk * a.pitch;                      // elements per staged sample
+    for (int gi = 0; gi < groups; ++gi) {
+      const bf16* src = dsb + ((long long)(n0 / TG_NB + gi) * a.HW) * TG_NB;
+      bf16* dstg = tile + gi * TG_NB * plane;
+      for (int m0 = threadIdx.x; m0 < n_rows_px; m0 += 4 * NT) {
+        uint4 v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        reinterpret_cast<uint16_t*>(dst + (long long)(2 * i) * a.rows_chunk * a.pitch)[0] = (uint16_t)(w[i] & 0xffffu);
-        reinterpret_cast<uint16_t*>(dst + (long long)(2 * i + 1) * a.rows_chunk * a.pitch)[0] = (uint16_t)(w[i] >> 16);
+        for (int u = 0; u < 4; ++u) {
+          const int m = m0 + u * NT;
+          v[u] = m < n_rows_px ? *reinterpret_cast<const uint4*>(src + m * TG_NB) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int m = m0 + u * NT;
+          if (m < n_rows_px) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(dstg + (m >> a.log2w) * a.pitch + (m & (a.W - 1)));
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dst[(2 * i) * plane] = (uint16_t)(w[i] & 0xffffu);
+              dst[(2 * i + 1) * plane] = (uint16_t)(w[i] >> 16);
+            }
+          }
+        }
       }
     }
     __syncthreads();
@@ -108,18 +132,24 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
       if (my_tile[ti] >= a.ntiles) continue;
       const int x0 = (my_tile[ti] % a.tiles_x) * TG_TILE, y0 = (my_tile[ti] / a.tiles_x) * TG_TILE;
       const float x_last = (float)min(x0 + TG_TILE - 1, a.Tw - 1), y_last = (float)min(y0 + TG_TILE - 1, a.Th - 1);
+      // integer -> float conversions hoisted out of the sample loop
+      const float xlo_f = (float)x0 - 1.0f, ylo_f = (float)y0 - 1.0f;
+      const float xa_f[2] = {(float)(x0 + gq), (float)(x0 + 16 + gq)};
+      float y_f[4];
+#pragma unroll
+      for (int yt = 0; yt < 4; ++yt) y_f[yt] = (float)(y0 + yt * 8 + gq);
+      const float r_f = (float)(r_base + 2 * t);
       for (int nl = n_phase; nl < nstage && n0 + nl < n_end; nl += n_step) {
-        const int n = n0 + nl;
-        const float bx = (1.0f - pbase[2 * n + 1]) * a.kx, by = (1.0f - pbase[2 * n]) * a.ky;
+        const float bx = s_bx[nl], by = s_by[nl];
         // queries whose footprint can meet the tile: x0 - 1 < ix < x_last + 1 (one cell of slack for rounding)
-        int c_lo = (int)floorf(((float)x0 - 1.0f - bx) * inv_ax) - 1, c_hi = (int)ceilf((x_last + 1.0f - bx) * inv_ax) + 1;
-        int r_lo = (int)floorf(((float)y0 - 1.0f - by) * inv_ay) - 1, r_hi = (int)ceilf((y_last + 1.0f - by) * inv_ay) + 1;
+        int c_lo = (int)floorf((xlo_f - bx) * inv_ax) - 1, c_hi = (int)ceilf((x_last + 1.0f - bx) * inv_ax) + 1;
+        int r_lo = (int)floorf((ylo_f - by) * inv_ay) - 1, r_hi = (int)ceilf((y_last + 1.0f - by) * inv_ay) + 1;
         c_lo = max(c_lo, 0); c_hi = min(c_hi, a.W - 1);
         r_lo = max(r_lo, r_base); r_hi = min(r_hi, r_base + rows - 1);
         if (c_lo > c_hi || r_lo > r_hi) continue;
         const int c16_lo = c_lo & ~15, c16_hi = c_hi | 15;
         const int rl_lo = (r_lo - r_base) & ~15, rl_hi = (r_hi - r_base) | 15;
-        const bf16* tl = tile + (long long)nl * a.rows_chunk * a.pitch;
+        const bf16* tl = tile + nl * (a.rows_chunk * a.pitch) + gq * a.pitch + 2 * t;   // + row * pitch + c0
         // rows_chunk <= 32: at most two 16-row chunks per CTA.  The hat operands of the first GEMM depend on
         // (x, c) only, so they are generated once per 16-query chunk and used for both row chunks.
         const bool use_r[2] = {rl_lo == 0, rl_hi >= 16};
@@ -132,14 +162,16 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
               for (int q = 0; q < 4; ++q) e[rc][mt][nt][q] = 0.f;
-        for (int c0 = c16_lo; c0 < c16_hi; c0 += 16) {
+        float c_f = (float)(c16_lo + 2 * t);
+        const float ax8 = 8.0f * a.ax;
+        for (int c0 = c16_lo; c0 < c16_hi; c0 += 16, c_f += 16.0f) {
           // A fragments: hat(ix(c) - x), x = x0 + mt * 16 + {gq, gq + 8}, c = c0 + {2t, 2t+1, 2t+8, 2t+9}
-          const float i0 = fmaf((float)(c0 + 2 * t), a.ax, bx), i1 = i0 + a.ax;
-          const float i2 = fmaf((float)(c0 + 2 * t + 8), a.ax, bx), i3 = i2 + a.ax;
+          const float i0 = fmaf(c_f, a.ax, bx), i1 = i0 + a.ax;
+          const float i2 = i0 + ax8, i3 = i2 + a.ax;
           uint32_t af[2][4];
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
-            const float xa = (float)(x0 + mt * 16 + gq), xb = xa + 8.0f;
+            const float xa = xa_f[mt], xb = xa + 8.0f;
             af[mt][0] = pack2(hat(i0 - xa), hat(i1 - xa));
             af[mt][1] = pack2(hat(i0 - xb), hat(i1 - xb));
             af[mt][2] = pack2(hat(i2 - xa), hat(i3 - xa));
@@ -150,7 +182,7 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
             if (!use_r[rc]) continue;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-              const bf16* rowp = tl + (long long)(rc * 16 + nt * 8 + gq) * a.pitch + c0 + 2 * t;
+              const bf16* rowp = tl + (rc * 16 + nt * 8) * a.pitch + c0;
               const uint32_t b0 = *reinterpret_cast<const uint32_t*>(rowp);
               const uint32_t b1 = *reinterpret_cast<const uint32_t*>(rowp + 8);
 #pragma unroll
@@ -170,11 +202,11 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
             ef[mt][2] = pack2(e[rc][mt][1][0], e[rc][mt][1][1]);
             ef[mt][3] = pack2(e[rc][mt][1][2], e[rc][mt][1][3]);
           }
-          const float j0 = fmaf((float)(r_base + rc * 16 + 2 * t), a.ay, by), j1 = j0 + a.ay;
-          const float j2 = fmaf((float)(r_base + rc * 16 + 2 * t + 8), a.ay, by), j3 = j2 + a.ay;
+          const float j0 = fmaf(r_f + (float)(rc * 16), a.ay, by), j1 = j0 + a.ay;
+          const float j2 = fmaf(r_f + (float)(rc * 16 + 8), a.ay, by), j3 = j2 + a.ay;
 #pragma unroll
           for (int yt = 0; yt < 4; ++yt) {
-            const float y = (float)(y0 + yt * 8 + gq);
+            const float y = y_f[yt];
             const uint32_t b0 = pack2(hat(j0 - y), hat(j1 - y)), b1 = pack2(hat(j2 - y), hat(j3 - y));
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) mma16816(acc[ti][mt][yt], ef[mt], b0, b1);
@@ -185,7 +217,7 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
   }
   // CTA reduction of the tile accumulators in shared memory, then one global atomic per touched cell
   __syncthreads();
-  for (int i = threadIdx.x; i < a.Th * a.Tw; i += TG_THREADS) sred[i] = 0.f;
+  for (int i = threadIdx.x; i < a.Th * a.Tw; i += NT) sred[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int ti = 0; ti < TPW; ++ti) {
@@ -204,7 +236,7 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
   }
   __syncthreads();
   float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
-  for (int i = threadIdx.x; i < a.Th * a.Tw; i += TG_THREADS) {
+  for (int i = threadIdx.x; i < a.Th * a.Tw; i += NT) {
     const float v = sred[i];
     if (v != 0.f) atomicAdd(dt_g + i, v);
   }
@@ -214,7 +246,7 @@ struct TgPlan {
   TgArgs a;
   dim3 grid;
   size_t smem;
-  int tpw;
+  int tpw, threads;
 };
 bool make_plan(const Shape& s, TgPlan* p) {
   if (s.W % 16 != 0 || s.H % 16 != 0 || s.Ns % TG_NB != 0 || s.W < 2 || s.H < 2) return false;
@@ -223,13 +255,18 @@ bool make_plan(const Shape& s, TgPlan* p) {
   a.tiles_x = (s.Tw + TG_TILE - 1) / TG_TILE;
   const int tiles_y = (s.Th + TG_TILE - 1) / TG_TILE;
   a.ntiles = a.tiles_x * tiles_y;
-  if (a.ntiles > 16) return false;
-  if (a.ntiles < 8 && (8 % a.ntiles) != 0) return false;     // warps share tiles evenly: 1, 2, 4 or >= 8 tiles
-  p->tpw = a.ntiles > 8 ? 2 : 1;
+  if (a.ntiles > 32) return false;
+  // 8 warps per CTA, 16 for large tables (one 32 x 32 tile per warp up to 16 tiles, two beyond)
+  p->threads = a.ntiles > 8 ? 512 : 256;
+  const int nw = p->threads / 32;
+  if (a.ntiles < nw && (nw % a.ntiles) != 0) return false;   // warps share tiles evenly: 1, 2, 4 or 8 tiles
+  p->tpw = a.ntiles > nw ? 2 : 1;
   a.pitch = s.W + 8;
   // rows per CTA: 32 (two 16-row chunks, see the kernel) - the staged block [8][rows][W + 8] bf16 is <= 70 KB
   const int rows = s.H < 32 ? s.H : 32;
-  if (s.W > 128) return false;
+  if (s.W > 128 || (s.W & (s.W - 1)) != 0) return false;
+  a.log2w = 0;
+  while ((1 << a.log2w) < s.W) ++a.log2w;
   a.rows_chunk = rows;
   const int r_chunks = (s.H + rows - 1) / rows;
   // 8-sample groups per staging step: as many as fit ~64 KB (small maps: fewer, longer steps)
@@ -267,15 +304,17 @@ int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* 
   TgPlan p;
   DAT_REQUIRE(make_plan(s, &p), "rpe_table_grad_mma: unsupported shape");
   DAT_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
-  if (p.tpw == 1) {
-    if (p.smem > 48 * 1024)
-      DAT_CUDA_OK(cudaFuncSetAttribute(rpe_table_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    rpe_table_grad_kernel<1><<<p.grid, TG_THREADS, p.smem, st>>>((const bf16*)ds, pos, d_table, p.a);
-  } else {
-    if (p.smem > 48 * 1024)
-      DAT_CUDA_OK(cudaFuncSetAttribute(rpe_table_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    rpe_table_grad_kernel<2><<<p.grid, TG_THREADS, p.smem, st>>>((const bf16*)ds, pos, d_table, p.a);
-  }
+#define TG_LAUNCH(TPWV, NTV)                                                                                          \
+  do {                                                                                                                \
+    auto kern = rpe_table_grad_kernel<TPWV, NTV>;                                                                     \
+    if (p.smem > 40 * 1024)   /* + 512 B static: stay clear of the 48 KB default limit */                           \
+      DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));              \
+    kern<<<p.grid, NTV, p.smem, st>>>((const bf16*)ds, pos, d_table, p.a);                                            \
+  } while (0)
+  if (p.threads == 256) TG_LAUNCH(1, 256);
+  else if (p.tpw == 1) TG_LAUNCH(1, 512);
+  else TG_LAUNCH(2, 512);
+#undef TG_LAUNCH
   DAT_LAUNCH_OK("rpe_table_grad_kernel");
   return DAT_OK;
 }
