@@ -1,10 +1,10 @@
 #!/bin/bash
-# Round-end validation: all GPU tests, smoke(), default bench (with CPU baseline), reference arm, 2-GPU bench.
+# Round-end evidence run: bench (with CPU baseline), reference arm, launch list, kernel rooflines, sweep, family.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -4
-timeout 900 python bench.py > gpurun_out/bench_final_1gpu.json 2> gpurun_out/bench_final_1gpu.err; echo "[bench] exit $?"; cut -c1-220 gpurun_out/bench_final_1gpu.json
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_final_ref.json 2>/dev/null; echo "[ref] exit $?"; cut -c1-200 gpurun_out/bench_final_ref.json
-if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_final_2gpu.json 2> gpurun_out/bench_final_2gpu.err; echo "[bench 2gpu] exit $?"; grep metric gpurun_out/bench_final_2gpu.json | cut -c1-220
-fi
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "[bench] exit $?"; cut -c1-300 gpurun_out/bench_final.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "[ref] exit $?"; cut -c1-300 gpurun_out/bench_reference.json
+bash tools/gpu_ncu_step.sh
+python tools/summarize_launches.py gpurun_out/launches_step.csv > gpurun_out/launches_step.md
+timeout 600 python tools/kernel_rooflines.py > gpurun_out/kernel_rooflines.md 2> gpurun_out/kernel_rooflines.err; echo "[rooflines] exit $?"
+timeout 600 python tools/sweep_dattn.py > gpurun_out/sweep_dattn.md 2> gpurun_out/sweep_dattn.err; echo "[sweep] exit $?"
+timeout 600 python tools/bench_family.py > gpurun_out/family.md 2> gpurun_out/family.err; echo "[family] exit $?"; tail -4 gpurun_out/family.md
