@@ -138,40 +138,13 @@ def run_reference(args):
 # roofline leg: the dominant hand-written kernel, timed alone on its launch stream
 # --------------------------------------------------------------------------------------
 
-def kernel_roofline(dev, pk):
-    """Attention core (QK^T + rpe bias + softmax + PV) at the stage-2 shape (9 of the 14 blocks),
-    batch 16, bf16.  Algorithmic FLOPs = 4*HW*Ns*C per image; algorithmic
-    bytes = q + o + k + v + pos + table."""
-    from dat_segmentation_b200 import _cabi
-    lib = _cabi.lib()
-    H, Cc, heads, groups, stride, ksize, qs, _ = STAGES[2]
-    B, HW, Ns = PER_GPU_BATCH, H * H, 256
-    d = _cabi.BlockDesc(B, H, H, heads, groups, stride, ksize, 2 * qs - 1, 2 * qs - 1, -1.0, _cabi.DAT_F32, _cabi.DAT_BF16)
-    g = torch.Generator(device=dev).manual_seed(0)
-    bf = torch.bfloat16
-    q = torch.randn(B, HW, Cc, device=dev, generator=g).to(bf)
-    k = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
-    v = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
-    pos = (torch.rand(B, groups, Ns, 2, device=dev, generator=g) * 2 - 1)
-    tab = torch.randn(heads, 2 * qs - 1, 2 * qs - 1, device=dev, generator=g) * 0.1
-    o = torch.empty_like(q)
-    lse = torch.empty(B, heads, HW, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def _time_launch(dev, launch, flush, reps=10):
+    """Median CUDA-event time (ms) of one launch on torch's current stream, L2 flushed before every launch."""
     st = torch.cuda.current_stream(dev)
-    sp = C.c_void_p(st.cuda_stream)
-    p = lambda t: C.c_void_p(t.data_ptr())
-
-    nws = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
-    ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
-
-    def launch():
-        _cabi.check(lib.dat_attention_fwd(C.byref(d), p(q), p(k), p(v), p(pos), p(tab), p(o), p(lse),
-                                          p(ws), nws, 0, sp), "attention_fwd")
-
     for _ in range(3):
         launch()
     times = []
-    for _ in range(10):
+    for _ in range(reps):
         flush.zero_()                       # > L2 (126 MB): next launch starts cold
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
@@ -179,18 +152,68 @@ def kernel_roofline(dev, pk):
         e1.record(st)
         torch.cuda.synchronize(dev)
         times.append(e0.elapsed_time(e1))
-    ms = sorted(times)[len(times) // 2]
+    return sorted(times)[len(times) // 2]
+
+
+def kernel_roofline(dev, pk):
+    """Roofline of the dominant kernel of the step, `gemm_tc_persistent_kernel` (12 % of the kernel time, 174
+    launches: profiles/r01_launches_step_790.md), at the shape that carries most of its time - the stage-2 MLP fc1
+    (M = B*HW = 16384, N = 1024, K = 256, bf16; 18 MLPs per step run it forward and as the fc2 data gradient).
+    Algorithmic bytes = X + W + Y once; its arithmetic intensity (202 FLOP/B) is below the measured
+    ridge (1658 TF/s / 6541 GB/s = 254 FLOP/B), so the bound is HBM.  `others`: the attention forward (the
+    kernel north_star asks tensor utilisation for) timed the same way."""
+    from dat_segmentation_b200 import _cabi
+    lib = _cabi.lib()
+    bf = torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    g = torch.Generator(device=dev).manual_seed(0)
+    # ---- dominant kernel: persistent tcgen05 GEMM, stage-2 fc1 shape ----
+    M, N, K = PER_GPU_BATCH * 32 * 32, 1024, 256
+    x = torch.randn(M, K, device=dev, generator=g).to(bf)
+    w = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).to(bf)
+    bias = torch.randn(N, device=dev, generator=g)
+    y = torch.empty(M, N, device=dev, dtype=bf)
+    ms = _time_launch(dev, lambda: _cabi.check(lib.dat_pointwise_fwd_tc(p(x), 1, p(w), p(bias), p(y), 1, M, N, K, sp),
+                                                "gemm"), flush)
+    gbytes = (M * K + N * K + M * N) * 2 + N * 4
+    gflops = 2.0 * M * N * K
+    roof = {"kernel": "gemm_tc_persistent_kernel (stage-2 MLP fc1: M=16384 N=1024 K=256, bf16)", "bound": "hbm",
+            "achieved": round(gbytes / (ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": round(gbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
+            # (profiles/r01_ncu_kernels.md): 8.9 MB + 0 - x and y are L2-resident at this size (42 MB < 126 MB L2)
+            "traffic": 8900000, "ms": round(ms, 4), "algorithmic_bytes": gbytes,
+            "tflops_at_this_time": round(gflops / (ms * 1e-3) / 1e12, 1), "tensor_frac": round(gflops / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4),
+            "peak_source": pk["source"]}
+    del x, w, y
+    # ---- attention forward, stage-2 shape ----
+    H, Cc, heads, groups, stride, ksize, qs, _ = STAGES[2]
+    B, HW, Ns = PER_GPU_BATCH, H * H, 256
+    d = _cabi.BlockDesc(B, H, H, heads, groups, stride, ksize, 2 * qs - 1, 2 * qs - 1, -1.0, _cabi.DAT_F32, _cabi.DAT_BF16)
+    q = torch.randn(B, HW, Cc, device=dev, generator=g).to(bf)
+    k = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
+    v = torch.randn(B, Ns, Cc, device=dev, generator=g).to(bf)
+    pos = (torch.rand(B, groups, Ns, 2, device=dev, generator=g) * 2 - 1)
+    tab = torch.randn(heads, 2 * qs - 1, 2 * qs - 1, device=dev, generator=g) * 0.1
+    o = torch.empty_like(q)
+    lse = torch.empty(B, heads, HW, device=dev)
+    nws = lib.dat_attention_fwd_workspace_bytes(C.byref(d))
+    ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+    ms_a = _time_launch(dev, lambda: _cabi.check(lib.dat_attention_fwd(C.byref(d), p(q), p(k), p(v), p(pos), p(tab), p(o),
+                                                                        p(lse), p(ws), nws, 0, sp), "attention_fwd"), flush)
     flops = 4.0 * HW * Ns * Cc * B
     byts = (2 * B * HW * Cc + 2 * B * Ns * Cc) * 2 + B * groups * Ns * 8 + heads * (2 * qs - 1) ** 2 * 4
-    achieved = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "dat_attention_fwd (stage-2 shape, B=16, bf16)", "bound": "tensor",
-            "achieved": round(achieved, 3), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": round(achieved / pk["bf16_tflops"], 5),
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
-            # (profiles/r01_ncu_kernels.md): 12.82 MB + 9 KB
-            "traffic": 12834048, "ms": round(ms, 4),
-            "algorithmic_bytes": byts, "hbm_gbs_at_this_time": round(byts / (ms * 1e-3) / 1e9, 1),
-            "peak_source": pk["source"]}
+    roof["others"] = [{
+        "kernel": "attn_fwd_tc_kernel (stage-2 shape, B=16, bf16)", "bound": "tensor",
+        "achieved": round(flops / (ms_a * 1e-3) / 1e12, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": round(flops / (ms_a * 1e-3) / 1e12 / pk["bf16_tflops"], 5), "traffic": 12834048, "ms": round(ms_a, 4),
+        "algorithmic_bytes": byts,
+        "note": "bound by CUDA-core issue rate (bias interpolation + softmax, ~32 instructions per score vs 128 MMA FLOP; "
+                "ncu: issue slots 50 % busy, tensor pipe 3 %): DESIGN.md 3.1 row 7"}]
+    roof["per_kernel_table"] = "profiles/r01_kernel_rooflines.md"
+    return roof
 
 
 # --------------------------------------------------------------------------------------
