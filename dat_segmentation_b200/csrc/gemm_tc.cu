@@ -89,6 +89,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;
+constexpr int TCP_THREADS = 320;          // persistent kernel: producer, MMA issuer, 8 epilogue warps
+constexpr int TCP_EPI_WARPS = 8;
 constexpr int CHUNK_BYTES = 128;          // K bytes per pipeline stage row (one swizzle atom)
 constexpr int A_STAGE_BYTES = TC_BM * CHUNK_BYTES;
 constexpr int EPI_COLS = 128;            // epilogue column group (staging area per warp: 32 x 128 outputs)
@@ -246,8 +248,15 @@ __device__ __forceinline__ void store8(bf16* p, float4 a, float4 b) {
 // i while the MMA warp accumulates tile i + 1: loads, MMAs and stores of a CTA overlap instead of
 // alternating (the one-tile kernel idles its loads ~60 % of a CTA's lifetime, profiles/r01_ncu_kernels.md).
 //   barriers: full/empty per ring stage, acc_full/acc_empty per TMEM buffer.
+// column group of the persistent kernel's epilogue: 64 columns when the tile is a multiple of 64 wide (two or four
+// groups shared by a quadrant's two warps), else the whole tile (32 / 96 columns, one warp)
+__host__ __device__ inline int persistent_gcols(int BN) { return BN % 64 == 0 ? 64 : BN; }
+
+// Epilogue: 8 warps, two per TMEM lane quadrant, taking alternate column groups of a tile.  With four warps the
+// epilogue (TMEM -> +bias -> bf16 -> staged, coalesced stores) bounded every wide-N / small-K shape: switching it off
+// took the stage-1 fc1 GEMM from 33 to 12.5 us and the stage-2 one from 22.9 to 12.6 us.
 template <bool TF32, typename TOut>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                           const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
@@ -284,7 +293,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);       // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], TCP_EPI_WARPS);       // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -341,8 +350,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   } else {
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;   // which of the quadrant's two warps: takes column groups chalf, chalf + 2, ...
     const int epi_tid = threadIdx.x - 64;
-    const int gcols = BN < EPI_COLS ? BN : EPI_COLS;
+    const int gcols = persistent_gcols(BN);
     const int seg_bytes = gcols * (int)sizeof(TOut);
     uint8_t* stage = sStage + (warp - 2) * 32 * stage_pitch;
     int li = 0;
@@ -350,28 +360,35 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int buf = li & 1;
       const int m0 = (t % m_tiles) * TC_BM, n0 = (t / m_tiles) * BN;
       float* bvec = sBias + buf * 256;
-      for (int i = epi_tid; i < BN; i += 128) bvec[i] = bias != nullptr ? bias[n0 + i] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps
+      for (int i = epi_tid; i < BN; i += 32 * TCP_EPI_WARPS) bvec[i] = bias != nullptr ? bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
       mbar_wait(&acc_full[buf], (uint32_t)((li >> 1) & 1));
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
       const int rows_here = min(32, M - (m0 + quad * 32));
       const int nch = gcols / 32;
-      for (int cg = 0; cg < BN; cg += gcols) {
-        // the whole column group (<= 128 columns) is fetched with back-to-back tcgen05.ld and one
+      const int cg_first = chalf * gcols;
+      if (cg_first >= BN) {              // a single column group: this warp only hands the buffer back
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
+      for (int cg = cg_first; cg < BN; cg += 2 * gcols) {
+        // the whole column group (<= 96 columns) is fetched with back-to-back tcgen05.ld and one
         // wait: one TMEM round trip per group instead of one per 32 columns
-        uint32_t r[4][32];
+        uint32_t r[3][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 3; ++c)
           if (c < nch) tmem_ld_32x32(t_addr + (uint32_t)(cg + c * 32), r[c]);
         tmem_wait_ld();
-        if (cg + gcols >= BN) {          // accumulator fully read: hand the TMEM buffer back early
+        if (cg + 2 * gcols >= BN) {      // this warp's share of the accumulator is read: hand the TMEM buffer back early
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 3; ++c) {
           if (c < nch) {
             const float* bp = bvec + cg + c * 32;
             TOut* dst = reinterpret_cast<TOut*>(stage + lane * stage_pitch) + c * 32;
@@ -514,9 +531,9 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
   if (std::getenv("DAT_B200_GEMM_LEGACY") == nullptr) {
     // persistent kernel: ring + separate epilogue staging in up to 224 KB, one CTA per SM
-    const int gcols = BN < EPI_COLS ? BN : EPI_COLS;
+    const int gcols = persistent_gcols(BN);
     const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
-    const int staging = 4 * 32 * stage_pitch;
+    const int staging = TCP_EPI_WARPS * 32 * stage_pitch;
     int stages = (224 * 1024 - 1024 - 3072 - staging) / stage_bytes;
     if (stages > 8) stages = 8;
     DAT_REQUIRE(stages >= 2, "pointwise_fwd_tc: tile does not fit shared memory");
@@ -529,7 +546,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   do {                                                                                            \
     auto kern = gemm_tc_persistent_kernel<TF, TO>;                                                \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,      \
+    kern<<<grid, TCP_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,     \
                                          k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch); \
   } while (0)
     if (tf32 && y_dt == DAT_F32) LAUNCH_P(true, float);

@@ -92,7 +92,10 @@ def test_pointwise_fwd(M, N, K, dt):
 
 
 @pytest.mark.parametrize("M,C", [(4096, 64), (1000, 128), (16384, 256), (300, 512), (513, 96), (256, 1024),
-                                 (700, 192), (640, 384), (300, 768), (260, 160)])
+                                 (700, 192), (640, 384), (300, 768), (260, 160),
+                                 # >= 296 tiles: the weight-stationary mode of the persistent kernel (panel resident,
+                                 # contiguous tile ranges; ragged last tile, two n-tiles at C = 512 / 128-wide tiles)
+                                 (45001, 64), (50000, 128), (40000, 256), (19000, 512)])
 @pytest.mark.parametrize("kind", ["tf32", "bf16"])
 def test_pointwise_fwd_tensor_core(M, C, kind):
     """tcgen05 GEMM (TMA-fed, TMEM accumulator) against an fp64 product of the same

@@ -19,7 +19,9 @@ SHAPES = [(64, 256, 2, 32, 32), (256, 64, 2, 32, 32), (128, 512, 2, 16, 16), (51
           (128, 512, 3, 5, 5),
           # DAT-S++ widths (C = 192, 384, 768; 96 x 4 = 384 columns out of a 96-wide input is not tileable)
           (192, 768, 2, 12, 12), (768, 192, 2, 12, 12), (384, 1536, 1, 9, 9), (1536, 384, 1, 9, 9),
-          (768, 3072, 1, 8, 8), (3072, 768, 1, 8, 8)]
+          (768, 3072, 1, 8, 8), (3072, 768, 1, 8, 8),
+          # many tiles: weight-stationary GEMM mode (fc1 / fc2 of stages 0-1 at full size)
+          (64, 256, 2, 160, 160), (256, 64, 2, 160, 160), (128, 512, 1, 200, 200), (512, 128, 1, 200, 200)]
 
 
 @pytest.mark.parametrize("cin,cout,B,H,W", SHAPES)
