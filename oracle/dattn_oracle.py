@@ -534,20 +534,35 @@ class OracleDAttention(torch.nn.Module):
                  stride, offset_range_factor, use_pe, dwc_pe, no_off, fixed_pe, ksize, log_cpb,
                  stage_i):
         super().__init__()
-        if not use_pe or dwc_pe or no_off or fixed_pe or log_cpb:
-            raise NotImplementedError("oracle covers the rpe_table (bilinear bias) variant only")
         nn = torch.nn
         q_size = tuple(q_size) if isinstance(q_size, (tuple, list)) else (q_size, q_size)
         self.cfg = BlockCfg(q_size[0], q_size[1], n_heads, n_head_channels, n_groups, stride, ksize,
-                            offset_range_factor)
+                            offset_range_factor, use_pe=bool(use_pe), dwc_pe=bool(dwc_pe), no_off=bool(no_off),
+                            fixed_pe=bool(fixed_pe), log_cpb=bool(log_cpb))
         c, cg = self.cfg.nc, self.cfg.cg
         self.conv_offset = nn.Sequential(nn.Conv2d(cg, cg, ksize, stride, self.cfg.pad, groups=cg),
                                          _LNHolder(cg), nn.GELU(), nn.Conv2d(cg, 2, 1, bias=False))
+        if no_off:
+            for prm in self.conv_offset.parameters():
+                prm.requires_grad_(False)
         self.proj_q, self.proj_k = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 1)
         self.proj_v, self.proj_out = nn.Conv2d(c, c, 1), nn.Conv2d(c, c, 1)
-        th, tw = self.cfg.table_hw
-        self.rpe_table = nn.Parameter(torch.zeros(n_heads, th, tw))
-        nn.init.trunc_normal_(self.rpe_table, std=0.01)
+        mode = self.cfg.pe_mode            # same parameter names / shapes as dat_blocks.py:84-104
+        if mode == "dwc":
+            self.rpe_table = nn.Conv2d(c, c, 3, 1, 1, groups=c)
+        elif mode == "fixed":
+            kv_h, kv_w = q_size[0] // stride, q_size[1] // stride
+            self.rpe_table = nn.Parameter(torch.zeros(n_heads, q_size[0] * q_size[1], kv_h * kv_w))
+            nn.init.trunc_normal_(self.rpe_table, std=0.01)
+        elif mode == "log_cpb":
+            self.rpe_table = nn.Sequential(nn.Linear(2, 32, bias=True), nn.ReLU(inplace=True),
+                                           nn.Linear(32, self.cfg.hg, bias=False))
+        elif mode == "rpe":
+            th, tw = self.cfg.table_hw
+            self.rpe_table = nn.Parameter(torch.zeros(n_heads, th, tw))
+            nn.init.trunc_normal_(self.rpe_table, std=0.01)
+        else:
+            self.rpe_table = None
 
     def forward(self, x):
         params = dict(self.named_parameters())

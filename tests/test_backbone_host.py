@@ -113,3 +113,35 @@ def test_backbone_family_cuda_vs_oracle_port(family):
         ob = gpu(x.cuda())
     for a, b in zip(ob, oc):
         assert _rel(a.float().cpu(), b.detach()) < 6e-2      # bf16 through 8 blocks; outputs are LayerNormed (O(1))
+
+
+@pytest.mark.gpu
+def test_backbone_with_variant_branches_cuda_vs_oracle_port():
+    """One variant branch per stage (dwc_pe, log_cpb, fixed_pe with a real resize, no_off) wired through the backbone's
+    per-stage flags exactly as `DAT.__init__` passes them (dat.py:99-116): fp32 CUDA backbone vs oracle-port backbone."""
+    from dat_segmentation_b200.backbone import DAT_TINY_PP
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(DAT_TINY_PP, img_size=128, depths=[2, 2, 2, 2], stage_spec=[["X", "D"]] * 3 + [["D", "D"]],
+               drop_path_rate=0.0, dwc_pes=[True, False, False, False], log_cpb=[False, True, False, False],
+               fixed_pes=[False, False, True, False], no_offs=[False, False, False, True])
+    torch.manual_seed(13)
+    gpu = build_dat(cfg).cuda()
+    kinds = [type(m.rpe_table).__name__ for m in gpu.modules() if type(m).__name__ == "DAttentionBaseline"]
+    assert kinds == ["Conv2d", "Sequential", "Parameter", "NoneType", "NoneType"], kinds
+    cpu = build_dat(cfg, attn_cls=orc.OracleDAttention)
+    cpu.load_state_dict({k: v.cpu() for k, v in gpu.state_dict().items()}, strict=True)
+    x = torch.randn(2, 3, 128, 160)
+    xg = x.cuda().requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    og, oc = gpu(xg), cpu(xc)
+    for a, b in zip(og, oc):
+        assert _rel(a.detach().cpu(), b.detach()) < 2e-4
+    sum(o.square().mean() for o in og).backward()
+    sum(o.square().mean() for o in oc).backward()
+    assert _rel(xg.grad.cpu(), xc.grad) < 5e-3
+    gp, cp = dict(gpu.named_parameters()), dict(cpu.named_parameters())
+    assert {k for k, v in gp.items() if v.grad is None} == {k for k, v in cp.items() if v.grad is None}
+    worst = max((_rel(gp[k].grad.cpu(), cp[k].grad), k) for k in gp if cp[k].grad is not None
+                and cp[k].grad.abs().max() > 1e-6)
+    assert worst[0] < 2e-2, worst
