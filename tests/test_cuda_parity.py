@@ -466,3 +466,44 @@ def test_block_backward_bf16_full_size_vs_oracle(stage):
     bad = {k: v for k, v in report.items()
            if v > (1.5e-1 if (k in loose or k.startswith("conv_offset")) else 3e-2)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("H,W,heads,groups,stride,ksize,qs", [
+    (32, 64, 4, 2, 4, 7, 28),      # 8 x 16 = 128 samples: the NS = 128 instantiation, non-square map, 2 x 2 table tiles
+    (64, 32, 2, 1, 4, 7, 14),      # 16 x 8 = 128 samples, one 27 x 27 table tile shared by all warps
+    (32, 128, 2, 2, 2, 5, 7),      # 16 x 64 = 1024 samples: split-KV forward, CUDA-core backward
+])
+def test_block_backward_bf16_other_sample_counts(H, W, heads, groups, stride, ksize, qs):
+    """bf16 block fwd+bwd at sample counts other than 256 (tensor-core backward with the table-gradient GEMMs for
+    Ns = 128; split-KV tensor-core forward + CUDA-core backward for Ns = 1024) against the fp32 analytic oracle."""
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+    torch.manual_seed(H + W + heads)
+    m = DAttentionBaseline((qs, qs), (qs, qs), heads, 32, groups, 0.0, 0.0, stride, 2, True, False,
+                           False, False, ksize, False, 0).cuda()
+    with torch.no_grad():
+        m.conv_offset[3].weight.mul_(2.0)
+        m.rpe_table.mul_(10.0)
+    B = 2
+    x = torch.randn(B, heads * 32, H, W)
+    dy = torch.randn(B, heads * 32, H, W)
+    xd = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y, _, _ = m(xd)
+    y.backward(dy.cuda().bfloat16())
+    cfg = orc.BlockCfg(qs, qs, heads, 32, groups, stride, ksize, 2)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    y_ref = orc.forward_libops(x, params, cfg)
+    assert (y.float().cpu() - y_ref).abs().max().item() < 2e-2
+    dx_ref, g_ref, _ = orc.backward_explicit(nhwc(x), params, cfg, nhwc(dy))
+
+    def l2(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    report = {"dx": l2(nhwc(xd.grad.cpu()), dx_ref)}
+    for key, p in m.named_parameters():
+        if key != "proj_k.bias":
+            report[key] = l2(p.grad.cpu(), g_ref[key])
+    loose = ("dx", "proj_q.weight", "proj_q.bias")
+    bad = {k: v for k, v in report.items()
+           if v > (1.5e-1 if (k in loose or k.startswith("conv_offset")) else 3e-2)}
+    assert not bad, bad
