@@ -430,49 +430,84 @@ offset_bwd_wgrad_rows_kernel(const TQ* __restrict__ q, const float* __restrict__
   }
 }
 
-// Data gradient, gather form: warp = one pixel x one 64-channel chunk; the <= ceil(k/s)^2 sample
-// points whose window covers the pixel are enumerated once per warp; transposed weights in smem.
-template <typename TQ, int K>
+// Data gradient, gather form: thread = one pixel x 8 channels (16-byte accesses to dq, 32-byte to dt and the
+// transposed filter in shared memory); the <= ceil(k/s)^2 sample points whose window covers the pixel are
+// enumerated per thread, all of them (<= 3 x 3) loaded before the first FMA.  A CTA walks image rows (the row's
+// window range i_lo..i_hi is computed once per row).  The index arithmetic is paid once per 8 channels: the
+// kernel was bound by it, not by memory (2 channels per lane: 118 us at stage 0 for 67 MB of traffic).
+template <typename TQ, int K, int MW>   // MW: windows per dimension of the unrolled path, >= ceil(k / stride) for it to be taken
 __global__ void __launch_bounds__(256)
 offset_bwd_dgrad_warp_kernel(const float* __restrict__ dt, const float* __restrict__ w_dw,
-                             TQ* __restrict__ dq, int n_items, OffsetArgs a) {
-  extern __shared__ float wT[];          // [K * K][Cg]
+                             TQ* __restrict__ dq, int n_rows, OffsetArgs a) {
+  extern __shared__ __align__(16) float wT[];          // [K * K][Cg]
   for (int i = threadIdx.x; i < K * K * a.Cg; i += blockDim.x) {
     const int uv = i / a.Cg, c = i - uv * a.Cg;
     wT[i] = w_dw[c * K * K + uv];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int chunks = a.C >> 6;
-  // grid-stride over the (pixel, chunk) items: the shared-memory filter is staged once per CTA
-  for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items;
-       item += gridDim.x * (blockDim.x >> 5)) {
-  const int pix = item / chunks, cf = (item - pix * chunks) * 64 + lane * 2;
-  const int x = pix % a.W, yy = pix / a.W;
-  const int y = yy % a.H, b = yy / a.H;
-  const int g = cf / a.Cg, c = cf - g * a.Cg;
-  // i*s - p + u = y, 0 <= u < k  ->  (y + p - k + 1)/s <= i <= (y + p)/s
-  int i_lo = y + a.pad - K + 1;
-  i_lo = i_lo <= 0 ? 0 : (i_lo + a.stride - 1) / a.stride;
-  const int i_hi = min(a.Hk - 1, (y + a.pad) / a.stride);
-  int j_lo = x + a.pad - K + 1;
-  j_lo = j_lo <= 0 ? 0 : (j_lo + a.stride - 1) / a.stride;
-  const int j_hi = min(a.Wk - 1, (x + a.pad) / a.stride);
-  float2 s = make_float2(0.f, 0.f);
-  const float* dtb = dt + ((long long)(b * a.G + g) * a.Ns) * a.Cg + c;
-  for (int i = i_lo; i <= i_hi; ++i) {
-    const int u = y + a.pad - i * a.stride;
-    for (int j = j_lo; j <= j_hi; ++j) {
-      const int v = x + a.pad - j * a.stride;
-      const float2 d = ld_pair(dtb + (long long)(i * a.Wk + j) * a.Cg);
-      const float2 w = *reinterpret_cast<const float2*>(wT + (u * K + v) * a.Cg + c);
-      s.x = fmaf(w.x, d.x, s.x);
-      s.y = fmaf(w.y, d.y, s.y);
+  const int c8s = a.C >> 3;              // 8-channel units per pixel
+  const int units = a.W * c8s;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int b = row / a.H, y = row - b * a.H;
+    // i*s - p + u = y, 0 <= u < k  ->  (y + p - k + 1)/s <= i <= (y + p)/s
+    int i_lo = y + a.pad - K + 1;
+    i_lo = i_lo <= 0 ? 0 : (i_lo + a.stride - 1) / a.stride;
+    const int i_hi = min(a.Hk - 1, (y + a.pad) / a.stride);
+    const int ni = i_hi - i_lo + 1;
+    for (int unit = threadIdx.x; unit < units; unit += blockDim.x) {
+      const int x = unit / c8s, cf = (unit - x * c8s) * 8;
+      const int g = cf / a.Cg, c = cf - g * a.Cg;
+      int j_lo = x + a.pad - K + 1;
+      j_lo = j_lo <= 0 ? 0 : (j_lo + a.stride - 1) / a.stride;
+      const int j_hi = min(a.Wk - 1, (x + a.pad) / a.stride);
+      const int nj = j_hi - j_lo + 1;
+      const float* dtb = dt + ((long long)(b * a.G + g) * a.Ns) * a.Cg + c;
+      TQ* dst = dq + ((long long)row * a.W + x) * a.C + cf;
+      const float4 o0 = load4(dst), o1 = load4(dst + 4);
+      float acc[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      if (ni <= MW && nj <= MW) {
+        // global loads of every covering window first (one round trip), the filter taps come from shared
+        // memory inside the FMA loop
+        float4 d[MW][MW][2];
+#pragma unroll
+        for (int ia = 0; ia < MW; ++ia)
+#pragma unroll
+          for (int jb = 0; jb < MW; ++jb) {
+            const bool ok = ia < ni && jb < nj;
+            const float* dp = dtb + (long long)((i_lo + ia) * a.Wk + j_lo + jb) * a.Cg;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[ia][jb][0] = ok ? *reinterpret_cast<const float4*>(dp) : z;
+            d[ia][jb][1] = ok ? *reinterpret_cast<const float4*>(dp + 4) : z;
+          }
+#pragma unroll
+        for (int ia = 0; ia < MW; ++ia)
+#pragma unroll
+          for (int jb = 0; jb < MW; ++jb) {
+            if (ia < ni && jb < nj) {
+              const int u = y + a.pad - (i_lo + ia) * a.stride, v = x + a.pad - (j_lo + jb) * a.stride;
+              const float* wp = wT + (u * K + v) * a.Cg + c;
+              const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+              acc[0] = fmaf(w0.x, d[ia][jb][0].x, acc[0]); acc[1] = fmaf(w0.y, d[ia][jb][0].y, acc[1]);
+              acc[2] = fmaf(w0.z, d[ia][jb][0].z, acc[2]); acc[3] = fmaf(w0.w, d[ia][jb][0].w, acc[3]);
+              acc[4] = fmaf(w1.x, d[ia][jb][1].x, acc[4]); acc[5] = fmaf(w1.y, d[ia][jb][1].y, acc[5]);
+              acc[6] = fmaf(w1.z, d[ia][jb][1].z, acc[6]); acc[7] = fmaf(w1.w, d[ia][jb][1].w, acc[7]);
+            }
+          }
+      } else {
+        for (int i = i_lo; i <= i_hi; ++i) {
+          const int u = y + a.pad - i * a.stride;
+          for (int j = j_lo; j <= j_hi; ++j) {
+            const int v = x + a.pad - j * a.stride;
+            const float* dp = dtb + (long long)(i * a.Wk + j) * a.Cg;
+            const float* wp = wT + (u * K + v) * a.Cg + c;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(wp[e], dp[e], acc[e]);
+          }
+        }
+      }
+      store4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      store4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
-  }
-  TQ* dst = dq + (long long)pix * a.C + cf;
-  const float2 old = ld_pair(dst);
-  st_pair(dst, make_float2(old.x + s.x, old.y + s.y));
   }
 }
 
@@ -628,12 +663,15 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
 
   long long total = (long long)s.B * s.HW * s.C;
   if (fast) {
-    const int n_items = (int)((long long)s.B * s.HW * (s.C / 64));
+    const int n_items = s.B * s.H;            // image rows; a CTA's 8 warps share the (pixel, chunk) items of a row
     const size_t wsm = (size_t)kk * s.Cg * sizeof(float);
-    const int dg_grid = ceil_div(n_items, 8) < 148 * 8 ? ceil_div(n_items, 8) : 148 * 8;
+    const int dg_grid = n_items < 148 * 8 ? n_items : 148 * 8;
+    const bool two = (s.ksize + s.stride - 1) / s.stride <= 2;   // covering windows per dimension
 #define LAUNCH_DG(TQ, KV)                                                                             \
-    offset_bwd_dgrad_warp_kernel<TQ, KV><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, \
-                                                                                 n_items, a)
+    do {                                                                                              \
+      if (two) offset_bwd_dgrad_warp_kernel<TQ, KV, 2><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, n_items, a); \
+      else offset_bwd_dgrad_warp_kernel<TQ, KV, 3><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, n_items, a);     \
+    } while (0)
 #define LAUNCH_DG_K(TQ)                                                             \
     do {                                                                            \
       if (s.ksize == 3) LAUNCH_DG(TQ, 3); else if (s.ksize == 5) LAUNCH_DG(TQ, 5);  \

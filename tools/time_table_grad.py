@@ -28,6 +28,10 @@ for stage, (H, heads, groups, stride, ksize, qs) in enumerate(STAGES):
         for _ in range(5):
             run()
         torch.cuda.synchronize()
-    rows = [(e.key, e.device_time_total / e.count) for e in prof.key_averages()
-            if "attn_bwd" in e.key or "rpe_table_grad" in e.key or "attn_fwd" in e.key]
-    print(f"stage {stage}: " + ", ".join(f"{k.split('::')[-1][:28]} {t:.0f} us" for k, t in rows), flush=True)
+    import re
+    allk = os.environ.get("ALL_KERNELS") is not None
+    rows = [(e.key, e.device_time_total / 5) for e in prof.key_averages()
+            if allk or "attn_bwd" in e.key or "rpe_table_grad" in e.key or "attn_fwd" in e.key]
+    rows.sort(key=lambda kv: -kv[1])
+    name = lambda k: re.sub(r"[(<].*", "", k.replace("(anonymous namespace)::", "").replace("void ", "").replace("dat::", ""))[:40]
+    print(f"stage {stage}: " + ", ".join(f"{name(k)} {t:.0f} us" for k, t in rows[:24]), flush=True)
