@@ -107,11 +107,11 @@ __global__ void sample_bwd_dpos_kernel(const TX* __restrict__ x, const float* __
   }
 }
 
-// d x scatter, sorted-run form.  grid = (B*G, Cg/32); block = 512 threads (256 for fewer than 256 samples).
+// d x scatter, sorted-run form.  grid = (B*G, Cg/32); block = 256 threads.
 // dynamic smem: keys[P] (uint32) + weight[4*Ns] (float), P = pow2 >= 4*Ns.
 // key = pixel << 14 | entry  (entry = n*4 + tap < 2^14, pixel < 2^18); invalid = ~0u.
 template <typename TD>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 sample_bwd_dx_kernel(const float* __restrict__ pos, const TD* __restrict__ dxs,
                      float* __restrict__ dx, int H, int W, int C, int G, int Cg, int Ns, int P) {
   extern __shared__ uint32_t smem_u[];
@@ -235,7 +235,7 @@ int sample_bwd_dx(const Shape& s, const float* pos, const void* dxs, float* dx, 
     if (smem > 48 * 1024)                                                                      \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                        (int)smem));                                            \
-    kern<<<grid, P >= 1024 ? 512 : 256, smem, st>>>(pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
+    kern<<<grid, 256, smem, st>>>(pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
   } while (0)
   if (s.act_dtype == DAT_F32) LAUNCH(float); else LAUNCH(bf16);
 #undef LAUNCH
