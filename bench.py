@@ -157,7 +157,7 @@ def _time_launch(dev, launch, flush, reps=10):
 
 def kernel_roofline(dev, pk):
     """Roofline of the dominant kernel of the step, `gemm_tc_persistent_kernel` (12 % of the kernel time, 174
-    launches: profiles/r01_launches_step_790.md), at the shape that carries most of its time - the stage-2 MLP fc1
+    launches: profiles/r01_launches_step_818.md), at the shape that carries most of its time - the stage-2 MLP fc1
     (M = B*HW = 16384, N = 1024, K = 256, bf16; 18 MLPs per step run it forward and as the fc2 data gradient).
     Algorithmic bytes = X + W + Y once; its arithmetic intensity (202 FLOP/B) is below the measured
     ridge (1658 TF/s / 6541 GB/s = 254 FLOP/B), so the bound is HBM.  `others`: the attention forward (the
