@@ -306,10 +306,23 @@ size_t dwconv7_partial_bytes(int B, int H, int W, int C) {
   return align_up((size_t)n_partials(B, H, W, C, th) * 50 * C * 4, 256);
 }
 
+// Rows per strip of the forward / data-gradient kernel.  Every input row costs the same whatever the number of
+// output rows it feeds, so taller strips do less work per output ((th + 6) / th input rows each); measured
+// optimum at batch 16 (DAT_B200_DW7_TH sweep, profiles/r01_kernel_rooflines.md): 32 rows for 128-row maps, 16
+// for 64 / 32, 8 for 16 - i.e. as tall as possible while ~32 k threads (7 warps per SM) remain.
+int fwd_rows_per_strip(int B, int H, int W, int C) {
+  if (const char* e = std::getenv("DAT_B200_DW7_TH")) { const int v = std::atoi(e); if (v > 0) return v < H ? v : H; }
+  const long long per_row_block = (long long)B * ceil_div(W, TW) * (C / 2);
+  int th = H >= 128 ? 32 : (H >= 32 ? 16 : 8);
+  if (th > H) th = H;
+  while (th > 4 && per_row_block * ceil_div(H, th) < 24 * 1024) th = (th + 1) / 2;
+  return th;
+}
+
 int dwconv7_fwd(const void* x, int x_dt, const float* w, const float* bias, void* y, int y_dt, int B, int H,
                 int W, int C, int flip, cudaStream_t st) {
   DAT_REQUIRE(C % 2 == 0, "dwconv7: C must be even");
-  const int th = rows_per_strip(B, H, W, C, 4, 3);
+  const int th = fwd_rows_per_strip(B, H, W, C);
   const int sx = ceil_div(W, TW), sy = ceil_div(H, th);
   const unsigned grid = (unsigned)ceil_div((long long)B * sx * sy * (C / 2), (long long)D7_THREADS);
   constexpr int smem = 49 * D7_THREADS * (int)sizeof(float2);
