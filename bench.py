@@ -289,7 +289,12 @@ def main():
     launches_per_step = (lib.dat_launch_count() - n0) // warmup
     if not args.no_graph:
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # The critical chain is captured on a high-priority stream; the weight-gradient / table-gradient branches run
+        # on default-priority side streams (library-owned and _streams.py), so when both have a kernel ready the
+        # block scheduler serves the critical chain first (kernel nodes keep their stream's priority).
+        prio = os.environ.get("DAT_B200_BENCH_PRIORITY", "-1")
+        cap_stream = torch.cuda.Stream(dev, priority=int(prio)) if prio != "none" else None
+        with torch.cuda.graph(graph, stream=cap_stream):
             static_loss = fwd_bwd()
 
     def step():
