@@ -267,6 +267,34 @@ def rpe_bias_explicit(pos: Tensor, table: Tensor, H: int, W: int, cfg: BlockCfg)
     return bias.reshape(B, h, H * W, Ns)
 
 
+def rpe_table_grad_separable(ds: Tensor, pos: Tensor, H: int, W: int, cfg: BlockCfg) -> Tensor:
+    """d rpe_table from dS = dL/d(score) in the separable form the CUDA kernel `rpe_table_grad_kernel`
+    (csrc/rpe_table_grad.cu) evaluates with tensor-core GEMMs: for every sample n
+
+        dT_n = A_n^T . dS_n . B_n,   A_n[r][y] = hat(iy(r, n) - y),  B_n[c][x] = hat(ix(c, n) - x),
+        hat(d) = max(0, 1 - |d|),   ix = ((d_x + 1) / 2)(Tw - 1),  d_x = (q_grid_x[c] - pos_x[n]) / 2
+
+    (the bilinear weights of `F.grid_sample(..., align_corners=True)` with zero padding are exactly these hat
+    products restricted to the table; dat_blocks.py:198-212).  ds (B,h,HW,Ns), pos (B,G,Hk,Wk,2) -> (h,Th,Tw)."""
+    B, G = pos.shape[0], pos.shape[1]
+    Ns = pos.shape[2] * pos.shape[3]
+    h, hg = cfg.n_heads, cfg.hg
+    th, tw = cfg.table_hw
+    qy, qx = query_grid(H, W, pos.dtype)
+    py, px = pos[..., 0].reshape(B, G, Ns), pos[..., 1].reshape(B, G, Ns)
+    iy = ((qy.reshape(1, 1, H, 1) - py.reshape(B, G, 1, Ns)) * 0.5 + 1) / 2 * (th - 1)     # (B,G,H,Ns)
+    ix = ((qx.reshape(1, 1, W, 1) - px.reshape(B, G, 1, Ns)) * 0.5 + 1) / 2 * (tw - 1)     # (B,G,W,Ns)
+    ys = torch.arange(th, dtype=pos.dtype).reshape(1, 1, 1, 1, th)
+    xs = torch.arange(tw, dtype=pos.dtype).reshape(1, 1, 1, 1, tw)
+    A = (1 - (iy[..., None] - ys).abs()).clamp_min(0)          # (B,G,H,Ns,Th)
+    Bm = (1 - (ix[..., None] - xs).abs()).clamp_min(0)         # (B,G,W,Ns,Tw)
+    dsr = ds.reshape(B, G, hg, H, W, Ns)
+    # dT[g,j,y,x] = sum_{b,n,r,c} A[b,g,r,n,y] dS[b,g,j,r,c,n] B[b,g,c,n,x]
+    e = torch.einsum("bgjrcn,bgcnx->bgjrnx", dsr, Bm)
+    dt = torch.einsum("bgrny,bgjrnx->gjyx", A, e)
+    return dt.reshape(h, th, tw)
+
+
 def forward_explicit(x: Tensor, p: Dict[str, Tensor], cfg: BlockCfg,
                      pos_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Whole block, channel-last.  x (B,H,W,C) → dict with y (B,H,W,C) and every

@@ -103,3 +103,19 @@ def test_variant_port_matches_reference(name):
     assert set(rec["grads"]) == {k for k, v in leaves.items() if v.grad is not None}
     for k, g in rec["grads"].items():
         assert rel_err(leaves[k].grad, g) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["stage3_small", "k_eq_s_orf1", "odd_c96_orf3"])
+def test_table_gradient_separable_form_matches_autograd(name):
+    """The GEMM form of d rpe_table used by csrc/rpe_table_grad.cu (dT_n = A_n^T dS_n B_n with hat weights) equals
+    autograd through the reference's own bias computation (F.grid_sample of the table at the displacements)."""
+    cfg, x, _, rec = load_case(name)
+    H, W = x.shape[2:]
+    pos = rec["pos_l"].double()
+    table = rec["params"]["rpe_table"].double().clone().requires_grad_(True)
+    bias = orc.rpe_bias_explicit(pos, table, H, W, cfg)                     # (B,h,HW,Ns), differentiable in table
+    g = torch.Generator().manual_seed(3)
+    ds = torch.randn(bias.shape, generator=g, dtype=torch.float64)
+    bias.backward(ds)
+    got = orc.rpe_table_grad_separable(ds, pos, H, W, cfg)
+    assert rel_err(got, table.grad) < 1e-10
