@@ -295,6 +295,19 @@ def rpe_table_grad_separable(ds: Tensor, pos: Tensor, H: int, W: int, cfg: Block
     return dt.reshape(h, th, tw)
 
 
+def merge_sample_chunks(o_parts, lse_parts):
+    """Merge of per-chunk attention results (the split-KV path of csrc/attention_tc.cu for Ns > 256):
+    chunk c holds O_c = softmax(S_c) V_c and lse_c = logsumexp(S_c) over its own samples; then
+    O = sum_c w_c O_c / sum_c w_c with w_c = exp(lse_c - max_c lse_c), lse = max + log sum_c w_c.
+    o_parts: list of (..., HW, d); lse_parts: list of (..., HW)."""
+    lse = torch.stack(lse_parts, 0)
+    mx = lse.max(0).values
+    w = (lse - mx).exp()
+    den = w.sum(0)
+    o = sum(wc[..., None] * oc for wc, oc in zip(w, o_parts)) / den[..., None]
+    return o, mx + den.log()
+
+
 def forward_explicit(x: Tensor, p: Dict[str, Tensor], cfg: BlockCfg,
                      pos_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Whole block, channel-last.  x (B,H,W,C) → dict with y (B,H,W,C) and every

@@ -119,3 +119,21 @@ def test_table_gradient_separable_form_matches_autograd(name):
     bias.backward(ds)
     got = orc.rpe_table_grad_separable(ds, pos, H, W, cfg)
     assert rel_err(got, table.grad) < 1e-10
+
+
+def test_split_kv_merge_equals_full_softmax():
+    """The chunk merge of the split-KV attention forward (attn_combine_kernel) is exact: 1024 samples as
+    256 + 256 + 256 + 128 + 64 + 64 against one softmax over all of them (fp64)."""
+    g = torch.Generator().manual_seed(5)
+    S = torch.randn(3, 40, 1024, generator=g, dtype=torch.float64) * 3
+    V = torch.randn(3, 1024, 32, generator=g, dtype=torch.float64)
+    full = torch.softmax(S, -1) @ V
+    o_parts, l_parts, n0 = [], [], 0
+    for n in (256, 256, 256, 128, 64, 64):
+        Sc, Vc = S[..., n0:n0 + n], V[:, n0:n0 + n]
+        o_parts.append(torch.softmax(Sc, -1) @ Vc)
+        l_parts.append(torch.logsumexp(Sc, -1))
+        n0 += n
+    o, lse = orc.merge_sample_chunks(o_parts, l_parts)
+    assert rel_err(o, full) < 1e-12
+    assert rel_err(lse, torch.logsumexp(S, -1)) < 1e-12
