@@ -116,3 +116,16 @@ def test_variant_modules_share_the_reference_state_dict(name):
     for k, v in mod.state_dict().items():
         assert torch.equal(v, rec["params"][k]), k
     mod.load_state_dict(rec["params"], strict=True)
+
+
+def test_pointwise_predicate_follows_the_library(cab):
+    """`pointwise._supported` asks the C ABI whether the weight-gradient kernel tiles a shape (a Python copy of the
+    rule once disagreed with the library for K = 192).  Host-only calls: no GPU needed."""
+    from dat_segmentation_b200.pointwise import _supported
+    lib = cab.lib()
+    for M, N, K in [(16384, 1024, 256), (16384, 256, 1024), (4096, 768, 192), (4096, 192, 768), (4096, 1536, 384),
+                    (262144, 64, 256), (1024, 3072, 768)]:
+        assert _supported(M, N, K), (M, N, K)
+        assert lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K) > 0
+    for M, N, K in [(4096, 384, 96), (4096, 96, 384), (32, 256, 256), (4096, 100, 64)]:
+        assert not _supported(M, N, K), (M, N, K)
