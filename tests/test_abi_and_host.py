@@ -129,3 +129,27 @@ def test_pointwise_predicate_follows_the_library(cab):
         assert lib.dat_pointwise_wgrad_tc_workspace_bytes(M, N, K) > 0
     for M, N, K in [(4096, 384, 96), (4096, 96, 384), (32, 256, 256), (4096, 100, 64)]:
         assert not _supported(M, N, K), (M, N, K)
+
+
+def test_variant_descriptors_and_workspace_queries(cab):
+    """pe_mode / no_off in dat_block_desc: the sample grid follows avg_pool2d for no_off (floor division, no padding,
+    dat_blocks.py:165-167), the dense-bias variants reserve the (B, h, HW, Ns) fp32 tensors the reference materialises,
+    a bad pe_mode is an argument error.  Host-only calls."""
+    lib = cab.lib()
+    hk, wk = C.c_int32(), C.c_int32()
+    d = cab.BlockDesc(2, 18, 22, 2, 1, 4, 7, 27, 27, 2.0, 0, 0, cab.PE_RPE, 1)          # no_off
+    assert lib.dat_sample_grid(C.byref(d), C.byref(hk), C.byref(wk)) == 0
+    assert (hk.value, wk.value) == (18 // 4, 22 // 4)
+    base = cab.BlockDesc(2, 16, 16, 4, 2, 2, 5, 27, 27, -1.0, 0, 0, cab.PE_RPE, 0)
+    n_rpe_f = lib.dat_block_fwd_workspace_bytes(C.byref(base))
+    n_rpe_b = lib.dat_block_bwd_workspace_bytes(C.byref(base))
+    dense = 2 * 4 * 256 * 64 * 4                                                       # B h HW Ns fp32
+    for mode, fwd_extra, bwd_extra in ((cab.PE_LOGCPB, dense, 2 * dense), (cab.PE_FIXED, dense // 2, dense // 2 + dense)):
+        dv = cab.BlockDesc(2, 16, 16, 4, 2, 2, 5, 64, 16, -1.0, 0, 0, mode, 0)
+        assert lib.dat_block_fwd_workspace_bytes(C.byref(dv)) >= n_rpe_f + fwd_extra
+        assert lib.dat_block_bwd_workspace_bytes(C.byref(dv)) >= n_rpe_b + bwd_extra
+    dv = cab.BlockDesc(2, 16, 16, 4, 2, 2, 5, 0, 0, -1.0, 0, 0, cab.PE_NONE, 0)         # no table: sizes ignored
+    assert lib.dat_block_bwd_workspace_bytes(C.byref(dv)) > 0
+    bad = cab.BlockDesc(2, 16, 16, 4, 2, 2, 5, 27, 27, -1.0, 0, 0, 9, 0)
+    assert lib.dat_sample_grid(C.byref(bad), C.byref(hk), C.byref(wk)) == -1
+    assert b"pe_mode" in lib.dat_last_error()
