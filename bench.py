@@ -244,6 +244,10 @@ def main():
     if world > 1:
         os.environ.pop("NCCL_P2P_DISABLE", None)   # the reference's launch scripts set it; NVSwitch wants P2P
         dist.init_process_group("nccl", device_id=dev)
+        # this script joins the weight-gradient side stream itself (end of backward()) before it packs and all-reduces
+        # the gradients, so the side stream stays on although a process group exists (no DDP hooks here)
+        from dat_segmentation_b200 import _streams
+        _streams.ALLOW_WITH_PROCESS_GROUP[0] = True
     lib = _cabi.lib()
     warmup = max(3, args.warmup)
 

@@ -2,7 +2,8 @@
 nothing later in the backward reads them).  Such work is enqueued on one extra stream per device,
 forked from the current stream when its inputs are ready, and joined once by an autograd-engine
 callback at the end of the backward pass.  Under CUDA-graph capture the fork / join become graph
-edges.  `DAT_B200_SERIAL_WGRAD=1` keeps everything on the current stream.
+edges.  `DAT_B200_SERIAL_WGRAD=1` keeps everything on the current stream, and so does an initialised
+torch.distributed process group unless `ALLOW_WITH_PROCESS_GROUP[0]` is set (see below).
 """
 import os
 
@@ -13,8 +14,21 @@ _PENDING = []
 _JOIN_QUEUED = [False]
 
 
+# A process group usually means DistributedDataParallel, whose gradient hooks hand a weight gradient to NCCL (on DDP's
+# own stream, ordered only after the *current* stream) as soon as autograd has produced it - before the
+# end-of-backward join of the side stream.  So with an initialised process group the side stream is off unless the
+# caller opts in because it synchronises itself (bench.py packs and all-reduces the gradients after backward()).
+ALLOW_WITH_PROCESS_GROUP = [False]
+
+
+def _process_group_initialised():
+    return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+
 def serial():
-    return bool(os.environ.get("DAT_B200_SERIAL_WGRAD"))
+    if os.environ.get("DAT_B200_SERIAL_WGRAD"):
+        return True
+    return _process_group_initialised() and not ALLOW_WITH_PROCESS_GROUP[0]
 
 
 def side_stream(dev):

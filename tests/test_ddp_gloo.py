@@ -65,3 +65,32 @@ def test_batch_sharded_gradients_match_single_process():
     mp.spawn(_worker, args=(world, _free_port(), x, ref_grads, ok), nprocs=world, join=True)
     assert len(ok) == world
     assert max(ok.values()) < 2e-3, dict(ok)     # fp32 summation order differs between 2x2 and 1x4
+
+
+def _serial_flags(rank, world, port, out):
+    from dat_segmentation_b200 import _streams
+    before = _streams.serial()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    with_pg = _streams.serial()
+    _streams.ALLOW_WITH_PROCESS_GROUP[0] = True
+    opted_in = _streams.serial()
+    dist.destroy_process_group()
+    out.put((before, with_pg, opted_in))
+
+
+def test_side_stream_is_off_under_a_process_group_unless_opted_in():
+    """DistributedDataParallel's hooks read weight gradients before the side stream's end-of-backward join: with an
+    initialised process group the 1x1-conv weight gradients stay on the current stream unless the caller (bench.py)
+    opts in."""
+    os.environ.pop("DAT_B200_SERIAL_WGRAD", None)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_serial_flags, args=(0, 1, port, q))
+    p.start()
+    before, with_pg, opted_in = q.get(timeout=120)
+    p.join(timeout=60)
+    assert (before, with_pg, opted_in) == (False, True, False)
