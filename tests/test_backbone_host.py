@@ -145,3 +145,31 @@ def test_backbone_with_variant_branches_cuda_vs_oracle_port():
     worst = max((_rel(gp[k].grad.cpu(), cp[k].grad), k) for k in gp if cp[k].grad is not None
                 and cp[k].grad.abs().max() > 1e-6)
     assert worst[0] < 2e-2, worst
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+def test_install_swaps_the_block_inside_the_reference_backbone():
+    """`dat_segmentation_b200.install.install()` makes the UNMODIFIED reference `DAT` build dat_b200 blocks (positional
+    16-argument construction, dat.py:99-116) with an unchanged state dict; `uninstall()` restores the reference class."""
+    blocks, dat = import_reference()
+    import dat_segmentation_b200.install as b200
+    from dat_segmentation_b200.dattention import DAttentionBaseline as B200Block
+    ref_cls = blocks.DAttentionBaseline
+    torch.manual_seed(3)
+    ref = dat.DAT(**DAT_TINY_PP)
+    try:
+        patched = b200.install()
+        assert "models.utils.dat_blocks" in patched and "models.backbones.dat" in patched
+        torch.manual_seed(3)
+        swapped = dat.DAT(**DAT_TINY_PP)
+        attn = [m for m in swapped.modules() if type(m).__name__ == "DAttentionBaseline"]
+        assert len(attn) == 14 and all(type(m) is B200Block for m in attn)
+        sd_ref, sd_new = ref.state_dict(), swapped.state_dict()
+        assert list(sd_ref.keys()) == list(sd_new.keys())
+        assert all(torch.equal(sd_ref[k], sd_new[k]) for k in sd_ref)        # same init stream too
+        swapped.load_state_dict(sd_ref, strict=True)
+        with pytest.raises(RuntimeError):
+            swapped(torch.randn(1, 3, 64, 64))                               # CPU tensor: the block has no CPU path
+    finally:
+        b200.uninstall()
+    assert blocks.DAttentionBaseline is ref_cls and dat.DAttentionBaseline is ref_cls
