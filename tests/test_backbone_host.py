@@ -173,3 +173,26 @@ def test_install_swaps_the_block_inside_the_reference_backbone():
     finally:
         b200.uninstall()
     assert blocks.DAttentionBaseline is ref_cls and dat.DAttentionBaseline is ref_cls
+
+
+def test_backbone_activation_checkpointing_gives_the_same_gradients():
+    """`use_checkpoint=True` (dat.py:161-165: every stage under torch.utils.checkpoint in training) must not change
+    outputs or gradients; CPU, oracle port of the block."""
+    small = dict(dim_stem=32, dims=[32, 64, 128, 256], depths=[2, 1, 1, 1], stage_spec=[["X", "D"], ["D"], ["D"], ["D"]],
+                 heads=[1, 2, 4, 8], groups=[1, 1, 2, 4], use_pes=[True] * 4, strides=[4, 2, 1, 1],
+                 offset_range_factor=[-1, 2, -1, 1], use_dwc_mlps=[True] * 4, use_lpus=[True] * 4, use_conv_patches=True,
+                 ksizes=[5, 3, 3, 3], nat_ksizes=[7] * 4, drop_path_rate=0.0, img_size=64)
+    torch.manual_seed(21)
+    a = build_dat(dict(small, use_checkpoint=False), attn_cls=orc.OracleDAttention).train()
+    b = build_dat(dict(small, use_checkpoint=True), attn_cls=orc.OracleDAttention).train()
+    b.load_state_dict(a.state_dict(), strict=True)
+    x = torch.randn(2, 3, 64, 64)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    oa, ob = a(xa), b(xb)
+    for u, v in zip(oa, ob):
+        assert torch.equal(u, v)
+    sum(o.square().mean() for o in oa).backward()
+    sum(o.square().mean() for o in ob).backward()
+    assert _rel(xb.grad, xa.grad) < 1e-6
+    ga, gb = dict(a.named_parameters()), dict(b.named_parameters())
+    assert all(_rel(gb[k].grad, ga[k].grad) < 1e-5 for k in ga if ga[k].grad is not None and ga[k].grad.abs().max() > 0)
