@@ -36,8 +36,16 @@ PARAM_KEYS = ("conv_offset.0.weight", "conv_offset.0.bias", "conv_offset.1.norm.
 SAVED_FIELDS = ("q", "t_dw", "off_raw", "pos", "xs", "k", "v", "o", "lse")
 
 
+# optional bf16 operand copies of the four projection weights (dat_block_params.w*_bf16; 0 = the library casts)
+BF16_FIELDS = ("wq_bf16", "wk_bf16", "wv_bf16", "wo_bf16")
+
+
 class BlockParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS + BF16_FIELDS]
+
+
+class CastItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int64)]
 
 
 class BlockGrads(C.Structure):
@@ -82,6 +90,9 @@ def lib():
     L.dat_pointwise_fwd_tc.argtypes = [vp, i32, vp, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_cast_bf16.argtypes = [f32p, vp, i64, vp]
     L.dat_cast_transpose_bf16.argtypes = [f32p, vp, i32, i32, vp]
+    L.dat_cast_bf16_multi.argtypes = [vp, i32, vp]
+    L.dat_pointwise_dgrad_tc.argtypes = [vp, vp, vp, i32, i64, i32, i32, vp]
+    L.dat_cast_bf16_multi.restype = L.dat_pointwise_dgrad_tc.restype = C.c_int
     L.dat_pointwise_wgrad_tc_workspace_bytes.argtypes = [i64, i32, i32]
     L.dat_pointwise_wgrad_tc_workspace_bytes.restype = C.c_size_t
     L.dat_pointwise_wgrad_tc.argtypes = [vp, vp, f32p, f32p, i64, i32, i32, vp, C.c_size_t, vp]
@@ -138,6 +149,7 @@ def exported_symbols():
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
             "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing", "dat_debug_attn_bwd_timing",
             "dat_cast_transpose_bf16", "dat_pointwise_wgrad_tc_workspace_bytes", "dat_pointwise_wgrad_tc",
+            "dat_cast_bf16_multi", "dat_pointwise_dgrad_tc",
             "dat_bias_grad",
             "dat_offset_pos_fwd",
             "dat_ref_points", "dat_sample_fwd",

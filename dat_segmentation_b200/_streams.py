@@ -31,6 +31,23 @@ def serial():
     return _process_group_initialised() and not ALLOW_WITH_PROCESS_GROUP[0]
 
 
+def grads_consumed_at_end_only(*params):
+    """True when nothing can read the gradients of `params` before the end-of-backward join: each parameter is a
+    leaf without `.grad` yet (autograd then just stores the returned tensor; an existing `.grad` would make
+    AccumulateGrad run `grad += dw` on the current stream while the side stream may still be writing dw -
+    gradient accumulation over micro-batches, `zero_grad(set_to_none=False)`, shared weights) and without tensor
+    hooks or post-accumulate-grad hooks (they would see dw before it is complete).  When this is False the caller
+    joins the side stream into the current stream before returning the gradients."""
+    for p in params:
+        if p is None:
+            continue
+        if not isinstance(p, torch.Tensor) or not p.is_leaf or p.grad is not None:
+            return False
+        if getattr(p, "_backward_hooks", None) or getattr(p, "_post_accumulate_grad_hooks", None):
+            return False
+    return True
+
+
 def side_stream(dev):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE:

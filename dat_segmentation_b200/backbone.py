@@ -20,6 +20,7 @@ from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GE
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
 from .pointwise import PointwiseConvCL
 from .residual import scale_residual
+from .weights import Bf16WeightCache
 
 __all__ = ["DAT", "TransformerStage", "DAT_TINY_PP", "DAT_SMALL_PP", "DAT_BASE_PP", "build_dat", "LayerNormProxy",
            "TorchLayerNormProxy"]
@@ -283,7 +284,21 @@ class DAT(nn.Module):
                 if isinstance(m, nn.Conv2d):
                     m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
+        # bf16 operand copies of every 1x1-conv weight, cast once per forward in one launch (weights.py)
+        self._bf16_weights = None
+        if b200_ops:
+            ents = []
+            for m in self.modules():
+                if isinstance(m, PointwiseConvCL):
+                    ents.append((m, "weight"))
+                elif isinstance(m, DAttentionBaseline):
+                    ents += [(c, "weight") for c in (m.proj_q, m.proj_k, m.proj_v, m.proj_out)]
+            self._bf16_weights = Bf16WeightCache(ents)
+
     def forward(self, x):
+        if (self._bf16_weights is not None and x.is_cuda and torch.is_autocast_enabled("cuda")
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16 and not os.environ.get("DAT_B200_NO_WEIGHT_CACHE")):
+            self._bf16_weights.refresh()
         x = self.patch_proj(x)
         outs = []
         for i in range(4):

@@ -89,6 +89,8 @@ struct BwdPlan {
   // the depthwise kernels' scratch (dwc_pe)
   float *bias, *dbias;
   void* ds_tab;     // bf16 dS (B * heads, HW, Ns) streamed out of the attention backward for the table gradient
+  void* tg_part;    // per-CTA partial tables of the table-gradient GEMMs (fixed-order reduction)
+  size_t tg_bytes;
   void *lepe, *o2, *dq_lepe, *dw_ws;
   size_t dw_ws_bytes;
   size_t sub_bytes, wg_bytes, total;
@@ -132,6 +134,7 @@ size_t fwd_fixed_bytes(const Shape& s) {   // bf16 weight copies + packed table 
 struct SideStreams {
   cudaStream_t s;
   cudaEvent_t ev[5];
+  pthread_mutex_t mu;   // one backward at a time per device enqueues on the stream / records the events
 };
 SideStreams* side_streams() {
   static SideStreams ctx[64];
@@ -150,11 +153,39 @@ SideStreams* side_streams() {
       pthread_mutex_unlock(&mu);
       return nullptr;
     }
+    pthread_mutex_init(&ctx[dev].mu, nullptr);
     made[dev] = true;
   }
   pthread_mutex_unlock(&mu);
   return &ctx[dev];
 }
+// Scope of one backward's use of the side stream: holds the per-device mutex (two host threads running backward
+// on one device must not interleave record / wait on the shared events) and joins the side stream into the
+// caller's stream on EVERY exit path, so an early error return never leaves the side stream reading the caller's
+// buffers (and never leaves an unjoined fork inside a CUDA-graph capture).
+struct SideScope {
+  SideStreams* ss;
+  cudaStream_t st;
+  bool forked = false;
+  SideScope(SideStreams* s_, cudaStream_t st_) : ss(s_), st(st_) {
+    if (ss != nullptr) pthread_mutex_lock(&ss->mu);
+  }
+  int fork(int i) {
+    if (ss != nullptr) {
+      DAT_CUDA_OK(cudaEventRecord(ss->ev[i], st));
+      DAT_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->ev[i], 0));
+      forked = true;
+    }
+    return DAT_OK;
+  }
+  ~SideScope() {
+    if (ss == nullptr) return;
+    if (forked) {
+      if (cudaEventRecord(ss->ev[4], ss->s) == cudaSuccess) cudaStreamWaitEvent(st, ss->ev[4], 0);
+    }
+    pthread_mutex_unlock(&ss->mu);
+  }
+};
 
 bool use_tc_attn_bwd(const Shape& s) { return tc_enabled() && attention_bwd_tc_supported(s); }
 // d rpe_table from the streamed dS as tensor-core GEMMs (rpe_table_grad.cu) instead of the in-kernel scatter;
@@ -213,6 +244,8 @@ BwdPlan plan_bwd(const Shape& s, void* ws) {
   p.bias = (float*)c.take(dense_bias_bytes(s));
   p.dbias = (float*)c.take(dense_bias_bytes(s) ? (size_t)s.B * s.heads * s.HW * s.Ns * 4 : 0);
   p.ds_tab = c.take(use_mma_table_grad(s) ? (size_t)s.B * s.heads * s.HW * s.Ns * 2 : 0);
+  p.tg_bytes = use_mma_table_grad(s) ? rpe_table_grad_mma_workspace(s) : 0;
+  p.tg_part = c.take(p.tg_bytes);
   p.lepe = c.take(dwc ? act : 0);
   p.o2 = c.take(dwc ? act : 0);
   p.dq_lepe = c.take(dwc ? act : 0);
@@ -293,6 +326,21 @@ int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_
                   size_t workspace_bytes, void* stream) {
   DAT_REQUIRE(dY && db && workspace, "bias_grad: NULL pointer");
   return bias_grad(dY, dy_dtype, db, M, N, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dat_cast_bf16_multi(const dat_cast_item* items, int32_t n_items, void* stream) {
+  DAT_REQUIRE(items != nullptr && n_items >= 0, "cast_bf16_multi: bad arguments");
+  return cast_bf16_multi(items, n_items, (cudaStream_t)stream);
+}
+
+int dat_pointwise_dgrad_tc(const void* dY, const void* W, void* dX, int32_t dx_dtype, int64_t M, int32_t N,
+                           int32_t K, void* stream) {
+  DAT_REQUIRE(dY && W && dX, "pointwise_dgrad_tc: NULL pointer");
+  if (!pointwise_dgrad_tc_supported(M, N, K)) {
+    set_error("pointwise_dgrad_tc: shape M=%lld N=%d K=%d not tileable with an MN-major weight", (long long)M, N, K);
+    return DAT_ERR_UNSUPPORTED;
+  }
+  return pointwise_dgrad_tc(dY, W, nullptr, nullptr, dX, dx_dtype, M, N, K, (cudaStream_t)stream);
 }
 
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
@@ -436,10 +484,17 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
                   pointwise_fwd_tc_supported(s.x_dtype, M, C, C);
   const size_t wsz = (size_t)C * C;
   bf16* wbf = (bf16*)workspace;   // [wk | wv | wo | wq]
+  // bf16 operand copies of the weights: the caller's once-per-step copies when given, else cast here
+  const bool pre = p->wk_bf16 && p->wv_bf16 && p->wo_bf16 && (s.x_dtype != DAT_BF16 || p->wq_bf16);
+  const bf16* wk_b = pre ? (const bf16*)p->wk_bf16 : wbf;
+  const bf16* wv_b = pre ? (const bf16*)p->wv_bf16 : wbf + wsz;
+  const bf16* wo_b = pre ? (const bf16*)p->wo_bf16 : wbf + 2 * wsz;
   if (tc) {
-    DAT_FWD(cast_weights_bf16(p->wk, p->wv, p->wo, wbf, (long long)wsz, st));
-    if (s.x_dtype == DAT_BF16) DAT_FWD(cast_weights_bf16(p->wq, nullptr, nullptr, wbf + 3 * wsz, (long long)wsz, st));
-    const void* wq = s.x_dtype == DAT_BF16 ? (const void*)(wbf + 3 * wsz) : (const void*)p->wq;
+    if (!pre) {
+      DAT_FWD(cast_weights_bf16(p->wk, p->wv, p->wo, wbf, (long long)wsz, st));
+      if (s.x_dtype == DAT_BF16) DAT_FWD(cast_weights_bf16(p->wq, nullptr, nullptr, wbf + 3 * wsz, (long long)wsz, st));
+    }
+    const void* wq = s.x_dtype == DAT_BF16 ? (pre ? p->wq_bf16 : (const void*)(wbf + 3 * wsz)) : (const void*)p->wq;
     DAT_FWD(pointwise_fwd_tc(x, s.x_dtype, wq, p->bq, sv->q, adt, M, C, C, st));
   } else {
     DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, adt, M, C, C, st));
@@ -452,8 +507,8 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
     DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
   }
   if (tc) {
-    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf, p->bk, sv->k, adt, Mk, C, C, st));
-    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wbf + wsz, p->bv, sv->v, adt, Mk, C, C, st));
+    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wk_b, p->bk, sv->k, adt, Mk, C, C, st));
+    DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wv_b, p->bv, sv->v, adt, Mk, C, C, st));
   } else {
     DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wk, p->bk, sv->k, adt, Mk, C, C, st));
     DAT_FWD(pointwise_fwd_simt(sv->xs, adt, p->wv, p->bv, sv->v, adt, Mk, C, C, st));
@@ -492,7 +547,7 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
     DAT_FWD(add2(sv->o, fv.lepe, fv.o2, adt, M * C, st));
     o_in = fv.o2;
   }
-  if (tc) DAT_FWD(pointwise_fwd_tc(o_in, adt, wbf + 2 * wsz, p->bo, y, adt, M, C, C, st));
+  if (tc) DAT_FWD(pointwise_fwd_tc(o_in, adt, wo_b, p->bo, y, adt, M, C, C, st));
   else DAT_FWD(pointwise_fwd_simt(o_in, adt, p->wo, p->bo, y, adt, M, C, C, st));
   return DAT_OK;
 }
@@ -513,21 +568,34 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   // transposed bf16 copies of the weights (one tiny transpose launch per backward)
   const bool tc = adt == DAT_BF16 && tc_enabled() && pointwise_fwd_tc_supported(DAT_BF16, M, C, C) &&
                   pointwise_fwd_tc_supported(DAT_BF16, Mk, C, C);
-  bf16* wT = (bf16*)w.wT;
+  bf16* wT = (bf16*)w.wT;          // [wo | wk | wv | wq]: transposed copies, or plain copies when read MN-major
   const size_t wsz = (size_t)C * C;
-  if (tc) DAT_FWD(cast_transpose_weights_bf16(p->wo, p->wk, p->wv, p->wq, wT, C, st));
+  // data gradients dX = dY W: the bf16 weight copy of the forward is read in place as an MN-major operand when C
+  // tiles by 64; other widths (C = 96 ...) use K-major products against transposed copies
+  const bool mn = tc && pointwise_dgrad_tc_supported(M, C, C) && pointwise_dgrad_tc_supported(Mk, C, C) &&
+                  getenv("DAT_B200_DGRAD_TRANSPOSE") == nullptr;
+  const bool pre = mn && p->wq_bf16 && p->wk_bf16 && p->wv_bf16 && p->wo_bf16;
+  const bf16* wo_b = pre ? (const bf16*)p->wo_bf16 : wT;
+  const bf16* wk_b = pre ? (const bf16*)p->wk_bf16 : wT + wsz;
+  const bf16* wv_b = pre ? (const bf16*)p->wv_bf16 : wT + 2 * wsz;
+  const bf16* wq_b = pre ? (const bf16*)p->wq_bf16 : wT + 3 * wsz;
+  if (tc && mn && !pre) {
+    DAT_FWD(cast_weights_bf16(p->wo, p->wk, p->wv, wT, (long long)wsz, st));
+    DAT_FWD(cast_weights_bf16(p->wq, nullptr, nullptr, wT + 3 * wsz, (long long)wsz, st));
+  } else if (tc && !mn) {
+    DAT_FWD(cast_transpose_weights_bf16(p->wo, p->wk, p->wv, p->wq, wT, C, st));
+  }
+  auto dgrad = [&](const void* dY, const bf16* W, const void* dY2, const bf16* W2, void* dX, int dx_dt, long long rows) -> int {
+    if (mn) return pointwise_dgrad_tc(dY, W, dY2, W2, dX, dx_dt, rows, C, C, st);
+    return pointwise_fwd_tc_dual(dY, W, dY2, W2, DAT_BF16, nullptr, dX, dx_dt, rows, C, C, st);
+  };
   // weight gradients dW = dY^T X on the tensor cores (both operands read MN-major), bias
   // gradients as column sums
   const bool tcw = tc && pointwise_wgrad_tc_supported(M, C, C) && pointwise_wgrad_tc_supported(Mk, C, C);
   SideStreams* ss = tcw && w.wg_bytes > 0 ? side_streams() : nullptr;
   cudaStream_t wst = ss != nullptr ? ss->s : st;       // stream of the tensor-core weight gradients
-  auto fork = [&](int i) -> int {                       // side stream waits for the work enqueued so far
-    if (ss != nullptr) {
-      DAT_CUDA_OK(cudaEventRecord(ss->ev[i], st));
-      DAT_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->ev[i], 0));
-    }
-    return DAT_OK;
-  };
+  SideScope scope(ss, st);
+  auto fork = [&](int i) -> int { return scope.fork(i); };   // side stream waits for the work enqueued so far
   auto wgrad = [&](const void* dY, const void* X, int x_dt, float* dW, float* db, long long rows) -> int {
     if (!tcw) return pointwise_wgrad_simt(dY, adt, X, x_dt, dW, db, rows, C, C, w.sub, w.sub_bytes, st);
     return pointwise_wgrad_tc(dY, X, dW, db, rows, C, C, w.wg, w.wg_bytes, wst);
@@ -544,7 +612,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   // proj_out
   DAT_FWD(fork(0));
   DAT_FWD(wgrad(dy, o_in, adt, g->wo, g->bo, M));
-  if (tc) DAT_FWD(pointwise_fwd_tc(dy, adt, wT, nullptr, w.d_o, adt, M, C, C, st));
+  if (tc) DAT_FWD(dgrad(dy, wo_b, nullptr, nullptr, w.d_o, adt, M));
   else DAT_FWD(pointwise_dgrad_simt(dy, adt, p->wo, w.d_o, adt, M, C, C, 0, st));
   // attention core
   if (use_tc_attn_bwd(s)) {
@@ -587,11 +655,11 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   // proj_k / proj_v
   DAT_FWD(fork(1));
   if (use_mma_table_grad(s))   // d rpe_table: nothing later reads it - on the side stream when there is one
-    DAT_FWD(rpe_table_grad_mma(s, w.ds_tab, sv->pos, g->rpe_table, wst));
+    DAT_FWD(rpe_table_grad_mma(s, w.ds_tab, sv->pos, g->rpe_table, w.tg_part, w.tg_bytes, wst));
   DAT_FWD(wgrad(w.dk, sv->xs, adt, g->wk, g->bk, Mk));
   DAT_FWD(wgrad(w.dv, sv->xs, adt, g->wv, g->bv, Mk));
   if (tc) {
-    DAT_FWD(pointwise_fwd_tc_dual(w.dk, wT + wsz, w.dv, wT + 2 * wsz, adt, nullptr, w.dxs, adt, Mk, C, C, st));
+    DAT_FWD(dgrad(w.dk, wk_b, w.dv, wv_b, w.dxs, adt, Mk));
   } else {
     DAT_FWD(pointwise_dgrad_simt(w.dk, adt, p->wk, w.dxs, adt, Mk, C, C, 0, st));
     DAT_FWD(pointwise_dgrad_simt(w.dv, adt, p->wv, w.dxs, adt, Mk, C, C, 1, st));
@@ -613,15 +681,11 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
   } else {
     DAT_FWD(wgrad(w.dq, x, s.x_dtype, g->wq, g->bq, M));
   }
-  if (tc) DAT_FWD(pointwise_fwd_tc(w.dq, adt, wT + 3 * wsz, nullptr, dx, DAT_F32, M, C, C, st));
+  if (tc) DAT_FWD(dgrad(w.dq, wq_b, nullptr, nullptr, dx, DAT_F32, M));
   else DAT_FWD(pointwise_dgrad_simt(w.dq, adt, p->wq, dx, DAT_F32, M, C, C, 0, st));
   if (s.no_off) DAT_FWD(avgpool_bwd(s, w.dxs, dx, st));
   else DAT_FWD(sample_bwd_dx(s, sv->pos, w.dxs, dx, st));
-  if (ss != nullptr) {                                  // join: the caller's stream owns every result again
-    DAT_CUDA_OK(cudaEventRecord(ss->ev[4], ss->s));
-    DAT_CUDA_OK(cudaStreamWaitEvent(st, ss->ev[4], 0));
-  }
-  return DAT_OK;
+  return DAT_OK;   // ~SideScope joins: the caller's stream owns every result again
 }
 
 }  // extern "C"

@@ -255,7 +255,11 @@ __host__ __device__ inline int persistent_gcols(int BN) { return BN % 64 == 0 ? 
 // Epilogue: 8 warps, two per TMEM lane quadrant, taking alternate column groups of a tile.  With four warps the
 // epilogue (TMEM -> +bias -> bf16 -> staged, coalesced stores) bounded every wide-N / small-K shape: switching it off
 // took the stage-1 fc1 GEMM from 33 to 12.5 us and the stage-2 one from 22.9 to 12.6 us.
-template <bool TF32, typename TOut>
+// BMN: the B operand is MN-major - a (K, N) row-major matrix, i.e. the weight W (N_fwd, K_fwd) itself when the
+// product is the data gradient dX = dY W: 64 x 64 TMA boxes (128B swizzle) are the canonical MN-major core-matrix
+// layout (8-row groups 1 KB apart, 64-column blocks 8 KB apart, gemm_tc_wgrad.cu), so no transposed copy of the
+// weight is ever made.  bf16 only, BN a multiple of 64.
+template <bool TF32, typename TOut, bool BMN = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -316,13 +320,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const bool second = kc >= k_chunks1;
           const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
           tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
-          tma_load_2d(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
+          if (BMN) {
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sB + s * b_stage_bytes + i * 8192, second ? &tmB2 : &tmB, &full[s], n0 + 64 * i, kcol);
+          } else {
+            tma_load_2d(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TC_BM, (uint32_t)BN);
+      const uint32_t idesc = make_instr_desc(TF32 ? FMT_TF32 : FMT_BF16, TC_BM, (uint32_t)BN, 0, BMN ? 1u : 0u);
       int it = 0, li = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
         const int buf = li & 1;
@@ -339,7 +348,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
           for (int k4 = 0; k4 < CHUNK_BYTES / 32; ++k4) {
             const uint64_t ad = make_smem_desc(a_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(b_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t bd = BMN ? make_smem_desc(b_addr + k4 * 2048, 8192, 1024, LAYOUT_SW128)
+                                    : make_smem_desc(b_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
             if (TF32) mma_tf32_ss(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
             else mma_bf16_ss(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
           }
@@ -452,6 +462,16 @@ __global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __res
   store4(out + (long long)blockIdx.y * n + i, load4(src + i));
 }
 
+// fp32 -> bf16 for a whole table of tensors in one launch (the bf16 operand copies of every 1x1-conv weight of a
+// model, once per step): blockIdx.y = table entry, blockIdx.x strides over its elements, 4 per thread.
+__global__ void cast_bf16_multi_kernel(const dat_cast_item* __restrict__ items) {
+  const dat_cast_item it = items[blockIdx.y];
+  const float* __restrict__ src = it.src;
+  bf16* __restrict__ dst = reinterpret_cast<bf16*>(it.dst);
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < it.n; i += (long long)gridDim.x * blockDim.x * 4)
+    store4(dst + i, load4(src + i));
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return e != nullptr && std::atoi(e) > 0 ? std::atoi(e) : dflt;
@@ -508,12 +528,33 @@ int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, voi
   return pointwise_fwd_tc_dual(X, W, nullptr, nullptr, x_dt, b, Y, y_dt, M, N, K, st);
 }
 
+int cast_bf16_multi(const dat_cast_item* items_dev, int n_items, cudaStream_t st) {
+  if (n_items <= 0) return DAT_OK;
+  dim3 grid(32, n_items);
+  cast_bf16_multi_kernel<<<grid, 256, 0, st>>>(items_dev);
+  DAT_LAUNCH_OK("cast_bf16_multi_kernel");
+  return DAT_OK;
+}
+
+// data gradient dX[M, K] = dY[M, N] W[N, K] (+ dY2 W2) with the bf16 weight read in place as an MN-major B operand
+bool pointwise_dgrad_tc_supported(long long M, int N, int K) {
+  return pointwise_fwd_tc_supported(DAT_BF16, M, K, N) && pick_bn(K) % 64 == 0 && K % 8 == 0;
+}
+int pointwise_dgrad_tc(const void* dY, const void* W, const void* dY2, const void* W2, void* dX, int dx_dt,
+                       long long M, int N, int K, cudaStream_t st) {
+  DAT_REQUIRE(pointwise_dgrad_tc_supported(M, N, K), "pointwise_dgrad_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
+  return pointwise_fwd_tc_dual(dY, W, dY2, W2, DAT_BF16, nullptr, dX, dx_dt, M, K, N, st, true);
+}
+
 // Y = X W^T (+ X2 W2^T) + b.  W: fp32 when x_dt == DAT_F32 (tf32 MMA), bf16 when x_dt == DAT_BF16.
+// w_mn: W (and W2) are (K, N) row-major bf16 matrices read as MN-major B operands (see the kernel's BMN flag).
 int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool w_mn) {
   DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
   const bool tf32 = x_dt == DAT_F32;
+  DAT_REQUIRE(!w_mn || (!tf32 && pick_bn(N) % 64 == 0 && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
+              "pointwise_fwd_tc: the MN-major weight operand needs bf16 and a tile width that is a multiple of 64");
   const int eb = tf32 ? 4 : 2;
   const int chunk_elems = CHUNK_BYTES / eb;
   const int BN = pick_bn(N);
@@ -521,12 +562,16 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   const int k_chunks = X2 != nullptr ? 2 * k_chunks1 : k_chunks1;
   CUtensorMap tmA, tmB, tmA2, tmB2;
   DAT_FWD(tc::make_tmap_2d(&tmA, X, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
-  DAT_FWD(tc::make_tmap_2d(&tmB, W, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
+  auto map_w = [&](CUtensorMap* tm, const void* w) -> int {
+    if (w_mn) return tc::make_tmap_2d(tm, w, 2, false, (uint64_t)K, (uint64_t)N, (uint64_t)N * 2, 64, 64, 128);
+    return tc::make_tmap_2d(tm, w, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128);
+  };
+  DAT_FWD(map_w(&tmB, W));
   tmA2 = tmA;
   tmB2 = tmB;
   if (X2 != nullptr) {
     DAT_FWD(tc::make_tmap_2d(&tmA2, X2, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
-    DAT_FWD(tc::make_tmap_2d(&tmB2, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN, chunk_elems, 128));
+    DAT_FWD(map_w(&tmB2, W2));
   }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
   if (std::getenv("DAT_B200_GEMM_LEGACY") == nullptr) {
@@ -542,17 +587,19 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     while (tmem_cols < 2 * BN) tmem_cols <<= 1;
     const int m_tiles = (int)ceil_div(M, (long long)TC_BM), total = m_tiles * (N / BN);
     const int grid = total < 148 ? total : 148;
-#define LAUNCH_P(TF, TO)                                                                          \
+#define LAUNCH_P(TF, TO, MN)                                                                      \
   do {                                                                                            \
-    auto kern = gemm_tc_persistent_kernel<TF, TO>;                                                \
+    auto kern = gemm_tc_persistent_kernel<TF, TO, MN>;                                            \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, TCP_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,     \
                                          k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch); \
   } while (0)
-    if (tf32 && y_dt == DAT_F32) LAUNCH_P(true, float);
-    else if (tf32) LAUNCH_P(true, bf16);
-    else if (y_dt == DAT_F32) LAUNCH_P(false, float);
-    else LAUNCH_P(false, bf16);
+    if (w_mn && y_dt == DAT_F32) LAUNCH_P(false, float, true);
+    else if (w_mn) LAUNCH_P(false, bf16, true);
+    else if (tf32 && y_dt == DAT_F32) LAUNCH_P(true, float, false);
+    else if (tf32) LAUNCH_P(true, bf16, false);
+    else if (y_dt == DAT_F32) LAUNCH_P(false, float, false);
+    else LAUNCH_P(false, bf16, false);
 #undef LAUNCH_P
     DAT_LAUNCH_OK("gemm_tc_persistent_kernel");
     return DAT_OK;

@@ -89,7 +89,12 @@ int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w
                                 void* out, int C, cudaStream_t st);
 int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
-                          cudaStream_t st);
+                          cudaStream_t st, bool w_mn = false);
+// dX[M, K] = dY[M, N] W[N, K] (+ dY2 W2): the bf16 weight is read in place as an MN-major operand (no transpose)
+bool pointwise_dgrad_tc_supported(long long M, int N, int K);
+int pointwise_dgrad_tc(const void* dY, const void* W, const void* dY2, const void* W2, void* dX, int dx_dt,
+                       long long M, int N, int K, cudaStream_t st);
+int cast_bf16_multi(const dat_cast_item* items_dev, int n_items, cudaStream_t st);
 }  // namespace dat
 
 namespace dat {
@@ -189,5 +194,7 @@ int logcpb_bias_bwd(const Shape& s, const float* dbias, const float* pos, const 
 namespace dat {
 // rpe_table_grad.cu - d rpe_table from the streamed dS as per-sample tensor-core GEMMs (mma.sync)
 bool rpe_table_grad_mma_supported(const Shape& s);
-int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, cudaStream_t st);
+size_t rpe_table_grad_mma_workspace(const Shape& s);
+int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
 }  // namespace dat

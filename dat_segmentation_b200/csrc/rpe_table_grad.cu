@@ -50,7 +50,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 // samples; 2: up to 2 NW tiles)
 template <int TPW, int NT>
 __global__ void __launch_bounds__(NT)
-rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos, float* __restrict__ d_table,
+rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos, float* __restrict__ part,
                       TgArgs a) {
   constexpr int NW = NT / 32;
   __shared__ float s_bx[TG_MAXN], s_by[TG_MAXN];                // (1 - pos) * k of the staged samples
@@ -215,31 +215,58 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
       }
     }
   }
-  // CTA reduction of the tile accumulators in shared memory, then one global atomic per touched cell
+  // CTA reduction of the tile accumulators in shared memory in a fixed order (warps that share a tile add
+  // their sample phases one after the other; within a phase every cell has exactly one owner), then the
+  // CTA's partial table goes to its own slot of `part`; tg_reduce_kernel sums the slots in a fixed order.
+  // No atomics anywhere: d rpe_table is bit-reproducible.
   __syncthreads();
   for (int i = threadIdx.x; i < a.Th * a.Tw; i += NT) sred[i] = 0.f;
   __syncthreads();
+  for (int ph = 0; ph < n_step; ++ph) {
+    if (ph == n_phase) {
 #pragma unroll
-  for (int ti = 0; ti < TPW; ++ti) {
-    if (my_tile[ti] >= a.ntiles) continue;
-    const int x0 = (my_tile[ti] % a.tiles_x) * TG_TILE, y0 = (my_tile[ti] / a.tiles_x) * TG_TILE;
+      for (int ti = 0; ti < TPW; ++ti) {
+        if (my_tile[ti] >= a.ntiles) continue;
+        const int x0 = (my_tile[ti] % a.tiles_x) * TG_TILE, y0 = (my_tile[ti] / a.tiles_x) * TG_TILE;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int yt = 0; yt < 4; ++yt)
+          for (int yt = 0; yt < 4; ++yt)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int x = x0 + mt * 16 + gq + (q >> 1) * 8, y = y0 + yt * 8 + 2 * t + (q & 1);
-          const float v = acc[ti][mt][yt][q];
-          if (x < a.Tw && y < a.Th && v != 0.f) atomicAdd(&sred[y * a.Tw + x], v);
-        }
+            for (int q = 0; q < 4; ++q) {
+              const int x = x0 + mt * 16 + gq + (q >> 1) * 8, y = y0 + yt * 8 + 2 * t + (q & 1);
+              if (x < a.Tw && y < a.Th) sred[y * a.Tw + x] += acc[ti][mt][yt][q];
+            }
+      }
+    }
+    if (n_step > 1) __syncthreads();
   }
   __syncthreads();
-  float* dt_g = d_table + (long long)eta * a.Th * a.Tw;
-  for (int i = threadIdx.x; i < a.Th * a.Tw; i += NT) {
-    const float v = sred[i];
-    if (v != 0.f) atomicAdd(dt_g + i, v);
+  const long long slot = ((long long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  float* dst = part + (slot * a.heads + eta) * (long long)(a.Th * a.Tw);
+  for (int i = threadIdx.x; i < a.Th * a.Tw; i += NT) dst[i] = sred[i];
+}
+
+// out[i] = sum_z part[z][i] in a fixed order: thread (e, zy) sums the slots z = zy, zy + 4, ... (4 loads in
+// flight), the four partial sums are combined in shared memory in ascending zy.
+__global__ void __launch_bounds__(256)
+tg_reduce_kernel(const float* __restrict__ part, int nslots, int count, float* __restrict__ out) {
+  __shared__ float red[4][64];
+  const int e = blockIdx.x * 64 + (threadIdx.x & 63), zy = threadIdx.x >> 6;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (e < count) {
+    int z = zy;
+    for (; z + 12 < nslots; z += 16) {
+      s0 += part[(long long)z * count + e];
+      s1 += part[(long long)(z + 4) * count + e];
+      s2 += part[(long long)(z + 8) * count + e];
+      s3 += part[(long long)(z + 12) * count + e];
+    }
+    for (; z < nslots; z += 4) s0 += part[(long long)z * count + e];
   }
+  red[zy][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (zy == 0 && e < count) out[e] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
 struct TgPlan {
@@ -299,23 +326,35 @@ bool rpe_table_grad_mma_supported(const Shape& s) {
   return s.pe_mode == DAT_PE_RPE && make_plan(s, &p);
 }
 
-// d_table (heads, Th, Tw) fp32 is overwritten.  ds: bf16 [B * heads][Ns / 8][HW][8].
-int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, cudaStream_t st) {
+size_t rpe_table_grad_mma_workspace(const Shape& s) {
+  TgPlan p;
+  if (s.pe_mode != DAT_PE_RPE || !make_plan(s, &p)) return 0;
+  return align_up((size_t)p.grid.x * p.grid.y * s.B * s.heads * s.Th * s.Tw * 4, 256);
+}
+
+// d_table (heads, Th, Tw) fp32 is overwritten.  ds: bf16 [B * heads][Ns / 8][HW][8].  ws: one partial table per
+// CTA (rpe_table_grad_mma_workspace bytes), summed in a fixed order by tg_reduce_kernel (deterministic).
+int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
   TgPlan p;
   DAT_REQUIRE(make_plan(s, &p), "rpe_table_grad_mma: unsupported shape");
-  DAT_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
+  DAT_REQUIRE(ws != nullptr && ws_bytes >= rpe_table_grad_mma_workspace(s), "rpe_table_grad_mma: workspace too small");
 #define TG_LAUNCH(TPWV, NTV)                                                                                          \
   do {                                                                                                                \
     auto kern = rpe_table_grad_kernel<TPWV, NTV>;                                                                     \
     if (p.smem > 40 * 1024)   /* + 512 B static: stay clear of the 48 KB default limit */                           \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));              \
-    kern<<<p.grid, NTV, p.smem, st>>>((const bf16*)ds, pos, d_table, p.a);                                            \
+    kern<<<p.grid, NTV, p.smem, st>>>((const bf16*)ds, pos, (float*)ws, p.a);                                         \
   } while (0)
   if (p.threads == 256) TG_LAUNCH(1, 256);
   else if (p.tpw == 1) TG_LAUNCH(1, 512);
   else TG_LAUNCH(2, 512);
 #undef TG_LAUNCH
   DAT_LAUNCH_OK("rpe_table_grad_kernel");
+  const int count = s.heads * s.Th * s.Tw;
+  const int nslots = (int)(p.grid.x * p.grid.y) * s.B;
+  tg_reduce_kernel<<<ceil_div(count, 64), 256, 0, st>>>((const float*)ws, nslots, count, d_table);
+  DAT_LAUNCH_OK("tg_reduce_kernel");
   return DAT_OK;
 }
 

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from .weights import cached_bf16
 
 __all__ = ["DAttentionBaseline", "LayerNormProxy"]
 
@@ -86,6 +87,9 @@ class _BlockFn(torch.autograd.Function):
                      e(B, H * W, Cc), e(B, meta["n_heads"], H * W, dt=f32)]
             y_l = e(B, H, W, Cc)
             pstruct = _fill_struct(_cabi.BlockParams(), _cabi.PARAM_FIELDS, p32)
+            w_bf = meta.get("w_bf16") if act == torch.bfloat16 else None
+            if w_bf is not None:      # the step's bf16 operand copies of proj_q / k / v / out (weights.py)
+                _fill_struct(pstruct, _cabi.BF16_FIELDS, w_bf)
             sstruct = _fill_struct(_cabi.BlockSaved(), _cabi.SAVED_FIELDS, saved)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             nbytes = lib.dat_block_fwd_workspace_bytes(C.byref(desc))
@@ -94,6 +98,7 @@ class _BlockFn(torch.autograd.Function):
                                               C.byref(sstruct), _ptr(ws), nbytes, stream),
                         "dat_block_forward")
         ctx.meta = meta
+        ctx.w_bf = w_bf
         ctx.desc = desc
         ctx.param_dtypes = [p.dtype if p is not None else None for p in params]
         ctx.present = [p is not None for p in params]
@@ -121,6 +126,8 @@ class _BlockFn(torch.autograd.Function):
             nbytes = lib.dat_block_bwd_workspace_bytes(C.byref(desc))
             ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
             pstruct = _fill_struct(_cabi.BlockParams(), _cabi.PARAM_FIELDS, p32)
+            if ctx.w_bf is not None:
+                _fill_struct(pstruct, _cabi.BF16_FIELDS, ctx.w_bf)
             gstruct = _fill_struct(_cabi.BlockGrads(), _cabi.PARAM_FIELDS, grads)
             sstruct = _fill_struct(_cabi.BlockSaved(), _cabi.SAVED_FIELDS, saved)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -236,6 +243,10 @@ class DAttentionBaseline(nn.Module):
                     ksize=self.ksize, table_h=self.rpe_table.shape[1] if has_table else 1,
                     table_w=self.rpe_table.shape[2] if has_table else 1,
                     orf=self.offset_range_factor, act_dtype=act, pe_mode=self.pe_mode, no_off=bool(self.no_off))
+        if act == torch.bfloat16:
+            w_bf = [cached_bf16(m) for m in (self.proj_q, self.proj_k, self.proj_v, self.proj_out)]
+            if all(w is not None for w in w_bf):
+                meta["w_bf16"] = w_bf
         y_l, pos = _BlockFn.apply(x_l, meta, *self._params())
         y = y_l.permute(0, 3, 1, 2)
         if not self.return_pos_ref:

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from ._streams import hold_until_join, serial as _serial, side_stream
+from ._streams import grads_consumed_at_end_only, hold_until_join, serial as _serial, side_stream
 
 __all__ = ["dwconv_cl", "DepthwiseConvCL"]
 
@@ -50,6 +50,7 @@ class _DwConvFn(torch.autograd.Function):
         ctx.save_for_backward(x_l, w32, z)
         ctx.mode, ctx.has_bias = mode, bias is not None
         ctx.wdtype = weight.dtype
+        ctx.param_refs = (weight, bias)
         return y
 
     @staticmethod
@@ -107,6 +108,8 @@ class _DwConvFn(torch.autograd.Function):
                                            _CODE[dx.dtype], B, H, W, Cc, k,
                                            MODE_PLAIN if mode == MODE_PLAIN else MODE_RESIDUAL, 1, _ptr(ws),
                                            nbytes, st), "dat_dwconv_fwd(dgrad)")
+            if wst is not cur and not grads_consumed_at_end_only(*ctx.param_refs):
+                cur.wait_stream(wst)   # dw / db are consumed right after this node: complete them first
         return dx, dw, db, None, None
 
 

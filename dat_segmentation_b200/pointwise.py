@@ -10,13 +10,15 @@ Shapes the kernels cannot tile, fp32 (non-autocast) execution and CPU tensors us
 convolution (`F.conv2d`) — this module is a "next row" outside the parity-critical block.
 """
 import ctypes as C
+import os as _os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _cabi
-from ._streams import hold_until_join, serial as _serial, side_stream
+from ._streams import grads_consumed_at_end_only, hold_until_join, serial as _serial, side_stream
+from .weights import cached_bf16
 
 __all__ = ["PointwiseConvCL"]
 
@@ -39,10 +41,11 @@ def _supported(M, N, K):
 
 
 class _PointwiseFn(torch.autograd.Function):
-    """x_l (M, K) contiguous (fp32 or bf16) -> y (M, N) bf16."""
+    """x_l (M, K) contiguous (fp32 or bf16) -> y (M, N) bf16.  `w_bf`: the step's bf16 copy of the weight
+    (weights.Bf16WeightCache) or None (cast here)."""
 
     @staticmethod
-    def forward(ctx, x_l, weight, bias):
+    def forward(ctx, x_l, weight, bias, w_bf):
         lib = _cabi.lib()
         M, K = x_l.shape
         N = weight.shape[0]
@@ -53,13 +56,17 @@ class _PointwiseFn(torch.autograd.Function):
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             if x_l.dtype == torch.float32:
                 w_op = w32                                   # tf32 MMA on the fp32 operands
+            elif w_bf is not None:
+                w_op = w_bf
             else:
-                w_op = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+                w_op = w_bf = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
                 _cabi.check(lib.dat_cast_bf16(_ptr(w32), _ptr(w_op), N * K, _stream(dev)), "dat_cast_bf16")
             _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(x_l), _CODE[x_l.dtype], _ptr(w_op), _ptr(b32), _ptr(y),
                                                  _cabi.DAT_BF16, M, N, K, _stream(dev)), "dat_pointwise_fwd_tc")
         ctx.save_for_backward(x_l, w32)
+        ctx.w_bf = w_bf               # bf16 (N, K) copy, re-used by the data gradient (None: made in backward)
         ctx.has_bias, ctx.wdtype, ctx.wshape = bias is not None, weight.dtype, weight.shape
+        ctx.param_refs = (weight, bias)   # backward only inspects .grad / hooks (see _streams.grads_consumed_at_end_only)
         return y
 
     @staticmethod
@@ -95,14 +102,26 @@ class _PointwiseFn(torch.autograd.Function):
                 db = db.to(ctx.wdtype) if db is not None else None
             if not serial:
                 hold_until_join(dy, x_l, xb, ws)   # what the side stream reads stays alive until the join
-            # dX = dY W: K-major GEMM against W^T (K, N) in bf16, on the current stream
+            early_join = not serial and not grads_consumed_at_end_only(*ctx.param_refs)
+            # dX = dY W on the current stream: the bf16 weight copy is read in place as an MN-major operand;
+            # widths without a 64-multiple tile use a K-major product against a transposed copy
             st = _stream(dev)
-            wT = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
-            _cabi.check(lib.dat_cast_transpose_bf16(_ptr(w32), _ptr(wT), N, K, st), "dat_cast_transpose_bf16")
             dx = torch.empty_like(x_l)
-            _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(dy), _cabi.DAT_BF16, _ptr(wT), None, _ptr(dx),
-                                                 _CODE[dx.dtype], M, K, N, st), "dat_pointwise_fwd_tc(dgrad)")
-        return dx, dw, db
+            if K % 64 == 0 and not _os.environ.get("DAT_B200_DGRAD_TRANSPOSE"):
+                w_bf = ctx.w_bf
+                if w_bf is None:
+                    w_bf = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+                    _cabi.check(lib.dat_cast_bf16(_ptr(w32), _ptr(w_bf), N * K, st), "dat_cast_bf16")
+                _cabi.check(lib.dat_pointwise_dgrad_tc(_ptr(dy), _ptr(w_bf), _ptr(dx), _CODE[dx.dtype], M, N, K, st),
+                            "dat_pointwise_dgrad_tc")
+            else:
+                wT = torch.empty(K, N, device=dev, dtype=torch.bfloat16)
+                _cabi.check(lib.dat_cast_transpose_bf16(_ptr(w32), _ptr(wT), N, K, st), "dat_cast_transpose_bf16")
+                _cabi.check(lib.dat_pointwise_fwd_tc(_ptr(dy), _cabi.DAT_BF16, _ptr(wT), None, _ptr(dx),
+                                                     _CODE[dx.dtype], M, K, N, st), "dat_pointwise_fwd_tc(dgrad)")
+            if early_join:      # dw / db are consumed right after this node (accumulation, hooks): complete them first
+                cur.wait_stream(wst)
+        return dx, dw, db, None
 
 
 class PointwiseConvCL(nn.Conv2d):
@@ -122,5 +141,5 @@ class PointwiseConvCL(nn.Conv2d):
         x_l = x.permute(0, 2, 3, 1)
         if not x_l.is_contiguous():
             x_l = x_l.contiguous()
-        y = _PointwiseFn.apply(x_l.reshape(B * H * W, K), self.weight, self.bias)
+        y = _PointwiseFn.apply(x_l.reshape(B * H * W, K), self.weight, self.bias, cached_bf16(self))
         return y.reshape(B, H, W, N).permute(0, 3, 1, 2)

@@ -15,7 +15,17 @@
  *     (CUDA-graph capturable; no host synchronisation inside).
  *   - Return value: DAT_OK (0) or a negative DAT_ERR_* code; never aborts.
  *     `dat_last_error()` returns a static, thread-local message for the last failure.
- *   - Re-entrant; no global mutable state.
+ *   - Re-entrant.  Global state: a launch counter (statistics) and, per device, ONE lazily
+ *     created side stream with its events, used only inside dat_block_backward (weight /
+ *     table gradients run next to the data-gradient chain) under a per-device mutex and
+ *     joined back into `stream` before the call returns, on every exit path.
+ *     DAT_B200_SERIAL_WGRAD=1 disables it.
+ *   - Determinism: every reduction of the bf16 tensor-core path (the path bench.py times)
+ *     has a fixed order, including d rpe_table (per-CTA partial tables + ordered sum): two
+ *     runs give bit-identical outputs and gradients.  The fp32 / generic-shape CUDA-core
+ *     attention backward and the in-kernel table scatter (DAT_B200_TABLE_SCATTER=1, maps
+ *     the GEMM form does not cover) accumulate d rpe_table with fp32 atomics: those values
+ *     can differ in the last bits from run to run.
  *   - dtype codes: DAT_F32 = 0, DAT_BF16 = 1.  Parameters and all gradients of
  *     parameters are fp32.  pos / lse / offsets are always fp32.
  */
@@ -81,6 +91,10 @@ typedef struct dat_block_params {
                               LOGCPB: rpe_table.0.weight (32, 2); NONE: ignored (may be NULL)               */
   const float* pe_b;       /* DWC: rpe_table.bias (C); LOGCPB: rpe_table.0.bias (32); else ignored          */
   const float* pe_w2;      /* LOGCPB: rpe_table.2.weight (hg, 32); else ignored                             */
+  /* Optional (may be NULL; bf16 activations only): bf16 copies (C, C) of proj_q / proj_k / proj_v / proj_out
+   * .weight made by the caller once per step (dat_cast_bf16_multi).  The forward reads them as K-major and the
+   * backward as MN-major tensor-core operands; when NULL the library casts into its workspace per call. */
+  const void* wq_bf16; const void* wk_bf16; const void* wv_bf16; const void* wo_bf16;
 } dat_block_params;
 
 /* Gradients of the same 14 tensors (fp32, OVERWRITTEN, not accumulated). */
@@ -167,11 +181,24 @@ int dat_cast_transpose_bf16(const float* w, void* out, int32_t N, int32_t K, voi
 size_t dat_pointwise_wgrad_tc_workspace_bytes(int64_t M, int32_t N, int32_t K);
 int dat_pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, int64_t M, int32_t N,
                            int32_t K, void* workspace, size_t workspace_bytes, void* stream);
+/* Data gradient with the weight read in place: dX[M,K] (dx_dtype) = dY[M,N] W[N,K], dY and W bf16.  W is the
+ * SAME bf16 copy the forward used (dat_cast_bf16): the tensor core takes it as an MN-major operand, so no
+ * transposed copy exists.  DAT_ERR_UNSUPPORTED when K has no tile width that is a multiple of 64. */
+int dat_pointwise_dgrad_tc(const void* dY, const void* W, void* dX, int32_t dx_dtype, int64_t M, int32_t N,
+                           int32_t K, void* stream);
 /* workspace >= 64 * N * 4 bytes */
 int dat_bias_grad(const void* dY, int32_t dy_dtype, float* db, int64_t M, int32_t N, void* workspace,
                   size_t workspace_bytes, void* stream);
 /* fp32 -> bf16 copy of n elements (n % 4 == 0), used for the weight operands above. */
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* The same for a whole table of tensors in ONE launch (every 1x1-conv weight of a model, once per step).
+ * `items` is a DEVICE array of n_items entries; every n is a multiple of 4, pointers 16-byte aligned. */
+typedef struct dat_cast_item {
+  const float* src;
+  void* dst;        /* bf16 */
+  int64_t n;
+} dat_cast_item;
+int dat_cast_bf16_multi(const dat_cast_item* items, int32_t n_items, void* stream);
 
 /* Offset network + reference points + range/clamp → pos
  * (dat_blocks.py:144-162 and _get_ref_points :108-121).
