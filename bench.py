@@ -218,6 +218,162 @@ def kernel_roofline(dev, pk):
 
 # --------------------------------------------------------------------------------------
 
+class TrainStep:
+    """The benchmarked step: DAT-T++ backbone fwd+bwd at 512x512, bf16 autocast, train mode, the whole fwd+bwd
+    captured once in a CUDA graph on a high-priority stream (weight- / table-gradient branches on side streams) and
+    replayed.  tests/test_bench_step.py drives exactly this object (graph replay vs serial eager, determinism,
+    oracle parity), so what is timed is what is tested."""
+
+    def __init__(self, dev, world=1, rank=0, batch=PER_GPU_BATCH, img=IMG, graph=True, cfg=None, seed=0,
+                 fixed_drop_path=None, buckets=None):
+        from dat_segmentation_b200 import _cabi
+        from dat_segmentation_b200.backbone import build_dat
+        self.dev, self.world, self.rank, self.batch = dev, world, rank, batch
+        self.lib = _cabi.lib()
+        torch.manual_seed(seed)
+        self.model = build_dat(cfg).to(dev).train()          # drop_path_rate 0.3 as in the shipped config
+        if fixed_drop_path is not None:                      # tests: the same stochastic-depth masks in every run
+            g = torch.Generator(device="cpu").manual_seed(fixed_drop_path)
+            for st in self.model.stages:
+                st.fix_drop_path_scales(batch, g, dev)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        # N > 1: the step's gradients are packed into flat fp32 buckets (multi-tensor copies inside the graph) that
+        # are all-reduced over NCCL; see `step()`
+        self.flat, self.bucket_slices, self.overlap = None, [], False
+        if world > 1:
+            self._make_buckets(buckets)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.imgs = torch.randn(batch, 3, img, img, device=dev, generator=gen)   # static step input
+        self.graph, self.static_loss = None, None
+        self.use_graph = graph
+        self.launches_per_step = 0
+
+    # Gradient buckets in backward order (stage 3 first): bucket i is all-reduced on a communication stream while
+    # the backward of the earlier stages still runs.  Stage 2 (18 of the 28 blocks) is split in two.
+    @staticmethod
+    def _bucket_key(name):
+        import re
+        m = re.match(r"(stages|norms)\.(\d)\.", name)
+        if m:
+            i = int(m.group(2))
+            if i == 2 and m.group(1) == "stages":
+                d = re.search(r"\.(\d+)\.", name[len("stages.2."):] + ".")
+                blk = int(d.group(1)) if d else 0
+                # layer_norms / layer_scales are indexed by 2d, 2d+1; every other list by d
+                if ".layer_norms." in name or ".layer_scales." in name:
+                    blk //= 2
+                return (2, 1 if blk >= 9 else 0)
+            return (i, 0) if i >= 2 else (1, 0)
+        m = re.match(r"down_projs\.(\d)\.", name)
+        if m:   # down_projs[i] feeds stage i + 1: its gradient arrives after that stage's backward
+            i = int(m.group(1)) + 1
+            return (i, 0) if i >= 2 else (1, 0)
+        return (1, 0)    # stem, stages 0-1: the tail of the backward
+
+    def _make_buckets(self, buckets):
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.dev)
+        groups = {}
+        for name, p in self.model.named_parameters():
+            if p.requires_grad:
+                groups.setdefault(self._bucket_key(name), []).append(p)
+        order = sorted(groups, reverse=True)                 # produced first in the backward -> first in the buffer
+        off = 0
+        self.bucket_params, self.bucket_views = [], []
+        for key in order:
+            start, views = off, []
+            for p in groups[key]:
+                views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self.bucket_slices.append((start, off))
+            self.bucket_params.append(groups[key])
+            self.bucket_views.append(views)
+        assert off == n
+        self.overlap = os.environ.get("DAT_B200_BENCH_OVERLAP", "1") != "0"
+        if self.overlap:
+            from dat_segmentation_b200 import _streams
+            self.comm = torch.cuda.Stream(self.dev)
+            self._pending = [0] * len(order)
+            for bi, plist in enumerate(self.bucket_params):
+                for p in plist:
+                    p.register_post_accumulate_grad_hook(lambda _p, bi=bi: self._grad_ready(bi))
+            # the hooks below order the communication stream after the weight-gradient side stream themselves
+            _streams.HOOKS_SYNC_THEMSELVES[0] = True
+
+    def _grad_ready(self, bi):
+        """Post-accumulate-grad hook: when the last gradient of bucket `bi` exists, pack the bucket and all-reduce it
+        on the communication stream (ordered after the current stream and the weight-gradient side stream).  Under
+        graph capture these become parallel branches of the step's graph."""
+        import torch.distributed as dist
+        from dat_segmentation_b200 import _streams
+        self._pending[bi] += 1
+        if self._pending[bi] < len(self.bucket_params[bi]):
+            return
+        self._pending[bi] = 0
+        cur = torch.cuda.current_stream(self.dev)
+        self.comm.wait_stream(cur)
+        side = _streams.existing_side_stream(self.dev)
+        if side is not None:
+            self.comm.wait_stream(side)
+        with torch.cuda.stream(self.comm):
+            torch._foreach_copy_(self.bucket_views[bi], [p.grad for p in self.bucket_params[bi]])
+            lo, hi = self.bucket_slices[bi]
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
+
+    def fwd_bwd(self):
+        for p in self.params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = self.model(self.imgs)
+        loss = loss_of(outs)
+        loss.backward()
+        if self.world > 1:
+            if self.overlap:
+                torch.cuda.current_stream(self.dev).wait_stream(self.comm)   # join: flat holds the averaged gradients
+            else:
+                for views, plist in zip(self.bucket_views, self.bucket_params):
+                    torch._foreach_copy_(views, [p.grad for p in plist])
+        return loss
+
+    def warm_and_capture(self, warmup):
+        dev = self.dev
+        n0 = self.lib.dat_launch_count()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.fwd_bwd()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.launches_per_step = (self.lib.dat_launch_count() - n0) // max(warmup, 1)
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            # The critical chain is captured on a high-priority stream; the weight-gradient / table-gradient branches
+            # run on default-priority side streams (library-owned and _streams.py), so when both have a kernel ready
+            # the block scheduler serves the critical chain first (kernel nodes keep their stream's priority).
+            prio = os.environ.get("DAT_B200_BENCH_PRIORITY", "-1")
+            cap_stream = torch.cuda.Stream(dev, priority=int(prio)) if prio != "none" else None
+            with torch.cuda.graph(self.graph, stream=cap_stream):
+                self.static_loss = self.fwd_bwd()
+
+    def step(self):
+        import torch.distributed as dist
+        loss = self.static_loss
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            loss = self.fwd_bwd()
+        if self.world > 1 and not self.overlap:   # the one exchange step of data-parallel training (new_train.py:116)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        return loss
+
+    def release(self):
+        """Destroy the captured graph before the process group (a graph that holds NCCL work keeps the
+        communicator busy at teardown)."""
+        self.graph = None
+        self.static_loss = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,8 +387,6 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from dat_segmentation_b200 import _cabi
-    from dat_segmentation_b200.backbone import build_dat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,79 +397,32 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.pop("NCCL_P2P_DISABLE", None)   # the reference's launch scripts set it; NVSwitch wants P2P
-        dist.init_process_group("nccl", device_id=dev)
+        # The bucketed all-reduces run next to the backward (TrainStep._grad_ready): cap the CTAs NCCL may take from
+        # it.  NVSwitch cost is latency- not link-bound at these sizes, a handful of CTAs carries a bucket.
+        pg_opts = None
+        max_ctas = int(os.environ.get("DAT_B200_NCCL_MAX_CTAS", "8"))
+        if max_ctas > 0 and hasattr(dist, "ProcessGroupNCCL"):
+            pg_opts = dist.ProcessGroupNCCL.Options()
+            pg_opts.config.max_ctas = max_ctas
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
         # this script joins the weight-gradient side stream itself (end of backward()) before it packs and all-reduces
         # the gradients, so the side stream stays on although a process group exists (no DDP hooks here)
         from dat_segmentation_b200 import _streams
         _streams.ALLOW_WITH_PROCESS_GROUP[0] = True
-    lib = _cabi.lib()
     warmup = max(3, args.warmup)
 
-    torch.manual_seed(0)
-    model = build_dat().to(dev).train()          # drop_path_rate 0.3 as in the shipped config
-    params = [p for p in model.parameters() if p.requires_grad]
-    # N > 1: the step's gradients are packed into one flat fp32 buffer (multi-tensor copy) and
-    # all-reduced with ONE NCCL call.  Autograd assigns fresh gradients every step (no accumulation
-    # pass into pre-zeroed buffers).
-    flat, views = None, []
-    if world > 1:
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
-        off = 0
-        for p in params:
-            views.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev, generator=gen)   # static step input
+    ts = TrainStep(dev, world, rank, graph=not args.no_graph)
+    imgs = ts.imgs
     host = torch.randn(PER_GPU_BATCH, 3, IMG, IMG).pin_memory()
-
-    def fwd_bwd():
-        for p in params:
-            p.grad = None
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            outs = model(imgs)
-        loss = loss_of(outs)
-        loss.backward()
-        if world > 1:
-            torch._foreach_copy_(views, [p.grad for p in params])
-        return loss
-
-    # The whole fwd+bwd is captured once in a CUDA graph (shapes are static) and replayed: the
-    # ~2000 launches of a step cost one graph launch.  --no-graph runs the same function eagerly.
-    graph, static_loss = None, None
-    n0 = lib.dat_launch_count()
-    side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for _ in range(warmup):
-            fwd_bwd()
-    torch.cuda.current_stream(dev).wait_stream(side)
-    torch.cuda.synchronize(dev)
-    launches_per_step = (lib.dat_launch_count() - n0) // warmup
-    if not args.no_graph:
-        graph = torch.cuda.CUDAGraph()
-        # The critical chain is captured on a high-priority stream; the weight-gradient / table-gradient branches run
-        # on default-priority side streams (library-owned and _streams.py), so when both have a kernel ready the
-        # block scheduler serves the critical chain first (kernel nodes keep their stream's priority).
-        prio = os.environ.get("DAT_B200_BENCH_PRIORITY", "-1")
-        cap_stream = torch.cuda.Stream(dev, priority=int(prio)) if prio != "none" else None
-        with torch.cuda.graph(graph, stream=cap_stream):
-            static_loss = fwd_bwd()
-
-    def step():
-        loss = static_loss
-        if graph is not None:
-            graph.replay()
-        else:
-            loss = fwd_bwd()
-        if world > 1:      # the one exchange step of data-parallel training (new_train.py:116)
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        return loss
+    ts.warm_and_capture(warmup)
+    launches_per_step = ts.launches_per_step
+    graph = ts.graph
+    step = ts.step
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-
     for _ in range(warmup):
         step()
     sync_all()
@@ -378,7 +485,9 @@ def main():
                        "implementation": "deformable-attention blocks, LayerNorms, residual/drop-path, MLP 1x1 convs and "
                                          "depthwise convs in dat_b200 kernels; conv stem / down-projections in library ops",
                        "per_gpu_batch": PER_GPU_BATCH, "global_batch": total,
-                       "parallelism": f"dp{world} (batch-sharded, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (batch-sharded; NCCL gradient all-reduce in {len(ts.bucket_slices)} buckets "
+                                       f"{'overlapped with the backward inside the captured step' if ts.overlap else 'after the step'})"
+                                       if world > 1 else "single GPU"),
                        "l2": "working set per step >> 126 MB L2 (no flush needed); roofline leg flushes L2 per launch",
                        "cuda_graph": graph is not None,
                        "drop_path_rate": 0.3},
@@ -393,6 +502,9 @@ def main():
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"],
                                     "kind": "port", "sample": r["sample"]}
         print(json.dumps(line), flush=True)
+    ts.release()
+    del graph, step
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.destroy_process_group()
 

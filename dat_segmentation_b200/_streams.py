@@ -21,6 +21,11 @@ _JOIN_QUEUED = [False]
 ALLOW_WITH_PROCESS_GROUP = [False]
 
 
+# Set by a caller whose gradient hooks order themselves after the side stream (bench.py's bucketed all-reduce waits
+# for `existing_side_stream()` before it reads a gradient): such hooks do not force the early join.
+HOOKS_SYNC_THEMSELVES = [False]
+
+
 def _process_group_initialised():
     return torch.distributed.is_available() and torch.distributed.is_initialized()
 
@@ -43,7 +48,8 @@ def grads_consumed_at_end_only(*params):
             continue
         if not isinstance(p, torch.Tensor) or not p.is_leaf or p.grad is not None:
             return False
-        if getattr(p, "_backward_hooks", None) or getattr(p, "_post_accumulate_grad_hooks", None):
+        if not HOOKS_SYNC_THEMSELVES[0] and (getattr(p, "_backward_hooks", None)
+                                             or getattr(p, "_post_accumulate_grad_hooks", None)):
             return False
     return True
 
@@ -53,6 +59,12 @@ def side_stream(dev):
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(dev)
     return _SIDE[key]
+
+
+def existing_side_stream(dev):
+    """The side stream of `dev` if one has been created (None otherwise)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _SIDE.get(key)
 
 
 def _join_side_streams():

@@ -169,7 +169,11 @@ class TransformerStage(nn.Module):
         ps = []
         for d in range(self.depths):
             ps += [getattr(self.drop_path[d], "p", 0.0)] * (1 if self.stage_spec[d] == "X" else 2)
-        if self.training and any(q > 0.0 for q in ps):
+        fixed = getattr(self, "_fixed_scales", None)
+        if self.training and fixed is not None:        # tests: pre-drawn masks (fix_drop_path_scales)
+            assert fixed.shape == (len(ps), B), (fixed.shape, len(ps), B)
+            scales = fixed
+        elif self.training and any(q > 0.0 for q in ps):
             keep = self._keep_probs(ps, x.device)
             scales = (torch.rand(len(ps), B, device=x.device) < keep).float() / keep
         else:
@@ -193,6 +197,27 @@ class TransformerStage(nn.Module):
                 x = scale_residual(self.layer_scales[2 * d + 1](m), x, scales[si + 1])
                 si += 2
         return x
+
+    def drop_path_calls(self):
+        """Drop probability of every drop_path call of one forward, in call order ('X': one call, 'D': two)."""
+        ps = []
+        for d in range(self.depths):
+            ps += [getattr(self.drop_path[d], "p", 0.0)] * (1 if self.stage_spec[d] == "X" else 2)
+        return ps
+
+    def fix_drop_path_scales(self, batch, generator=None, device=None):
+        """Testing hook: draw the stochastic-depth scales (mask / keep_prob, one row per drop_path call) once and
+        re-use them in every training forward, so that two runs (eager / graph replay / another implementation)
+        see the same masks.  `batch=None` switches back to a fresh draw per forward.  Returns the (calls, batch)
+        tensor."""
+        if batch is None:
+            self._fixed_scales = None
+            return None
+        ps = self.drop_path_calls()
+        keep = torch.tensor([1.0 - q for q in ps]).view(-1, 1)
+        scales = (torch.rand(len(ps), batch, generator=generator) < keep).float() / keep
+        self._fixed_scales = scales.to(device) if device is not None else scales
+        return self._fixed_scales
 
     def _keep_probs(self, ps, device):
         key = (tuple(ps), str(device))
