@@ -21,6 +21,8 @@
 //  * scale * log2(e) is folded into the S -> exp2 FMA; normalisation is deferred to O.
 // No score / bias / displacement tensor ever reaches HBM: algorithmic bytes per launch =
 // B*HW*C*2 (q) + B*HW*C*2 (o) + 2*B*Ns*C*2 (k, v) + pos + table + lse.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -348,6 +350,364 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =====================================================================================================================
+// Version 2 of the fused forward (default; DAT_B200_ATTN_V1=1 selects the kernel above).  Same mapping of the scores to
+// threads, restructured so that neither the tensor pipe nor the softmax warps wait for each other and with roughly half
+// the CUDA-core instructions per score:
+//  * S is double-buffered in tensor memory (2 x 256 columns): QK^T of tile i + 1 is issued while the softmax warps work
+//    on tile i; O = PV of tile i accumulates in columns [0, 32) of S buffer i after its scores have been read, and its
+//    epilogue (normalise, store) runs in the middle of tile i + 1 - no thread ever waits for an MMA it has just caused.
+//  * the row sums come out of the tensor core: one extra N = 16 MMA per K step multiplies P by a tile of ones into
+//    columns [32, 48) (exactly the bf16 P that PV uses), so the softmax warps neither add nor exchange them.
+//  * one bar.sync per tile (the row-max exchange); the per-(image row, sample) table of the y footprint is built one tile
+//    ahead into a second buffer.
+//  * per score: ONE 16-byte broadcast LDS brings (row address, y fraction as bf16x2, x constant), one LEA forms the tap
+//    address from the magic-number float, ONE 8-byte LDS fetches the four taps stored as bf16 {mid, dif} of row y and
+//    their differences to row y + 1, ONE HFMA2.BF16 blends in y, two shifts unpack, two FMAs blend in x and add the
+//    scaled score.  Offsets clamped to [-1, 1] (offset_range_factor < 0, dat_blocks.py:159-162) cannot leave the table,
+//    so that instantiation has no per-score range clamps.
+//  13 (15 with clamps) + 2.6 instructions per score instead of 22 + 3.6.
+// =====================================================================================================================
+
+constexpr int A2_THREADS = 576;     // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2-17: softmax
+constexpr int A2_SBUF = 256;        // tensor-memory columns per S buffer
+constexpr int A2_ONES = 2048;       // bf16 ones read by the row-sum MMA
+
+__device__ __forceinline__ void soft2_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ uint32_t hfma2_bf16(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+
+// rpe table -> zero-padded copy in (mid, dif) form, log2(e)-scaled, entry (y, x) at (y + 2) * Wp + (x + 2):
+//   .x = bf16x2 {m0 = (T[y][x] + T[y][x+1]) / 2, d0 = T[y][x+1] - T[y][x]}      .y = bf16x2 {m1 - m0, d1 - d0} (row y + 1)
+// bilinear value at (y + fy, x + 1/2 + fx'):  (m0 + fy (m1 - m0)) + fx' (d0 + fy (d1 - d0))
+__global__ void pack_table2_kernel(const float* __restrict__ table, uint2* __restrict__ out, int heads, int Th, int Tw) {
+  const int Wp = Tw + 3, Hp = Th + 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= heads * Hp * Wp) return;
+  const int eta = idx / (Hp * Wp), rem = idx % (Hp * Wp);
+  const int y = rem / Wp - 2, x = rem % Wp - 2;
+  const float* t = table + (long long)eta * Th * Tw;
+  auto at = [&](int yy, int xx) {
+    return (yy >= 0 && yy < Th && xx >= 0 && xx < Tw) ? t[yy * Tw + xx] * LOG2E : 0.f;
+  };
+  const float t00 = at(y, x), t01 = at(y, x + 1), t10 = at(y + 1, x), t11 = at(y + 1, x + 1);
+  const float m0 = 0.5f * (t00 + t01), d0 = t01 - t00, m1 = 0.5f * (t10 + t11), d1 = t11 - t10;
+  out[idx] = make_uint2(pack_bf16x2(m0, d0), pack_bf16x2(m1 - m0, d1 - d0));
+}
+
+struct Smem2Plan {
+  uint32_t q, k, v, p, ones, tab, yt[2], xk, yk, red, bars, total;
+};
+__host__ __device__ inline Smem2Plan plan_smem2(int NS, int Hp, int Wp, int rows_max) {
+  Smem2Plan s;
+  uint32_t off = 0;
+  s.q = off; off += TQ * 64;
+  s.k = off; off += NS * 64;
+  s.v = off; off += NS * 64;
+  s.p = off; off += (NS / 64) * 16384;
+  s.ones = off; off += A2_ONES;
+  s.tab = off; off += ((uint32_t)(Hp * Wp) * 8 + 15) & ~15u;
+  s.yt[0] = off; off += (uint32_t)rows_max * NS * 16;
+  s.yt[1] = off; off += (uint32_t)rows_max * NS * 16;
+  s.xk = off; off += NS * 4;
+  s.yk = off; off += NS * 4;
+  s.red = off; off += 2 * NPART * TQ * 4;   // row maxima, double-buffered by tile parity
+  s.bars = off; off += 16 * 8;
+  s.total = off + 1024;   // slack for the manual 1024-byte alignment
+  return s;
+}
+
+template <int NS, bool XCLAMP>
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const float* __restrict__ pos,
+                    const uint2* __restrict__ tab_packed, bf16* __restrict__ o, float* __restrict__ lse, AtcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  const Smem2Plan sp = plan_smem2(NS, a.Hp, a.Wp, a.rows_max);
+  uint8_t* sQ = smem + sp.q;
+  uint8_t* sK = smem + sp.k;
+  uint8_t* sV = smem + sp.v;
+  uint8_t* sP = smem + sp.p;
+  uint2* sTab = reinterpret_cast<uint2*>(smem + sp.tab);
+  float* sXk = reinterpret_cast<float*>(smem + sp.xk);
+  float* sYk = reinterpret_cast<float*>(smem + sp.yk);
+  float* sMaxBase = reinterpret_cast<float*>(smem + sp.red);  // [2][NPART][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sp.bars);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;
+  uint64_t* s_full = bars + 3;    // [2]
+  uint64_t* s_free = bars + 5;    // [2]
+  uint64_t* p_ready = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  const int n_off = a.n_off0 + (int)blockIdx.z * NS;   // first sample of this CTA's KV chunk
+  o += (long long)(a.z0 + (int)blockIdx.z) * a.o_zstride;
+  lse += (long long)(a.z0 + (int)blockIdx.z) * a.lse_zstride;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA (>= 1)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(&s_free[0], SOFT_THREADS);
+    mbar_init(&s_free[1], SOFT_THREADS);
+    mbar_init(p_ready, SOFT_THREADS);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  {
+    const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
+    for (int i = threadIdx.x; i < a.Hp * a.Wp; i += A2_THREADS) sTab[i] = src[i];
+    const float* pp = pos + (((long long)b * a.G + g) * a.ns_total + n_off) * 2;
+    for (int n = threadIdx.x; n < NS; n += A2_THREADS) {
+      float py = pp[2 * n], px = pp[2 * n + 1];
+      // without the per-score range clamps the positions themselves are confined to [-1, 1] (they already are when
+      // offset_range_factor < 0, dat_blocks.py:159-162): every tap index then stays inside the padded table
+      if (!XCLAMP) px = fminf(fmaxf(px, -1.0f), 1.0f);
+      sYk[n] = py * a.ky;
+      sXk[n] = px * a.kx;
+    }
+    for (int i = threadIdx.x; i < A2_ONES / 4; i += A2_THREADS) reinterpret_cast<uint32_t*>(smem + sp.ones)[i] = 0x3f803f80u;
+    fence_proxy_async_smem();          // the ones tile is read by the tensor core (async proxy)
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: K, V once; one Q slot (S is double-buffered in tensor memory, so the slot is free again
+      //      long before the next tile's QK^T is due) ------------------------------------------------------------
+      mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
+      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * a.ns_total + n_off);
+      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * a.ns_total + n_off);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(q_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(q_full, TQ * 64u);
+        tma_load_2d(sQ, &tmQ, q_full, eta * 32, b * a.HW + tile * TQ);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer -----------------------------------------------------------------------------------------
+      const uint32_t idesc_s = make_instr_desc(FMT_BF16, TQ, NS);
+      const uint32_t idesc_o = make_instr_desc(FMT_BF16, TQ, 32, 0, 1);   // B (= V) is MN-major
+      const uint32_t idesc_1 = make_instr_desc(FMT_BF16, TQ, 16, 0, 1);   // B = ones
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      const uint64_t onesd = make_smem_desc(smem_u32(smem + sp.ones), 8192, 1024, LAYOUT_SW128);
+      mbar_wait(kv_full, 0);
+      auto issue_s = [&](int j) {
+        const int sb = j & 1;
+        mbar_wait(q_full, (uint32_t)j & 1u);
+        if (j >= 2) mbar_wait(&s_free[sb], ((uint32_t)(j - 2) >> 1) & 1u);   // epilogue of tile j - 2 has drained the buffer
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(sb * A2_SBUF);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {     // head dim 32 = 2 x K16
+          const uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
+          const uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
+          mma_bf16_ss(d, ad, bd, idesc_s, (uint32_t)k);
+        }
+        tc_commit(q_empty);
+        tc_commit(&s_full[sb]);
+      };
+      issue_s(0);
+      for (int it = 0; it < n_my; ++it) {
+        if (it + 1 < n_my) issue_s(it + 1);
+        mbar_wait(p_ready, (uint32_t)it & 1u);
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)((it & 1) * A2_SBUF);
+#pragma unroll
+        for (int kk = 0; kk < NS / 16; ++kk) {
+          const uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
+          mma_bf16_ss(d, ad, bd, idesc_o, (uint32_t)(kk > 0));
+          mma_bf16_ss(d + 32u, ad, onesd, idesc_1, (uint32_t)(kk > 0));   // row sums of P
+        }
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    // ---- softmax + epilogue -------------------------------------------------------------------------------------
+    const int quad = warp & 3, part = (warp - 2) >> 2;   // TMEM lane quadrant; column part 0..NPART-1
+    const int row = quad * 32 + lane;
+    const int stid = threadIdx.x - 64;
+    constexpr int NH = NS / NPART;                   // columns per thread
+    constexpr int LOG_NS = NS == 256 ? 8 : (NS == 128 ? 7 : 6);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tab_addr = smem_u32(sTab);
+    const float xhi = (float)a.Tw - 0.5f, yhi = (float)a.Th - 0.5f;
+
+    auto build_yt = [&](int tile, int buf) {
+      uint4* dst = reinterpret_cast<uint4*>(smem + sp.yt[buf]);
+      const int r0 = (tile * TQ) / a.W;
+      const int r_last = min(a.HW - 1, tile * TQ + TQ - 1) / a.W;
+      for (int e = stid; e < ((r_last - r0 + 1) << LOG_NS); e += SOFT_THREADS) {
+        const int rr = e >> LOG_NS, n = e & (NS - 1);
+        const float gy = fmaf((float)(r0 + rr), a.gsy, -1.0f);
+        const float ay = (gy * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
+        float u = ay - sYk[n];
+        u = fminf(fmaxf(u, -1.5f), yhi);
+        const float aa = u + MAGIC;
+        const float fy = (u - (aa - MAGIC)) + 0.5f;
+        const int y0 = __float_as_int(aa) - MAGIC_BITS;            // in [-2, Th]
+        const uint32_t ro8 = tab_addr + ((uint32_t)((y0 + 2) * a.Wp + 2) << 3) - ((uint32_t)MAGIC_BITS << 3);
+        dst[e] = make_uint4(ro8, pack_bf16x2(fy, fy), __float_as_uint(sXk[n]), 0u);
+      }
+    };
+    // epilogue of a finished tile: O (fp32, columns [0, 32) of its S buffer) / row sum (column 32) -> bf16
+    auto epilogue = [&](int it_e, int tile_e, float mx_e) {
+      mbar_wait(o_full, (uint32_t)it_e & 1u);
+      tc_fence_after_sync();
+      const uint32_t tb = t_lane + (uint32_t)((it_e & 1) * A2_SBUF);
+      const int m = tile_e * TQ + row;
+      uint32_t ov[16];
+      uint32_t lv = 0u;
+      if (part < 2) {                       // parts 0 and 1 write 16 output channels each
+        tmem_ld_32x16(tb + (uint32_t)(part * 16), ov);
+        lv = tmem_ld_32x1(tb + 32u);
+        tmem_wait_ld();
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&s_free[it_e & 1]);
+      if (part < 2 && m < a.HW) {
+        const float l = __uint_as_float(lv);
+        const float inv = __fdividef(1.0f, l);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pk[i] = pack_bf16x2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(o + ((long long)b * a.HW + m) * a.C + eta * 32 + part * 16);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (part == 0) lse[(long long)bh * a.HW + m] = (mx_e + __log2f(l)) * LN2;
+      }
+    };
+
+    build_yt(blockIdx.x, 0);
+    soft2_bar_sync();
+    float mx_prev = 0.f;
+    int tile_prev = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int m = tile * TQ + row;
+      const int mm = m < a.HW ? m : a.HW - 1;
+      const int r = mm / a.W, c = mm - r * a.W;
+      const int r0 = (tile * TQ) / a.W;
+      const float ax = (fmaf((float)c, a.gsx, -1.0f) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
+
+      mbar_wait(&s_full[it & 1], ((uint32_t)it >> 1) & 1u);
+      tc_fence_after_sync();
+      // pass 1: val = s * scale*log2e + bias*log2e, running max.  The scores are processed 16 columns at a time and
+      // the values go straight back into the S buffer (tcgen05.st): only 16 of them are ever live in registers, which
+      // leaves the compiler room to interleave the dependent LDS -> FADD -> LDS -> HFMA2 -> FMA chains of neighbouring
+      // scores (with all 64 values resident the kernel ran at the 96-register cap and issued them one after the other)
+      const uint32_t s_cols = t_lane + (uint32_t)((it & 1) * A2_SBUF + part * NH);
+      const uint4* yt = reinterpret_cast<const uint4*>(smem + sp.yt[it & 1]) + ((r - r0) << LOG_NS) + part * NH;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < NH / 16; ++ch) {
+        uint32_t t[16];
+        tmem_ld_32x16(s_cols + (uint32_t)(ch * 16), t);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint4 ye = yt[ch * 16 + j];
+          float u = ax - __uint_as_float(ye.z);
+          if (XCLAMP) u = fminf(fmaxf(u, -1.5f), xhi);
+          const float aa = u + MAGIC;
+          const float fxp = u - (aa - MAGIC);                       // x fraction - 1/2
+          const uint2 e = lds64(ye.x + (__float_as_uint(aa) << 3));
+          const uint32_t md = hfma2_bf16(ye.y, e.y, e.x);           // blend in y: {mid, dif}
+          const float bias = fmaf(fxp, __uint_as_float(md & 0xffff0000u), __uint_as_float(md << 16));
+          const float val = fmaf(__uint_as_float(t[j]), a.c1, bias);
+          t[j] = __float_as_uint(val);
+          mx = fmaxf(mx, val);
+        }
+        tmem_st_32x16(s_cols + (uint32_t)(ch * 16), t);
+      }
+      // y table of the next tile into the other buffer (its readers are two barriers away)
+      if (tile + (int)gridDim.x < a.n_tiles) build_yt(tile + gridDim.x, (it + 1) & 1);
+      // row maxima of the four column parts: the slots alternate with the tile parity, so a fast thread's write for
+      // tile it + 1 cannot overtake a slow thread's read for tile it (one bar.sync per tile separates same-parity uses)
+      float* sMax = sMaxBase + (it & 1) * (NPART * TQ);
+      sMax[part * TQ + row] = mx;
+      // the previous tile's PV is long done: its epilogue also frees its S buffer for QK^T of tile it + 1 and
+      // guarantees that the tensor core has finished reading P before pass 2 overwrites it
+      if (it > 0) epilogue(it - 1, tile_prev, mx_prev);
+      tmem_wait_st();                 // this thread's values are back in tensor memory before pass 2 re-reads them
+      soft2_bar_sync();
+#pragma unroll
+      for (int pp = 0; pp < NPART; ++pp) mx = fmaxf(mx, sMax[pp * TQ + row]);
+
+      // pass 2: p = 2^(val - max), bf16 -> shared memory (K-major, 128B swizzle)
+      uint8_t* prow = sP + row * 128;
+#pragma unroll 1
+      for (int c2 = 0; c2 < NH / 16; ++c2) {
+        uint32_t t[16];
+        tmem_ld_32x16(s_cols + (uint32_t)(c2 * 16), t);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = ex2(__uint_as_float(t[j + i]) - mx);
+          const int n = part * NH + c2 * 16 + j;
+          const int kb = n >> 6, ch = (n & 63) >> 3;
+          uint4 w = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
+                               pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+          *reinterpret_cast<uint4*>(prow + kb * 16384 + ((ch ^ (row & 7)) << 4)) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(p_ready);
+      mx_prev = mx;
+      tile_prev = tile;
+    }
+    epilogue(it - 1, tile_prev, mx_prev);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 int rows_spanned_max(int HW, int W) {
   int n_tiles = (HW + TQ - 1) / TQ, best = 1;
   for (int t = 0; t < n_tiles; ++t) {
@@ -431,6 +791,15 @@ size_t table_bytes(const Shape& s) { return align_up((size_t)s.heads * (s.Th + 3
 
 }  // namespace
 
+// version 2 (double-buffered S, tensor-core row sums) whenever its shared-memory plan fits; DAT_B200_ATTN_V1=1 keeps
+// the first kernel (A/B measurements)
+bool attention_fwd_tc_v2(const Shape& s) {
+  static const int v1 = [] { const char* e = getenv("DAT_B200_ATTN_V1"); return e && e[0] == '1' ? 1 : 0; }();
+  if (v1) return false;
+  const Smem2Plan sp = plan_smem2(s.Ns < KV_MAX ? s.Ns : KV_MAX, s.Th + 3, s.Tw + 3, rows_spanned_max(s.HW, s.W));
+  return sp.total <= 227 * 1024;
+}
+
 size_t attention_fwd_tc_workspace(const Shape& s) {
   // packed table, then (Ns > 256 only) the split-KV partial outputs (bf16) and log-sum-exps
   size_t n = table_bytes(s);
@@ -465,7 +834,9 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   DAT_REQUIRE(ws != nullptr && ws_bytes >= attention_fwd_tc_workspace(s), "attention_fwd_tc: workspace too small");
   AtcArgs a = make_args(s);
   const int ntab = s.heads * a.Hp * a.Wp;
-  pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
+  const bool v2 = attention_fwd_tc_v2(s);
+  if (v2) pack_table2_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
+  else pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table_kernel");
   const int nch = kv_chunks(s.Ns);
   bf16* o_dst = (bf16*)o;
@@ -491,6 +862,24 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
     dim3 grid(gx, s.B * s.heads, count);
     a.n_off0 = n_off;
     a.z0 = z;
+    if (v2) {
+      const Smem2Plan sp2 = plan_smem2(size, a.Hp, a.Wp, a.rows_max);
+      const bool xclamp = !(s.orf < 0.f);   // clamped offsets (orf < 0) never leave the padded table
+#define LAUNCH2(NSV, XC)                                                                          \
+  do {                                                                                            \
+    auto kern = attn_fwd_tc2_kernel<NSV, XC>;                                                     \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp2.total)); \
+    kern<<<grid, A2_THREADS, sp2.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
+  } while (0)
+      if (size == 256) { if (xclamp) LAUNCH2(256, true); else LAUNCH2(256, false); }
+      else if (size == 128) { if (xclamp) LAUNCH2(128, true); else LAUNCH2(128, false); }
+      else { if (xclamp) LAUNCH2(64, true); else LAUNCH2(64, false); }
+#undef LAUNCH2
+      DAT_LAUNCH_OK("attn_fwd_tc2_kernel");
+      n_off += count * size;
+      z += count;
+      continue;
+    }
 #define LAUNCH(NSV)                                                                              \
   do {                                                                                           \
     auto kern = attn_fwd_tc_kernel<NSV>;                                                         \

@@ -486,6 +486,13 @@ int pick_bn(int N) {
   return 0;
 }
 
+// MN-major weight operand: 64-column TMA boxes, so the tile width is a multiple of 64
+int pick_bn_mn(int N) {
+  for (int bn : {256, 128, 64})
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
 }  // namespace
 
 int debug_gemm_timing(unsigned long long* out8) {
@@ -538,7 +545,7 @@ int cast_bf16_multi(const dat_cast_item* items_dev, int n_items, cudaStream_t st
 
 // data gradient dX[M, K] = dY[M, N] W[N, K] (+ dY2 W2) with the bf16 weight read in place as an MN-major B operand
 bool pointwise_dgrad_tc_supported(long long M, int N, int K) {
-  return pointwise_fwd_tc_supported(DAT_BF16, M, K, N) && pick_bn(K) % 64 == 0 && K % 8 == 0;
+  return M > 0 && pick_bn_mn(K) != 0 && N % 8 == 0;
 }
 int pointwise_dgrad_tc(const void* dY, const void* W, const void* dY2, const void* W2, void* dX, int dx_dt,
                        long long M, int N, int K, cudaStream_t st) {
@@ -553,11 +560,11 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
                           cudaStream_t st, bool w_mn) {
   DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
   const bool tf32 = x_dt == DAT_F32;
-  DAT_REQUIRE(!w_mn || (!tf32 && pick_bn(N) % 64 == 0 && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
+  DAT_REQUIRE(!w_mn || (!tf32 && pick_bn_mn(N) != 0 && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
               "pointwise_fwd_tc: the MN-major weight operand needs bf16 and a tile width that is a multiple of 64");
   const int eb = tf32 ? 4 : 2;
   const int chunk_elems = CHUNK_BYTES / eb;
-  const int BN = pick_bn(N);
+  const int BN = w_mn ? pick_bn_mn(N) : pick_bn(N);
   const int k_chunks1 = (K + chunk_elems - 1) / chunk_elems;
   const int k_chunks = X2 != nullptr ? 2 * k_chunks1 : k_chunks1;
   CUtensorMap tmA, tmB, tmA2, tmB2;

@@ -110,6 +110,9 @@ class _DwConvFn(torch.autograd.Function):
                                            nbytes, st), "dat_dwconv_fwd(dgrad)")
             if wst is not cur and not grads_consumed_at_end_only(*ctx.param_refs):
                 cur.wait_stream(wst)   # dw / db are consumed right after this node: complete them first
+                for t in (dw, db):     # allocated on the side stream, read (then freed) on the current one
+                    if t is not None:
+                        t.record_stream(cur)
         return dx, dw, db, None, None
 
 

@@ -121,6 +121,9 @@ class _PointwiseFn(torch.autograd.Function):
                                                      _CODE[dx.dtype], M, K, N, st), "dat_pointwise_fwd_tc(dgrad)")
             if early_join:      # dw / db are consumed right after this node (accumulation, hooks): complete them first
                 cur.wait_stream(wst)
+                for t in (dw, db):      # allocated on the side stream, read (then freed) on the current one
+                    if t is not None:
+                        t.record_stream(cur)
         return dx, dw, db, None
 
 
