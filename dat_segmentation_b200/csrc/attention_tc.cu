@@ -51,6 +51,7 @@ struct AtcArgs {
   // the samples [n_off0 + z * NS, + NS) of ns_total and writes its normalised partial output / log-sum-exp into
   // slot z0 + z (strides o_zstride / lse_zstride elements); attn_combine_kernel merges the slots.
   int ns_total, n_off0, z0;
+  int force_xclamp;   // debug: -1 = per-CTA choice, 0 / 1 = force the unclamped / clamped pass (DAT_B200_ATTN_XCLAMP)
   long long o_zstride, lse_zstride;
 };
 
@@ -365,8 +366,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //  * per score: ONE 16-byte broadcast LDS brings (row address, y fraction as bf16x2, x constant), one LEA forms the tap
 //    address from the magic-number float, ONE 8-byte LDS fetches the four taps stored as bf16 {mid, dif} of row y and
 //    their differences to row y + 1, ONE HFMA2.BF16 blends in y, two shifts unpack, two FMAs blend in x and add the
-//    scaled score.  Offsets clamped to [-1, 1] (offset_range_factor < 0, dat_blocks.py:159-162) cannot leave the table,
-//    so that instantiation has no per-score range clamps.
+//    scaled score.  Samples inside [-1, 1] (always the case when offset_range_factor < 0, dat_blocks.py:159-162) cannot
+//    leave the padded table: a CTA whose samples all are runs the pass without per-score range clamps (run-time choice).
 //  13 (15 with clamps) + 2.6 instructions per score instead of 22 + 3.6.
 // =====================================================================================================================
 
@@ -431,7 +432,7 @@ __host__ __device__ inline Smem2Plan plan_smem2(int NS, int Hp, int Wp, int rows
   s.ones = off; off += A2_ONES;
   s.tab = off; off += ((uint32_t)(Hp * Wp) * 8 + 15) & ~15u;
   s.yt[0] = off; off += (uint32_t)rows_max * NS * 16;
-  s.yt[1] = off; off += (uint32_t)rows_max * NS * 16;
+  s.yt[1] = off; off += (uint32_t)rows_max * NS * 16 + 64;   // + the 4-entry read-ahead of the last thread
   s.xk = off; off += NS * 4;
   s.yk = off; off += NS * 4;
   s.red = off; off += 2 * NPART * TQ * 4;   // row maxima, double-buffered by tile parity
@@ -440,7 +441,59 @@ __host__ __device__ inline Smem2Plan plan_smem2(int NS, int Hp, int Wp, int rows
   return s;
 }
 
-template <int NS, bool XCLAMP>
+// pass 1 over one thread's NH columns of the S buffer: val = s * scale*log2e + bias*log2e written back in place
+// (tcgen05.st), returns the running maximum.  XCLAMP: per-score range clamps of the x footprint (needed only when some
+// sample of the CTA lies outside [-1, 1]; decided per CTA at run time, so the result never depends on it).
+template <int NH, bool XCLAMP>
+__device__ __forceinline__ float attn2_pass1(uint32_t s_cols, const uint4* __restrict__ yt, float ax, float xhi, float c1) {
+  // Software pipeline over groups of 4 scores: the per-sample parameters of group g + 1 are loaded while the four tap
+  // loads of group g are in flight, and the blends of group g run after them - four independent LDS -> FADD -> LDS ->
+  // HFMA2 -> FMA chains per thread instead of one or two (the profile of the plain loop was latency-bound:
+  // short_scoreboard 2.7 + wait 1.9 warps per issue at 48 % issue utilisation).  The volatile tap loads keep their
+  // program order, so the grouping survives the compiler's scheduling.
+  constexpr int G = 4;
+  float mx = -INFINITY;
+  uint4 ye[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) ye[i] = yt[i];
+#pragma unroll 1
+  for (int ch = 0; ch < NH / 16; ++ch) {
+    uint32_t t[16];
+    tmem_ld_32x16(s_cols + (uint32_t)(ch * 16), t);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 16 / G; ++g) {
+      uint2 e[G];
+      float fxp[G];
+      uint32_t fy2[G];
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        float u = ax - __uint_as_float(ye[i].z);
+        if (XCLAMP) u = fminf(fmaxf(u, -1.5f), xhi);
+        const float aa = u + MAGIC;
+        e[i] = lds64(ye[i].x + (__float_as_uint(aa) << 3));
+        fxp[i] = u - (aa - MAGIC);                                // x fraction - 1/2
+        fy2[i] = ye[i].y;
+      }
+      // parameters of the next group (the last group of the last chunk reads 4 entries past the thread's range:
+      // still inside the table buffer, never used)
+#pragma unroll
+      for (int i = 0; i < G; ++i) ye[i] = yt[ch * 16 + (g + 1) * G + i];
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const uint32_t md = hfma2_bf16(fy2[i], e[i].y, e[i].x);   // blend in y: {mid, dif}
+        const float bias = fmaf(fxp[i], __uint_as_float(md & 0xffff0000u), __uint_as_float(md << 16));
+        const float val = fmaf(__uint_as_float(t[g * G + i]), c1, bias);
+        t[g * G + i] = __float_as_uint(val);
+        mx = fmaxf(mx, val);
+      }
+    }
+    tmem_st_32x16(s_cols + (uint32_t)(ch * 16), t);
+  }
+  return mx;
+}
+
+template <int NS>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ pos,
@@ -466,6 +519,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_ready = bars + 7;
   uint64_t* o_full = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint32_t* oob_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
@@ -488,17 +542,20 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(p_ready, SOFT_THREADS);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    *oob_flag = 0u;
   }
+  __syncthreads();                    // the flag is zero before any thread may raise it
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  int oob = 0;
   {
     const uint2* src = tab_packed + (long long)eta * a.Hp * a.Wp;
     for (int i = threadIdx.x; i < a.Hp * a.Wp; i += A2_THREADS) sTab[i] = src[i];
     const float* pp = pos + (((long long)b * a.G + g) * a.ns_total + n_off) * 2;
     for (int n = threadIdx.x; n < NS; n += A2_THREADS) {
-      float py = pp[2 * n], px = pp[2 * n + 1];
-      // without the per-score range clamps the positions themselves are confined to [-1, 1] (they already are when
-      // offset_range_factor < 0, dat_blocks.py:159-162): every tap index then stays inside the padded table
-      if (!XCLAMP) px = fminf(fmaxf(px, -1.0f), 1.0f);
+      const float py = pp[2 * n], px = pp[2 * n + 1];
+      // positions inside [-1, 1] (always the case when offset_range_factor < 0, dat_blocks.py:159-162) keep every
+      // tap index inside the padded table: the CTA then runs the pass without per-score range clamps
+      if (!(fabsf(px) <= 1.0f)) oob = 1;
       sYk[n] = py * a.ky;
       sXk[n] = px * a.kx;
     }
@@ -506,7 +563,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_proxy_async_smem();          // the ones tile is read by the tensor core (async proxy)
   }
   tc_fence_before_sync();
+  if (oob) *oob_flag = 1u;            // benign race: every writer stores the same value
   __syncthreads();
+  const bool xclamp = a.force_xclamp >= 0 ? a.force_xclamp != 0 : *oob_flag != 0u;
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -641,28 +700,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // scores (with all 64 values resident the kernel ran at the 96-register cap and issued them one after the other)
       const uint32_t s_cols = t_lane + (uint32_t)((it & 1) * A2_SBUF + part * NH);
       const uint4* yt = reinterpret_cast<const uint4*>(smem + sp.yt[it & 1]) + ((r - r0) << LOG_NS) + part * NH;
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < NH / 16; ++ch) {
-        uint32_t t[16];
-        tmem_ld_32x16(s_cols + (uint32_t)(ch * 16), t);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint4 ye = yt[ch * 16 + j];
-          float u = ax - __uint_as_float(ye.z);
-          if (XCLAMP) u = fminf(fmaxf(u, -1.5f), xhi);
-          const float aa = u + MAGIC;
-          const float fxp = u - (aa - MAGIC);                       // x fraction - 1/2
-          const uint2 e = lds64(ye.x + (__float_as_uint(aa) << 3));
-          const uint32_t md = hfma2_bf16(ye.y, e.y, e.x);           // blend in y: {mid, dif}
-          const float bias = fmaf(fxp, __uint_as_float(md & 0xffff0000u), __uint_as_float(md << 16));
-          const float val = fmaf(__uint_as_float(t[j]), a.c1, bias);
-          t[j] = __float_as_uint(val);
-          mx = fmaxf(mx, val);
-        }
-        tmem_st_32x16(s_cols + (uint32_t)(ch * 16), t);
-      }
+      float mx = xclamp ? attn2_pass1<NH, true>(s_cols, yt, ax, xhi, a.c1) : attn2_pass1<NH, false>(s_cols, yt, ax, xhi, a.c1);
       // y table of the next tile into the other buffer (its readers are two barriers away)
       if (tile + (int)gridDim.x < a.n_tiles) build_yt(tile + gridDim.x, (it + 1) & 1);
       // row maxima of the four column parts: the slots alternate with the tile parity, so a fast thread's write for
@@ -746,6 +784,8 @@ AtcArgs make_args(const Shape& s) {
   a.gsx = 2.0f / (float)(s.W - 1);
   a.gsy = 2.0f / (float)(s.H - 1);
   a.ns_total = s.Ns; a.n_off0 = 0; a.z0 = 0; a.o_zstride = 0; a.lse_zstride = 0;
+  const char* fx = getenv("DAT_B200_ATTN_XCLAMP");
+  a.force_xclamp = fx != nullptr ? atoi(fx) : -1;
   return a;
 }
 
@@ -864,16 +904,15 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
     a.z0 = z;
     if (v2) {
       const Smem2Plan sp2 = plan_smem2(size, a.Hp, a.Wp, a.rows_max);
-      const bool xclamp = !(s.orf < 0.f);   // clamped offsets (orf < 0) never leave the padded table
-#define LAUNCH2(NSV, XC)                                                                          \
+#define LAUNCH2(NSV)                                                                              \
   do {                                                                                            \
-    auto kern = attn_fwd_tc2_kernel<NSV, XC>;                                                     \
+    auto kern = attn_fwd_tc2_kernel<NSV>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp2.total)); \
     kern<<<grid, A2_THREADS, sp2.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
   } while (0)
-      if (size == 256) { if (xclamp) LAUNCH2(256, true); else LAUNCH2(256, false); }
-      else if (size == 128) { if (xclamp) LAUNCH2(128, true); else LAUNCH2(128, false); }
-      else { if (xclamp) LAUNCH2(64, true); else LAUNCH2(64, false); }
+      if (size == 256) LAUNCH2(256);
+      else if (size == 128) LAUNCH2(128);
+      else LAUNCH2(64);
 #undef LAUNCH2
       DAT_LAUNCH_OK("attn_fwd_tc2_kernel");
       n_off += count * size;

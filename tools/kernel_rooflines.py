@@ -192,7 +192,7 @@ for s, (Hh, Cc, heads, G, stride, ksize, qs) in enumerate(BLOCK_STAGES):
         nbytes=B * HWn * Cc * (2 + 4 + 4) + saved_bytes + 8 * Cc * Cc * 4, flops=2.0 * dense_f + 2.0 * HWn * Ns * Cc * B)
     del xa, qa, ka, va, oa, xsa, saved, ya, dya, dxa
 
-print("# dat_b200 kernels against the measured B200 peaks (round 1)\n")
+print("# dat_b200 kernels against the measured B200 peaks\n")
 print(f"HBM peak {HBM:.0f} GB/s, dense bf16 peak {TF:.1f} TFLOP/s (MEASURED_PEAKS.json).  Each kernel launched alone through the C ABI, "
       f"batch {B}, 3 rotating buffer sets, {REP} launches between CUDA events (tools/kernel_rooflines.py).  "
       "GB/s = algorithmic bytes (every tensor once) / time.\n")
