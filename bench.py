@@ -318,7 +318,8 @@ class TrainStep:
         with torch.cuda.stream(self.comm):
             torch._foreach_copy_(self.bucket_views[bi], [p.grad for p in self.bucket_params[bi]])
             lo, hi = self.bucket_slices[bi]
-            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
+            if not os.environ.get("DAT_B200_BENCH_SKIP_AR"):      # debug: cost of the packing / stream structure alone
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
 
     def fwd_bwd(self):
         for p in self.params:
