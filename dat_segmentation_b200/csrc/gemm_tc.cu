@@ -432,6 +432,186 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// CTA-pair version (cta_group::2): two SMs of a TPC own one 256 x BN output tile.  Each CTA streams its own 128 rows of
+// A and only HALF of the B panel (BN / 2 weight rows); one M = 256 tcgen05.mma issued by the even CTA reads both shared
+// memories and accumulates each CTA's 128 rows in its own tensor memory.  The single-CTA kernel is bound by the
+// L2 -> shared-memory fill (every 128-row tile re-reads the whole weight panel: 98 MB of fills for the 42 MB stage-2
+// fc1 GEMM); pairing halves the weight-panel traffic per output element, which is what the kernel waits for.
+//   barriers: full[s] lives in the even CTA (2 producer arrivals + the bytes of both CTAs' loads); empty[s],
+//   acc_full[b] are multicast by tcgen05.commit to both CTAs; acc_empty[b] (even CTA) collects the epilogue warps of both.
+template <bool TF32, typename TOut, bool BMN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCP_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
+                    int k_chunks1, int BN, int stages, int tmem_cols, int m_pairs, int total_tiles,
+                    int stage_pitch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int BH = BN / 2;                              // weight rows (output columns) staged by this CTA
+  const int b_stage_bytes = BH * CHUNK_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sBias = reinterpret_cast<float*>(smem + 1024);
+  uint8_t* sA = smem + 3072;
+  uint8_t* sB = sA + stages * A_STAGE_BYTES;
+  uint8_t* sStage = sB + stages * b_stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr int CHUNK_ELEMS = TF32 ? 32 : 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (k_chunks1 < k_chunks) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 2);                          // the producers of both CTAs
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 2 * TCP_EPI_WARPS);     // the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = cid; t < total_tiles; t += n_clusters) {
+        const int m0 = (t % m_pairs) * (2 * TC_BM) + (int)rank * TC_BM, n0 = (t / m_pairs) * BN + (int)rank * BH;
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);               // the pair's MMAs have read this slot (commit multicast)
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+          else mbar_arrive_leader(&full[s]);
+          const bool second = kc >= k_chunks1;
+          const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
+          tma_load_2d_pair(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
+          if (BMN) {
+            for (int i = 0; i < BH / 64; ++i)
+              tma_load_2d_pair(sB + s * b_stage_bytes + i * 8192, second ? &tmB2 : &tmB, &full[s], n0 + 64 * i, kcol);
+          } else {
+            tma_load_2d_pair(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_instr_desc(TF32 ? FMT_TF32 : FMT_BF16, 2 * TC_BM, (uint32_t)BN, 0, BMN ? 1u : 0u);
+      int it = 0, li = 0;
+      for (int t = cid; t < total_tiles; t += n_clusters, ++li) {
+        const int buf = li & 1;
+        mbar_wait(&acc_empty[buf], (uint32_t)((li >> 1) & 1) ^ 1u);   // both CTAs' epilogues have drained this buffer
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < k_chunks; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * b_stage_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < CHUNK_BYTES / 32; ++k4) {
+            const uint64_t ad = make_smem_desc(a_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t bd = BMN ? make_smem_desc(b_addr + k4 * 2048, 8192, 1024, LAYOUT_SW128)
+                                    : make_smem_desc(b_addr + k4 * 32, 16, 1024, LAYOUT_SW128);
+            if (TF32) mma_tf32_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+            else mma_bf16_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)((kc | k4) != 0));
+          }
+          tc_commit_pair(&empty[s], 3);
+        }
+        tc_commit_pair(&acc_full[buf], 3);
+      }
+    }
+  } else {
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;   // which of the quadrant's two warps: takes column groups chalf, chalf + 2, ...
+    const int epi_tid = threadIdx.x - 64;
+    const int gcols = persistent_gcols(BN);
+    const int seg_bytes = gcols * (int)sizeof(TOut);
+    uint8_t* stage = sStage + (warp - 2) * 32 * stage_pitch;
+    int li = 0;
+    for (int t = cid; t < total_tiles; t += n_clusters, ++li) {
+      const int buf = li & 1;
+      const int m0 = (t % m_pairs) * (2 * TC_BM) + (int)rank * TC_BM, n0 = (t / m_pairs) * BN;
+      float* bvec = sBias + buf * 256;
+      for (int i = epi_tid; i < BN; i += 32 * TCP_EPI_WARPS) bvec[i] = bias != nullptr ? bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
+      mbar_wait(&acc_full[buf], (uint32_t)((li >> 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      const int rows_here = min(32, M - (m0 + quad * 32));
+      const int nch = gcols / 32;
+      const int cg_first = chalf * gcols;
+      if (cg_first >= BN) {              // a single column group: this warp only hands the buffer back
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+        continue;
+      }
+      for (int cg = cg_first; cg < BN; cg += 2 * gcols) {
+        uint32_t r[3][32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < nch) tmem_ld_32x32(t_addr + (uint32_t)(cg + c * 32), r[c]);
+        tmem_wait_ld();
+        if (cg + 2 * gcols >= BN) {      // this warp's share of the accumulator is read: hand the TMEM buffer back early
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c < nch) {
+            const float* bp = bvec + cg + c * 32;
+            TOut* dst = reinterpret_cast<TOut*>(stage + lane * stage_pitch) + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bp + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bp + j + 4);
+              const float4 v0 = make_float4(__uint_as_float(r[c][j]) + b0.x, __uint_as_float(r[c][j + 1]) + b0.y,
+                                            __uint_as_float(r[c][j + 2]) + b0.z, __uint_as_float(r[c][j + 3]) + b0.w);
+              const float4 v1 = make_float4(__uint_as_float(r[c][j + 4]) + b1.x, __uint_as_float(r[c][j + 5]) + b1.y,
+                                            __uint_as_float(r[c][j + 6]) + b1.z, __uint_as_float(r[c][j + 7]) + b1.w);
+              store8(dst + j, v0, v1);
+            }
+          }
+        }
+        __syncwarp();
+        const int lanes_per_row = seg_bytes / 16;
+        const int rows_per_it = 32 / lanes_per_row;
+        const int rsub = lane / lanes_per_row, off = (lane % lanes_per_row) * 16;
+        for (int rr = rsub; rr < rows_here; rr += rows_per_it) {
+          uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0 + cg);
+          *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(stage + rr * stage_pitch + off);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();                    // neither CTA leaves (or frees tensor memory) while the pair's MMAs may touch it
+  if (warp == 1) tmem_dealloc2(tmem_base, (uint32_t)tmem_cols);
+}
+
 // fp32 (C x C) -> transposed bf16 for up to 4 matrices in one launch: out[z][k][n] = w_z[n][k].
 // The data-gradient GEMMs dX = dY W are then plain K-major products with "weight" W^T.
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
@@ -581,6 +761,49 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     DAT_FWD(map_w(&tmB2, W2));
   }
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
+  // CTA pairs (cta_group::2, 256 x BN tiles): tiles of 128 or 256 columns, at least one full pair of row tiles.
+  // Opt-in (DAT_B200_GEMM_PAIR=1): measured on B200 it halves the weight-panel fills but is no faster than the
+  // single-CTA kernel at any DAT-T++ shape (20.8 vs 20.9 us stage-2 fc1, 16.7 vs 16.8 us fc2, 16.6 vs 14.8 us stage-3
+  // fc1: profiles/r02_gemm_pair.md) - the kernel is bound by ring depth x fill latency and by its epilogue, not by
+  // L2 -> shared-memory bandwidth.
+  static const int pair_off = [] { const char* e = std::getenv("DAT_B200_GEMM_PAIR"); return e && e[0] == '1' ? 0 : 1; }();
+  if (!pair_off && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr && (BN == 256 || BN == 128) && M >= 2 * TC_BM) {
+    const int gcols = persistent_gcols(BN);
+    const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
+    const int staging = TCP_EPI_WARPS * 32 * stage_pitch;
+    const int pstage_bytes = A_STAGE_BYTES + (BN / 2) * CHUNK_BYTES;
+    int stages = (224 * 1024 - 1024 - 3072 - staging) / pstage_bytes;
+    if (stages > 8) stages = 8;
+    DAT_REQUIRE(stages >= 2, "pointwise_fwd_tc: tile does not fit shared memory");
+    const size_t smem = 1024 + 3072 + (size_t)stages * pstage_bytes + staging;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+    const int m_pairs = (int)ceil_div(M, (long long)(2 * TC_BM)), total = m_pairs * (N / BN);
+    const int clusters = total < 74 ? total : 74;
+    CUtensorMap tmBp = tmB, tmB2p = tmB2;
+    if (!w_mn) {     // K-major weight: this CTA's half of the panel is one box of BN / 2 rows
+      DAT_FWD(tc::make_tmap_2d(&tmBp, W, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN / 2, chunk_elems, 128));
+      tmB2p = tmBp;
+      if (X2 != nullptr)
+        DAT_FWD(tc::make_tmap_2d(&tmB2p, W2, eb, tf32, (uint64_t)N, (uint64_t)K, (uint64_t)K * eb, BN / 2, chunk_elems, 128));
+    }
+#define LAUNCH_PAIR(TF, TO, MN)                                                                   \
+  do {                                                                                            \
+    auto kern = gemm_tc_pair_kernel<TF, TO, MN>;                                                  \
+    DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<2 * clusters, TCP_THREADS, smem, st>>>(tmA, tmBp, tmA2, tmB2p, b, (TO*)Y, (int)M, N, k_chunks, \
+                                                  k_chunks1, BN, stages, tmem_cols, m_pairs, total, stage_pitch); \
+  } while (0)
+    if (w_mn && y_dt == DAT_F32) LAUNCH_PAIR(false, float, true);
+    else if (w_mn) LAUNCH_PAIR(false, bf16, true);
+    else if (tf32 && y_dt == DAT_F32) LAUNCH_PAIR(true, float, false);
+    else if (tf32) LAUNCH_PAIR(true, bf16, false);
+    else if (y_dt == DAT_F32) LAUNCH_PAIR(false, float, false);
+    else LAUNCH_PAIR(false, bf16, false);
+#undef LAUNCH_PAIR
+    DAT_LAUNCH_OK("gemm_tc_pair_kernel");
+    return DAT_OK;
+  }
   if (std::getenv("DAT_B200_GEMM_LEGACY") == nullptr) {
     // persistent kernel: ring + separate epilogue staging in up to 224 KB, one CTA per SM
     const int gcols = persistent_gcols(BN);
