@@ -113,6 +113,39 @@ def cpu_port_run(steps, warmup, batch):
                 sample=f"{steps} steps of batch {batch} @512x512 fwd+bwd, bf16 autocast, {warmup} warm-up")
 
 
+def gpu_library_run(dev, steps, warmup):
+    """Informational GPU yardstick: the oracle port of the backbone - the reference's own operator
+    sequence on library kernels (cuDNN convolutions, cuBLAS bmm, ATen grid_sample / softmax / LayerNorm) - on the same
+    B200, same batch, bf16 autocast, fwd+bwd, eager.  Not the product path and not the reference arm."""
+    from dat_segmentation_b200.backbone import build_dat
+    from oracle.dattn_oracle import OracleDAttention
+    torch.manual_seed(0)
+    model = build_dat(attn_cls=OracleDAttention).to(dev).train()
+    imgs = torch.randn(PER_GPU_BATCH, 3, IMG, IMG, device=dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = model(imgs)
+        loss_of(outs).backward()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": round(PER_GPU_BATCH / (ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "what": "oracle-port backbone on library kernels (cuDNN / cuBLAS / ATen), same GPU, batch 16, bf16 autocast, "
+                    "eager fwd+bwd"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,6 +188,16 @@ def _time_launch(dev, launch, flush, reps=10):
     return sorted(times)[len(times) // 2]
 
 
+def ncu_traffic():
+    """DRAM traffic per launch of the two roofline kernels, from the committed ncu summary of THIS command line
+    (`python bench.py --roofline-only` under `ncu --set full`, i.e. the same launches with the same L2 flush before each
+    of them: profiles/r02_ncu_traffic.json, written by tools/summarize_ncu_traffic.py).  None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    return json.load(open(path))
+
+
 def kernel_roofline(dev, pk):
     """Roofline of the dominant kernel of the step, `gemm_tc_persistent_kernel` (12 % of the kernel time, 174
     launches: profiles/r01_launches_step_818.md), at the shape that carries most of its time - the stage-2 MLP fc1
@@ -164,6 +207,7 @@ def kernel_roofline(dev, pk):
     kernel north_star asks tensor utilisation for) timed the same way."""
     from dat_segmentation_b200 import _cabi
     lib = _cabi.lib()
+    traffic = ncu_traffic()
     bf = torch.bfloat16
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -182,9 +226,10 @@ def kernel_roofline(dev, pk):
     roof = {"kernel": "gemm_tc_persistent_kernel (stage-2 MLP fc1: M=16384 N=1024 K=256, bf16)", "bound": "hbm",
             "achieved": round(gbytes / (ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": round(gbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full
-            # (profiles/r01_ncu_kernels.md): 8.9 MB + 0 - x and y are L2-resident at this size (42 MB < 126 MB L2)
-            "traffic": 8900000, "ms": round(ms, 4), "algorithmic_bytes": gbytes,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu summary of
+            # `bench.py --roofline-only` (same L2 flush before the launch); null when no summary is committed
+            "traffic": traffic.get("gemm", {}).get("dram_bytes"), "traffic_source": traffic.get("gemm", {}).get("source"),
+            "ms": round(ms, 4), "algorithmic_bytes": gbytes,
             "tflops_at_this_time": round(gflops / (ms * 1e-3) / 1e12, 1), "tensor_frac": round(gflops / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4),
             "peak_source": pk["source"]}
     del x, w, y
@@ -208,11 +253,13 @@ def kernel_roofline(dev, pk):
     roof["others"] = [{
         "kernel": "attn_fwd_tc_kernel (stage-2 shape, B=16, bf16)", "bound": "tensor",
         "achieved": round(flops / (ms_a * 1e-3) / 1e12, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": round(flops / (ms_a * 1e-3) / 1e12 / pk["bf16_tflops"], 5), "traffic": 12834048, "ms": round(ms_a, 4),
+        "frac": round(flops / (ms_a * 1e-3) / 1e12 / pk["bf16_tflops"], 5),
+        "traffic": traffic.get("attention", {}).get("dram_bytes"), "traffic_source": traffic.get("attention", {}).get("source"),
+        "hbm_frac": round(byts / (ms_a * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "ms": round(ms_a, 4),
         "algorithmic_bytes": byts,
-        "note": "bound by CUDA-core issue rate (bias interpolation + softmax, ~32 instructions per score vs 128 MMA FLOP; "
-                "ncu: issue slots 50 % busy, tensor pipe 3 %): DESIGN.md 3.1 row 7"}]
-    roof["per_kernel_table"] = "profiles/r01_kernel_rooflines.md"
+        "note": "attn_fwd_tc2_kernel; bound by CUDA-core issue rate + MUFU (bias interpolation + softmax, ~16 instructions "
+                "per score vs 128 MMA FLOP): DESIGN.md 3.1 row 7, profiles/r02_ncu_kernels.md"}]
+    roof["per_kernel_table"] = "profiles/r02_kernel_rooflines.md"
     return roof
 
 
@@ -383,9 +430,18 @@ def main():
     ap.add_argument("--impl", default="dat_b200", choices=["dat_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--roofline-only", action="store_true", help="only the roofline leg (the command ncu wraps)")
+    ap.add_argument("--gpu-library-baseline", action="store_true",
+                    help="also time the oracle-port backbone (library operators: cuDNN / cuBLAS / ATen) on the same GPU, "
+                         "same step, eager - informational yardstick, adds a `gpu_library_baseline` key")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.roofline_only:
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+        print(json.dumps(kernel_roofline(dev, peaks())), flush=True)
+        return
 
     import torch.distributed as dist
 
@@ -498,6 +554,9 @@ def main():
             "clocks": clocks,
             "roofline": roof,
         }
+        line["roofline_attention"] = roof["others"][0]      # the same entry at top level (drivers that flatten `roofline`)
+        if args.gpu_library_baseline and world == 1:
+            line["gpu_library_baseline"] = gpu_library_run(dev, max(3, args.steps), 3)
         if not args.no_cpu_baseline and world == 1:
             r = cpu_port_run(3, 1, 2)
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"],
