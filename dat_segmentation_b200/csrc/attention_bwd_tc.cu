@@ -23,6 +23,7 @@
 //     reduction and only run leaders issue shared-memory atomics into a per-CTA padded fp32
 //     copy of the table, flushed with one global atomic per cell at the end.
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -92,6 +93,36 @@ __device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// the same for bf16x2-packed pairs: lane L returns {sum_rows lo[L], sum_rows hi[L]} (31 shuffles, 31 packed adds)
+__device__ __forceinline__ uint32_t hadd2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t column_sums32_bf16x2(uint32_t (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const uint32_t send = upper ? v[i] : v[i + w];
+      const uint32_t keep = upper ? v[i + w] : v[i];
+      v[i] = hadd2_bf16(keep, __shfl_xor_sync(FULL, send, w));
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ uint32_t hfma2_bf16_b(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint2 lds64_b(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 // compact packed table: entry (y, x) at (y + 2) * Wp + (x + 2) = bf16x2 {T[y][x], T[y][x+1]} * log2(e),
 // zero outside the table
 __global__ void pack_table_compact_kernel(const float* __restrict__ table, uint32_t* __restrict__ out,
@@ -111,8 +142,10 @@ __global__ void pack_table_compact_kernel(const float* __restrict__ table, uint3
 struct SmemPlanB {
   uint32_t q[2], d_o[2], k, v, p, ds, tab, dtab, yt, xk, yk, dpos, bars, total;
 };
+// yt_bytes: 8 = {row offset, y fraction} (scatter / compact variants), 16 = {row address, y fraction bf16x2, x constant, -}
+// (FAST variant: one broadcast LDS.128 per score, as in the forward v2)
 __host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int rows_max, bool compact,
-                                                 int ndt, int nslots) {
+                                                 int ndt, int nslots, int yt_bytes = 8) {
   SmemPlanB s;
   uint32_t off = 0;
   s.q[0] = off; off += TQ * 64;          // Q slots are contiguous: slot i at q[0] + i * 8 KB
@@ -125,7 +158,7 @@ __host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int row
   s.ds = off; off += 2 * 16384;
   s.tab = off; off += ((uint32_t)(Hp * Wp) * (compact ? 4 : 8) + 15) & ~15u;
   s.dtab = off; off += ((uint32_t)(ndt * Hp * Wp) * 4 + 15) & ~15u;
-  s.yt = off; off += (uint32_t)rows_max * NS * 8;
+  s.yt = off; off += (uint32_t)rows_max * NS * yt_bytes;
   s.xk = off; off += NS * 4;
   s.yk = off; off += NS * 4;
   s.dpos = s.p;                            // per-warp column sums [8][NS][2] alias P/dS at the end
@@ -154,10 +187,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    BtcArgs a) {
   constexpr int NHALF = NS / NHC;
   constexpr int NDT = !TBL ? 0 : (PRIV ? 8 : 1);          // copies of the table gradient
+  // FAST (dS streamed out, 8-byte table entries - every DAT++ stage but the 111 x 111 table of stage 0): the bias and
+  // its two derivatives use the forward-v2 scheme ((mid, dif) table, one LDS.128 of per-sample parameters, HFMA2 blend
+  // in y, range clamps only when a sample of the CTA lies outside [-1, 1]) and the d pos column sums run on bf16x2 pairs
+  constexpr bool FAST = !TBL && !COMPACT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
-  const SmemPlanB sp = plan_smem_b(NS, a.Hp, a.Wp, a.rows_max, COMPACT, NDT, a.nslots);
+  const SmemPlanB sp = plan_smem_b(NS, a.Hp, a.Wp, a.rows_max, COMPACT, NDT, a.nslots, FAST ? 16 : 8);
   uint8_t* sQ0 = smem + sp.q[0];
   uint8_t* sDO0 = smem + sp.d_o[0];
   uint8_t* sK = smem + sp.k;
@@ -180,11 +217,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint32_t* oob_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
 
   if (threadIdx.x == 0) {
+    *oob_flag = 0u;
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmK);
@@ -200,6 +239,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(dq_free, COMP_THREADS);
     fence_barrier_init();
   }
+  if (FAST) __syncthreads();            // the out-of-range flag is zero before any thread may raise it
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   {
     if (COMPACT) {
@@ -212,14 +252,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int i = threadIdx.x; i < NDT * a.Hp * a.Wp; i += BTC_THREADS) sDTab[i] = 0.f;
     const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
     for (int n = threadIdx.x; n < NS; n += BTC_THREADS) {
+      const float px = pp[2 * n + 1];
+      if (FAST && !(fabsf(px) <= 1.0f)) *oob_flag = 1u;     // benign race: every writer stores the same value
       sYk[n] = pp[2 * n] * a.ky;
-      sXk[n] = pp[2 * n + 1] * a.kx;
+      sXk[n] = px * a.kx;
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const bool xclamp = FAST ? *oob_flag != 0u : true;      // samples inside [-1, 1] never leave the padded table
 
   if (warp == 0) {
     if (lane == 0) {
@@ -325,12 +368,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float aa = u + MAGIC;
         const float fy = (u - (aa - MAGIC)) + 0.5f;
         const int y0 = __float_as_int(aa) - MAGIC_BITS;
-        sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
+        if (FAST) {
+          const uint32_t ro8 = smem_u32(sTab) + ((uint32_t)((y0 + 2) * a.Wp + 2) << 3) - ((uint32_t)MAGIC_BITS << 3);
+          reinterpret_cast<uint4*>(sYt)[e] = make_uint4(ro8, pack_bf16x2(fy, fy), __float_as_uint(sXk[n]), 0u);
+        } else {
+          sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
+        }
       }
       comp_bar_sync();
       const float ax = (fmaf((float)c, a.gsx, -1.0f) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
       const float xhi = (float)a.Tw - 0.5f;
-      const float lse2 = lse[(long long)bh * a.HW + mm] * LOG2E;
+      // FAST: rows beyond HW get lse = +inf, i.e. p = 2^(-inf) = 0, instead of a select per score
+      const float lse2 = (FAST && !valid) ? INFINITY : lse[(long long)bh * a.HW + mm] * LOG2E;
       const float dl = delta[(long long)bh * a.HW + mm];
       const int r_up = __shfl_up_sync(FULL, r, 1);
       const bool row_head = lane == 0 || r_up != r;
@@ -351,6 +400,66 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(sdp_full, e_idx & 1u);
         tc_fence_after_sync();
         pf_wait += clock64() - pf_t;
+        if constexpr (FAST) {
+          auto fast_body = [&](auto xc_tag) {
+            constexpr bool XC = decltype(xc_tag)::value;
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+              const int col0 = chalf * 64 + sub * 32;          // column within the half
+              uint32_t sv[32], dpv[32];
+              pf_t = clock64();
+              tmem_ld_32x32(t_lane + TM_S + (uint32_t)col0, sv);
+              tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
+              tmem_wait_ld();
+              const int nbase = h * NHC + col0;
+              const uint4* yt = reinterpret_cast<const uint4*>(sYt) + (r - r0) * NS + nbase;
+              uint32_t g2[32];
+              uint32_t pp[4], dd[4];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint4 ye = yt[j];
+                float u = ax - __uint_as_float(ye.z);
+                if (XC) u = fminf(fmaxf(u, -1.5f), xhi);
+                const float aa = u + MAGIC;
+                const float fxp = u - (aa - MAGIC);                               // x fraction - 1/2
+                const uint2 e = lds64_b(ye.x + (__float_as_uint(aa) << 3));
+                const uint32_t md = hfma2_bf16_b(ye.y, e.y, e.x);                 // blend in y: {mid, dif}
+                const float dxb = __uint_as_float(md & 0xffff0000u);              // d bias / d ix  (x log2e)
+                const float bias = fmaf(fxp, dxb, __uint_as_float(md << 16));
+                const float dyb = fmaf(fxp, __uint_as_float(e.y & 0xffff0000u), __uint_as_float(e.y << 16));   // d bias / d iy
+                const float tv = fmaf(__uint_as_float(sv[j]), a.c1, bias);
+                const float p = ex2(tv - lse2);
+                const float ds = p * (__uint_as_float(dpv[j]) - dl);
+                g2[j] = pack_bf16x2(ds * dxb, ds * dyb);
+                if (j & 1) {
+                  pp[(j >> 1) & 3] = pack_bf16x2(__uint_as_float(sv[j - 1]), p);
+                  dd[(j >> 1) & 3] = pack_bf16x2(__uint_as_float(dpv[j - 1]), ds);
+                } else {                                             // park p, ds until the pair is complete
+                  sv[j] = __float_as_uint(p);
+                  dpv[j] = __float_as_uint(ds);
+                }
+                if ((j & 7) == 7) {
+                  const int ch = sub * 4 + (j >> 3);
+                  const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
+                  *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                  *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                  if (valid)      // the same 8 dS values, [m][n] layout, for the tensor-core table gradient
+                    *reinterpret_cast<uint4*>(ds_row + (long long)((nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                }
+              }
+              // d pos: column sums over this warp's 32 rows on bf16x2 pairs {x part, y part} (lane L ends up with
+              // column L); the running sums over tiles stay fp32
+              const long long pf_m = clock64();
+              pf_score += pf_m - pf_t;
+              const uint32_t cs = column_sums32_bf16x2(g2, lane);
+              dpx_acc[h * 2 + sub] += __uint_as_float(cs << 16);
+              dpy_acc[h * 2 + sub] += __uint_as_float(cs & 0xffff0000u);
+              pf_col += clock64() - pf_m;
+            }
+          };
+          if (xclamp) fast_body(std::true_type{});
+          else fast_body(std::false_type{});
+        } else {
 #pragma unroll 1
         for (int sub = 0; sub < 2; ++sub) {
           const int col0 = chalf * 64 + sub * 32;          // column within the half
@@ -494,6 +603,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           dpy_acc[h * 2 + sub] += column_sums32(gys, lane);
           pf_col += clock64() - pf_m;
         }
+        }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(pds_ready);
@@ -635,7 +745,8 @@ BtcVariant pick_variant(const Shape& s, bool tbl = true) {
   const int tries[4][3] = {{0, 1, 2}, {0, 0, 2}, {1, 0, 2}, {1, 0, 1}};   // {compact, priv, nslots}
   for (int t = 0; t < 4; ++t) {
     if (tries[t][1] && (!priv_ok || !tbl)) continue;
-    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, !tbl ? 0 : (tries[t][1] ? 8 : 1), tries[t][2]);
+    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, !tbl ? 0 : (tries[t][1] ? 8 : 1), tries[t][2],
+                               (!tbl && tries[t][0] == 0) ? 16 : 8);
     if (sp.total <= lim) {
       v.ok = 1; v.compact = tries[t][0]; v.priv = tries[t][1]; v.nslots = tries[t][2]; v.smem = sp.total;
       return v;
@@ -653,6 +764,15 @@ int debug_attn_bwd_timing(unsigned long long* out8) {
 
 bool attention_bwd_tc_supported(const Shape& s) { return s.pe_mode == DAT_PE_RPE && pick_variant(s).ok != 0; }
 bool attention_bwd_tc_compact_table(const Shape& s, bool tbl) { return pick_variant(s, tbl).compact != 0; }
+
+// packed table in the format the kernel variant of this shape reads: compact {T, T_x+1} entries, the forward-v2
+// (mid, dif) entries (dS streamed out, FAST score loop) or the 4-tap entries of the scatter variants
+int attention_bwd_pack_table(const Shape& s, const float* table, void* out, bool tbl, cudaStream_t st) {
+  const BtcVariant var = pick_variant(s, tbl);
+  if (var.compact) return attention_pack_table_compact(s, table, out, st);
+  if (!tbl) return attention_pack_table2(s, table, out, st);
+  return attention_pack_table(s, table, out, st);
+}
 
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st) {
   const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);

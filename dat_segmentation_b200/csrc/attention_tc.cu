@@ -858,6 +858,14 @@ int attention_pack_table(const Shape& s, const float* table, void* out, cudaStre
   return DAT_OK;
 }
 
+// (mid, dif) packed table of the forward v2 / backward FAST kernels into `out`, attention_fwd_tc_workspace(s) bytes
+int attention_pack_table2(const Shape& s, const float* table, void* out, cudaStream_t st) {
+  const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
+  pack_table2_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)out, s.heads, s.Th, s.Tw);
+  DAT_LAUNCH_OK("pack_table2_kernel");
+  return DAT_OK;
+}
+
 bool attention_fwd_tc_supported(const Shape& s) {
   if (s.act_dtype != DAT_BF16 || s.pe_mode != DAT_PE_RPE) return false;
   // one CTA holds up to 256 samples; more are split into chunks of 256 (+ a 128 and / or a 64 remainder)

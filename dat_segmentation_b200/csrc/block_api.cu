@@ -625,8 +625,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     DAT_FWD(attention_delta(s, w.d_o, sv->o, delta, st));
     const bool mma_table = use_mma_table_grad(s);
     if (!mma_table) DAT_CUDA_OK(cudaMemsetAsync(g->rpe_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
-    if (attention_bwd_tc_compact_table(s, !mma_table)) DAT_FWD(attention_pack_table_compact(s, p->rpe_table, tabp, st));
-    else DAT_FWD(attention_pack_table(s, p->rpe_table, tabp, st));
+    DAT_FWD(attention_bwd_pack_table(s, p->rpe_table, tabp, !mma_table, st));
     DAT_FWD(attention_bwd_tc(s, sv->q, sv->k, sv->v, w.d_o, sv->lse, delta, sv->pos, tabp, w.dq, dk_part,
                              dv_part, g->rpe_table, w.dpos_part, st, mma_table ? w.ds_tab : nullptr));
     DAT_FWD(reduce_partials(dk_part, chunks, (long long)s.B * s.Ns * C, w.dk, adt, st));

@@ -112,6 +112,8 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
 namespace dat {
 bool attention_bwd_tc_compact_table(const Shape& s, bool tbl = true);
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st);
+int attention_pack_table2(const Shape& s, const float* table, void* out, cudaStream_t st);
+int attention_bwd_pack_table(const Shape& s, const float* table, void* out, bool tbl, cudaStream_t st);
 }  // namespace dat
 
 namespace dat {

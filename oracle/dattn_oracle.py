@@ -511,11 +511,11 @@ def forward_libops(x_nchw: Tensor, p: Dict[str, Tensor], cfg: BlockCfg) -> Tenso
     Ns = hk * wk
     orf = cfg.offset_range_factor
     if orf >= 0:
-        rng = torch.tensor([1.0 / (hk - 1.0), 1.0 / (wk - 1.0)]).reshape(1, 2, 1, 1)  # fp32, :150
+        rng = torch.tensor([1.0 / (hk - 1.0), 1.0 / (wk - 1.0)], device=off.device).reshape(1, 2, 1, 1)  # fp32, :150
         off = off.tanh().mul(rng).mul(orf)
     off = off.permute(0, 2, 3, 1)
     ry, rx = ref_points(hk, wk, x_nchw.dtype)
-    ref = torch.stack(torch.meshgrid(ry, rx, indexing="ij"), -1)[None]
+    ref = torch.stack(torch.meshgrid(ry, rx, indexing="ij"), -1)[None].to(off.device)   # (device: GPU yardstick runs)
     pos = off + ref
     if orf < 0:
         pos = pos.clamp(-1.0, 1.0)
@@ -534,7 +534,7 @@ def forward_libops(x_nchw: Tensor, p: Dict[str, Tensor], cfg: BlockCfg) -> Tenso
     lepe = None
     if mode in ("rpe", "log_cpb"):
         qy, qx = query_grid(H, W, x_nchw.dtype)
-        qg = torch.stack(torch.meshgrid(qy, qx, indexing="ij"), -1).reshape(1, H * W, 1, 2)
+        qg = torch.stack(torch.meshgrid(qy, qx, indexing="ij"), -1).reshape(1, H * W, 1, 2).to(pos.device)
     if mode == "rpe":        # :198-214
         disp = (qg - pos.reshape(B * G, 1, Ns, 2)).mul(0.5)
         th, tw = p["rpe_table"].shape[1:]
