@@ -128,6 +128,21 @@ def lib():
     L.dat_dwconv_bwd.restype = C.c_int
     L.dat_layernorm_fwd.restype = C.c_int
     L.dat_layernorm_bwd.restype = C.c_int
+    L.dat_conv3x3s2_kp.argtypes = [i32]
+    L.dat_conv3x3s2_kp.restype = i32
+    L.dat_im2col3x3s2.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp]
+    L.dat_col2im3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.dat_conv_weight_pack.argtypes = [f32p, vp, i32, i32, vp]
+    L.dat_conv_weight_unpack.argtypes = [f32p, f32p, i32, i32, vp]
+    L.dat_gelu_fwd.argtypes = [vp, i32, vp, i32, i64, vp]
+    L.dat_gelu_bwd_mixed.argtypes = [vp, i32, vp, vp, i32, i64, vp]
+    L.dat_gelu_bwd_mixed.restype = C.c_int
+    L.dat_pointwise_wgrad_workspace_bytes.argtypes = [i64, i32, i32]
+    L.dat_pointwise_wgrad_workspace_bytes.restype = C.c_size_t
+    L.dat_pointwise_wgrad.argtypes = [vp, i32, vp, i32, f32p, f32p, i64, i32, i32, vp, C.c_size_t, vp]
+    for name in ("dat_im2col3x3s2", "dat_col2im3x3s2", "dat_conv_weight_pack", "dat_conv_weight_unpack", "dat_gelu_fwd",
+                 "dat_pointwise_wgrad"):
+        getattr(L, name).restype = C.c_int
     for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
                  "dat_pointwise_fwd_tc", "dat_cast_bf16",
                  "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd", "dat_attention_fwd",
@@ -156,4 +171,6 @@ def exported_symbols():
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
             "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd",
             "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad",
-            "dat_dwconv_bwd", "dat_scale_residual"]
+            "dat_dwconv_bwd", "dat_scale_residual",
+            "dat_conv3x3s2_kp", "dat_im2col3x3s2", "dat_col2im3x3s2", "dat_conv_weight_pack", "dat_conv_weight_unpack",
+            "dat_gelu_fwd", "dat_gelu_bwd_mixed", "dat_pointwise_wgrad_workspace_bytes", "dat_pointwise_wgrad"]

@@ -15,6 +15,7 @@ import os
 import torch
 import torch.nn as nn
 
+from .conv import Conv3x3s2CL, GeluCL
 from .dattention import DAttentionBaseline, _pair
 from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
@@ -274,10 +275,16 @@ class DAT(nn.Module):
             raise NotImplementedError("use_cmt_mlps (BatchNorm MLP variant) is not implemented")
         self.out_indices = out_indices
         half = dim_stem // 2
+        # b200_ops: the stride-2 3x3 convolutions (stem, down-projections) run as im2col + tcgen05 GEMMs (conv.py)
+        own_convs = b200_ops and use_conv_patches and patch_size == 4
+        conv3 = (lambda cin, cout, bias=True: Conv3x3s2CL(cin, cout, bias=bias)) if own_convs else \
+                (lambda cin, cout, bias=True: nn.Conv2d(cin, cout, 3, 2, 1, bias=bias))
         if use_conv_patches:
             self.patch_proj = nn.Sequential(
-                nn.Conv2d(3, half, 3, patch_size // 2, 1), norm_cls(half), nn.GELU(),
-                nn.Conv2d(half, dim_stem, 3, patch_size // 2, 1), norm_cls(dim_stem))
+                conv3(3, half) if patch_size == 4 else nn.Conv2d(3, half, 3, patch_size // 2, 1), norm_cls(half),
+                GeluCL() if own_convs else nn.GELU(),
+                conv3(half, dim_stem) if patch_size == 4 else nn.Conv2d(half, dim_stem, 3, patch_size // 2, 1),
+                norm_cls(dim_stem))
         else:
             self.patch_proj = nn.Sequential(nn.Conv2d(3, dim_stem, patch_size, patch_size, 0),
                                             norm_cls(dim_stem))
@@ -298,7 +305,7 @@ class DAT(nn.Module):
             fmap //= 2
         self.down_projs = nn.ModuleList()
         for i in range(3):
-            conv = (nn.Conv2d(dims[i], dims[i + 1], 3, 2, 1, bias=False) if use_conv_patches
+            conv = (conv3(dims[i], dims[i + 1], bias=False) if use_conv_patches
                     else nn.Conv2d(dims[i], dims[i + 1], 2, 2, 0, bias=False))
             self.down_projs.append(nn.Sequential(conv, norm_cls(dims[i + 1])))
         if b200_ops and os.environ.get("DAT_B200_NCHW_CONVS") is None:
@@ -306,7 +313,7 @@ class DAT(nn.Module):
             # channels_last too, so their outputs feed the LayerNorm kernels without NCHW <-> NHWC copies.
             # Shapes and state-dict contents are unchanged (only the parameters' strides differ).
             for m in list(self.patch_proj) + [dp[0] for dp in self.down_projs]:
-                if isinstance(m, nn.Conv2d):
+                if isinstance(m, nn.Conv2d) and not isinstance(m, Conv3x3s2CL):
                     m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
 
         # bf16 operand copies of every 1x1-conv weight, cast once per forward in one launch (weights.py)

@@ -343,6 +343,49 @@ int dat_pointwise_dgrad_tc(const void* dY, const void* W, void* dX, int32_t dx_d
   return pointwise_dgrad_tc(dY, W, nullptr, nullptr, dX, dx_dtype, M, N, K, (cudaStream_t)stream);
 }
 
+int32_t dat_conv3x3s2_kp(int32_t C) { return conv3x3s2_kp(C); }
+
+int dat_im2col3x3s2(const void* x, int32_t x_dtype, int32_t nchw_rgb, void* cols, int32_t B, int32_t H, int32_t W,
+                    int32_t C, void* stream) {
+  DAT_REQUIRE(x && cols && B > 0 && H > 0 && W > 0 && C > 0, "im2col3x3s2: bad arguments");
+  return im2col3x3s2(x, x_dtype, nchw_rgb, cols, B, H, W, C, (cudaStream_t)stream);
+}
+
+int dat_col2im3x3s2(const void* dcols, void* dx, int32_t dx_dtype, int32_t B, int32_t H, int32_t W, int32_t C,
+                    void* stream) {
+  DAT_REQUIRE(dcols && dx && B > 0 && H > 0 && W > 0 && C > 0, "col2im3x3s2: bad arguments");
+  return col2im3x3s2(dcols, dx, dx_dtype, B, H, W, C, (cudaStream_t)stream);
+}
+
+int dat_conv_weight_pack(const float* w, void* w2, int32_t Cout, int32_t C, void* stream) {
+  DAT_REQUIRE(w && w2 && Cout > 0 && C > 0, "conv_weight_pack: bad arguments");
+  return conv_weight_pack(w, w2, Cout, C, (cudaStream_t)stream);
+}
+
+int dat_conv_weight_unpack(const float* dw2, float* dw, int32_t Cout, int32_t C, void* stream) {
+  DAT_REQUIRE(dw2 && dw && Cout > 0 && C > 0, "conv_weight_unpack: bad arguments");
+  return conv_weight_unpack(dw2, dw, Cout, C, (cudaStream_t)stream);
+}
+
+int dat_gelu_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, void* stream) {
+  DAT_REQUIRE(x && y && n > 0, "gelu_fwd: bad arguments");
+  return gelu_fwd(x, x_dtype, y, y_dtype, n, (cudaStream_t)stream);
+}
+
+int dat_gelu_bwd_mixed(const void* dy, int32_t dy_dtype, const void* x, void* dx, int32_t x_dtype, int64_t n, void* stream) {
+  DAT_REQUIRE(dy && x && dx && n > 0, "gelu_bwd_mixed: bad arguments");
+  return gelu_bwd_mixed(dy, dy_dtype, x, dx, x_dtype, n, (cudaStream_t)stream);
+}
+
+size_t dat_pointwise_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K) { return pointwise_wgrad_workspace(M, N, K); }
+
+int dat_pointwise_wgrad(const void* dY, int32_t dy_dtype, const void* X, int32_t x_dtype, float* dW, float* db,
+                        int64_t M, int32_t N, int32_t K, void* workspace, size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(dY && X && dW && workspace, "pointwise_wgrad: NULL pointer");
+  DAT_REQUIRE(workspace_bytes >= pointwise_wgrad_workspace(M, N, K), "pointwise_wgrad: workspace too small");
+  return pointwise_wgrad_simt(dY, dy_dtype, X, x_dtype, dW, db, M, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int dat_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
   DAT_REQUIRE(src && dst && n > 0, "cast_bf16: bad arguments");
   return cast_weights_bf16(src, nullptr, nullptr, dst, n, (cudaStream_t)stream);

@@ -200,3 +200,14 @@ size_t rpe_table_grad_mma_workspace(const Shape& s);
 int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* d_table, void* ws, size_t ws_bytes,
                        cudaStream_t st);
 }  // namespace dat
+
+namespace dat {
+// conv_im2col.cu - data movement of the strided 3 x 3 convolutions (conv stem, down-projections) run as GEMMs
+int conv3x3s2_kp(int C);
+int im2col3x3s2(const void* x, int x_dt, int nchw_rgb, void* cols, int B, int H, int W, int C, cudaStream_t st);
+int col2im3x3s2(const void* dcols, void* dx, int dx_dt, int B, int H, int W, int C, cudaStream_t st);
+int conv_weight_pack(const float* w, void* w2, int Cout, int C, cudaStream_t st);
+int conv_weight_unpack(const float* dw2, float* dw, int Cout, int C, cudaStream_t st);
+int gelu_fwd(const void* x, int x_dt, void* y, int y_dt, long long n, cudaStream_t st);
+int gelu_bwd_mixed(const void* dy, int dy_dt, const void* x, void* dx, int x_dt, long long n, cudaStream_t st);
+}  // namespace dat

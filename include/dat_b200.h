@@ -269,6 +269,31 @@ int dat_dwconv_wgrad(const void* x, int32_t x_dtype, const void* dz, int32_t dz_
                      float* db, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ---- "next" row: the strided 3 x 3 convolutions around the stages ------------------
+ * Conv stem (dat.py:213-218) and down-projections (dat.py:264-274), kernel 3, stride 2, padding 1, run as GEMMs on
+ * the tensor-core kernels above:  cols = im2col(x);  Y = dat_pointwise_fwd_tc(cols, W2, b);  dW2 =
+ * dat_pointwise_wgrad_tc(dY, cols);  dcols = dat_pointwise_dgrad_tc(dY, W2);  dx = col2im(dcols).
+ * cols / dcols: (B * Ho * Wo, Kp) bf16, column t * C + c = tap t = kh * 3 + kw of channel c, Kp =
+ * dat_conv3x3s2_kp(C) = 9 C rounded up to a multiple of 64 (zero columns); W2: (Cout, Kp) bf16 in the same column
+ * order (dat_conv_weight_pack from the (Cout, C, 3, 3) fp32 parameter; dat_conv_weight_unpack maps dW2 back).
+ * x / dx are channel-last (B, H, W, C), C % 8 == 0; nchw_rgb = 1 reads the fp32 NCHW image (C = 3) of the stem. */
+int32_t dat_conv3x3s2_kp(int32_t C);
+int dat_im2col3x3s2(const void* x, int32_t x_dtype, int32_t nchw_rgb, void* cols, int32_t B, int32_t H, int32_t W,
+                    int32_t C, void* stream);
+int dat_col2im3x3s2(const void* dcols, void* dx, int32_t dx_dtype, int32_t B, int32_t H, int32_t W, int32_t C,
+                    void* stream);
+int dat_conv_weight_pack(const float* w, void* w2, int32_t Cout, int32_t C, void* stream);
+int dat_conv_weight_unpack(const float* dw2, float* dw, int32_t Cout, int32_t C, void* stream);
+/* y = gelu(x) (exact erf form, nn.GELU of the stem, dat.py:215), n % 4 == 0; backward: dat_gelu_bwd. */
+int dat_gelu_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, void* stream);
+/* dx = dy * gelu'(x): dy of dy_dtype, x and dx of x_dtype. */
+int dat_gelu_bwd_mixed(const void* dy, int32_t dy_dtype, const void* x, void* dx, int32_t x_dtype, int64_t n, void* stream);
+/* CUDA-core weight / bias gradient of a 1x1 convolution for shapes the tensor-core kernel does not tile (the
+ * 32-channel stem convolution): dW[N,K] = dY^T X, db[N] = column sums of dY (may be NULL); deterministic. */
+size_t dat_pointwise_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int dat_pointwise_wgrad(const void* dY, int32_t dy_dtype, const void* X, int32_t x_dtype, float* dW, float* db,
+                        int64_t M, int32_t N, int32_t K, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused backward of the 3 x 3 case (k must be 3, C even): one pass over dy, z (mode 2 only), x forms
  * dz = dy * gelu'(z) on the fly and produces dx (dtype of x), dw (C,1,3,3), db (C; may be NULL);
  * all overwritten, deterministic.  dy / z have dtype d_dtype.  Autograd of dat.py:135-138 and
