@@ -76,7 +76,8 @@ def test_gelu_kernel_matches_library():
     assert (x.grad - xr.grad).abs().max().item() < 1e-5
     with torch.autocast("cuda", dtype=torch.bfloat16):
         yb = g(x.detach())
-    assert yb.dtype == torch.bfloat16 and (yb.float() - yr.detach()).abs().max().item() < 2e-2
+    assert yb.dtype == torch.bfloat16                                   # one bf16 rounding of the fp32 value
+    assert ((yb.float() - yr.detach()).abs() <= yr.detach().abs() * 2.0 ** -8 + 1e-6).all()
 
 
 def test_backbone_has_no_library_convolutions_left():
