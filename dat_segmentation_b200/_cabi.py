@@ -137,6 +137,8 @@ def lib():
     L.dat_gelu_fwd.argtypes = [vp, i32, vp, i32, i64, vp]
     L.dat_gelu_bwd_mixed.argtypes = [vp, i32, vp, vp, i32, i64, vp]
     L.dat_gelu_bwd_mixed.restype = C.c_int
+    L.dat_transpose_pc.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.dat_transpose_pc.restype = C.c_int
     L.dat_pointwise_wgrad_workspace_bytes.argtypes = [i64, i32, i32]
     L.dat_pointwise_wgrad_workspace_bytes.restype = C.c_size_t
     L.dat_pointwise_wgrad.argtypes = [vp, i32, vp, i32, f32p, f32p, i64, i32, i32, vp, C.c_size_t, vp]
@@ -173,4 +175,4 @@ def exported_symbols():
             "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad",
             "dat_dwconv_bwd", "dat_scale_residual",
             "dat_conv3x3s2_kp", "dat_im2col3x3s2", "dat_col2im3x3s2", "dat_conv_weight_pack", "dat_conv_weight_unpack",
-            "dat_gelu_fwd", "dat_gelu_bwd_mixed", "dat_pointwise_wgrad_workspace_bytes", "dat_pointwise_wgrad"]
+            "dat_gelu_fwd", "dat_gelu_bwd_mixed", "dat_transpose_pc", "dat_pointwise_wgrad_workspace_bytes", "dat_pointwise_wgrad"]

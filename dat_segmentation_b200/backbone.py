@@ -15,7 +15,7 @@ import os
 import torch
 import torch.nn as nn
 
-from .conv import Conv3x3s2CL, GeluCL
+from .conv import Conv3x3s2CL, GeluCL, to_nchw_contiguous
 from .dattention import DAttentionBaseline, _pair
 from .dwconv import DepthwiseConvCL, MODE_PLAIN, MODE_RESIDUAL, MODE_RESIDUAL_GELU
 from .layernorm import LayerNormProxy, TorchLayerNormProxy
@@ -335,7 +335,7 @@ class DAT(nn.Module):
         outs = []
         for i in range(4):
             x = self.stages[i](x)
-            outs.append(self.norms[i](x).contiguous())
+            outs.append(to_nchw_contiguous(self.norms[i](x)))
             if i < 3:
                 x = self.down_projs[i](x)
         return outs

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import _cabi
 
-__all__ = ["Conv3x3s2CL", "GeluCL"]
+__all__ = ["Conv3x3s2CL", "GeluCL", "to_nchw_contiguous"]
 
 _CODE = {torch.float32: _cabi.DAT_F32, torch.bfloat16: _cabi.DAT_BF16}
 
@@ -171,3 +171,41 @@ class GeluCL(nn.GELU):
             return super().forward(x)
         out_dtype = torch.bfloat16 if _bf16_autocast(x) else x.dtype
         return _GeluFn.apply(x_l, out_dtype).permute(0, 3, 1, 2)
+
+
+class _ToNCHWFn(torch.autograd.Function):
+    """x_l (B, H, W, C) contiguous -> (B, C, H, W) contiguous."""
+
+    @staticmethod
+    def forward(ctx, x_l):
+        lib = _cabi.lib()
+        B, H, W, Cc = x_l.shape
+        dev = x_l.device
+        with torch.cuda.device(dev):
+            y = torch.empty(B, Cc, H, W, device=dev, dtype=x_l.dtype)
+            _cabi.check(lib.dat_transpose_pc(_ptr(x_l), _ptr(y), _CODE[x_l.dtype], B, H * W, Cc, _stream(dev)), "dat_transpose_pc")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.lib()
+        B, Cc, H, W = dy.shape
+        dev = dy.device
+        if dy.dtype not in _CODE:
+            dy = dy.float()
+        dy = dy.contiguous()
+        with torch.cuda.device(dev):
+            dx = torch.empty(B, H, W, Cc, device=dev, dtype=dy.dtype)
+            _cabi.check(lib.dat_transpose_pc(_ptr(dy), _ptr(dx), _CODE[dy.dtype], B, Cc, H * W, _stream(dev)), "dat_transpose_pc")
+        return dx
+
+
+def to_nchw_contiguous(x):
+    """`x.contiguous()` for an NCHW-shaped view of channel-last storage (the backbone outputs, dat.py:308-309) as one
+    dat_b200 transpose kernel each way; anything else goes to the library copy."""
+    if x.is_contiguous():
+        return x
+    x_l = x.permute(0, 2, 3, 1)
+    if not (x.is_cuda and x.dtype in _CODE and x_l.is_contiguous()) or os.environ.get("DAT_B200_LIBRARY_CONVS"):
+        return x.contiguous()
+    return _ToNCHWFn.apply(x_l)

@@ -377,6 +377,11 @@ int dat_gelu_bwd_mixed(const void* dy, int32_t dy_dtype, const void* x, void* dx
   return gelu_bwd_mixed(dy, dy_dtype, x, dx, x_dtype, n, (cudaStream_t)stream);
 }
 
+int dat_transpose_pc(const void* x, void* y, int32_t dtype, int32_t B, int32_t P, int32_t C, void* stream) {
+  DAT_REQUIRE(x && y && B > 0 && P > 0 && C > 0, "transpose_pc: bad arguments");
+  return transpose_pc(x, y, dtype, B, P, C, (cudaStream_t)stream);
+}
+
 size_t dat_pointwise_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K) { return pointwise_wgrad_workspace(M, N, K); }
 
 int dat_pointwise_wgrad(const void* dY, int32_t dy_dtype, const void* X, int32_t x_dtype, float* dW, float* db,

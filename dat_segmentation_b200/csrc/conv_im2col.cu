@@ -152,7 +152,35 @@ __global__ void gelu_bwd_mixed_kernel(const TD* __restrict__ dy, const TX* __res
   store4(dx + 4 * i, make_float4(d.x * gelu_dexact(z.x), d.y * gelu_dexact(z.y), d.z * gelu_dexact(z.z), d.w * gelu_dexact(z.w)));
 }
 
+// y[b][c][p] = x[b][p][c]: 32 x 32 tiles through shared memory, both sides coalesced.  The four backbone outputs are
+// returned NCHW-contiguous like the reference's (dat.py:308-309 `.contiguous()`); the same kernel with (P, C) swapped
+// is the gradient.
+template <typename T>
+__global__ void transpose_pc_kernel(const T* __restrict__ x, T* __restrict__ y, int P, int C) {
+  __shared__ T tile[32][33];
+  const long long base = (long long)blockIdx.z * P * C;
+  const int p0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < P && c < C) tile[r][threadIdx.x] = x[base + (long long)p * C + c];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < C && p < P) y[base + (long long)c * P + p] = tile[threadIdx.x][r];
+  }
+}
+
 }  // namespace
+
+int transpose_pc(const void* x, void* y, int dt, int B, int P, int C, cudaStream_t st) {
+  dim3 grid(ceil_div(C, 32), ceil_div(P, 32), B), block(32, 8);
+  DAT_REQUIRE(B <= 65535 && grid.y <= 65535, "transpose: tensor too large");
+  if (dt == DAT_F32) transpose_pc_kernel<float><<<grid, block, 0, st>>>((const float*)x, (float*)y, P, C);
+  else transpose_pc_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (bf16*)y, P, C);
+  DAT_LAUNCH_OK("transpose_pc_kernel");
+  return DAT_OK;
+}
 
 // dx = dy * gelu'(x); dy bf16 or fp32, x and dx of one dtype (the stem: dy bf16, x / dx fp32)
 int gelu_bwd_mixed(const void* dy, int dy_dt, const void* x, void* dx, int x_dt, long long n, cudaStream_t st) {

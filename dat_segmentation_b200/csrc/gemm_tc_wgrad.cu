@@ -171,7 +171,7 @@ int wg_bnk(int C) { return C % 128 == 0 ? 128 : 64; }
 bool pointwise_wgrad_tc_supported(long long M, int N, int K) {
   // N = 64 (and N = 32: the RGB stem convolution) run as partly empty 128-row tiles (the out-of-range part of the
   // dY box is zero-filled by TMA, the rows beyond N are never stored)
-  return M >= 64 && N % 32 == 0 && K % 64 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
+  return M >= 64 && (N % 64 == 0 || N == 32) && K % 64 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
 }
 
 int pointwise_wgrad_tc_splits(long long M, int N, int K) {

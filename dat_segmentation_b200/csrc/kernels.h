@@ -209,5 +209,6 @@ int col2im3x3s2(const void* dcols, void* dx, int dx_dt, int B, int H, int W, int
 int conv_weight_pack(const float* w, void* w2, int Cout, int C, cudaStream_t st);
 int conv_weight_unpack(const float* dw2, float* dw, int Cout, int C, cudaStream_t st);
 int gelu_fwd(const void* x, int x_dt, void* y, int y_dt, long long n, cudaStream_t st);
+int transpose_pc(const void* x, void* y, int dt, int B, int P, int C, cudaStream_t st);
 int gelu_bwd_mixed(const void* dy, int dy_dt, const void* x, void* dx, int x_dt, long long n, cudaStream_t st);
 }  // namespace dat

@@ -288,6 +288,9 @@ int dat_conv_weight_unpack(const float* dw2, float* dw, int32_t Cout, int32_t C,
 int dat_gelu_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, void* stream);
 /* dx = dy * gelu'(x): dy of dy_dtype, x and dx of x_dtype. */
 int dat_gelu_bwd_mixed(const void* dy, int32_t dy_dtype, const void* x, void* dx, int32_t x_dtype, int64_t n, void* stream);
+/* y[b][c][p] = x[b][p][c] (B, P, C) -> (B, C, P): channel-last -> NCHW-contiguous copy of the backbone outputs
+ * (dat.py:308-309); the gradient is the same call with P and C swapped. */
+int dat_transpose_pc(const void* x, void* y, int32_t dtype, int32_t B, int32_t P, int32_t C, void* stream);
 /* CUDA-core weight / bias gradient of a 1x1 convolution for shapes the tensor-core kernel does not tile (the
  * 32-channel stem convolution): dW[N,K] = dY^T X, db[N] = column sums of dY (may be NULL); deterministic. */
 size_t dat_pointwise_wgrad_workspace_bytes(int64_t M, int32_t N, int32_t K);

@@ -86,3 +86,15 @@ def test_backbone_has_no_library_convolutions_left():
     m = build_dat()
     convs = [c for c in list(m.patch_proj) + [dp[0] for dp in m.down_projs] if isinstance(c, torch.nn.Conv2d)]
     assert len(convs) == 5 and all(isinstance(c, Conv3x3s2CL) for c in convs)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_to_nchw_contiguous_matches_library_copy(dt):
+    from dat_segmentation_b200.conv import to_nchw_contiguous
+    torch.manual_seed(2)
+    x = torch.randn(3, 20, 13, 40, device="cuda").to(dt).permute(0, 3, 1, 2).requires_grad_(True)   # (B, C, H, W) view
+    y = to_nchw_contiguous(x)
+    assert y.is_contiguous() and torch.equal(y, x.detach().contiguous())
+    dy = torch.randn(3, 40, 20, 13, device="cuda").to(dt)
+    y.backward(dy)
+    assert torch.equal(x.grad, dy)
