@@ -158,7 +158,7 @@ __host__ __device__ inline SmemPlanB plan_smem_b(int NS, int Hp, int Wp, int row
   s.ds = off; off += 2 * 16384;
   s.tab = off; off += ((uint32_t)(Hp * Wp) * (compact ? 4 : 8) + 15) & ~15u;
   s.dtab = off; off += ((uint32_t)(ndt * Hp * Wp) * 4 + 15) & ~15u;
-  s.yt = off; off += (uint32_t)rows_max * NS * yt_bytes;
+  s.yt = off; off += 2u * (uint32_t)rows_max * NS * yt_bytes;   // double-buffered: built one tile ahead
   s.xk = off; off += NS * 4;
   s.yk = off; off += NS * 4;
   s.dpos = s.p;                            // per-warp column sums [8][NS][2] alias P/dS at the end
@@ -216,6 +216,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* pds_ready = bars + 6;
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_free = bars + 8;
+  uint64_t* pds_free = bars + 11;   // (bars + 9, + 10 hold the tensor-memory slot and the out-of-range flag)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   uint32_t* oob_flag = tmem_slot + 1;
 
@@ -237,6 +238,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(pds_ready, COMP_THREADS);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, COMP_THREADS);
+    mbar_init(pds_free, 1);
     fence_barrier_init();
   }
   if (FAST) __syncthreads();            // the out-of-range flag is zero before any thread may raise it
@@ -288,55 +290,63 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       mbar_wait(kv_full, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int slot = it % a.nslots;
-        mbar_wait(&qdo_full[slot], (uint32_t)(it / a.nslots) & 1u);
+      const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int E = n_my * NHALF;                       // halves this CTA processes
+      // S_h = Q K_h^T, dP_h = dO V_h^T into the (single) S / dP buffer
+      auto issue_sdp = [&](int e) {
+        const int it_e = e / NHALF, h = e % NHALF, slot = it_e % a.nslots;
+        if (h == 0) mbar_wait(&qdo_full[slot], (uint32_t)(it_e / a.nslots) & 1u);
+        tc_fence_after_sync();
         const uint32_t q_addr = smem_u32(sQ0 + slot * (TQ * 64));
         const uint32_t do_addr = smem_u32(sDO0 + slot * (TQ * 64));
 #pragma unroll
-        for (int h = 0; h < NHALF; ++h) {
-          const uint32_t e = (uint32_t)(it * NHALF + h);
-          tc_fence_after_sync();
-          // S_h = Q K_h^T, dP_h = dO V_h^T  (in-order tensor pipe: the previous half's
-          // consumers of TMEM S/dP finished before pds_ready, which was waited below)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            mma_bf16_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64),
-                        make_smem_desc(k_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s,
-                        (uint32_t)k);
-          }
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            mma_bf16_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16, 512, LAYOUT_SW64),
-                        make_smem_desc(v_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s,
-                        (uint32_t)k);
-          }
-          tc_commit(sdp_full);
-          mbar_wait(pds_ready, e & 1u);
-          if (h == 0 && it > 0) mbar_wait(dq_free, (uint32_t)(it - 1) & 1u);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int j = 0; j < NHC / 16; ++j) {     // contraction over the 128 queries of the tile
-            const uint64_t a_p = make_smem_desc(p_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
-            const uint64_t a_ds = make_smem_desc(ds_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
-            const uint64_t b_do = make_smem_desc(do_addr + j * 1024, 512, 512, LAYOUT_SW64);
-            const uint64_t b_q = make_smem_desc(q_addr + j * 1024, 512, 512, LAYOUT_SW64);
-            const uint32_t acc = (uint32_t)((it | j) != 0);
-            mma_bf16_ss(tmem_base + TM_DV + h * 32, a_p, b_do, idesc_kv, acc);
-            mma_bf16_ss(tmem_base + TM_DK + h * 32, a_ds, b_q, idesc_kv, acc);
-          }
-#pragma unroll
-          for (int kk = 0; kk < NHC / 16; ++kk) {  // contraction over the 128 keys of the half
-            const uint64_t a_ds = make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-            const uint64_t b_k = make_smem_desc(k_addr + (h * NHC + kk * 16) * 64, 512, 512, LAYOUT_SW64);
-            mma_bf16_ss(tmem_base + TM_DQ, a_ds, b_k, idesc_q, (uint32_t)((h | kk) != 0));
-          }
-          if (h == NHALF - 1) {
-            tc_commit(dq_full);
-            tc_commit(&qdo_empty[slot]);
-          }
+        for (int k = 0; k < 2; ++k) {
+          mma_bf16_ss(tmem_base + TM_S, make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64),
+                      make_smem_desc(k_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s, (uint32_t)k);
         }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          mma_bf16_ss(tmem_base + TM_DP, make_smem_desc(do_addr + k * 32, 16, 512, LAYOUT_SW64),
+                      make_smem_desc(v_addr + h * NHC * 64 + k * 32, 16, 512, LAYOUT_SW64), idesc_s, (uint32_t)k);
+        }
+        tc_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int e = 0; e < E; ++e) {
+        const int it = e / NHALF, h = e % NHALF, slot = it % a.nslots;
+        const uint32_t q_addr = smem_u32(sQ0 + slot * (TQ * 64));
+        const uint32_t do_addr = smem_u32(sDO0 + slot * (TQ * 64));
+        mbar_wait(pds_ready, (uint32_t)e & 1u);        // P_h / dS_h are in shared memory, S / dP have been read
+        // The next half's S / dP go FIRST: the compute warps get their next scores after 4 MMAs instead of after
+        // the 24 gradient MMAs of this half (which they wait for only before overwriting the P / dS tiles: pds_free).
+        // A single Q / dO slot cannot do that across a tile boundary (the next tile's Q arrives only after this
+        // tile's last MMAs have released the slot).
+        const bool early = e + 1 < E && !(a.nslots == 1 && h == NHALF - 1);
+        if (early) issue_sdp(e + 1);
+        if (h == 0 && it > 0) mbar_wait(dq_free, (uint32_t)(it - 1) & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < NHC / 16; ++j) {     // contraction over the 128 queries of the tile
+          const uint64_t a_p = make_smem_desc(p_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
+          const uint64_t a_ds = make_smem_desc(ds_addr + j * 2048, 16384, 1024, LAYOUT_SW128);
+          const uint64_t b_do = make_smem_desc(do_addr + j * 1024, 512, 512, LAYOUT_SW64);
+          const uint64_t b_q = make_smem_desc(q_addr + j * 1024, 512, 512, LAYOUT_SW64);
+          const uint32_t acc = (uint32_t)((it | j) != 0);
+          mma_bf16_ss(tmem_base + TM_DV + h * 32, a_p, b_do, idesc_kv, acc);
+          mma_bf16_ss(tmem_base + TM_DK + h * 32, a_ds, b_q, idesc_kv, acc);
+        }
+#pragma unroll
+        for (int kk = 0; kk < NHC / 16; ++kk) {  // contraction over the 128 keys of the half
+          const uint64_t a_ds = make_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t b_k = make_smem_desc(k_addr + (h * NHC + kk * 16) * 64, 512, 512, LAYOUT_SW64);
+          mma_bf16_ss(tmem_base + TM_DQ, a_ds, b_k, idesc_q, (uint32_t)((h | kk) != 0));
+        }
+        tc_commit(pds_free);                     // the P / dS tiles of this half have been consumed
+        if (h == NHALF - 1) {
+          tc_commit(dq_full);
+          tc_commit(&qdo_empty[slot]);
+        }
+        if (!early && e + 1 < E) issue_sdp(e + 1);
       }
     }
   } else if (warp >= 4) {
@@ -350,18 +360,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int i = 0; i < NHALF * 2; ++i) dpx_acc[i] = dpy_acc[i] = 0.f;
     int it = 0;
     long long pf_total = clock64(), pf_wait = 0, pf_score = 0, pf_col = 0, pf_dq = 0, pf_setup = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      long long pf_t = clock64();
-      const int m = tile * TQ + row;
-      const bool valid = m < a.HW;
-      const int mm = valid ? m : a.HW - 1;
-      const int r = mm / a.W, c = mm - r * a.W;
-      const int r0 = (tile * TQ) / a.W;
-      const int r_last = min(a.HW - 1, tile * TQ + TQ - 1) / a.W;
-      comp_bar_sync();     // previous tile finished with sYt
-      for (int e = ctid; e < (r_last - r0 + 1) * NS; e += COMP_THREADS) {
+    // per-(image row of the tile, sample) y footprint, double-buffered: the table of tile i + 1 is built after the score
+    // loops of tile i, so a tile starts with ONE barrier and no table build on its critical path
+    const uint32_t yt_stride = (uint32_t)a.rows_max * NS * (FAST ? 16u : 8u);
+    auto build_yt = [&](int tile_b, int buf) {
+      uint8_t* dstb = reinterpret_cast<uint8_t*>(sYt) + (size_t)buf * yt_stride;
+      const int r0b = (tile_b * TQ) / a.W;
+      const int r_lastb = min(a.HW - 1, tile_b * TQ + TQ - 1) / a.W;
+      for (int e = ctid; e < (r_lastb - r0b + 1) * NS; e += COMP_THREADS) {
         const int rr = e / NS, n = e - rr * NS;
-        const float gy = fmaf((float)(r0 + rr), a.gsy, -1.0f);
+        const float gy = fmaf((float)(r0b + rr), a.gsy, -1.0f);
         const float ay = (gy * 0.25f + 0.5f) * (float)(a.Th - 1) - 0.5f;
         float u = ay - sYk[n];
         u = fminf(fmaxf(u, -1.5f), (float)a.Th - 0.5f);
@@ -370,12 +378,44 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int y0 = __float_as_int(aa) - MAGIC_BITS;
         if (FAST) {
           const uint32_t ro8 = smem_u32(sTab) + ((uint32_t)((y0 + 2) * a.Wp + 2) << 3) - ((uint32_t)MAGIC_BITS << 3);
-          reinterpret_cast<uint4*>(sYt)[e] = make_uint4(ro8, pack_bf16x2(fy, fy), __float_as_uint(sXk[n]), 0u);
+          reinterpret_cast<uint4*>(dstb)[e] = make_uint4(ro8, pack_bf16x2(fy, fy), __float_as_uint(sXk[n]), 0u);
         } else {
-          sYt[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
+          reinterpret_cast<int2*>(dstb)[e] = make_int2((y0 + 2) * a.Wp + 2 - MAGIC_BITS, __float_as_int(fy));
         }
       }
-      comp_bar_sync();
+    };
+    // dQ of a finished tile: TMEM -> * scale -> bf16 -> global (each compute warp writes 16 channels).  Deferred into
+    // the first half of the NEXT tile: its MMAs are long done by then, so no thread waits for the tensor pipe
+    auto dq_epilogue = [&](int it_e, int m_e, bool valid_e) {
+      mbar_wait(dq_full, (uint32_t)it_e & 1u);
+      tc_fence_after_sync();
+      uint32_t qv[16];
+      tmem_ld_32x16(t_lane + TM_DQ + (uint32_t)(chalf * 16), qv);
+      tmem_wait_ld();
+      tc_fence_before_sync();
+      mbar_arrive(dq_free);
+      if (valid_e) {
+        uint32_t pk8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pk8[i] = pack_bf16x2(__uint_as_float(qv[2 * i]) * a.scale, __uint_as_float(qv[2 * i + 1]) * a.scale);
+        uint4* dst = reinterpret_cast<uint4*>(dq + ((long long)b * a.HW + m_e) * a.C + eta * 32 + chalf * 16);
+        dst[0] = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
+        dst[1] = make_uint4(pk8[4], pk8[5], pk8[6], pk8[7]);
+      }
+    };
+    build_yt(blockIdx.x, 0);
+    int m_prev = 0;
+    bool valid_prev = false;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      long long pf_t = clock64();
+      const int m = tile * TQ + row;
+      const bool valid = m < a.HW;
+      const int mm = valid ? m : a.HW - 1;
+      const int r = mm / a.W, c = mm - r * a.W;
+      const int r0 = (tile * TQ) / a.W;
+      comp_bar_sync();     // this tile's y table is complete; the other buffer is free for the next tile's
+      const uint8_t* yt_base = reinterpret_cast<const uint8_t*>(sYt) + (size_t)(it & 1) * yt_stride;
       const float ax = (fmaf((float)c, a.gsx, -1.0f) * 0.25f + 0.5f) * (float)(a.Tw - 1) - 0.5f;
       const float xhi = (float)a.Tw - 0.5f;
       // FAST: rows beyond HW get lse = +inf, i.e. p = 2^(-inf) = 0, instead of a select per score
@@ -412,7 +452,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
               tmem_wait_ld();
               const int nbase = h * NHC + col0;
-              const uint4* yt = reinterpret_cast<const uint4*>(sYt) + (r - r0) * NS + nbase;
+              const uint4* yt = reinterpret_cast<const uint4*>(yt_base) + (r - r0) * NS + nbase;
               uint32_t g2[32];
               uint32_t pp[4], dd[4];
 #pragma unroll
@@ -439,6 +479,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                   dpv[j] = __float_as_uint(ds);
                 }
                 if ((j & 7) == 7) {
+                  // first store of this half: the tensor core must have consumed the previous half's tiles
+                  if (j == 7 && sub == 0 && e_idx > 0) mbar_wait(pds_free, (e_idx - 1u) & 1u);
                   const int ch = sub * 4 + (j >> 3);
                   const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
                   *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
@@ -469,7 +511,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
           tmem_wait_ld();
           const int nbase = h * NHC + col0;
-          const int2* yt = sYt + (r - r0) * NS + nbase;
+          const int2* yt = reinterpret_cast<const int2*>(yt_base) + (r - r0) * NS + nbase;
           const float* xk = sXk + nbase;
           float gxs[32], gys[32];
           uint32_t pp[16], dd[16];
@@ -512,6 +554,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             if ((j & 7) == 7) {
               // P_h, dS_h -> shared memory (K-major, 128B swizzle), 16 bytes per 8 columns
+              if (j == 7 && sub == 0 && e_idx > 0) mbar_wait(pds_free, (e_idx - 1u) & 1u);   // previous tiles consumed
               const int ch = sub * 4 + (j >> 3);
               const uint32_t sw = (uint32_t)((ch ^ (row & 7)) << 4);
               *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
@@ -604,29 +647,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           pf_col += clock64() - pf_m;
         }
         }
+        if (h == 0 && it > 0) {         // the previous tile's dQ (its MMAs finished long ago); frees the accumulator
+          pf_t = clock64();             // before this half's dQ MMAs are issued (they follow pds_ready)
+          dq_epilogue(it - 1, m_prev, valid_prev);
+          pf_dq += clock64() - pf_t;
+        }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(pds_ready);
       }
-
-      // dQ tile: TMEM -> * scale -> bf16 -> global (each compute warp writes 16 channels)
       pf_t = clock64();
-      mbar_wait(dq_full, (uint32_t)it & 1u);
-      tc_fence_after_sync();
-      uint32_t qv[16];
-      tmem_ld_32x16(t_lane + TM_DQ + (uint32_t)(chalf * 16), qv);
-      tmem_wait_ld();
-      tc_fence_before_sync();
-      mbar_arrive(dq_free);
-      if (valid) {
-        uint32_t pk8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          pk8[i] = pack_bf16x2(__uint_as_float(qv[2 * i]) * a.scale, __uint_as_float(qv[2 * i + 1]) * a.scale);
-        uint4* dst = reinterpret_cast<uint4*>(dq + ((long long)b * a.HW + m) * a.C + eta * 32 + chalf * 16);
-        dst[0] = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
-        dst[1] = make_uint4(pk8[4], pk8[5], pk8[6], pk8[7]);
-      }
+      if (tile + (int)gridDim.x < a.n_tiles) build_yt(tile + gridDim.x, (it + 1) & 1);
+      pf_setup += clock64() - pf_t;
+      m_prev = m;
+      valid_prev = valid;
+    }
+    {
+      const long long pf_t = clock64();
+      dq_epilogue(it - 1, m_prev, valid_prev);      // the last tile's dQ; also: every MMA of the CTA has completed
       pf_dq += clock64() - pf_t;
     }
     if (warp == 4 && lane == 0) {
