@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdat_b200.so")
+# DAT_B200_LIB: another build of the same library (A/B timing of two builds in one process environment: tools/ only)
+LIB_PATH = os.environ.get("DAT_B200_LIB") or os.path.join(_HERE, "libdat_b200.so")
 
 DAT_F32, DAT_BF16 = 0, 1
 HEAD_DIM = 32

@@ -127,6 +127,7 @@ __device__ __forceinline__ uint2 lds64_b(uint32_t addr) {
 // zero outside the table
 __global__ void pack_table_compact_kernel(const float* __restrict__ table, uint32_t* __restrict__ out,
                                           int heads, int Th, int Tw) {
+  pdl_enter();
   const int Wp = Tw + 3, Hp = Th + 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= heads * Hp * Wp) return;
@@ -185,6 +186,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    bf16* __restrict__ dq, float* __restrict__ dk_part, float* __restrict__ dv_part,
                    float* __restrict__ d_table, float* __restrict__ dpos_part, bf16* __restrict__ ds_out,
                    BtcArgs a) {
+  pdl_enter();
   constexpr int NHALF = NS / NHC;
   constexpr int NDT = !TBL ? 0 : (PRIV ? 8 : 1);          // copies of the table gradient
   // FAST (dS streamed out, 8-byte table entries - every DAT++ stage but the 111 x 111 table of stage 0): the bias and
@@ -814,7 +816,7 @@ int attention_bwd_pack_table(const Shape& s, const float* table, void* out, bool
 
 int attention_pack_table_compact(const Shape& s, const float* table, void* out, cudaStream_t st) {
   const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
-  pack_table_compact_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint32_t*)out, s.heads, s.Th, s.Tw);
+  launch_k(pack_table_compact_kernel, ceil_div(ntab, 256), 256, 0, st, table, (uint32_t*)out, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table_compact_kernel");
   return DAT_OK;
 }
@@ -856,7 +858,7 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
   do {                                                                                           \
     auto kern = attn_bwd_tc_kernel<NSV, CP, PV, TB>;                                             \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem)); \
-    kern<<<grid, BTC_THREADS, var.smem, st>>>(tmQ, tmDO, tmK, tmV, pos, tab_packed, lse, delta,  \
+    launch_k(kern, grid, BTC_THREADS, var.smem, st, tmQ, tmDO, tmK, tmV, pos, tab_packed, lse, delta,  \
                                               (bf16*)dq, dk_part, dv_part, d_table, dpos_part, (bf16*)ds_out, a); \
   } while (0)
 #define LAUNCH_NS(NSV)                                   \

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                      const float* __restrict__ pos, const float* __restrict__ table,
                      T* __restrict__ o, float* __restrict__ lse, AttnArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem[];
   const int tsz = a.table_in_smem ? ((a.Th * a.Tw + 3) & ~3) : 0;
   float* tab_s = smem;
@@ -207,6 +208,7 @@ attn_fwd_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
 // bias (B, heads, HW, Ns) alone — test hook for the rpe path
 __global__ void rpe_bias_kernel(const float* __restrict__ pos, const float* __restrict__ table,
                                 float* __restrict__ bias, AttnArgs a, long long total) {
+  pdl_enter();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int n = (int)(idx % a.Ns);
@@ -224,6 +226,7 @@ template <typename T>
 __global__ void attn_delta_kernel(const T* __restrict__ d_o, const T* __restrict__ o,
                                   float* __restrict__ delta, int HW, int C, int heads,
                                   long long total) {
+  pdl_enter();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, m, eta)
   if (idx >= total) return;
   const int eta = (int)(idx % heads);
@@ -251,6 +254,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
                    const float* __restrict__ delta, const float* __restrict__ pos,
                    const float* __restrict__ table, T* __restrict__ dq,
                    float* __restrict__ d_table, AttnArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem[];
   const int tsz = (a.Th * a.Tw + 3) & ~3;
   float* tab_s = smem;
@@ -342,6 +346,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
                     const float* __restrict__ table, float* __restrict__ dk_part,
                     float* __restrict__ dv_part, float* __restrict__ dpos_part, int q_per_split,
                     AttnArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float smem[];
   const int tsz = a.table_in_smem ? ((a.Th * a.Tw + 3) & ~3) : 0;
   float* tab_s = smem;
@@ -475,7 +480,7 @@ int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void*
     using T = decltype(tv);
     constexpr int BM = decltype(bmc)::value;
     DAT_FWD(set_smem(attn_fwd_simt_kernel<T, BM>, smem));
-    attn_fwd_simt_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, pos, table,
+    launch_k(attn_fwd_simt_kernel<T, BM>, grid, ATT_THREADS, smem, st, (const T*)q, (const T*)k, (const T*)v, pos, table,
                                                                    (T*)o, lse, a);
     return DAT_OK;
   }));
@@ -486,7 +491,7 @@ int attention_fwd_simt(const Shape& s, const void* q, const void* k, const void*
 int rpe_bias(const Shape& s, const float* pos, const float* table, float* bias, cudaStream_t st) {
   AttnArgs a = make_args(s);
   long long total = (long long)s.B * s.heads * s.HW * s.Ns;
-  rpe_bias_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pos, table, bias, a, total);
+  launch_k(rpe_bias_kernel, ceil_div(total, 256), 256, 0, st, pos, table, bias, a, total);
   DAT_LAUNCH_OK("rpe_bias_kernel");
   return DAT_OK;
 }
@@ -503,9 +508,9 @@ int attention_bwd_qsplit(const Shape& s) {
 int attention_delta(const Shape& s, const void* d_o, const void* o, float* delta, cudaStream_t st) {
   long long tot = (long long)s.B * s.HW * s.heads;
   if (s.act_dtype == DAT_F32)
-    attn_delta_kernel<float><<<ceil_div(tot, 256), 256, 0, st>>>((const float*)d_o, (const float*)o, delta, s.HW, s.C, s.heads, tot);
+    launch_k(attn_delta_kernel<float>, ceil_div(tot, 256), 256, 0, st, (const float*)d_o, (const float*)o, delta, s.HW, s.C, s.heads, tot);
   else
-    attn_delta_kernel<bf16><<<ceil_div(tot, 256), 256, 0, st>>>((const bf16*)d_o, (const bf16*)o, delta, s.HW, s.C, s.heads, tot);
+    launch_k(attn_delta_kernel<bf16>, ceil_div(tot, 256), 256, 0, st, (const bf16*)d_o, (const bf16*)o, delta, s.HW, s.C, s.heads, tot);
   DAT_LAUNCH_OK("attn_delta_kernel");
   return DAT_OK;
 }
@@ -546,7 +551,7 @@ int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void*
       using T = decltype(tv);
       constexpr int BM = decltype(bmc)::value;
       DAT_FWD(set_smem(attn_bwd_dq_kernel<T, BM>, smem));
-      attn_bwd_dq_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
+      launch_k(attn_bwd_dq_kernel<T, BM>, grid, ATT_THREADS, smem, st, (const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
                                                                    delta, pos, table, (T*)dq, d_table, a);
       return DAT_OK;
     }));
@@ -561,7 +566,7 @@ int attention_bwd_simt(const Shape& s, const void* q, const void* k, const void*
       using T = decltype(tv);
       constexpr int BM = decltype(bmc)::value;
       DAT_FWD(set_smem(attn_bwd_dkv_kernel<T, BM>, smem));
-      attn_bwd_dkv_kernel<T, BM><<<grid, ATT_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
+      launch_k(attn_bwd_dkv_kernel<T, BM>, grid, ATT_THREADS, smem, st, (const T*)q, (const T*)k, (const T*)v, (const T*)d_o, lse,
                                                                     delta, pos, table, dk_part, dv_part, dpos_part, qps, a);
       return DAT_OK;
     }));

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 //   .x = bf16x2 {T[y][x],   T[y][x+1]   - T[y][x]}      .y = bf16x2 {T[y+1][x], T[y+1][x+1] - T[y+1][x]}
 __global__ void pack_table_kernel(const float* __restrict__ table, uint2* __restrict__ out,
                                   int heads, int Th, int Tw) {
+  pdl_enter();
   const int Wp = Tw + 3, Hp = Th + 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= heads * Hp * Wp) return;
@@ -123,6 +124,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const float* __restrict__ pos,
                    const uint2* __restrict__ tab_packed, bf16* __restrict__ o,
                    float* __restrict__ lse, AtcArgs a) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -405,6 +407,7 @@ __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
 //   .x = bf16x2 {m0 = (T[y][x] + T[y][x+1]) / 2, d0 = T[y][x+1] - T[y][x]}      .y = bf16x2 {m1 - m0, d1 - d0} (row y + 1)
 // bilinear value at (y + fy, x + 1/2 + fx'):  (m0 + fy (m1 - m0)) + fx' (d0 + fy (d1 - d0))
 __global__ void pack_table2_kernel(const float* __restrict__ table, uint2* __restrict__ out, int heads, int Th, int Tw) {
+  pdl_enter();
   const int Wp = Tw + 3, Hp = Th + 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= heads * Hp * Wp) return;
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ pos,
                     const uint2* __restrict__ tab_packed, bf16* __restrict__ o, float* __restrict__ lse, AtcArgs a) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -794,6 +798,7 @@ AtcArgs make_args(const Shape& s) {
 __global__ void attn_combine_kernel(const bf16* __restrict__ o_part, const float* __restrict__ lse_part,
                                     bf16* __restrict__ o, float* __restrict__ lse, int nch, int HW, int C, int heads,
                                     long long o_zstride, long long lse_zstride, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, m, eta, 8-channel group)
   if (idx >= total) return;
   const int c8 = (int)(idx & 3);
@@ -853,7 +858,7 @@ size_t attention_fwd_tc_workspace(const Shape& s) {
 // packed table (see pack_table_kernel) into `out`, attention_fwd_tc_workspace(s) bytes
 int attention_pack_table(const Shape& s, const float* table, void* out, cudaStream_t st) {
   const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
-  pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)out, s.heads, s.Th, s.Tw);
+  launch_k(pack_table_kernel, ceil_div(ntab, 256), 256, 0, st, table, (uint2*)out, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table_kernel");
   return DAT_OK;
 }
@@ -861,7 +866,7 @@ int attention_pack_table(const Shape& s, const float* table, void* out, cudaStre
 // (mid, dif) packed table of the forward v2 / backward FAST kernels into `out`, attention_fwd_tc_workspace(s) bytes
 int attention_pack_table2(const Shape& s, const float* table, void* out, cudaStream_t st) {
   const int ntab = s.heads * (s.Th + 3) * (s.Tw + 3);
-  pack_table2_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)out, s.heads, s.Th, s.Tw);
+  launch_k(pack_table2_kernel, ceil_div(ntab, 256), 256, 0, st, table, (uint2*)out, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table2_kernel");
   return DAT_OK;
 }
@@ -883,8 +888,8 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   AtcArgs a = make_args(s);
   const int ntab = s.heads * a.Hp * a.Wp;
   const bool v2 = attention_fwd_tc_v2(s);
-  if (v2) pack_table2_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
-  else pack_table_kernel<<<ceil_div(ntab, 256), 256, 0, st>>>(table, (uint2*)ws, s.heads, s.Th, s.Tw);
+  if (v2) launch_k(pack_table2_kernel, ceil_div(ntab, 256), 256, 0, st, table, (uint2*)ws, s.heads, s.Th, s.Tw);
+  else launch_k(pack_table_kernel, ceil_div(ntab, 256), 256, 0, st, table, (uint2*)ws, s.heads, s.Th, s.Tw);
   DAT_LAUNCH_OK("pack_table_kernel");
   const int nch = kv_chunks(s.Ns);
   bf16* o_dst = (bf16*)o;
@@ -916,7 +921,7 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   do {                                                                                            \
     auto kern = attn_fwd_tc2_kernel<NSV>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp2.total)); \
-    kern<<<grid, A2_THREADS, sp2.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
+    launch_k(kern, grid, A2_THREADS, sp2.total, st, tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
   } while (0)
       if (size == 256) LAUNCH2(256);
       else if (size == 128) LAUNCH2(128);
@@ -931,7 +936,7 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   do {                                                                                           \
     auto kern = attn_fwd_tc_kernel<NSV>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total)); \
-    kern<<<grid, ATC_THREADS, sp.total, st>>>(tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
+    launch_k(kern, grid, ATC_THREADS, sp.total, st, tmQ, tmK, tmV, pos, (const uint2*)ws, o_dst, lse_dst, a); \
   } while (0)
     if (size == 256) LAUNCH(256);
     else if (size == 128) LAUNCH(128);
@@ -943,7 +948,7 @@ int attention_fwd_tc(const Shape& s, const void* q, const void* k, const void* v
   }
   if (nch > 1) {
     const long long total = (long long)s.B * s.HW * s.heads * 4;
-    attn_combine_kernel<<<ceil_div(total, 256), 256, 0, st>>>(o_dst, lse_dst, (bf16*)o, lse, nch, s.HW, s.C, s.heads,
+    launch_k(attn_combine_kernel, ceil_div(total, 256), 256, 0, st, o_dst, lse_dst, (bf16*)o, lse, nch, s.HW, s.C, s.heads,
                                                                a.o_zstride, a.lse_zstride, total);
     DAT_LAUNCH_OK("attn_combine_kernel");
   }

@@ -14,6 +14,10 @@ namespace dat {
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;  // statistics only (relaxed atomic increments)
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("DAT_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/dat_b200.h"
 
 namespace dat {
@@ -65,6 +67,36 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // ---- device helpers --------------------------------------------------------------
 #ifdef __CUDACC__
+
+// ---- programmatic dependent launch ---------------------------------------------------------
+// Every kernel of the library starts with pdl_enter() and is launched through launch_k(): the launch carries the
+// programmatic-stream-serialization attribute, so the grid may be scheduled while the previous kernel of the stream is
+// still draining (its CTAs have all started and signalled `launch_dependents`); `griddepcontrol.wait` then blocks
+// until that kernel has completed and its writes are visible.  Nothing is read or written before the wait, so the
+// semantics are those of a plain in-order stream - only launch latency, CTA scheduling and the flush at the kernel
+// boundary overlap the previous kernel's tail.  Captured into CUDA graphs as programmatic edges.
+// DAT_B200_PDL=0 launches without the attribute (the wait is then a no-op).
+__device__ __forceinline__ void pdl_enter() {
+#ifdef DAT_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface in DAT_LAUNCH_OK
+}
 
 typedef __nv_bfloat16 bf16;
 

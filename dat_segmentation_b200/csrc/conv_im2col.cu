@@ -28,6 +28,7 @@ __device__ __forceinline__ uint4 load8_bf16(const float* p) {
 template <typename TI>
 __global__ void im2col3x3s2_kernel(const TI* __restrict__ x, bf16* __restrict__ cols, int B, int H, int W, int C,
                                    int Ho, int Wo, int Kp, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int groups = Kp >> 3;
@@ -49,6 +50,7 @@ __global__ void im2col3x3s2_kernel(const TI* __restrict__ x, bf16* __restrict__ 
 // zero padding up to Kp = 64 as eight 16-byte pieces
 __global__ void im2col3x3s2_rgb_kernel(const float* __restrict__ x, bf16* __restrict__ cols, int B, int H, int W,
                                        int Ho, int Wo, int Kp, long long M) {
+  pdl_enter();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int wo = (int)(m % Wo);
@@ -79,6 +81,7 @@ __global__ void im2col3x3s2_rgb_kernel(const float* __restrict__ x, bf16* __rest
 template <typename TO>
 __global__ void col2im3x3s2_kernel(const bf16* __restrict__ dcols, TO* __restrict__ dx, int B, int H, int W, int C,
                                    int Ho, int Wo, int Kp, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int groups = C >> 3;
@@ -113,6 +116,7 @@ __global__ void col2im3x3s2_kernel(const bf16* __restrict__ dcols, TO* __restric
 
 // w (Cout, C, 3, 3) fp32 -> W2 (Cout, Kp) bf16, W2[co][t * C + c] = w[co][c][t], zero padding columns
 __global__ void conv_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ w2, int Cout, int C, int Kp) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * Kp) return;
   const int co = idx / Kp, col = idx - co * Kp;
@@ -125,6 +129,7 @@ __global__ void conv_weight_pack_kernel(const float* __restrict__ w, bf16* __res
 }
 // dW2 (Cout, Kp) fp32 -> dw (Cout, C, 3, 3) fp32
 __global__ void conv_weight_unpack_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int Cout, int C, int Kp) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * C * 9) return;
   const int t = idx % 9, c = (idx / 9) % C, co = idx / (9 * C);
@@ -134,6 +139,7 @@ __global__ void conv_weight_unpack_kernel(const float* __restrict__ dw2, float* 
 __device__ __forceinline__ float gelu_exact(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f)); }
 template <typename TI, typename TO>
 __global__ void gelu_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = load4(x + 4 * i);
@@ -146,6 +152,7 @@ __device__ __forceinline__ float gelu_dexact(float z) {
 }
 template <typename TD, typename TX, typename TO>
 __global__ void gelu_bwd_mixed_kernel(const TD* __restrict__ dy, const TX* __restrict__ x, TO* __restrict__ dx, long long n4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 d = load4(dy + 4 * i), z = load4(x + 4 * i);
@@ -157,6 +164,7 @@ __global__ void gelu_bwd_mixed_kernel(const TD* __restrict__ dy, const TX* __res
 // is the gradient.
 template <typename T>
 __global__ void transpose_pc_kernel(const T* __restrict__ x, T* __restrict__ y, int P, int C) {
+  pdl_enter();
   __shared__ T tile[32][33];
   const long long base = (long long)blockIdx.z * P * C;
   const int p0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -176,8 +184,8 @@ __global__ void transpose_pc_kernel(const T* __restrict__ x, T* __restrict__ y, 
 int transpose_pc(const void* x, void* y, int dt, int B, int P, int C, cudaStream_t st) {
   dim3 grid(ceil_div(C, 32), ceil_div(P, 32), B), block(32, 8);
   DAT_REQUIRE(B <= 65535 && grid.y <= 65535, "transpose: tensor too large");
-  if (dt == DAT_F32) transpose_pc_kernel<float><<<grid, block, 0, st>>>((const float*)x, (float*)y, P, C);
-  else transpose_pc_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, (bf16*)y, P, C);
+  if (dt == DAT_F32) launch_k(transpose_pc_kernel<float>, grid, block, 0, st, (const float*)x, (float*)y, P, C);
+  else launch_k(transpose_pc_kernel<bf16>, grid, block, 0, st, (const bf16*)x, (bf16*)y, P, C);
   DAT_LAUNCH_OK("transpose_pc_kernel");
   return DAT_OK;
 }
@@ -187,10 +195,10 @@ int gelu_bwd_mixed(const void* dy, int dy_dt, const void* x, void* dx, int x_dt,
   DAT_REQUIRE(n % 4 == 0, "gelu_bwd: n must be a multiple of 4");
   const long long n4 = n / 4;
   const int grid = ceil_div(n4, 256);
-  if (dy_dt == DAT_BF16 && x_dt == DAT_F32) gelu_bwd_mixed_kernel<bf16, float, float><<<grid, 256, 0, st>>>((const bf16*)dy, (const float*)x, (float*)dx, n4);
-  else if (dy_dt == DAT_BF16) gelu_bwd_mixed_kernel<bf16, bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (bf16*)dx, n4);
-  else if (x_dt == DAT_F32) gelu_bwd_mixed_kernel<float, float, float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)x, (float*)dx, n4);
-  else gelu_bwd_mixed_kernel<float, bf16, bf16><<<grid, 256, 0, st>>>((const float*)dy, (const bf16*)x, (bf16*)dx, n4);
+  if (dy_dt == DAT_BF16 && x_dt == DAT_F32) launch_k(gelu_bwd_mixed_kernel<bf16, float, float>, grid, 256, 0, st, (const bf16*)dy, (const float*)x, (float*)dx, n4);
+  else if (dy_dt == DAT_BF16) launch_k(gelu_bwd_mixed_kernel<bf16, bf16, bf16>, grid, 256, 0, st, (const bf16*)dy, (const bf16*)x, (bf16*)dx, n4);
+  else if (x_dt == DAT_F32) launch_k(gelu_bwd_mixed_kernel<float, float, float>, grid, 256, 0, st, (const float*)dy, (const float*)x, (float*)dx, n4);
+  else launch_k(gelu_bwd_mixed_kernel<float, bf16, bf16>, grid, 256, 0, st, (const float*)dy, (const bf16*)x, (bf16*)dx, n4);
   DAT_LAUNCH_OK("gelu_bwd_mixed_kernel");
   return DAT_OK;
 }
@@ -202,14 +210,14 @@ int im2col3x3s2(const void* x, int x_dt, int nchw_rgb, void* cols, int B, int H,
   const long long M = (long long)B * Ho * Wo;
   if (nchw_rgb) {
     DAT_REQUIRE(C == 3 && x_dt == DAT_F32, "im2col: the NCHW path is the fp32 RGB stem only");
-    im2col3x3s2_rgb_kernel<<<ceil_div(M, 256), 256, 0, st>>>((const float*)x, (bf16*)cols, B, H, W, Ho, Wo, Kp, M);
+    launch_k(im2col3x3s2_rgb_kernel, ceil_div(M, 256), 256, 0, st, (const float*)x, (bf16*)cols, B, H, W, Ho, Wo, Kp, M);
   } else {
     DAT_REQUIRE(C % 8 == 0, "im2col: C must be a multiple of 8");
     const long long total = M * (Kp >> 3);
     if (x_dt == DAT_F32)
-      im2col3x3s2_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)x, (bf16*)cols, B, H, W, C, Ho, Wo, Kp, total);
+      launch_k(im2col3x3s2_kernel<float>, ceil_div(total, 256), 256, 0, st, (const float*)x, (bf16*)cols, B, H, W, C, Ho, Wo, Kp, total);
     else
-      im2col3x3s2_kernel<bf16><<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)cols, B, H, W, C, Ho, Wo, Kp, total);
+      launch_k(im2col3x3s2_kernel<bf16>, ceil_div(total, 256), 256, 0, st, (const bf16*)x, (bf16*)cols, B, H, W, C, Ho, Wo, Kp, total);
   }
   DAT_LAUNCH_OK("im2col3x3s2_kernel");
   return DAT_OK;
@@ -220,22 +228,22 @@ int col2im3x3s2(const void* dcols, void* dx, int dx_dt, int B, int H, int W, int
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Kp = conv3x3s2_kp(C);
   const long long total = (long long)B * H * W * (C >> 3);
   if (dx_dt == DAT_F32)
-    col2im3x3s2_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)dcols, (float*)dx, B, H, W, C, Ho, Wo, Kp, total);
+    launch_k(col2im3x3s2_kernel<float>, ceil_div(total, 256), 256, 0, st, (const bf16*)dcols, (float*)dx, B, H, W, C, Ho, Wo, Kp, total);
   else
-    col2im3x3s2_kernel<bf16><<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)dcols, (bf16*)dx, B, H, W, C, Ho, Wo, Kp, total);
+    launch_k(col2im3x3s2_kernel<bf16>, ceil_div(total, 256), 256, 0, st, (const bf16*)dcols, (bf16*)dx, B, H, W, C, Ho, Wo, Kp, total);
   DAT_LAUNCH_OK("col2im3x3s2_kernel");
   return DAT_OK;
 }
 
 int conv_weight_pack(const float* w, void* w2, int Cout, int C, cudaStream_t st) {
   const int Kp = conv3x3s2_kp(C);
-  conv_weight_pack_kernel<<<ceil_div((long long)Cout * Kp, 256), 256, 0, st>>>(w, (bf16*)w2, Cout, C, Kp);
+  launch_k(conv_weight_pack_kernel, ceil_div((long long)Cout * Kp, 256), 256, 0, st, w, (bf16*)w2, Cout, C, Kp);
   DAT_LAUNCH_OK("conv_weight_pack_kernel");
   return DAT_OK;
 }
 int conv_weight_unpack(const float* dw2, float* dw, int Cout, int C, cudaStream_t st) {
   const int Kp = conv3x3s2_kp(C);
-  conv_weight_unpack_kernel<<<ceil_div((long long)Cout * C * 9, 256), 256, 0, st>>>(dw2, dw, Cout, C, Kp);
+  launch_k(conv_weight_unpack_kernel, ceil_div((long long)Cout * C * 9, 256), 256, 0, st, dw2, dw, Cout, C, Kp);
   DAT_LAUNCH_OK("conv_weight_unpack_kernel");
   return DAT_OK;
 }
@@ -244,10 +252,10 @@ int gelu_fwd(const void* x, int x_dt, void* y, int y_dt, long long n, cudaStream
   DAT_REQUIRE(n % 4 == 0, "gelu_fwd: n must be a multiple of 4");
   const long long n4 = n / 4;
   const int grid = ceil_div(n4, 256);
-  if (x_dt == DAT_F32 && y_dt == DAT_F32) gelu_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n4);
-  else if (x_dt == DAT_F32) gelu_fwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, n4);
-  else if (y_dt == DAT_F32) gelu_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n4);
-  else gelu_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n4);
+  if (x_dt == DAT_F32 && y_dt == DAT_F32) launch_k(gelu_fwd_kernel<float, float>, grid, 256, 0, st, (const float*)x, (float*)y, n4);
+  else if (x_dt == DAT_F32) launch_k(gelu_fwd_kernel<float, bf16>, grid, 256, 0, st, (const float*)x, (bf16*)y, n4);
+  else if (y_dt == DAT_F32) launch_k(gelu_fwd_kernel<bf16, float>, grid, 256, 0, st, (const bf16*)x, (float*)y, n4);
+  else launch_k(gelu_fwd_kernel<bf16, bf16>, grid, 256, 0, st, (const bf16*)x, (bf16*)y, n4);
   DAT_LAUNCH_OK("gelu_fwd_kernel");
   return DAT_OK;
 }

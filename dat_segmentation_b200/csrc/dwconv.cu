@@ -34,6 +34,7 @@ __device__ __forceinline__ float gelu_df(float z) {
 // (C, k*k) -> (k*k, C), optionally spatially flipped (for the data gradient)
 __global__ void dw_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int C, int kk,
                                     int flip) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * kk) return;
   const int c = idx % C, uv = idx / C;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256)
 dwconv_cl_kernel(const TI* __restrict__ x, const float* __restrict__ wT, const float* __restrict__ bias,
                  TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int k_rt,
                  int tiles_x, int tiles_y) {
+  pdl_enter();
   constexpr int VEC = VecOf<TI>::N;
   const int k = K > 0 ? K : k_rt;
   const int p = k >> 1;
@@ -136,6 +138,7 @@ dwconv_cl_kernel(const TI* __restrict__ x, const float* __restrict__ wT, const f
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz,
                                 long long n4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 d = load4(dy + 4 * i), zz = load4(z + 4 * i);
@@ -163,6 +166,7 @@ template <typename TX, typename TD, int KK, int CV>
 __global__ void __launch_bounds__(128)
 dwconv_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* __restrict__ partial,
                     int B, int H, int W, int C, int k, long long pix_per_split) {
+  pdl_enter();
   constexpr int KS = KK == 9 ? 3 : (KK == 25 ? 5 : 7);   // compile-time filter size: constant tap offsets
   (void)k;
   constexpr int p = KS >> 1;
@@ -232,6 +236,7 @@ dwconv_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* 
 // block (32, 32): fixed-order reduction over the splits; writes dw (C, kk) and db (C)
 __global__ void dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int kk, int C,
                                            float* __restrict__ dw, float* __restrict__ db) {
+  pdl_enter();
   __shared__ float red[32][33];
   const int idx = blockIdx.x * 32 + threadIdx.x;    // row * C + c, row in [0, kk]
   const int n_out = (kk + 1) * C;
@@ -266,7 +271,7 @@ size_t dwconv_workspace(int B, int H, int W, int C, int k) {
 }
 
 int dwconv_wgrad_reduce(const float* partial, int nsplit, int kk, int C, float* dw, float* db, cudaStream_t st) {
-  dwconv_wgrad_reduce_kernel<<<ceil_div((kk + 1) * C, 32), dim3(32, 32), 0, st>>>(partial, nsplit, kk, C, dw, db);
+  launch_k(dwconv_wgrad_reduce_kernel, ceil_div((kk + 1) * C, 32), dim3(32, 32), 0, st, partial, nsplit, kk, C, dw, db);
   DAT_LAUNCH_OK("dwconv_wgrad_reduce_kernel");
   return DAT_OK;
 }
@@ -284,14 +289,14 @@ int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void*
   DAT_REQUIRE(ws_bytes >= (size_t)k * k * C * 4, "dwconv: workspace too small");
   DAT_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || z_out != nullptr), "dwconv: bad mode");
   float* wT = (float*)ws;
-  dw_transpose_kernel<<<ceil_div(C * k * k, 256), 256, 0, st>>>(w, wT, C, k * k, flip);
+  launch_k(dw_transpose_kernel, ceil_div(C * k * k, 256), 256, 0, st, w, wT, C, k * k, flip);
   DAT_LAUNCH_OK("dw_transpose_kernel");
   const int tiles_x = ceil_div(W, 8), tiles_y = ceil_div(H, 8);
   const int vec = x_dt == DAT_F32 ? 4 : 8;
   DAT_REQUIRE(C % vec == 0, "dwconv: C must be a multiple of %d for this dtype", vec);
   dim3 grid(tiles_x * tiles_y * B, ceil_div(C, 4 * vec));
 #define LAUNCH(TI, TO, MD, KV)                                                                  \
-  dwconv_cl_kernel<TI, TO, MD, KV><<<grid, 256, 0, st>>>((const TI*)x, wT, bias, (TO*)y, (TO*)z_out, B, \
+  launch_k(dwconv_cl_kernel<TI, TO, MD, KV>, grid, 256, 0, st, (const TI*)x, wT, bias, (TO*)y, (TO*)z_out, B, \
                                                          H, W, C, k, tiles_x, tiles_y)
 #define LAUNCH_K(TI, TO, MD)                                                  \
   do {                                                                        \
@@ -317,8 +322,8 @@ int dwconv_fwd(const void* x, int x_dt, const float* w, const float* bias, void*
 int gelu_bwd(const void* dy, const void* z, void* dz, int dt, long long n, cudaStream_t st) {
   DAT_REQUIRE(n % 4 == 0, "gelu_bwd: n %% 4 != 0");
   const long long n4 = n / 4;
-  if (dt == DAT_F32) gelu_bwd_kernel<float><<<ceil_div(n4, 256), 256, 0, st>>>((const float*)dy, (const float*)z, (float*)dz, n4);
-  else gelu_bwd_kernel<bf16><<<ceil_div(n4, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)z, (bf16*)dz, n4);
+  if (dt == DAT_F32) launch_k(gelu_bwd_kernel<float>, ceil_div(n4, 256), 256, 0, st, (const float*)dy, (const float*)z, (float*)dz, n4);
+  else launch_k(gelu_bwd_kernel<bf16>, ceil_div(n4, 256), 256, 0, st, (const bf16*)dy, (const bf16*)z, (bf16*)dz, n4);
   DAT_LAUNCH_OK("gelu_bwd_kernel");
   return DAT_OK;
 }
@@ -338,7 +343,7 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
   DAT_REQUIRE(C % cv == 0, "dwconv_wgrad: C must be a multiple of %d", cv);
   dim3 grid(ceil_div(C, 32 * cv), nsplit);
 #define LAUNCH(TX, TD, KKV, CVV)                                                                    \
-  dwconv_wgrad_kernel<TX, TD, KKV, CVV><<<grid, 128, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
+  launch_k(dwconv_wgrad_kernel<TX, TD, KKV, CVV>, grid, 128, 0, st, (const TX*)x, (const TD*)dz, part, B, H, W, C, k, pps)
 #define LAUNCH_K(TX, TD)                                  \
   do {                                                    \
     if (k == 3) LAUNCH(TX, TD, 9, 4); else if (k == 5) LAUNCH(TX, TD, 25, 2); else LAUNCH(TX, TD, 49, 2); \
@@ -350,7 +355,7 @@ int dwconv_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw, 
 #undef LAUNCH_K
 #undef LAUNCH
   DAT_LAUNCH_OK("dwconv_wgrad_kernel");
-  dwconv_wgrad_reduce_kernel<<<ceil_div((k * k + 1) * C, 32), dim3(32, 32), 0, st>>>(part, nsplit, k * k, C, dw, db);
+  launch_k(dwconv_wgrad_reduce_kernel, ceil_div((k * k + 1) * C, 32), dim3(32, 32), 0, st, part, nsplit, k * k, C, dw, db);
   DAT_LAUNCH_OK("dwconv_wgrad_reduce_kernel");
   return DAT_OK;
 }

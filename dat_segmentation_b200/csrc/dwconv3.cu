@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(D3_THREADS, 5)
 dwconv3_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    TO* __restrict__ y, TO* __restrict__ z_out, int B, int H, int W, int C, int th,
                    int strips_x, int strips_y, int flip) {
+  pdl_enter();
   using RI = Raw2<TI>;
   const Strip s = strip_of(B, C, th, strips_x, strips_y);
   if (!s.ok) return;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(D3_THREADS, 4)
 dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD* __restrict__ z,
                    const float* __restrict__ w, TX* __restrict__ dx, float* __restrict__ partial, int B,
                    int H, int W, int C, int th, int strips_x, int strips_y, int spc) {
+  pdl_enter();
   using RD = Raw2<TD>;
   using RX = Raw2<TX>;
   const Strip s = strip_of(B, C, th, strips_x, strips_y);
@@ -354,7 +356,7 @@ int dwconv3_fwd(const void* x, int x_dt, const float* w, const float* bias, void
   const long long threads = (long long)B * sx * sy * (C / 2);
   const unsigned grid = (unsigned)ceil_div(threads, (long long)D3_THREADS);
 #define LAUNCH_A(TI, TO, MD, AL)                                                                        \
-  dwconv3_fwd_kernel<TI, TO, MD, AL><<<grid, D3_THREADS, 0, st>>>((const TI*)x, w, bias, (TO*)y, (TO*)z_out, B, \
+  launch_k(dwconv3_fwd_kernel<TI, TO, MD, AL>, grid, D3_THREADS, 0, st, (const TI*)x, w, bias, (TO*)y, (TO*)z_out, B, \
                                                                    H, W, C, th, sx, sy, flip)
 #define LAUNCH(TI, TO, MD)                                                    \
   do {                                                                        \
@@ -390,7 +392,7 @@ int dwconv3_bwd(const void* x, int x_dt, const void* dy, const void* z, int d_dt
   float* part = (float*)ws;
   const int spc = strips_per_cta(C);
 #define LAUNCH_A(TX, TD, MD, AL)                                                                              \
-  dwconv3_bwd_kernel<TX, TD, MD, AL><<<grid, D3_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (const TD*)z, w, \
+  launch_k(dwconv3_bwd_kernel<TX, TD, MD, AL>, grid, D3_THREADS, 0, st, (const TX*)x, (const TD*)dy, (const TD*)z, w, \
                                                                    (TX*)dx, part, B, H, W, C, th, sx, sy, spc)
 #define LAUNCH(TX, TD, MD)                                                    \
   do {                                                                        \

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(D7_THREADS, 4)
 dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    TO* __restrict__ y, int B, int H, int W, int C, int th, int strips_x, int strips_y,
                    int flip) {
+  pdl_enter();
   using RI = Raw2<TI>;
   // The CTA's threads cover min(C, 256) consecutive channels (modulo C): their filters are staged cooperatively
   // with coalesced loads into w_s[49][256] (tap-major), each thread then reads its channel pair as one LDS.64.
@@ -169,6 +170,7 @@ template <typename TX, typename TD, int U0, int NU, bool ALIGNED>
 __global__ void __launch_bounds__(D7_THREADS, 3)
 dwconv7_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dz, float* __restrict__ partial, int B,
                      int H, int W, int C, int th, int strips_x, int strips_y, int spc) {
+  pdl_enter();
   using RX = Raw2<TX>;
   using RD = Raw2<TD>;
   const Strip s = strip_of(B, C, th, strips_x, strips_y);
@@ -330,7 +332,7 @@ int dwconv7_fwd(const void* x, int x_dt, const float* w, const float* bias, void
   do {                                                                                                        \
     auto kern = dwconv7_fwd_kernel<TI, TO, AL>;                                                               \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));               \
-    kern<<<grid, D7_THREADS, smem, st>>>((const TI*)x, w, bias, (TO*)y, B, H, W, C, th, sx, sy, flip);        \
+    launch_k(kern, grid, D7_THREADS, smem, st, (const TI*)x, w, bias, (TO*)y, B, H, W, C, th, sx, sy, flip);        \
   } while (0)
 #define LAUNCH(TI, TO)                                                \
   do {                                                                \
@@ -358,9 +360,9 @@ int dwconv7_wgrad(const void* x, int x_dt, const void* dz, int dz_dt, float* dw,
   float* part = (float*)ws;
 #define LAUNCH_A(TX, TD, AL)                                                                                   \
   do {                                                                                                         \
-    dwconv7_wgrad_kernel<TX, TD, 0, 4, AL><<<grid, D7_THREADS, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, \
+    launch_k(dwconv7_wgrad_kernel<TX, TD, 0, 4, AL>, grid, D7_THREADS, 0, st, (const TX*)x, (const TD*)dz, part, B, H, W, \
                                                                         C, th, sx, sy, spc);                   \
-    dwconv7_wgrad_kernel<TX, TD, 4, 3, AL><<<grid, D7_THREADS, 0, st>>>((const TX*)x, (const TD*)dz, part, B, H, W, \
+    launch_k(dwconv7_wgrad_kernel<TX, TD, 4, 3, AL>, grid, D7_THREADS, 0, st, (const TX*)x, (const TD*)dz, part, B, H, W, \
                                                                         C, th, sx, sy, spc);                   \
   } while (0)
 #define LAUNCH(TX, TD)                                                \

@@ -22,6 +22,7 @@ template <typename TX, typename TO>
 __global__ void sample_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ pos,
                                   TO* __restrict__ xs, int32_t* __restrict__ taps, int B, int H,
                                   int W, int C, int G, int Cg, int Ns, long long total) {
+  pdl_enter();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4n = C >> 2;
@@ -62,6 +63,7 @@ __global__ void sample_bwd_dpos_kernel(const TX* __restrict__ x, const float* __
                                        const float* __restrict__ dpos_bias_part, int qsplit,
                                        float* __restrict__ dpos, int B, int H, int W, int C, int G,
                                        int Cg, int hg, int Ns, long long n_points) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long sp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (sp >= n_points) return;
@@ -114,6 +116,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256)
 sample_bwd_dx_kernel(const float* __restrict__ pos, const TD* __restrict__ dxs,
                      float* __restrict__ dx, int H, int W, int C, int G, int Cg, int Ns, int P) {
+  pdl_enter();
   extern __shared__ uint32_t smem_u[];
   uint32_t* keys = smem_u;
   float* wts = reinterpret_cast<float*>(smem_u + P);
@@ -193,7 +196,7 @@ int sample_fwd(const Shape& s, const void* x, const float* pos, void* xs, int32_
   long long total = (long long)s.B * s.Ns * (s.C / 4);
   int grid = ceil_div(total, 256);
 #define LAUNCH(TX, TO)                                                                        \
-  sample_fwd_kernel<TX, TO><<<grid, 256, 0, st>>>((const TX*)x, pos, (TO*)xs, taps, s.B, s.H, \
+  launch_k(sample_fwd_kernel<TX, TO>, grid, 256, 0, st, (const TX*)x, pos, (TO*)xs, taps, s.B, s.H, \
                                                   s.W, s.C, s.G, s.Cg, s.Ns, total)
   if (s.x_dtype == DAT_F32 && s.act_dtype == DAT_F32) LAUNCH(float, float);
   else if (s.x_dtype == DAT_F32) LAUNCH(float, bf16);
@@ -209,7 +212,7 @@ int sample_bwd_dpos(const Shape& s, const void* x, const float* pos, const void*
   long long pts = (long long)s.B * s.G * s.Ns;
   int grid = ceil_div(pts, 8);
 #define LAUNCH(TX, TD)                                                                         \
-  sample_bwd_dpos_kernel<TX, TD><<<grid, 256, 0, st>>>((const TX*)x, pos, (const TD*)dxs,      \
+  launch_k(sample_bwd_dpos_kernel<TX, TD>, grid, 256, 0, st, (const TX*)x, pos, (const TD*)dxs,      \
                                                        dpos_bias_part, qsplit, dpos, s.B, s.H, \
                                                        s.W, s.C, s.G, s.Cg, s.hg, s.Ns, pts)
   if (s.x_dtype == DAT_F32 && s.act_dtype == DAT_F32) LAUNCH(float, float);
@@ -235,7 +238,7 @@ int sample_bwd_dx(const Shape& s, const float* pos, const void* dxs, float* dx, 
     if (smem > 48 * 1024)                                                                      \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                        (int)smem));                                            \
-    kern<<<grid, 256, smem, st>>>(pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
+    launch_k(kern, grid, 256, smem, st, pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
   } while (0)
   if (s.act_dtype == DAT_F32) LAUNCH(float); else LAUNCH(bf16);
 #undef LAUNCH

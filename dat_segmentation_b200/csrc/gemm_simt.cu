@@ -28,6 +28,7 @@ gemm_simt_kernel(const TA* __restrict__ A, long long sai, long long sal,
                  TC* __restrict__ C, long long ldc, const float* __restrict__ bias,
                  int accumulate, int I, int J, int L, int l_chunk,
                  float* __restrict__ partial) {
+  pdl_enter();
   __shared__ __align__(16) float As[BK][BM + PADM];
   __shared__ __align__(16) float Bs[BK][BN + PADM];
   const int tid = threadIdx.x;
@@ -104,6 +105,7 @@ template <typename TC>
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nsplit,
                                        long long count, int J, const float* __restrict__ bias,
                                        TC* __restrict__ out) {
+  pdl_enter();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   float v = 0.f;
@@ -116,6 +118,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int ns
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, long long M, int N, long long rows_per_block,
                               float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + cx;
@@ -140,7 +143,7 @@ int launch_gemm(const void* A, long long sai, long long sal, const void* Bm, lon
                 int J, int L, int nsplit, float* partial, cudaStream_t st) {
   dim3 grid(ceil_div(J, BN), ceil_div(I, BM), nsplit);
   int l_chunk = ceil_div(ceil_div(L, nsplit), BK) * BK;
-  gemm_simt_kernel<TA, TB, TC, A_LC, B_LC><<<grid, GEMM_THREADS, 0, st>>>(
+  launch_k(gemm_simt_kernel<TA, TB, TC, A_LC, B_LC>, grid, GEMM_THREADS, 0, st, 
       (const TA*)A, sai, sal, (const TB*)Bm, sbl, sbj, (TC*)C, ldc, bias, accumulate, I, J, L,
       l_chunk, partial);
   DAT_LAUNCH_OK("gemm_simt_kernel");
@@ -215,7 +218,7 @@ int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, flo
   DAT_FWD(rc);
   if (nsplit > 1) {
     long long count = (long long)N * K;
-    reduce_partials_kernel<float><<<ceil_div(count, 256), 256, 0, st>>>(part, nsplit, count, K,
+    launch_k(reduce_partials_kernel<float>, ceil_div(count, 256), 256, 0, st, part, nsplit, count, K,
                                                                         nullptr, dW);
     DAT_LAUNCH_OK("reduce_partials_kernel");
   }
@@ -224,11 +227,11 @@ int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, flo
     long long rows = (M + cs - 1) / cs;
     dim3 grid(ceil_div(N, 32), cs);
     if (dy_dt == DAT_F32)
-      colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, M, N, rows, cpart);
+      launch_k(colsum_kernel<float>, grid, 256, 0, st, (const float*)dY, M, N, rows, cpart);
     else
-      colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, M, N, rows, cpart);
+      launch_k(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)dY, M, N, rows, cpart);
     DAT_LAUNCH_OK("colsum_kernel");
-    reduce_partials_kernel<float><<<ceil_div(N, 256), 256, 0, st>>>(cpart, cs, N, N, nullptr, db);
+    launch_k(reduce_partials_kernel<float>, ceil_div(N, 256), 256, 0, st, cpart, cs, N, N, nullptr, db);
     DAT_LAUNCH_OK("reduce_partials_kernel");
   }
   return DAT_OK;
@@ -242,10 +245,10 @@ int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws
   float* cpart = (float*)ws;
   const long long rows = (M + cs - 1) / cs;
   dim3 grid(ceil_div(N, 32), cs);
-  if (dy_dt == DAT_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dY, M, N, rows, cpart);
-  else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dY, M, N, rows, cpart);
+  if (dy_dt == DAT_F32) launch_k(colsum_kernel<float>, grid, 256, 0, st, (const float*)dY, M, N, rows, cpart);
+  else launch_k(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)dY, M, N, rows, cpart);
   DAT_LAUNCH_OK("colsum_kernel");
-  reduce_partials_kernel<float><<<ceil_div(N, 256), 256, 0, st>>>(cpart, cs, N, N, nullptr, db);
+  launch_k(reduce_partials_kernel<float>, ceil_div(N, 256), 256, 0, st, cpart, cs, N, N, nullptr, db);
   DAT_LAUNCH_OK("reduce_partials_kernel");
   return DAT_OK;
 }
@@ -254,10 +257,10 @@ int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws
 int reduce_partials(const float* part, int nsplit, long long count, void* out, int out_dt,
                     cudaStream_t st) {
   if (out_dt == DAT_F32)
-    reduce_partials_kernel<float><<<ceil_div(count, 256), 256, 0, st>>>(part, nsplit, count, 1,
+    launch_k(reduce_partials_kernel<float>, ceil_div(count, 256), 256, 0, st, part, nsplit, count, 1,
                                                                         nullptr, (float*)out);
   else
-    reduce_partials_kernel<bf16><<<ceil_div(count, 256), 256, 0, st>>>(part, nsplit, count, 1,
+    launch_k(reduce_partials_kernel<bf16>, ceil_div(count, 256), 256, 0, st, part, nsplit, count, 1,
                                                                        nullptr, (bf16*)out);
   DAT_LAUNCH_OK("reduce_partials_kernel");
   return DAT_OK;

@@ -102,6 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
                int k_chunks1, int BN, int stages, int tmem_cols) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -230,6 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ void store8(float* p, float4 a, float4 b) {
   *reinterpret_cast<float4*>(p) = a;
   *reinterpret_cast<float4*>(p + 4) = b;
@@ -263,21 +268,24 @@ template <bool TF32, typename TOut, bool BMN = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                          const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
-                          int k_chunks1, int BN, int stages, int tmem_cols, int m_tiles, int total_tiles,
-                          int stage_pitch) {
+                          const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias,
+                          TOut* __restrict__ Y, int M, int N, int k_chunks, int k_chunks1, int BN, int stages,
+                          int tmem_cols, int m_tiles, int total_tiles, int stage_pitch, int bias_bytes, int dbg) {
+  pdl_enter();
+  // dbg (DAT_B200_GEMM_DBG, timing decomposition only - results are wrong): 1 = no global stores, 2 = B loaded for the
+  // CTA's first tile only, 4 = A loaded for the first tile only, 8 = epilogue only hands the accumulator back
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int b_stage_bytes = BN * CHUNK_BYTES;
-  // [barriers 1 KB][bias 2 x 256 floats][ring: A stages | B stages (1 KB aligned)][epilogue staging]
+  // [barriers 1 KB][bias: all N floats, staged once per CTA][ring: A stages | B stages (1 KB aligned)][epilogue staging]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sBias = reinterpret_cast<float*>(smem + 1024);
-  uint8_t* sA = smem + 3072;
+  uint8_t* sA = smem + 1024 + bias_bytes;
   uint8_t* sB = sA + stages * A_STAGE_BYTES;
   uint8_t* sStage = sB + stages * b_stage_bytes;
 
@@ -291,6 +299,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
     }
+    if (BN % 64 == 0) tma_prefetch_desc(&tmY);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -302,6 +311,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  for (int i = threadIdx.x; i < N; i += TCP_THREADS) sBias[i] = bias != nullptr ? bias[i] : 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -316,10 +326,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+          const bool first_tile = t == (int)blockIdx.x;
+          const bool ld_a = first_tile || !(dbg & 4), ld_b = first_tile || !(dbg & 2);
+          if (!ld_a && !ld_b) { mbar_arrive(&full[s]); continue; }
+          mbar_arrive_expect_tx(&full[s], (uint32_t)((ld_a ? A_STAGE_BYTES : 0) + (ld_b ? b_stage_bytes : 0)));
           const bool second = kc >= k_chunks1;
           const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
-          tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
+          if (ld_a) tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
+          if (!ld_b) continue;
           if (BMN) {
             for (int i = 0; i < BN / 64; ++i)
               tma_load_2d(sB + s * b_stage_bytes + i * 8192, second ? &tmB2 : &tmB, &full[s], n0 + 64 * i, kcol);
@@ -361,24 +375,96 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   } else {
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int chalf = (warp - 2) >> 2;   // which of the quadrant's two warps: takes column groups chalf, chalf + 2, ...
-    const int epi_tid = threadIdx.x - 64;
     const int gcols = persistent_gcols(BN);
     const int seg_bytes = gcols * (int)sizeof(TOut);
     uint8_t* stage = sStage + (warp - 2) * 32 * stage_pitch;
     int li = 0;
+    if (BN % 64 == 0) {
+      // TMA-store epilogue: a warp's 32 rows x 64 columns go TMEM -> registers -> (+ bias, convert) -> a 128B-swizzled
+      // shared-memory tile (conflict-free 16-byte stores) -> ONE cp.async.bulk.tensor store issued by lane 0.  The
+      // store is asynchronous: the warp only waits (wait_group.read) until the tile has been read out of shared memory
+      // before it stages the next group, and rows beyond M are clipped by the tensor map.
+      constexpr int BOX_COLS = 128 / (int)sizeof(TOut);               // 64 bf16 / 32 fp32 columns = one 128-byte row
+      constexpr int NBOX = 64 / BOX_COLS;
+      uint8_t* tstage = sStage + (warp - 2) * (NBOX * 4096);
+      const uint32_t srow = smem_u32(tstage) + (uint32_t)lane * 128u;
+      const uint32_t sxor = (uint32_t)(lane & 7);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+        const int buf = li & 1;
+        const int m0 = (t % m_tiles) * TC_BM, n0 = (t / m_tiles) * BN;
+        mbar_wait(&acc_full[buf], (uint32_t)((li >> 1) & 1));
+        tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+        const int cg_first = chalf * 64;
+        if (cg_first >= BN || (dbg & 8)) {   // a single column group: this warp only hands the buffer back
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          continue;
+        }
+        for (int cg = cg_first; cg < BN; cg += 128) {
+          uint32_t r[2][32];
+          tmem_ld_32x32(t_addr + (uint32_t)cg, r[0]);
+          tmem_ld_32x32(t_addr + (uint32_t)(cg + 32), r[1]);
+          tmem_wait_ld();
+          if (cg + 128 >= BN) {           // this warp's share of the accumulator is read: hand the TMEM buffer back early
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          if (lane == 0) bulk_wait_group_read<0>();      // the previous store has read the staging tile
+          __syncwarp();
+          const float* bp = sBias + n0 + cg;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bp + c * 32 + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bp + c * 32 + j + 4);
+              const float v0 = __uint_as_float(r[c][j]) + b0.x, v1 = __uint_as_float(r[c][j + 1]) + b0.y;
+              const float v2 = __uint_as_float(r[c][j + 2]) + b0.z, v3 = __uint_as_float(r[c][j + 3]) + b0.w;
+              const float v4 = __uint_as_float(r[c][j + 4]) + b1.x, v5 = __uint_as_float(r[c][j + 5]) + b1.y;
+              const float v6 = __uint_as_float(r[c][j + 6]) + b1.z, v7 = __uint_as_float(r[c][j + 7]) + b1.w;
+              if (sizeof(TOut) == 2) {     // 8 columns = one 16-byte chunk of the 64-column box
+                const uint32_t chunk = (uint32_t)(c * 4 + (j >> 3));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((chunk ^ sxor) << 4)),
+                             "r"(pack_bf16x2(v0, v1)), "r"(pack_bf16x2(v2, v3)), "r"(pack_bf16x2(v4, v5)),
+                             "r"(pack_bf16x2(v6, v7))
+                             : "memory");
+              } else {                     // 8 columns = two 16-byte chunks of box c (32 fp32 columns)
+                const uint32_t chunk = (uint32_t)(j >> 2);
+                const uint32_t bbase = srow + (uint32_t)c * 4096u;
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bbase + ((chunk ^ sxor) << 4)), "f"(v0),
+                             "f"(v1), "f"(v2), "f"(v3)
+                             : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bbase + (((chunk + 1) ^ sxor) << 4)),
+                             "f"(v4), "f"(v5), "f"(v6), "f"(v7)
+                             : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(dbg & 1) && m0 + quad * 32 < M) {
+#pragma unroll
+            for (int bx = 0; bx < NBOX; ++bx) tma_store_2d(&tmY, tstage + bx * 4096, n0 + cg + bx * BOX_COLS, m0 + quad * 32);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_group<0>();
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const int buf = li & 1;
       const int m0 = (t % m_tiles) * TC_BM, n0 = (t / m_tiles) * BN;
-      float* bvec = sBias + buf * 256;
-      for (int i = epi_tid; i < BN; i += 32 * TCP_EPI_WARPS) bvec[i] = bias != nullptr ? bias[n0 + i] : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
+      const float* bvec = sBias + n0;
       mbar_wait(&acc_full[buf], (uint32_t)((li >> 1) & 1));
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
       const int rows_here = min(32, M - (m0 + quad * 32));
       const int nch = gcols / 32;
       const int cg_first = chalf * gcols;
-      if (cg_first >= BN) {              // a single column group: this warp only hands the buffer back
+      if (cg_first >= BN || (dbg & 8)) {   // a single column group: this warp only hands the buffer back
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -419,7 +505,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int lanes_per_row = seg_bytes / 16;
         const int rows_per_it = 32 / lanes_per_row;
         const int rsub = lane / lanes_per_row, off = (lane % lanes_per_row) * 16;
-        for (int rr = rsub; rr < rows_here; rr += rows_per_it) {
+        for (int rr = rsub; rr < ((dbg & 1) ? 0 : rows_here); rr += rows_per_it) {
           uint8_t* grow = reinterpret_cast<uint8_t*>(Y + (long long)(m0 + quad * 32 + rr) * N + n0 + cg);
           *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(stage + rr * stage_pitch + off);
         }
@@ -446,6 +532,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const float* __restrict__ bias, TOut* __restrict__ Y, int M, int N, int k_chunks,
                     int k_chunks1, int BN, int stages, int tmem_cols, int m_pairs, int total_tiles,
                     int stage_pitch) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -617,6 +704,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                            const float* __restrict__ w2, const float* __restrict__ w3,
                                            bf16* __restrict__ out, int N, int K) {
+  pdl_enter();
   __shared__ float tile[32][33];          // w_z is (N, K) row-major, out[z] is (K, N)
   const float* src = blockIdx.z == 0 ? w0 : (blockIdx.z == 1 ? w1 : (blockIdx.z == 2 ? w2 : w3));
   if (src == nullptr) return;
@@ -636,6 +724,7 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ w0, const f
 // fp32 -> bf16 for up to 3 equally sized matrices in one launch (weights of a block)
 __global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                  const float* __restrict__ c, bf16* __restrict__ out, long long n) {
+  pdl_enter();
   const float* src = blockIdx.y == 0 ? a : (blockIdx.y == 1 ? b : c);
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (src == nullptr || i >= n) return;
@@ -645,6 +734,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ a, const float* __res
 // fp32 -> bf16 for a whole table of tensors in one launch (the bf16 operand copies of every 1x1-conv weight of a
 // model, once per step): blockIdx.y = table entry, blockIdx.x strides over its elements, 4 per thread.
 __global__ void cast_bf16_multi_kernel(const dat_cast_item* __restrict__ items) {
+  pdl_enter();
   const dat_cast_item it = items[blockIdx.y];
   const float* __restrict__ src = it.src;
   bf16* __restrict__ dst = reinterpret_cast<bf16*>(it.dst);
@@ -689,7 +779,7 @@ int cast_weights_bf16(const float* a, const float* b, const float* c, void* out,
                       cudaStream_t st) {
   DAT_REQUIRE(n % 4 == 0, "cast_weights: n must be a multiple of 4");
   dim3 grid(ceil_div(n / 4, 256), 3);
-  cast_bf16_kernel<<<grid, 256, 0, st>>>(a, b, c, (bf16*)out, n);
+  launch_k(cast_bf16_kernel, grid, 256, 0, st, a, b, c, (bf16*)out, n);
   DAT_LAUNCH_OK("cast_bf16_kernel");
   return DAT_OK;
 }
@@ -697,7 +787,7 @@ int cast_weights_bf16(const float* a, const float* b, const float* c, void* out,
 int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w2, const float* w3,
                                 void* out, int C, cudaStream_t st) {
   dim3 grid(ceil_div(C, 32), ceil_div(C, 32), 4), block(32, 8);
-  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w0, w1, w2, w3, (bf16*)out, C, C);
+  launch_k(cast_transpose_bf16_kernel, grid, block, 0, st, w0, w1, w2, w3, (bf16*)out, C, C);
   DAT_LAUNCH_OK("cast_transpose_bf16_kernel");
   return DAT_OK;
 }
@@ -705,7 +795,7 @@ int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w
 // one (N, K) fp32 matrix -> (K, N) bf16
 int cast_transpose_bf16(const float* w, void* out, int N, int K, cudaStream_t st) {
   dim3 grid(ceil_div(K, 32), ceil_div(N, 32), 1), block(32, 8);
-  cast_transpose_bf16_kernel<<<grid, block, 0, st>>>(w, nullptr, nullptr, nullptr, (bf16*)out, N, K);
+  launch_k(cast_transpose_bf16_kernel, grid, block, 0, st, w, nullptr, nullptr, nullptr, (bf16*)out, N, K);
   DAT_LAUNCH_OK("cast_transpose_bf16_kernel");
   return DAT_OK;
 }
@@ -718,7 +808,7 @@ int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, voi
 int cast_bf16_multi(const dat_cast_item* items_dev, int n_items, cudaStream_t st) {
   if (n_items <= 0) return DAT_OK;
   dim3 grid(32, n_items);
-  cast_bf16_multi_kernel<<<grid, 256, 0, st>>>(items_dev);
+  launch_k(cast_bf16_multi_kernel, grid, 256, 0, st, items_dev);
   DAT_LAUNCH_OK("cast_bf16_multi_kernel");
   return DAT_OK;
 }
@@ -791,7 +881,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   do {                                                                                            \
     auto kern = gemm_tc_pair_kernel<TF, TO, MN>;                                                  \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<2 * clusters, TCP_THREADS, smem, st>>>(tmA, tmBp, tmA2, tmB2p, b, (TO*)Y, (int)M, N, k_chunks, \
+    launch_k(kern, 2 * clusters, TCP_THREADS, smem, st, tmA, tmBp, tmA2, tmB2p, b, (TO*)Y, (int)M, N, k_chunks, \
                                                   k_chunks1, BN, stages, tmem_cols, m_pairs, total, stage_pitch); \
   } while (0)
     if (w_mn && y_dt == DAT_F32) LAUNCH_PAIR(false, float, true);
@@ -808,21 +898,31 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     // persistent kernel: ring + separate epilogue staging in up to 224 KB, one CTA per SM
     const int gcols = persistent_gcols(BN);
     const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
-    const int staging = TCP_EPI_WARPS * 32 * stage_pitch;
-    int stages = (224 * 1024 - 1024 - 3072 - staging) / stage_bytes;
+    // tiles that are a multiple of 64 columns wide leave through TMA stores: one 128B-swizzled [32 rows x 128 bytes]
+    // box (bf16) or two (fp32) per epilogue warp; other widths use the padded, row-coalesced st.global staging
+    const bool tma_out = BN % 64 == 0;
+    const int staging = tma_out ? TCP_EPI_WARPS * 4096 * (int)(dtype_size(y_dt) / 2) : TCP_EPI_WARPS * 32 * stage_pitch;
+    const int bias_bytes = (int)align_up((size_t)N * 4, 1024);
+    int stages = (226 * 1024 - 1024 - 1024 - bias_bytes - staging) / stage_bytes;
     if (stages > 8) stages = 8;
     DAT_REQUIRE(stages >= 2, "pointwise_fwd_tc: tile does not fit shared memory");
-    const size_t smem = 1024 + 3072 + (size_t)stages * stage_bytes + staging;
+    const size_t smem = 1024 + 1024 + (size_t)bias_bytes + (size_t)stages * stage_bytes + staging;
     int tmem_cols = 32;
     while (tmem_cols < 2 * BN) tmem_cols <<= 1;
     const int m_tiles = (int)ceil_div(M, (long long)TC_BM), total = m_tiles * (N / BN);
     const int grid = total < 148 ? total : 148;
+    CUtensorMap tmY = tmA;
+    if (tma_out) {
+      const int eo = (int)dtype_size(y_dt);
+      DAT_FWD(tc::make_tmap_2d(&tmY, Y, eo, y_dt == DAT_F32, (uint64_t)M, (uint64_t)N, (uint64_t)N * eo, 32, 128 / eo, 128));
+    }
+    static const int gemm_dbg = [] { const char* e = std::getenv("DAT_B200_GEMM_DBG"); return e ? std::atoi(e) : 0; }();
 #define LAUNCH_P(TF, TO, MN)                                                                      \
   do {                                                                                            \
     auto kern = gemm_tc_persistent_kernel<TF, TO, MN>;                                            \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, TCP_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,     \
-                                         k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch); \
+    launch_k(kern, grid, TCP_THREADS, smem, st, tmA, tmB, tmA2, tmB2, tmY, b, (TO*)Y, (int)M, N, k_chunks,     \
+                                         k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch, bias_bytes, gemm_dbg); \
   } while (0)
     if (w_mn && y_dt == DAT_F32) LAUNCH_P(false, float, true);
     else if (w_mn) LAUNCH_P(false, bf16, true);
@@ -850,7 +950,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   do {                                                                                          \
     auto kern = gemm_tc_kernel<TF, TO>;                                                         \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,    \
+    launch_k(kern, grid, TC_THREADS, smem, st, tmA, tmB, tmA2, tmB2, b, (TO*)Y, (int)M, N, k_chunks,    \
                                          k_chunks1, BN, stages, tmem_cols);                       \
   } while (0)
   if (tf32 && y_dt == DAT_F32) LAUNCH(true, float);

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      float* __restrict__ partial, float* __restrict__ db_partial, int N, int K, int BNK,
                      int rows_per_split, long long M, int stages, int tmem_cols) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -192,6 +193,7 @@ namespace {
 __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, const float* __restrict__ bpart,
                                     int splits, long long nk, int n, float* __restrict__ dW,
                                     float* __restrict__ db) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nk) {
     float s = 0.f;
@@ -234,12 +236,12 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long
     bpart = splits > 1 ? (float*)((char*)ws + align_up((size_t)splits * N * K * 4, 256)) : db;
   dim3 grid((N + WG_BM - 1) / WG_BM, K / BNK, splits);
   DAT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, part, bpart, N, K, BNK, (int)rps, M, stages,
+  launch_k(gemm_tc_wgrad_kernel, grid, WG_THREADS, smem, st, tmDY, tmX, part, bpart, N, K, BNK, (int)rps, M, stages,
                                                        tmem_cols);
   DAT_LAUNCH_OK("gemm_tc_wgrad_kernel");
   if (splits > 1) {
     const long long nk = (long long)N * K;
-    wgrad_reduce_kernel<<<(unsigned)ceil_div(nk + N, 256ll), 256, 0, st>>>(part, bpart, splits, nk, N, dW, db);
+    launch_k(wgrad_reduce_kernel, (unsigned)ceil_div(nk + N, 256ll), 256, 0, st, part, bpart, splits, nk, N, dW, db);
     DAT_LAUNCH_OK("wgrad_reduce_kernel");
   }
   return DAT_OK;

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  pdl_enter();
   constexpr int R = RowsOf<NV>::R;
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * R;
@@ -98,6 +99,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, TI* __restrict__ dx,
                      const TI* __restrict__ dres, float* __restrict__ partial, long long rows, int C) {
+  pdl_enter();
   constexpr int R = NV == 1 ? 2 : 1;   // 4 rows / iteration measured slower: registers -> occupancy
   extern __shared__ float red[];     // [LN_WARPS][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,6 +189,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
 // summation order (lane-strided partial sums, then lanes 0..31): deterministic.
 __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int C,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_enter();
   __shared__ float red[32][33];
   const int idx = blockIdx.x * 32 + threadIdx.x, zl = threadIdx.y;
   float s = 0.f;
@@ -222,7 +225,7 @@ int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta
   const int rows_per_warp = nv == 1 ? 4 : (nv == 2 ? 2 : 1);      // RowsOf<NV>::R
   const int grid = (int)ceil_div(rows, (long long)LN_WARPS * rows_per_warp);
 #define LAUNCH(TI, TO, NVV)                                                                    \
-  layernorm_fwd_kernel<TI, TO, NVV><<<grid, LN_WARPS * 32, 0, st>>>((const TI*)x, gamma, beta, \
+  launch_k(layernorm_fwd_kernel<TI, TO, NVV>, grid, LN_WARPS * 32, 0, st, (const TI*)x, gamma, beta, \
                                                                      (TO*)y, mean, rstd, rows, C, eps)
 #define LAUNCH_NV(TI, TO)                                                      \
   do {                                                                         \
@@ -259,7 +262,7 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
     DAT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LN_WARPS * 32, smem));  \
     if (occ < 1) occ = 1;                                                                         \
     if (nblk > 148 * occ) nblk = 148 * occ;                                                       \
-    kern<<<nblk, LN_WARPS * 32, smem, st>>>((const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
+    launch_k(kern, nblk, LN_WARPS * 32, smem, st, (const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
                                             (const TI*)dres, part, rows, C);                                    \
   } while (0)
 #define LAUNCH_NV(TI, TD)                                                      \
@@ -275,7 +278,7 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
 #undef LAUNCH_NV
 #undef LAUNCH
   DAT_LAUNCH_OK("layernorm_bwd_kernel");
-  layernorm_bwd_reduce_kernel<<<ceil_div(2 * C, 32), dim3(32, 32), 0, st>>>(part, nblk, C, dgamma, dbeta);
+  launch_k(layernorm_bwd_reduce_kernel, ceil_div(2 * C, 32), dim3(32, 32), 0, st, part, nblk, C, dgamma, dbeta);
   DAT_LAUNCH_OK("layernorm_bwd_reduce_kernel");
   return DAT_OK;
 }

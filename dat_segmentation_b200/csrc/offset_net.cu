@@ -40,6 +40,7 @@ offset_pos_fwd_kernel(const TQ* __restrict__ q, const float* __restrict__ w_dw,
                       const float* __restrict__ ln_b, const float* __restrict__ w_pw,
                       float* __restrict__ t_dw, float* __restrict__ off_raw,
                       float* __restrict__ pos, OffsetArgs a) {
+  pdl_enter();
   extern __shared__ float wsm[];
   const int kk = a.ksize * a.ksize;
   for (int idx = threadIdx.x; idx < kk * a.Cg; idx += blockDim.x) {
@@ -128,6 +129,7 @@ offset_pos_fwd_kernel(const TQ* __restrict__ q, const float* __restrict__ w_dw,
 }
 
 __global__ void ref_points_kernel(int Hk, int Wk, float* ry, float* rx) {
+  pdl_enter();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < Hk) ry[t] = ref_point(t, Hk);
   if (t < Wk) rx[t] = ref_point(t, Wk);
@@ -144,6 +146,7 @@ offset_bwd_point_kernel(const float* __restrict__ dpos, const float* __restrict_
                         const float* __restrict__ t_dw, const float* __restrict__ ln_g,
                         const float* __restrict__ ln_b, const float* __restrict__ w_pw,
                         float* __restrict__ dt, float* __restrict__ partial, OffsetArgs a) {
+  pdl_enter();
   extern __shared__ float red[];  // [OFF_WARPS][5][Cg]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g_py[MAXCPL], g_px[MAXCPL], g_g[MAXCPL], g_b[MAXCPL], g_b0[MAXCPL];
@@ -245,6 +248,7 @@ offset_bwd_point_kernel(const float* __restrict__ dpos, const float* __restrict_
 __global__ void offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cg,
                                          float* __restrict__ g_pw, float* __restrict__ g_ln_g,
                                          float* __restrict__ g_ln_b, float* __restrict__ g_dw_b) {
+  pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 5 * Cg) return;
   float s = 0.f;
@@ -265,6 +269,7 @@ template <typename TQ>
 __global__ void __launch_bounds__(256)
 offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
                         float* __restrict__ partial, long long pts_per_split, OffsetArgs a) {
+  pdl_enter();
   const int kk = a.ksize * a.ksize;
   const int cthreads = a.Cg < (int)blockDim.x ? a.Cg : (int)blockDim.x;   // channels per pass
   const int uvg_n = blockDim.x / cthreads;                                // tap groups
@@ -308,6 +313,7 @@ offset_bwd_wgrad_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
 // Fixed summation order (lane-strided partial sums, then lanes 0..31): deterministic.
 __global__ void offset_bwd_wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit,
                                                int kk, int Cg, float* __restrict__ g_dw_w) {
+  pdl_enter();
   __shared__ float red[32][33];
   const int idx = blockIdx.x * 32 + threadIdx.x;  // uv * Cg + c
   const int n_out = kk * Cg;
@@ -331,6 +337,7 @@ template <typename TQ>
 __global__ void offset_bwd_dgrad_kernel(const float* __restrict__ dt,
                                         const float* __restrict__ w_dw, TQ* __restrict__ dq,
                                         long long total, OffsetArgs a) {
+  pdl_enter();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cf = (int)(idx % a.C);
@@ -382,6 +389,7 @@ template <typename TQ, int K>
 __global__ void __launch_bounds__(K * WGR_PG * 32)
 offset_bwd_wgrad_rows_kernel(const TQ* __restrict__ q, const float* __restrict__ dt,
                              float* __restrict__ partial, int pts_per_split, OffsetArgs a) {
+  pdl_enter();
   __shared__ float2 red[(WGR_PG - 1) * K * K][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u = warp % K, pg = warp / K;
@@ -439,6 +447,7 @@ template <typename TQ, int K, int MW>   // MW: windows per dimension of the unro
 __global__ void __launch_bounds__(256)
 offset_bwd_dgrad_warp_kernel(const float* __restrict__ dt, const float* __restrict__ w_dw,
                              TQ* __restrict__ dq, int n_rows, OffsetArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float wT[];          // [K * K][Cg]
   for (int i = threadIdx.x; i < K * K * a.Cg; i += blockDim.x) {
     const int uv = i / a.Cg, c = i - uv * a.Cg;
@@ -553,7 +562,7 @@ int offset_pos_fwd(const Shape& s, const dat_block_params* p, const void* q, flo
     if (smem > 48 * 1024)                                                                      \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                        (int)smem));                                            \
-    kern<<<grid, OFF_WARPS * 32, smem, st>>>((const TQ*)q, p->off_dw_w, p->off_dw_b,           \
+    launch_k(kern, grid, OFF_WARPS * 32, smem, st, (const TQ*)q, p->off_dw_w, p->off_dw_b,           \
                                              p->off_ln_g, p->off_ln_b, p->off_pw_w, t_dw,      \
                                              off_raw, pos, a);                                 \
   } while (0)
@@ -574,7 +583,7 @@ int offset_pos_fwd(const Shape& s, const dat_block_params* p, const void* q, flo
 int ref_points(int Hk, int Wk, float* ry, float* rx, cudaStream_t st) {
   DAT_REQUIRE(Hk > 1 && Wk > 1, "ref_points: Hk, Wk must be > 1");
   int n = Hk > Wk ? Hk : Wk;
-  ref_points_kernel<<<ceil_div(n, 128), 128, 0, st>>>(Hk, Wk, ry, rx);
+  launch_k(ref_points_kernel, ceil_div(n, 128), 128, 0, st, Hk, Wk, ry, rx);
   DAT_LAUNCH_OK("ref_points_kernel");
   return DAT_OK;
 }
@@ -622,7 +631,7 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
     if (smem > 48 * 1024)                                                                    \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                        (int)smem));                                          \
-    kern<<<nblk, OFF_WARPS * 32, smem, st>>>(dpos, off_raw, t_dw, p->off_ln_g, p->off_ln_b,  \
+    launch_k(kern, nblk, OFF_WARPS * 32, smem, st, dpos, off_raw, t_dw, p->off_ln_g, p->off_ln_b,  \
                                              p->off_pw_w, dt, part1, a);                     \
   } while (0)
   if (cpl == 2) LAUNCH(2); else if (cpl == 4) LAUNCH(4); else if (cpl == 8) LAUNCH(8); else LAUNCH(16);
@@ -634,7 +643,7 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
     DAT_CUDA_OK(cudaEventRecord(fork_ev, st));
     DAT_CUDA_OK(cudaStreamWaitEvent(pst, fork_ev, 0));
   }
-  offset_bwd_reduce_kernel<<<ceil_div(5 * s.Cg, 128), 128, 0, pst>>>(
+  launch_k(offset_bwd_reduce_kernel, ceil_div(5 * s.Cg, 128), 128, 0, pst, 
       part1, nblk, s.Cg, g->off_pw_w, g->off_ln_g, g->off_ln_b, g->off_dw_b);
   DAT_LAUNCH_OK("offset_bwd_reduce_kernel");
 
@@ -643,7 +652,7 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
   const bool fast = offset_bwd_fast_supported(s);
   if (fast) {
 #define LAUNCH_WG(TQ, KV) \
-    offset_bwd_wgrad_rows_kernel<TQ, KV><<<nsplit, KV * WGR_PG * 32, 0, pst>>>((const TQ*)q, dt, part2, (int)pps, a)
+    launch_k(offset_bwd_wgrad_rows_kernel<TQ, KV>, nsplit, KV * WGR_PG * 32, 0, pst, (const TQ*)q, dt, part2, (int)pps, a)
 #define LAUNCH_WG_K(TQ)                                                             \
     do {                                                                            \
       if (s.ksize == 3) LAUNCH_WG(TQ, 3); else if (s.ksize == 5) LAUNCH_WG(TQ, 5);  \
@@ -653,11 +662,11 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
 #undef LAUNCH_WG_K
 #undef LAUNCH_WG
   } else if (s.act_dtype == DAT_F32)
-    offset_bwd_wgrad_kernel<float><<<nsplit, 256, 0, pst>>>((const float*)q, dt, part2, pps, a);
+    launch_k(offset_bwd_wgrad_kernel<float>, nsplit, 256, 0, pst, (const float*)q, dt, part2, pps, a);
   else
-    offset_bwd_wgrad_kernel<bf16><<<nsplit, 256, 0, pst>>>((const bf16*)q, dt, part2, pps, a);
+    launch_k(offset_bwd_wgrad_kernel<bf16>, nsplit, 256, 0, pst, (const bf16*)q, dt, part2, pps, a);
   DAT_LAUNCH_OK("offset_bwd_wgrad_kernel");
-  offset_bwd_wgrad_reduce_kernel<<<ceil_div(kk * s.Cg, 32), dim3(32, 32), 0, pst>>>(part2, nsplit, kk, s.Cg,
+  launch_k(offset_bwd_wgrad_reduce_kernel, ceil_div(kk * s.Cg, 32), dim3(32, 32), 0, pst, part2, nsplit, kk, s.Cg,
                                                                                     g->off_dw_w);
   DAT_LAUNCH_OK("offset_bwd_wgrad_reduce_kernel");
 
@@ -669,8 +678,8 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
     const bool two = (s.ksize + s.stride - 1) / s.stride <= 2;   // covering windows per dimension
 #define LAUNCH_DG(TQ, KV)                                                                             \
     do {                                                                                              \
-      if (two) offset_bwd_dgrad_warp_kernel<TQ, KV, 2><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, n_items, a); \
-      else offset_bwd_dgrad_warp_kernel<TQ, KV, 3><<<dg_grid, 256, wsm, st>>>(dt, p->off_dw_w, (TQ*)dq, n_items, a);     \
+      if (two) launch_k(offset_bwd_dgrad_warp_kernel<TQ, KV, 2>, dg_grid, 256, wsm, st, dt, p->off_dw_w, (TQ*)dq, n_items, a); \
+      else launch_k(offset_bwd_dgrad_warp_kernel<TQ, KV, 3>, dg_grid, 256, wsm, st, dt, p->off_dw_w, (TQ*)dq, n_items, a);     \
     } while (0)
 #define LAUNCH_DG_K(TQ)                                                             \
     do {                                                                            \
@@ -684,9 +693,9 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
     return DAT_OK;
   }
   if (s.act_dtype == DAT_F32)
-    offset_bwd_dgrad_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>(dt, p->off_dw_w, (float*)dq, total, a);
+    launch_k(offset_bwd_dgrad_kernel<float>, ceil_div(total, 256), 256, 0, st, dt, p->off_dw_w, (float*)dq, total, a);
   else
-    offset_bwd_dgrad_kernel<bf16><<<ceil_div(total, 256), 256, 0, st>>>(dt, p->off_dw_w, (bf16*)dq, total, a);
+    launch_k(offset_bwd_dgrad_kernel<bf16>, ceil_div(total, 256), 256, 0, st, dt, p->off_dw_w, (bf16*)dq, total, a);
   DAT_LAUNCH_OK("offset_bwd_dgrad_kernel");
   return DAT_OK;
 }

@@ -68,6 +68,7 @@ offset_pos_fwd_vec_kernel(const TQ* __restrict__ q, const float* __restrict__ w_
                           const float* __restrict__ ln_b, const float* __restrict__ w_pw,
                           float* __restrict__ t_dw, float* __restrict__ off_raw,
                           float* __restrict__ pos, VArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float wsm[];   // [k*k][Cg]
   const int kk = a.ksize * a.ksize;
   for (int idx = threadIdx.x; idx < kk * a.Cg; idx += blockDim.x) {
@@ -174,7 +175,7 @@ int offset_pos_fwd_vec(const Shape& s, const dat_block_params* p, const void* q,
     auto kern = offset_pos_fwd_vec_kernel<TQ, V>;                                              \
     if (smem > 48 * 1024)                                                                      \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, WARPS * 32, smem, st>>>((const TQ*)q, p->off_dw_w, p->off_dw_b, p->off_ln_g,  \
+    launch_k(kern, grid, WARPS * 32, smem, st, (const TQ*)q, p->off_dw_w, p->off_dw_b, p->off_ln_g,  \
                                          p->off_ln_b, p->off_pw_w, t_dw, off_raw, pos, a);     \
   } while (0)
 #define LAUNCH_T(TQ)                          \

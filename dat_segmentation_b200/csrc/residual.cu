@@ -15,6 +15,7 @@ template <typename TA, typename TX, typename TY, bool HAS_X>
 __global__ void __launch_bounds__(256)
 scale_residual_kernel(const TA* __restrict__ a, const TX* __restrict__ x, const float* __restrict__ s,
                       TY* __restrict__ y, long long n4, long long per_sample4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float sc = s[i / per_sample4];
@@ -36,7 +37,7 @@ int scale_residual(const void* a, int a_dt, const void* x, int x_dt, const float
   if (n4 == 0) return DAT_OK;
   const unsigned grid = (unsigned)ceil_div(n4, 256ll);
 #define LAUNCH(TA, TX, TY, HX) \
-  scale_residual_kernel<TA, TX, TY, HX><<<grid, 256, 0, st>>>((const TA*)a, (const TX*)x, s, (TY*)y, n4, ps4)
+  launch_k(scale_residual_kernel<TA, TX, TY, HX>, grid, 256, 0, st, (const TA*)a, (const TX*)x, s, (TY*)y, n4, ps4)
 #define LAUNCH_Y(TA, TX, HX)                                                       \
   do {                                                                             \
     if (y_dt == DAT_F32) LAUNCH(TA, TX, float, HX); else LAUNCH(TA, TX, bf16, HX); \

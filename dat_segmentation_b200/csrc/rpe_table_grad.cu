@@ -52,6 +52,7 @@ template <int TPW, int NT>
 __global__ void __launch_bounds__(NT)
 rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos, float* __restrict__ part,
                       TgArgs a) {
+  pdl_enter();
   constexpr int NW = NT / 32;
   __shared__ float s_bx[TG_MAXN], s_by[TG_MAXN];                // (1 - pos) * k of the staged samples
   extern __shared__ __align__(16) uint8_t tg_smem[];
@@ -251,6 +252,7 @@ rpe_table_grad_kernel(const bf16* __restrict__ ds, const float* __restrict__ pos
 // flight), the four partial sums are combined in shared memory in ascending zy.
 __global__ void __launch_bounds__(256)
 tg_reduce_kernel(const float* __restrict__ part, int nslots, int count, float* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[4][64];
   const int e = blockIdx.x * 64 + (threadIdx.x & 63), zy = threadIdx.x >> 6;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -344,7 +346,7 @@ int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* 
     auto kern = rpe_table_grad_kernel<TPWV, NTV>;                                                                     \
     if (p.smem > 40 * 1024)   /* + 512 B static: stay clear of the 48 KB default limit */                           \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));              \
-    kern<<<p.grid, NTV, p.smem, st>>>((const bf16*)ds, pos, (float*)ws, p.a);                                         \
+    launch_k(kern, p.grid, NTV, p.smem, st, (const bf16*)ds, pos, (float*)ws, p.a);                                         \
   } while (0)
   if (p.threads == 256) TG_LAUNCH(1, 256);
   else if (p.tpw == 1) TG_LAUNCH(1, 512);
@@ -353,7 +355,7 @@ int rpe_table_grad_mma(const Shape& s, const void* ds, const float* pos, float* 
   DAT_LAUNCH_OK("rpe_table_grad_kernel");
   const int count = s.heads * s.Th * s.Tw;
   const int nslots = (int)(p.grid.x * p.grid.y) * s.B;
-  tg_reduce_kernel<<<ceil_div(count, 64), 256, 0, st>>>((const float*)ws, nslots, count, d_table);
+  launch_k(tg_reduce_kernel, ceil_div(count, 64), 256, 0, st, (const float*)ws, nslots, count, d_table);
   DAT_LAUNCH_OK("tg_reduce_kernel");
   return DAT_OK;
 }

@@ -89,6 +89,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// shared memory tile (box layout of `map`, written through the generic proxy + fence_proxy_async_smem) -> global at
+// (c0 = column, c1 = row); rows / columns outside the tensor are clipped.  Bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups still READ their shared-memory source / are still in flight
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- tensor memory --------------------------------------------------------------------
 // Whole warp; writes the allocated base address (lane 0, column c) to *smem_result.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

@@ -20,6 +20,7 @@ constexpr int LC_MAX_HG = 16;    // heads per group the log-CPB kernels keep in 
 template <typename TX, typename T>
 __global__ void avgpool_fwd_kernel(const TX* __restrict__ x, T* __restrict__ xs, int H, int W, int C, int Hk, int Wk,
                                    int s, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, c4)
   if (idx >= total) return;
   const int c4 = (int)(idx % (C / 4));
@@ -41,6 +42,7 @@ __global__ void avgpool_fwd_kernel(const TX* __restrict__ x, T* __restrict__ xs,
 template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dxs, float* __restrict__ dx, int H, int W, int C, int Hk,
                                    int Wk, int s, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, pixel, c4)
   if (idx >= total) return;
   const int c4 = (int)(idx % (C / 4));
@@ -59,6 +61,7 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dxs, float* __restrict_
 // y = a + b, elementwise (n % 4 == 0); y may alias a
 template <typename T>
 __global__ void add2_kernel(const T* a, const T* __restrict__ b, T* y, long long n4) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 u = load4(a + 4 * i), v = load4(b + 4 * i);
@@ -84,6 +87,7 @@ __device__ __forceinline__ Lin lin_index(int dst, int in, int out) {
 
 __global__ void fixed_bias_fwd_kernel(const float* __restrict__ table, float* __restrict__ bias, int heads, int Tq,
                                       int Tk, int HW, int Ns, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (eta, m, n)
   if (idx >= total) return;
   const int n = (int)(idx % Ns);
@@ -99,6 +103,7 @@ __global__ void fixed_bias_fwd_kernel(const float* __restrict__ table, float* __
 // d table (zeroed by the caller) += resize^T (sum over the batch of dS)
 __global__ void fixed_bias_bwd_kernel(const float* __restrict__ dbias, float* __restrict__ dtable, int B, int heads,
                                       int Tq, int Tk, int HW, int Ns, long long total) {
+  pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (eta, m, n)
   if (idx >= total) return;
   const int n = (int)(idx % Ns);
@@ -130,6 +135,7 @@ __device__ __forceinline__ float logcpb_coord(float grid, float pos, float* dt_d
 __global__ void logcpb_bias_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ w1,
                                        const float* __restrict__ b1, const float* __restrict__ w2,
                                        float* __restrict__ bias, int H, int W, int G, int hg, int Ns, long long total) {
+  pdl_enter();
   __shared__ float s_w1[LC_HID * 2], s_b1[LC_HID], s_w2[LC_MAX_HG * LC_HID];
   for (int i = threadIdx.x; i < LC_HID * 2; i += blockDim.x) s_w1[i] = w1[i];
   for (int i = threadIdx.x; i < LC_HID; i += blockDim.x) s_b1[i] = b1[i];
@@ -168,6 +174,7 @@ logcpb_bias_bwd_kernel(const float* __restrict__ dbias, const float* __restrict_
                        const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ dw1,
                        float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ dpos, int H, int W, int G,
                        int hg, int Ns, long long n_warps) {
+  pdl_enter();
   __shared__ float acc[LC_HID * (3 + LC_MAX_HG)];
   for (int i = threadIdx.x; i < LC_HID * (3 + LC_MAX_HG); i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
@@ -238,10 +245,10 @@ int avgpool_fwd(const Shape& s, const void* x, void* xs, cudaStream_t st) {
   const long long total = (long long)s.B * s.Ns * (s.C / 4);
   const int grid = ceil_div(total, 256);
   const bool xf = s.x_dtype == DAT_F32, af = s.act_dtype == DAT_F32;
-  if (xf && af) avgpool_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
-  else if (xf) avgpool_fwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
-  else if (af) avgpool_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
-  else avgpool_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  if (xf && af) launch_k(avgpool_fwd_kernel<float, float>, grid, 256, 0, st, (const float*)x, (float*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  else if (xf) launch_k(avgpool_fwd_kernel<float, bf16>, grid, 256, 0, st, (const float*)x, (bf16*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  else if (af) launch_k(avgpool_fwd_kernel<bf16, float>, grid, 256, 0, st, (const bf16*)x, (float*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  else launch_k(avgpool_fwd_kernel<bf16, bf16>, grid, 256, 0, st, (const bf16*)x, (bf16*)xs, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
   DAT_LAUNCH_OK("avgpool_fwd_kernel");
   return DAT_OK;
 }
@@ -249,8 +256,8 @@ int avgpool_fwd(const Shape& s, const void* x, void* xs, cudaStream_t st) {
 int avgpool_bwd(const Shape& s, const void* dxs, float* dx, cudaStream_t st) {
   const long long total = (long long)s.B * s.HW * (s.C / 4);
   const int grid = ceil_div(total, 256);
-  if (s.act_dtype == DAT_F32) avgpool_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dxs, dx, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
-  else avgpool_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dxs, dx, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  if (s.act_dtype == DAT_F32) launch_k(avgpool_bwd_kernel<float>, grid, 256, 0, st, (const float*)dxs, dx, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
+  else launch_k(avgpool_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dxs, dx, s.H, s.W, s.C, s.Hk, s.Wk, s.stride, total);
   DAT_LAUNCH_OK("avgpool_bwd_kernel");
   return DAT_OK;
 }
@@ -258,15 +265,15 @@ int avgpool_bwd(const Shape& s, const void* dxs, float* dx, cudaStream_t st) {
 int add2(const void* a, const void* b, void* y, int dt, long long n, cudaStream_t st) {
   DAT_REQUIRE(n % 4 == 0, "add2: n must be a multiple of 4");
   const long long n4 = n / 4;
-  if (dt == DAT_F32) add2_kernel<float><<<ceil_div(n4, 256), 256, 0, st>>>((const float*)a, (const float*)b, (float*)y, n4);
-  else add2_kernel<bf16><<<ceil_div(n4, 256), 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n4);
+  if (dt == DAT_F32) launch_k(add2_kernel<float>, ceil_div(n4, 256), 256, 0, st, (const float*)a, (const float*)b, (float*)y, n4);
+  else launch_k(add2_kernel<bf16>, ceil_div(n4, 256), 256, 0, st, (const bf16*)a, (const bf16*)b, (bf16*)y, n4);
   DAT_LAUNCH_OK("add2_kernel");
   return DAT_OK;
 }
 
 int fixed_bias_fwd(const Shape& s, const float* table, float* bias, cudaStream_t st) {
   const long long total = (long long)s.heads * s.HW * s.Ns;
-  fixed_bias_fwd_kernel<<<ceil_div(total, 256), 256, 0, st>>>(table, bias, s.heads, s.Th, s.Tw, s.HW, s.Ns, total);
+  launch_k(fixed_bias_fwd_kernel, ceil_div(total, 256), 256, 0, st, table, bias, s.heads, s.Th, s.Tw, s.HW, s.Ns, total);
   DAT_LAUNCH_OK("fixed_bias_fwd_kernel");
   return DAT_OK;
 }
@@ -274,7 +281,7 @@ int fixed_bias_fwd(const Shape& s, const float* table, float* bias, cudaStream_t
 int fixed_bias_bwd(const Shape& s, const float* dbias, float* dtable, cudaStream_t st) {
   const long long total = (long long)s.heads * s.HW * s.Ns;
   DAT_CUDA_OK(cudaMemsetAsync(dtable, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
-  fixed_bias_bwd_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dbias, dtable, s.B, s.heads, s.Th, s.Tw, s.HW, s.Ns, total);
+  launch_k(fixed_bias_bwd_kernel, ceil_div(total, 256), 256, 0, st, dbias, dtable, s.B, s.heads, s.Th, s.Tw, s.HW, s.Ns, total);
   DAT_LAUNCH_OK("fixed_bias_bwd_kernel");
   return DAT_OK;
 }
@@ -285,7 +292,7 @@ int logcpb_bias_fwd(const Shape& s, const float* pos, const float* w1, const flo
                     cudaStream_t st) {
   DAT_REQUIRE(logcpb_supported(s), "log_cpb: at most %d heads per group", LC_MAX_HG);
   const long long total = (long long)s.B * s.G * s.HW * s.Ns;
-  logcpb_bias_fwd_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pos, w1, b1, w2, bias, s.H, s.W, s.G, s.hg, s.Ns, total);
+  launch_k(logcpb_bias_fwd_kernel, ceil_div(total, 256), 256, 0, st, pos, w1, b1, w2, bias, s.H, s.W, s.G, s.hg, s.Ns, total);
   DAT_LAUNCH_OK("logcpb_bias_fwd_kernel");
   return DAT_OK;
 }
@@ -297,7 +304,7 @@ int logcpb_bias_bwd(const Shape& s, const float* dbias, const float* pos, const 
   DAT_CUDA_OK(cudaMemsetAsync(db1, 0, LC_HID * 4, st));
   DAT_CUDA_OK(cudaMemsetAsync(dw2, 0, (size_t)s.hg * LC_HID * 4, st));
   const long long n_warps = (long long)s.B * s.G * s.Ns;
-  logcpb_bias_bwd_kernel<<<ceil_div(n_warps, 8), 256, 0, st>>>(dbias, pos, w1, b1, w2, dw1, db1, dw2, dpos, s.H, s.W, s.G,
+  launch_k(logcpb_bias_bwd_kernel, ceil_div(n_warps, 8), 256, 0, st, dbias, pos, w1, b1, w2, dw1, db1, dw2, dpos, s.H, s.W, s.G,
                                                                 s.hg, s.Ns, n_warps);
   DAT_LAUNCH_OK("logcpb_bias_bwd_kernel");
   return DAT_OK;
