@@ -97,6 +97,26 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface in DAT_LAUNCH_OK
 }
+// the same with a run-time thread-block cluster shape
+template <typename... KArgs, typename... Args>
+inline void launch_k_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster.x;
+  at[0].val.clusterDim.y = cluster.y;
+  at[0].val.clusterDim.z = cluster.z;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 

@@ -4,12 +4,18 @@
 // so both operands are MN-major: TMA boxes of 64 rows x 64 columns (128B swizzle) are used
 // directly as the canonical MN-major core-matrix layout (8-row groups 1 KB apart, 64-column
 // blocks 8 KB apart) - no transposed copy of either activation is ever made.
-// One CTA = one 128 (out-channel) x BNK (in-channel, <= 256) tile of dW over one slice of the
-// pixels; fp32 partial tiles per slice are reduced in a fixed order afterwards (deterministic).
+// One CTA = one 128 (out-channel) x BNK (in-channel, <= 128) tile of dW over one slice of the
+// pixels.  The CTAs of up to 8 consecutive slices form a thread-block cluster: every CTA parks its fp32
+// accumulator tile in its own shared memory and, after a cluster barrier, CTA r sums rows [r * 128 / CS, ...) of all
+// CS tiles through distributed shared memory in rank order (deterministic) and writes ONE partial tile per cluster -
+// 8 x fewer partial bytes to write and to reduce afterwards, and no reduction launch at all when one cluster covers
+// the pixels.  Remaining per-cluster partials are summed in a fixed order by wgrad_reduce_kernel.
 // The bias gradient db[n] = sum_m dY[m, n] rides along: the CTAs of the first in-channel tile issue
 // one extra N = 16 MMA per step against a shared-memory tile of ones (accumulated in 16 spare
 // TMEM columns), so dY is not read a second time by a column-sum kernel.
 // Warp roles as in gemm_tc.cu: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -28,7 +34,7 @@ constexpr int ONES_BYTES = 2048;     // bf16 ones read by the N = 16 bias-gradie
 __global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      float* __restrict__ partial, float* __restrict__ db_partial, int N, int K, int BNK,
-                     int rows_per_split, long long M, int stages, int tmem_cols) {
+                     int rows_per_split, long long M, int stages, int tmem_cols, int CS) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -112,54 +118,79 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
       tc_commit(tmem_full);
     }
   } else {
+    // accumulator tile -> this CTA's shared memory (the ring is idle once tmem_full has fired), row pitch + 16 bytes:
+    // conflict-free 16-byte stores with one row per lane
     const int quad = warp & 3;
-    float* out = partial + ((long long)split * N + n0 + quad * 32) * K + k0;
-    // column groups of 128 keep the staging area at 66 KB: two CTAs per SM overlap their phases
-    const int gcols = BNK < 128 ? BNK : 128;
-    const int seg_bytes = gcols * 4, pitch = seg_bytes + 16;
-    uint8_t* stage = sA + (warp - 2) * 32 * pitch;
     if (chunks > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after_sync();
     }
-    const int rows_here = min(32, N - (n0 + quad * 32));
-    if (with_db) {                       // column BNK of this lane's row = sum over the slice's pixels
+    const int pitch = BNK * 4 + 16;
+    uint8_t* myrow = sA + (quad * 32 + lane) * pitch;
+    for (int c = 0; c < BNK / 32; ++c) {
       uint32_t r[32];
       if (chunks > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)BNK, r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_wait_ld();
       } else {
-        r[0] = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (lane < rows_here) db_partial[(long long)split * N + n0 + quad * 32 + lane] = __uint_as_float(r[0]);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(myrow + (c * 32 + j) * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     }
-    for (int cg = 0; cg < BNK; cg += gcols) {
-      for (int c = 0; c < gcols / 32; ++c) {
-        uint32_t r[32];
-        if (chunks > 0) {
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cg + c * 32), r);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        float* dst = reinterpret_cast<float*>(stage + lane * pitch) + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    if (db_partial != nullptr) {           // column BNK of this lane's row = sum of dY over the slice's pixels
+      uint32_t r[32];
+      r[0] = 0u;
+      if (chunks > 0 && with_db) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)BNK, r);
+        tmem_wait_ld();
       }
-      __syncwarp();
-      for (int rr = 0; rr < rows_here; ++rr) {
-        uint8_t* grow = reinterpret_cast<uint8_t*>(out + (long long)rr * K + cg);
-        const uint8_t* srow = stage + rr * pitch;
-        for (int off = lane * 16; off < seg_bytes; off += 512)
-          *reinterpret_cast<uint4*>(grow + off) = *reinterpret_cast<const uint4*>(srow + off);
-      }
-      __syncwarp();
+      reinterpret_cast<float*>(sA + 128 * pitch)[quad * 32 + lane] = __uint_as_float(r[0]);
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();                      // every tile of the cluster is parked (release / acquire at cluster scope)
+  {
+    const int crank = (int)cluster_ctarank();
+    const int pitch = BNK * 4 + 16;
+    const int rows_per = WG_BM / CS, r0 = crank * rows_per;
+    const int part_idx = split / CS;       // one partial tile per cluster
+    const int n4 = BNK / 4;
+    const uint32_t my = smem_u32(sA);
+    for (int i = threadIdx.x; i < rows_per * n4; i += WG_THREADS) {
+      const int row = r0 + i / n4, c4 = i - (i / n4) * n4;
+      if (n0 + row >= N) continue;         // 64-row tail tile
+      const uint32_t local = my + (uint32_t)(row * pitch + c4 * 16);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int z = 0; z < CS; ++z) {       // rank order: the sum does not depend on scheduling
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(z));
+        float4 v;
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(remote)
+                     : "memory");
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partial + ((long long)part_idx * N + n0 + row) * K + k0 + c4 * 4) = acc;
+    }
+    if (with_db && (int)threadIdx.x < rows_per && n0 + r0 + (int)threadIdx.x < N) {
+      const int row = r0 + threadIdx.x;
+      const uint32_t local = my + (uint32_t)(128 * pitch + row * 4);
+      float acc = 0.f;
+      for (int z = 0; z < CS; ++z) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(z));
+        float v;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+        acc += v;
+      }
+      db_partial[(long long)part_idx * N + n0 + row] = acc;
+    }
+  }
+  cluster_sync_all();                      // nobody leaves while a peer still reads its tile
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -175,17 +206,54 @@ bool pointwise_wgrad_tc_supported(long long M, int N, int K) {
   return M >= 64 && (N % 64 == 0 || N == 32) && K % 64 == 0 && (K % wg_bnk(K)) == 0 && M < (1ll << 31);
 }
 
+// CTAs of clusters of size c that are resident at once with two CTAs per SM.  A cluster lives inside one GPC (16 - 20
+// of the 148 SMs): 4 clusters of 8 per GPC but 8 - 10 clusters of 4.  Measured on B200: 32 clusters of 8 run as one wave
+// (stage-2 fc2 weight gradient 24.8 -> 22.7 us), 36 or 38 take two (stage-1: 29.8 -> 35.8 us).
+// (cudaOccupancyMaxActiveClusters reports one CTA per SM for this kernel - 15 / 33 / 74 clusters of 8 / 4 / 2 - and
+// was not usable for this plan.)
+static int wg_cluster_slots(int c) { return c >= 8 ? 256 : c == 4 ? 272 : c == 2 ? 288 : 296; }
+
+// slices of the pixels and cluster size (slices per cluster): one wave of resident CTAs; the cluster size trades
+// resident CTAs (fewer with larger clusters) against partial tiles to write and reduce (one per cluster)
+static void wg_plan(long long M, int N, int K, int* splits, int* cs) {
+  const int BNK = wg_bnk(K);
+  const int tiles = ((N + WG_BM - 1) / WG_BM) * (K / BNK);
+  const long long cap = (M + 127) / 128;            // at least 2 chunks per slice
+  double best = 1e30;
+  *splits = 1;
+  *cs = 1;
+  for (int c = 8; c >= 1; c >>= 1) {
+    const int slots = wg_cluster_slots(c);
+    long long s = slots / tiles / c * c;            // whole clusters, one wave
+    if (s > cap) s = cap / c * c;
+    if (s < c) {
+      if (c > 1) continue;
+      s = 1;
+    }
+    const double chunks = (double)((M + s - 1) / s + WG_CHUNK - 1) / WG_CHUNK;
+    const double t_mma = chunks * (BNK == 128 ? 370.0 : 190.0);                       // cycles per 64-pixel chunk
+    const double parts = (double)(s / c);
+    const double t_red = parts > 1 ? parts * N * K * 8.0 / 2000.0 + 4000.0 : 0.0;     // partial write + read, + a launch
+    if (t_mma + t_red < best) {
+      best = t_mma + t_red;
+      *splits = (int)s;
+      *cs = c;
+    }
+  }
+  if (std::getenv("DAT_B200_WG_DEBUG"))
+    fprintf(stderr, "wgrad plan M=%lld N=%d K=%d: %d tiles x %d slices, clusters of %d\n", M, N, K, tiles, *splits, *cs);
+}
 int pointwise_wgrad_tc_splits(long long M, int N, int K) {
-  const int tiles = ((N + WG_BM - 1) / WG_BM) * (K / wg_bnk(K));
-  long long want = (2 * 148 + tiles - 1) / tiles;   // two CTAs per SM
-  long long cap = (M + 127) / 128;            // at least 2 chunks per slice
-  long long s = want < cap ? want : cap;
-  return (int)(s < 1 ? 1 : s);
+  int s, c;
+  wg_plan(M, N, K, &s, &c);
+  return s;
 }
 
 size_t pointwise_wgrad_tc_workspace(long long M, int N, int K) {
-  const size_t splits = (size_t)pointwise_wgrad_tc_splits(M, N, K);
-  return align_up(splits * N * K * 4, 256) + align_up(splits * N * 4, 256);
+  int s, c;
+  wg_plan(M, N, K, &s, &c);
+  const size_t parts = (size_t)(s / c);             // one partial tile per cluster
+  return align_up(parts * N * K * 4, 256) + align_up(parts * N * 4, 256);
 }
 
 namespace {
@@ -215,7 +283,9 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long
   DAT_REQUIRE(pointwise_wgrad_tc_supported(M, N, K), "pointwise_wgrad_tc: unsupported shape");
   DAT_REQUIRE(ws_bytes >= pointwise_wgrad_tc_workspace(M, N, K), "pointwise_wgrad_tc: workspace too small");
   const int BNK = wg_bnk(K);
-  const int splits = pointwise_wgrad_tc_splits(M, N, K);
+  int splits, CS;
+  wg_plan(M, N, K, &splits, &CS);
+  const int parts = splits / CS;
   long long rps = (M + splits - 1) / splits;
   rps = (rps + WG_CHUNK - 1) / WG_CHUNK * WG_CHUNK;
   CUtensorMap tmDY, tmX;
@@ -225,23 +295,23 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long
   int stages = 100 * 1024 / stage_bytes;      // two CTAs per SM
   if (stages > 6) stages = 6;
   size_t buf = (size_t)stages * stage_bytes;
-  const size_t out_stage = (size_t)4 * 32 * ((BNK < 128 ? BNK : 128) * 4 + 16);
+  const size_t out_stage = (size_t)WG_BM * (BNK * 4 + 16) + WG_BM * 4;   // parked accumulator tile + bias-gradient column
   if (out_stage > buf) buf = out_stage;
   const size_t smem = 1024 + 1024 + ONES_BYTES + buf;
   int tmem_cols = 32;
   while (tmem_cols < BNK + 32) tmem_cols <<= 1;      // + the bias-gradient columns (read 32 wide)
-  float* part = splits > 1 ? (float*)ws : dW;
+  float* part = parts > 1 ? (float*)ws : dW;
   float* bpart = nullptr;
   if (db != nullptr)
-    bpart = splits > 1 ? (float*)((char*)ws + align_up((size_t)splits * N * K * 4, 256)) : db;
+    bpart = parts > 1 ? (float*)((char*)ws + align_up((size_t)parts * N * K * 4, 256)) : db;
   dim3 grid((N + WG_BM - 1) / WG_BM, K / BNK, splits);
   DAT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  launch_k(gemm_tc_wgrad_kernel, grid, WG_THREADS, smem, st, tmDY, tmX, part, bpart, N, K, BNK, (int)rps, M, stages,
-                                                       tmem_cols);
+  launch_k_cluster(gemm_tc_wgrad_kernel, grid, WG_THREADS, smem, st, dim3(1, 1, CS), tmDY, tmX, part, bpart, N, K, BNK,
+                   (int)rps, M, stages, tmem_cols, CS);
   DAT_LAUNCH_OK("gemm_tc_wgrad_kernel");
-  if (splits > 1) {
+  if (parts > 1) {
     const long long nk = (long long)N * K;
-    launch_k(wgrad_reduce_kernel, (unsigned)ceil_div(nk + N, 256ll), 256, 0, st, part, bpart, splits, nk, N, dW, db);
+    launch_k(wgrad_reduce_kernel, (unsigned)ceil_div(nk + N, 256ll), 256, 0, st, part, bpart, parts, nk, N, dW, db);
     DAT_LAUNCH_OK("wgrad_reduce_kernel");
   }
   return DAT_OK;
