@@ -9,11 +9,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libdat_b200.so")
+# DAT_B200_BUILD_TAG=x builds a second variant (build_x/, libdat_b200_x.so) next to the product library: A/B timing only
+_TAG = os.environ.get("DAT_B200_BUILD_TAG", "")
+OBJ = os.path.join(PKG, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(PKG, "libdat_b200" + ("_" + _TAG if _TAG else "") + ".so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # no --use_fast_math: reference points / tap indices must be bit-exact (IEEE div, no ftz)
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("DAT_B200_BUILD_DEFS", "").split()     # e.g. -DDAT_PDL_NO_EARLY_TRIGGER (A/B builds)
 
 
 def _nvcc():
