@@ -109,11 +109,13 @@ __global__ void sample_bwd_dpos_kernel(const TX* __restrict__ x, const float* __
   }
 }
 
-// d x scatter, sorted-run form.  grid = (B*G, Cg/32); block = 256 threads.
+// d x scatter, sorted-run form.  grid = (B*G, Cg/32); block = min(P, 1024) threads: one (sample, tap) entry per thread,
+// so the read-modify-write of every run head is ONE round trip to memory for the whole CTA (with 256 threads a thread
+// walked 4 entries one after the other, each a dependent load -> FMA -> store chain through the same dx array).
 // dynamic smem: keys[P] (uint32) + weight[4*Ns] (float), P = pow2 >= 4*Ns.
 // key = pixel << 14 | entry  (entry = n*4 + tap < 2^14, pixel < 2^18); invalid = ~0u.
 template <typename TD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sample_bwd_dx_kernel(const float* __restrict__ pos, const TD* __restrict__ dxs,
                      float* __restrict__ dx, int H, int W, int C, int G, int Cg, int Ns, int P) {
   pdl_enter();
@@ -238,7 +240,7 @@ int sample_bwd_dx(const Shape& s, const float* pos, const void* dxs, float* dx, 
     if (smem > 48 * 1024)                                                                      \
       DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                        (int)smem));                                            \
-    launch_k(kern, grid, 256, smem, st, pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
+    launch_k(kern, grid, P < 1024 ? P : 1024, smem, st, pos, (const TD*)dxs, dx, s.H, s.W, s.C, s.G, s.Cg, s.Ns, P); \
   } while (0)
   if (s.act_dtype == DAT_F32) LAUNCH(float); else LAUNCH(bf16);
 #undef LAUNCH

@@ -311,7 +311,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
-  for (int i = threadIdx.x; i < N; i += TCP_THREADS) sBias[i] = bias != nullptr ? bias[i] : 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -379,6 +378,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int seg_bytes = gcols * (int)sizeof(TOut);
     uint8_t* stage = sStage + (warp - 2) * 32 * stage_pitch;
     int li = 0;
+    // the whole bias vector is staged once per CTA by the epilogue warps alone: the producer and the MMA issuer start
+    // their first tile without waiting for this global load
+    for (int i = threadIdx.x - 64; i < N; i += 32 * TCP_EPI_WARPS) sBias[i] = bias != nullptr ? bias[i] : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
     if (BN % 64 == 0) {
       // TMA-store epilogue: a warp's 32 rows x 64 columns go TMEM -> registers -> (+ bias, convert) -> a 128B-swizzled
       // shared-memory tile (conflict-free 16-byte stores) -> ONE cp.async.bulk.tensor store issued by lane 0.  The
