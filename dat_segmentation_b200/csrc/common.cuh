@@ -77,14 +77,18 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // boundary overlap the previous kernel's tail.  Captured into CUDA graphs as programmatic edges.
 // No early `griddepcontrol.launch_dependents`: with it the next grid becomes resident (and holds registers / shared
 // memory / tensor memory) while the current one still runs; measured on the training step that costs 9 % (816 vs
-// 894 images/s, also with the side-branch streams excluded, 772 with a single stream) where the implicit trigger at
-// CTA exit gains 1.1 % over plain launches.
+// 894 images/s, also with the side-branch streams excluded, 772 with a single stream; triggering AFTER the wait, which
+// bounds the look-ahead to one grid, costs the same: 815 vs 877) where the implicit trigger at CTA exit gains 1.1 % over
+// plain launches.
 // DAT_B200_PDL=0 launches without the attribute (the wait is then a no-op).
 __device__ __forceinline__ void pdl_enter() {
 #ifdef DAT_PDL_EARLY_TRIGGER     // measured on B200: 816 vs 894 images/s - see the note above
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef DAT_PDL_TRIGGER_AFTER_WAIT
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
