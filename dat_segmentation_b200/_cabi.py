@@ -128,6 +128,11 @@ def lib():
                                  C.c_size_t, vp]
     L.dat_dwconv_bwd.restype = C.c_int
     L.dat_layernorm_fwd.restype = C.c_int
+    L.dat_residual_layernorm_fwd.argtypes = [vp, f32p, i64, vp, i32, f32p, f32p, vp, vp, i32, f32p, f32p, i64, i32,
+                                             C.c_float, vp]
+    L.dat_residual_layernorm_bwd.argtypes = [vp, i32, vp, i32, f32p, f32p, f32p, vp, vp, vp, f32p, i64, f32p, f32p,
+                                             i64, i32, vp, C.c_size_t, vp]
+    L.dat_residual_layernorm_fwd.restype = L.dat_residual_layernorm_bwd.restype = C.c_int
     L.dat_layernorm_bwd.restype = C.c_int
     L.dat_conv3x3s2_kp.argtypes = [i32]
     L.dat_conv3x3s2_kp.restype = i32
@@ -173,6 +178,7 @@ def exported_symbols():
             "dat_ref_points", "dat_sample_fwd",
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
             "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd",
+            "dat_residual_layernorm_fwd", "dat_residual_layernorm_bwd",
             "dat_dwconv_workspace_bytes", "dat_dwconv_fwd", "dat_gelu_bwd", "dat_dwconv_wgrad",
             "dat_dwconv_bwd", "dat_scale_residual",
             "dat_conv3x3s2_kp", "dat_im2col3x3s2", "dat_col2im3x3s2", "dat_conv_weight_pack", "dat_conv_weight_unpack",

@@ -192,8 +192,9 @@ class TransformerStage(nn.Module):
             else:
                 x, ln = self.layer_norms[2 * d].forward_fork(x)
                 a, _, _ = self.attns[d](ln)
-                x = scale_residual(self.layer_scales[2 * d](a), x, scales[si])
-                x, ln = self.layer_norms[2 * d + 1].forward_fork(x, out_dtype=mlp_in)
+                # `x = drop_path(attn) + x` and the norm that follows it in one kernel (forward and backward)
+                x, ln = self.layer_norms[2 * d + 1].forward_residual_fork(self.layer_scales[2 * d](a), x, scales[si],
+                                                                          out_dtype=mlp_in)
                 m = self.mlps[d](ln)
                 x = scale_residual(self.layer_scales[2 * d + 1](m), x, scales[si + 1])
                 si += 2

@@ -469,6 +469,26 @@ int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x
                        workspace_bytes, (cudaStream_t)stream);
 }
 
+int dat_residual_layernorm_fwd(const void* a, const float* scale, int64_t rows_per_sample, const void* x,
+                               int32_t x_dtype, const float* gamma, const float* beta, void* xout, void* y,
+                               int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
+                               void* stream) {
+  DAT_REQUIRE(a && scale && x && gamma && beta && xout && y && mean && rstd && rows_per_sample > 0,
+              "residual_layernorm_fwd: NULL pointer / bad size");
+  return residual_layernorm_fwd(a, scale, rows_per_sample, x, x_dtype, gamma, beta, xout, y, y_dtype, mean, rstd, rows, C,
+                                eps, (cudaStream_t)stream);
+}
+
+int dat_residual_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma,
+                               const float* mean, const float* rstd, void* dx, const void* dres, void* da,
+                               const float* scale, int64_t rows_per_sample, float* dgamma, float* dbeta, int64_t rows,
+                               int32_t C, void* workspace, size_t workspace_bytes, void* stream) {
+  DAT_REQUIRE(dy && x && gamma && mean && rstd && dx && da && scale && dgamma && dbeta && workspace && rows_per_sample > 0,
+              "residual_layernorm_bwd: NULL pointer / bad size");
+  return residual_layernorm_bwd(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dx, dres, da, scale, rows_per_sample, dgamma,
+                                dbeta, rows, C, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int dat_scale_residual(const void* a, int32_t a_dtype, const void* x, int32_t x_dtype, const float* scale,
                        void* y, int32_t y_dtype, int64_t B, int64_t per_sample, void* stream) {
   DAT_REQUIRE(a && scale && y && B >= 0 && per_sample >= 0, "scale_residual: NULL pointer / bad size");
@@ -680,8 +700,7 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     DAT_FWD(attention_bwd_pack_table(s, p->rpe_table, tabp, !mma_table, st));
     DAT_FWD(attention_bwd_tc(s, sv->q, sv->k, sv->v, w.d_o, sv->lse, delta, sv->pos, tabp, w.dq, dk_part,
                              dv_part, g->rpe_table, w.dpos_part, st, mma_table ? w.ds_tab : nullptr));
-    DAT_FWD(reduce_partials(dk_part, chunks, (long long)s.B * s.Ns * C, w.dk, adt, st));
-    DAT_FWD(reduce_partials(dv_part, chunks, (long long)s.B * s.Ns * C, w.dv, adt, st));
+    DAT_FWD(reduce_partials_pair(dk_part, dv_part, chunks, (long long)s.B * s.Ns * C, w.dk, w.dv, adt, st));
   } else {
     long long bias_bstride = 0;
     if (s.pe_mode == DAT_PE_FIXED) {

@@ -114,6 +114,24 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int ns
   out[idx] = from_f32<TC>(v);
 }
 
+// Two reductions of the same shape in one launch (dK and dV partials of the attention backward), 4 elements per thread:
+// out{A,B}[i] = sum_z part{A,B}[z][i]; blockIdx.y selects the pair member.  count % 4 == 0.
+template <typename TC>
+__global__ void reduce_partials_pair_kernel(const float* __restrict__ partA, const float* __restrict__ partB, int nsplit,
+                                            long long count, TC* __restrict__ outA, TC* __restrict__ outB) {
+  pdl_enter();
+  const float* part = blockIdx.y == 0 ? partA : partB;
+  TC* out = blockIdx.y == 0 ? outA : outB;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx >= count) return;
+  float4 v = *reinterpret_cast<const float4*>(part + idx);
+  for (int z = 1; z < nsplit; ++z) {
+    const float4 o = *reinterpret_cast<const float4*>(part + (long long)z * count + idx);
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  store4(out + idx, v);
+}
+
 // Column sums of a (M, N) row-major matrix over a row range: partial[y][n].
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, long long M, int N, long long rows_per_block,
@@ -250,6 +268,18 @@ int bias_grad(const void* dY, int dy_dt, float* db, long long M, int N, void* ws
   DAT_LAUNCH_OK("colsum_kernel");
   launch_k(reduce_partials_kernel<float>, ceil_div(N, 256), 256, 0, st, cpart, cs, N, N, nullptr, db);
   DAT_LAUNCH_OK("reduce_partials_kernel");
+  return DAT_OK;
+}
+
+int reduce_partials_pair(const float* partA, const float* partB, int nsplit, long long count, void* outA, void* outB,
+                         int out_dt, cudaStream_t st) {
+  DAT_REQUIRE(count % 4 == 0, "reduce_partials_pair: count must be a multiple of 4");
+  dim3 grid(ceil_div(count / 4, 256), 2);
+  if (out_dt == DAT_F32)
+    launch_k(reduce_partials_pair_kernel<float>, grid, 256, 0, st, partA, partB, nsplit, count, (float*)outA, (float*)outB);
+  else
+    launch_k(reduce_partials_pair_kernel<bf16>, grid, 256, 0, st, partA, partB, nsplit, count, (bf16*)outA, (bf16*)outB);
+  DAT_LAUNCH_OK("reduce_partials_pair_kernel");
   return DAT_OK;
 }
 

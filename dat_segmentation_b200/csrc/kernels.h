@@ -20,6 +20,8 @@ int colsum_splits(long long M);
 size_t pointwise_wgrad_workspace(long long M, int N, int K);
 int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, float* dW, float* db,
                          long long M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+int reduce_partials_pair(const float* partA, const float* partB, int nsplit, long long count, void* outA, void* outB,
+                         int out_dt, cudaStream_t st);
 int reduce_partials(const float* part, int nsplit, long long count, void* out, int out_dt,
                     cudaStream_t st);
 
@@ -129,6 +131,13 @@ int pointwise_wgrad_tc(const void* dY, const void* X, float* dW, float* db, long
 namespace dat {
 // layernorm.cu
 size_t layernorm_bwd_workspace(long long rows, int C);
+int residual_layernorm_fwd(const void* a, const float* scale, long long rows_per_sample, const void* x, int x_dt,
+                           const float* gamma, const float* beta, void* xout, void* y, int y_dt, float* mean,
+                           float* rstd, long long rows, int C, float eps, cudaStream_t st);
+int residual_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
+                           const float* mean, const float* rstd, void* dx, const void* dres, void* da,
+                           const float* scale, long long rows_per_sample, float* dgamma, float* dbeta,
+                           long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st);
 int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st);
 int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,

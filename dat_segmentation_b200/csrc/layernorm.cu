@@ -22,6 +22,11 @@ __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ float2 ld2(const bf16* p) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
 }
+// the value as the stream holds it after the store (fp32: unchanged, bf16: rounded)
+__device__ __forceinline__ float2 ld2_round(const float*, float2 v) { return v; }
+__device__ __forceinline__ float2 ld2_round(const bf16*, float2 v) {
+  return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y));
+}
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 __device__ __forceinline__ void st2(bf16* p, float2 v) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
@@ -36,7 +41,12 @@ template <typename TI, typename TO, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, long long rows, int C, float eps) {
+                     float* __restrict__ rstd_out, long long rows, int C, float eps,
+                     const TO* __restrict__ a, const float* __restrict__ scale, long long rows_per_sample,
+                     TI* __restrict__ xout) {
+  // a != NULL: the residual add with stochastic depth that precedes the norm (dat.py:147-151) rides along -
+  // xout = x + a * scale[sample] is formed in registers, stored as the new residual stream and normalised, so the
+  // stream is not written and re-read by a separate kernel
   pdl_enter();
   constexpr int R = RowsOf<NV>::R;
   const int lane = threadIdx.x & 31;
@@ -50,6 +60,21 @@ layernorm_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 2;
       v[r][i] = (c < C && row0 + r < rows) ? ld2(xr + c) : make_float2(0.f, 0.f);
+    }
+    if (a != nullptr && row0 + r < rows) {
+      const float sc = scale[(row0 + r) / rows_per_sample];
+      const TO* ar = a + (row0 + r) * C;
+      TI* xo = xout + (row0 + r) * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 2;
+        if (c < C) {
+          const float2 av = ld2(ar + c);
+          v[r][i] = make_float2(fmaf(av.x, sc, v[r][i].x), fmaf(av.y, sc, v[r][i].y));
+          st2(xo + c, v[r][i]);
+          v[r][i] = ld2_round(xo + c, v[r][i]);
+        }
+      }
     }
   }
   float2 g[NV], b[NV];
@@ -98,7 +123,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, TI* __restrict__ dx,
-                     const TI* __restrict__ dres, float* __restrict__ partial, long long rows, int C) {
+                     const TI* __restrict__ dres, float* __restrict__ partial, long long rows, int C,
+                     TDY* __restrict__ da, const float* __restrict__ scale, long long rows_per_sample) {
+  // da != NULL: the branch gradient of the fused residual add, da = dx * scale[sample], leaves in the same pass
   pdl_enter();
   constexpr int R = NV == 1 ? 2 : 1;   // 4 rows / iteration measured slower: registers -> occupancy
   extern __shared__ float red[];     // [LN_WARPS][2][C]
@@ -155,13 +182,19 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
       m2 = warp_sum(m2) * inv_c;
       if (row < rows) {
         TI* dxr = dx + row * C;
+        const float sc = da != nullptr ? scale[row / rows_per_sample] : 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const int c = (i * 32 + lane) * 2;
           if (c < C) {
             // + gradient of the residual path through x (dat.py:147-156)
-            st2(dxr + c, make_float2(rstd[r] * (dg[i].x - m1 - xh[i].x * m2) + rv[r][i].x,
-                                     rstd[r] * (dg[i].y - m1 - xh[i].y * m2) + rv[r][i].y));
+            const float2 g2 = make_float2(rstd[r] * (dg[i].x - m1 - xh[i].x * m2) + rv[r][i].x,
+                                          rstd[r] * (dg[i].y - m1 - xh[i].y * m2) + rv[r][i].y);
+            st2(dxr + c, g2);
+            if (da != nullptr) {
+              const float2 gr = ld2_round(dxr + c, g2);      // what a separate kernel would read back from dx
+              st2(da + row * C + c, make_float2(gr.x * sc, gr.y * sc));
+            }
           }
         }
       }
@@ -220,13 +253,22 @@ size_t layernorm_bwd_workspace(long long rows, int C) {
 
 int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta, void* y, int y_dt,
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t st) {
+  return residual_layernorm_fwd(nullptr, nullptr, 1, x, x_dt, gamma, beta, nullptr, y, y_dt, mean, rstd, rows, C, eps, st);
+}
+
+// a (may be NULL; y's dtype): xout = x + a * scale[row / rows_per_sample] (x's dtype), y = LayerNorm(xout)
+int residual_layernorm_fwd(const void* a, const float* scale, long long rows_per_sample, const void* x, int x_dt,
+                           const float* gamma, const float* beta, void* xout, void* y, int y_dt, float* mean,
+                           float* rstd, long long rows, int C, float eps, cudaStream_t st) {
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
+  DAT_REQUIRE(a == nullptr || (scale != nullptr && xout != nullptr && rows_per_sample > 0),
+              "residual_layernorm_fwd: scale / xout missing");
   const int nv = nv_of(C);
   const int rows_per_warp = nv == 1 ? 4 : (nv == 2 ? 2 : 1);      // RowsOf<NV>::R
   const int grid = (int)ceil_div(rows, (long long)LN_WARPS * rows_per_warp);
 #define LAUNCH(TI, TO, NVV)                                                                    \
   launch_k(layernorm_fwd_kernel<TI, TO, NVV>, grid, LN_WARPS * 32, 0, st, (const TI*)x, gamma, beta, \
-                                                                     (TO*)y, mean, rstd, rows, C, eps)
+           (TO*)y, mean, rstd, rows, C, eps, (const TO*)a, scale, rows_per_sample, (TI*)xout)
 #define LAUNCH_NV(TI, TO)                                                      \
   do {                                                                         \
     if (nv == 1) LAUNCH(TI, TO, 1); else if (nv == 2) LAUNCH(TI, TO, 2);       \
@@ -246,7 +288,17 @@ int layernorm_fwd(const void* x, int x_dt, const float* gamma, const float* beta
 int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
                   const float* mean, const float* rstd, void* dx, const void* dres, float* dgamma,
                   float* dbeta, long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return residual_layernorm_bwd(dy, dy_dt, x, x_dt, gamma, mean, rstd, dx, dres, nullptr, nullptr, 1, dgamma, dbeta,
+                                rows, C, ws, ws_bytes, st);
+}
+
+// da (may be NULL; dy's dtype): da = dx * scale[row / rows_per_sample], the gradient of the branch of the fused add
+int residual_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* gamma,
+                           const float* mean, const float* rstd, void* dx, const void* dres, void* da,
+                           const float* scale, long long rows_per_sample, float* dgamma, float* dbeta,
+                           long long rows, int C, void* ws, size_t ws_bytes, cudaStream_t st) {
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
+  DAT_REQUIRE(da == nullptr || (scale != nullptr && rows_per_sample > 0), "residual_layernorm_bwd: scale missing");
   DAT_REQUIRE(ws_bytes >= layernorm_bwd_workspace(rows, C), "layernorm_bwd: workspace too small");
   int nblk = ln_bwd_blocks(rows);
   const int nv = nv_of(C);
@@ -263,7 +315,7 @@ int layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const floa
     if (occ < 1) occ = 1;                                                                         \
     if (nblk > 148 * occ) nblk = 148 * occ;                                                       \
     launch_k(kern, nblk, LN_WARPS * 32, smem, st, (const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx, \
-                                            (const TI*)dres, part, rows, C);                                    \
+             (const TI*)dres, part, rows, C, (TD*)da, scale, rows_per_sample);                          \
   } while (0)
 #define LAUNCH_NV(TI, TD)                                                      \
   do {                                                                         \

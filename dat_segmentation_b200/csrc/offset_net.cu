@@ -245,19 +245,39 @@ offset_bwd_point_kernel(const float* __restrict__ dpos, const float* __restrict_
   }
 }
 
+// block (32, 32): threadIdx.x = output within a 32-wide slice, threadIdx.y = partial lane; fixed summation order
+// (lane-strided partial sums with 4 independent accumulators, then lanes 0..31): deterministic.  (The first version
+// walked all per-CTA partials - 2048 at stage 2 - with one dependent load after the other: 15 us per launch.)
 __global__ void offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cg,
                                          float* __restrict__ g_pw, float* __restrict__ g_ln_g,
                                          float* __restrict__ g_ln_b, float* __restrict__ g_dw_b) {
   pdl_enter();
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 5 * Cg) return;
-  float s = 0.f;
-  for (int blk = 0; blk < nblocks; ++blk) s += partial[(size_t)blk * 5 * Cg + idx];
-  int row = idx / Cg, c = idx % Cg;
-  if (row < 2) g_pw[row * Cg + c] = s;
-  else if (row == 2) g_ln_g[c] = s;
-  else if (row == 3) g_ln_b[c] = s;
-  else g_dw_b[c] = s;
+  __shared__ float red[32][33];
+  const int idx = blockIdx.x * 32 + threadIdx.x, zl = threadIdx.y;
+  const size_t pitch = (size_t)5 * Cg;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (idx < 5 * Cg) {
+    int z = zl;
+    for (; z + 96 < nblocks; z += 128) {
+      s0 += partial[(size_t)z * pitch + idx];
+      s1 += partial[(size_t)(z + 32) * pitch + idx];
+      s2 += partial[(size_t)(z + 64) * pitch + idx];
+      s3 += partial[(size_t)(z + 96) * pitch + idx];
+    }
+    for (; z < nblocks; z += 32) s0 += partial[(size_t)z * pitch + idx];
+  }
+  red[zl][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (zl == 0 && idx < 5 * Cg) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) s += red[l][threadIdx.x];
+    const int row = idx / Cg, c = idx % Cg;
+    if (row < 2) g_pw[row * Cg + c] = s;
+    else if (row == 2) g_ln_g[c] = s;
+    else if (row == 3) g_ln_b[c] = s;
+    else g_dw_b[c] = s;
+  }
 }
 
 // Depthwise weight gradient: dw[c,u,v] = sum_points dt[point, c] * q[window(point,u,v), c].
@@ -643,8 +663,8 @@ int offset_bwd(const Shape& s, const dat_block_params* p, const void* q, const f
     DAT_CUDA_OK(cudaEventRecord(fork_ev, st));
     DAT_CUDA_OK(cudaStreamWaitEvent(pst, fork_ev, 0));
   }
-  launch_k(offset_bwd_reduce_kernel, ceil_div(5 * s.Cg, 128), 128, 0, pst, 
-      part1, nblk, s.Cg, g->off_pw_w, g->off_ln_g, g->off_ln_b, g->off_dw_b);
+  launch_k(offset_bwd_reduce_kernel, ceil_div(5 * s.Cg, 32), dim3(32, 32), 0, pst,
+           part1, nblk, s.Cg, g->off_pw_w, g->off_ln_g, g->off_ln_b, g->off_dw_b);
   DAT_LAUNCH_OK("offset_bwd_reduce_kernel");
 
   int nsplit = offset_wgrad_splits(s);

@@ -15,6 +15,7 @@ import ctypes as C
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _cabi
 from .weights import cached_bf16
@@ -222,8 +223,10 @@ class DAttentionBaseline(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("DAttentionBaseline (dat_b200) runs on CUDA only; there is no CPU path")
-        if self.training and (self.attn_drop_p > 0 or self.proj_drop_p > 0):
-            raise NotImplementedError("attn_drop / proj_drop > 0 in training is not implemented")
+        if self.training and self.attn_drop_p > 0:
+            # dropout on the softmax probabilities lives inside the fused attention kernel (the reference draws its mask
+            # over the materialised (B*h, HW, Ns) tensor, dat_blocks.py:217): not implemented; every shipped config uses 0
+            raise NotImplementedError("attn_drop > 0 in training is not implemented")
         B, Cc, H, W = x.shape
         if Cc != self.nc:
             raise ValueError(f"expected {self.nc} channels, got {Cc}")
@@ -249,6 +252,8 @@ class DAttentionBaseline(nn.Module):
                 meta["w_bf16"] = w_bf
         y_l, pos = _BlockFn.apply(x_l, meta, *self._params())
         y = y_l.permute(0, 3, 1, 2)
+        if self.training and self.proj_drop_p > 0:     # dat_blocks.py:225: library dropout on the block output (same
+            y = F.dropout(y, self.proj_drop_p, True)   # distribution as the reference's mask, not the same draw)
         if not self.return_pos_ref:
             return y, None, None
         hk = H // self.stride if self.no_off else (H + 2 * self.conv_offset[0].padding[0] - self.ksize) // self.stride + 1

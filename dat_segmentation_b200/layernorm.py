@@ -88,6 +88,59 @@ class _LayerNormForkFn(torch.autograd.Function):
         return _LayerNormFn.backward(ctx, dy, dres)
 
 
+class _ResidualLayerNormForkFn(torch.autograd.Function):
+    """(a_l, x_l, scale) -> (x_l + a_l * scale[b], LayerNorm(x_l + a_l * scale[b])): the residual add with stochastic
+    depth that precedes a norm (`x = drop_path(attn) + x; ... layer_norms[2d+1](x)`, dat.py:147-151) inside the norm's
+    kernel, forward and backward (the branch gradient d a = d x * scale leaves the LayerNorm backward kernel too)."""
+
+    @staticmethod
+    def forward(ctx, a_l, x_l, scale, weight, bias, eps, out_dtype):
+        lib = _cabi.lib()
+        Cc = x_l.shape[-1]
+        rows = x_l.numel() // Cc
+        dev = x_l.device
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            xout = torch.empty_like(x_l)
+            y = torch.empty(x_l.shape, device=dev, dtype=out_dtype)
+            mean = torch.empty(rows, device=dev, dtype=torch.float32)
+            rstd = torch.empty(rows, device=dev, dtype=torch.float32)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(lib.dat_residual_layernorm_fwd(_ptr(a_l), _ptr(scale), rows // x_l.shape[0], _ptr(x_l),
+                                                       _CODE[x_l.dtype], _ptr(w32), _ptr(b32), _ptr(xout), _ptr(y),
+                                                       _CODE[out_dtype], _ptr(mean), _ptr(rstd), rows, Cc, float(eps), st),
+                        "dat_residual_layernorm_fwd")
+        ctx.save_for_backward(xout, w32, mean, rstd, scale)
+        ctx.param_dtype, ctx.a_dtype = weight.dtype, a_l.dtype
+        return xout, y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        lib = _cabi.lib()
+        xout, w32, mean, rstd, scale = ctx.saved_tensors
+        Cc = xout.shape[-1]
+        rows = xout.numel() // Cc
+        dev = xout.device
+        if dy is None:                      # the norm's output was not used: only the residual path carries a gradient
+            dy = torch.zeros(xout.shape, device=dev, dtype=ctx.a_dtype)
+        dy = dy.to(ctx.a_dtype).contiguous()
+        if dres is not None:
+            dres = dres.to(xout.dtype).contiguous()
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(xout)
+            da = torch.empty(xout.shape, device=dev, dtype=ctx.a_dtype)
+            dg = torch.empty(Cc, device=dev, dtype=torch.float32)
+            db = torch.empty(Cc, device=dev, dtype=torch.float32)
+            nbytes = lib.dat_layernorm_bwd_workspace_bytes(rows, Cc)
+            ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(lib.dat_residual_layernorm_bwd(_ptr(dy), _CODE[dy.dtype], _ptr(xout), _CODE[xout.dtype],
+                                                       _ptr(w32), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dres), _ptr(da),
+                                                       _ptr(scale), rows // xout.shape[0], _ptr(dg), _ptr(db), rows, Cc,
+                                                       _ptr(ws), nbytes, st), "dat_residual_layernorm_bwd")
+        return da, dx, None, dg.to(ctx.param_dtype), db.to(ctx.param_dtype), None, None
+
+
 class LayerNormProxy(nn.Module):
     """LayerNorm over the channels of an NCHW tensor on the dat_b200 kernels."""
 
@@ -122,6 +175,19 @@ class LayerNormProxy(nn.Module):
         return x_p.permute(0, 3, 1, 2), y_l.permute(0, 3, 1, 2)
 
 
+    def forward_residual_fork(self, a, x, scale, out_dtype=None):
+        """(x + a * scale[b], LayerNorm(x + a * scale[b])) in one kernel; a (the branch output) must have the dtype the
+        norm writes (`out_dtype`) and the layout of x, else the two-kernel path is taken."""
+        from .residual import scale_residual
+        x_l, out_dtype = self._prep(x, out_dtype)
+        a_l = a.permute(0, 2, 3, 1)
+        if (a.dtype != out_dtype or not a_l.is_contiguous() or a.dtype not in _CODE
+                or torch.result_type(a, x) != x.dtype):
+            return self.forward_fork(scale_residual(a, x, scale), out_dtype)
+        x_p, y_l = _ResidualLayerNormForkFn.apply(a_l, x_l, scale, self.norm.weight, self.norm.bias, self.norm.eps, out_dtype)
+        return x_p.permute(0, 3, 1, 2), y_l.permute(0, 3, 1, 2)
+
+
 class TorchLayerNormProxy(nn.Module):
     """Library-operator twin (CPU baseline / CPU tests); identical parameters."""
 
@@ -134,4 +200,8 @@ class TorchLayerNormProxy(nn.Module):
         return y if out_dtype is None else y.to(out_dtype)
 
     def forward_fork(self, x, out_dtype=None):
+        return x, self.forward(x, out_dtype)
+
+    def forward_residual_fork(self, a, x, scale, out_dtype=None):
+        x = x + a * scale.view(-1, 1, 1, 1).to(a.dtype)
         return x, self.forward(x, out_dtype)

@@ -243,6 +243,21 @@ int dat_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x
                       const void* dres, float* dgamma, float* dbeta, int64_t rows, int32_t C,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The residual add that precedes a norm, fused into it (dat.py:147-151: `x = drop_path(attn) + x` followed by
+ * `layer_norms[2d+1](x)`): xout = x + a * scale[row / rows_per_sample] (x's dtype: the new residual stream),
+ * y = LayerNorm(xout).  a has y's dtype; scale is a device array of rows / rows_per_sample floats (mask / keep_prob).
+ * One pass over the stream instead of dat_scale_residual + dat_layernorm_fwd. */
+int dat_residual_layernorm_fwd(const void* a, const float* scale, int64_t rows_per_sample, const void* x,
+                               int32_t x_dtype, const float* gamma, const float* beta, void* xout, void* y,
+                               int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
+                               void* stream);
+/* Its backward: dx = LayerNorm-backward(dy) + dres (gradient w.r.t. xout, which is also the gradient w.r.t. x) and the
+ * branch gradient da = dx * scale[row / rows_per_sample] (dy's dtype) in the same pass.  x is the saved xout. */
+int dat_residual_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma,
+                               const float* mean, const float* rstd, void* dx, const void* dres, void* da,
+                               const float* scale, int64_t rows_per_sample, float* dgamma, float* dbeta, int64_t rows,
+                               int32_t C, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Residual add with stochastic depth (dat.py:147-156, `x = drop_path(branch) + x`):
  * y[b, :] = x[b, :] + a[b, :] * scale[b]; x may be NULL ('X' blocks, dat.py:140-144).  a, x, y are
  * dense tensors of one layout whose outermost dimension is the sample (per_sample elements each,

@@ -507,3 +507,25 @@ def test_block_backward_bf16_other_sample_counts(H, W, heads, groups, stride, ks
     bad = {k: v for k, v in report.items()
            if v > (1.5e-1 if (k in loose or k.startswith("conv_offset")) else 3e-2)}
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_proj_drop_in_training_is_a_dropout_of_the_block_output():
+    """dat_blocks.py:225: proj_drop acts on proj_out's result.  With p > 0 in training every output element is either
+    zero or the p = 0 value / (1 - p), and about p of them are zero; attn_drop > 0 stays rejected."""
+    import torch
+    from dat_segmentation_b200.dattention import DAttentionBaseline
+
+    def make(attn_drop, proj_drop):
+        torch.manual_seed(0)
+        return DAttentionBaseline((8, 8), (8, 8), 2, 32, 1, attn_drop, proj_drop, 2, -1, True, False, False, False, 5,
+                                  False, 2).cuda().train()
+
+    x = torch.randn(2, 64, 16, 16, device="cuda")
+    y0 = make(0.0, 0.0)(x)[0]
+    y1 = make(0.0, 0.5)(x)[0]
+    kept = y1 != 0
+    assert 0.35 < 1.0 - kept.float().mean().item() < 0.65
+    torch.testing.assert_close(y1[kept], (y0 * 2.0)[kept], rtol=1e-6, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        make(0.1, 0.0)(x)

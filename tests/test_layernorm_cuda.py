@@ -50,3 +50,37 @@ def test_layernorm_large_rows_deterministic():
         y.backward(torch.ones_like(y) * 0.5 + y.detach())
         outs.append((y.detach().clone(), x.grad.clone(), m.norm.weight.grad.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stream_dtype,branch_dtype", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32)])
+@pytest.mark.parametrize("C", [64, 256, 512])
+def test_residual_add_fused_into_the_norm_matches_the_two_kernel_path(stream_dtype, branch_dtype, C):
+    """`x = drop_path(attn) + x; ln = LayerNorm(x)` (dat.py:147-151) in one kernel == scale_residual + LayerNorm fork:
+    new stream, normed output and every gradient (branch, stream, gamma, beta)."""
+    from dat_segmentation_b200.layernorm import LayerNormProxy
+    from dat_segmentation_b200.residual import scale_residual
+    torch.manual_seed(C)
+    B, H, W = 3, 8, 12
+    ln = LayerNormProxy(C).cuda()
+    with torch.no_grad():
+        ln.norm.weight.uniform_(0.5, 1.5)
+        ln.norm.bias.uniform_(-0.5, 0.5)
+    scale = torch.tensor([0.0, 1.0 / 0.7, 1.0 / 0.7], device="cuda")
+    x0 = torch.randn(B, H, W, C, device="cuda", dtype=stream_dtype).permute(0, 3, 1, 2)
+    a0 = torch.randn(B, H, W, C, device="cuda").to(branch_dtype).permute(0, 3, 1, 2)
+    gy = torch.randn(B, H, W, C, device="cuda").to(branch_dtype).permute(0, 3, 1, 2)
+    gx = torch.randn(B, H, W, C, device="cuda", dtype=stream_dtype).permute(0, 3, 1, 2)
+    res = []
+    for fused in (True, False):
+        x, a = x0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+        ln.zero_grad(set_to_none=True)
+        if fused:
+            xo, y = ln.forward_residual_fork(a, x, scale, out_dtype=branch_dtype)
+        else:
+            xo, y = ln.forward_fork(scale_residual(a, x, scale), out_dtype=branch_dtype)
+        (xo * gx).sum().backward(retain_graph=True)
+        (y.float() * gy.float()).sum().backward()
+        res.append([t.detach().float().clone() for t in (xo, y, x.grad, a.grad, ln.norm.weight.grad, ln.norm.bias.grad)])
+    for f, u, name in zip(res[0], res[1], ["stream", "norm", "d stream", "d branch", "d gamma", "d beta"]):
+        torch.testing.assert_close(f, u, rtol=2e-6, atol=2e-6, msg=lambda m, name=name: f"{name}: {m}")
