@@ -54,6 +54,8 @@ constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 288, TM_DV = 352;
 struct BtcArgs {
   int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
   int n_tiles, rows_max, chunks, nslots, light_table;
+  int ns_total;            // samples of the block; a CTA works on the NS of them that start at blockIdx.z * NS
+  long long dq_slab;       // elements between the dq outputs of consecutive sample chunks (B * HW * C)
   float c1, scale, kx, ky, gsx, gsy;
 };
 
@@ -224,6 +226,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / a.heads, eta = bh % a.heads, g = eta / a.hg;
+  // More than 256 samples (a 512 x 2048 crop has 1024): the saved log-sum-exp and delta make sample chunks independent
+  // in the backward - P = exp(S - lse) needs no running maximum - so chunk blockIdx.z is simply another CTA: its dK / dV /
+  // d pos / dS cover disjoint samples, its dQ goes to its own slab and the slabs are summed afterwards.
+  const int n_off = (int)blockIdx.z * NS;
 
   if (threadIdx.x == 0) {
     *oob_flag = 0u;
@@ -254,7 +260,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int i = threadIdx.x; i < a.Hp * a.Wp; i += BTC_THREADS) sTab[i] = src[i];
     }
     for (int i = threadIdx.x; i < NDT * a.Hp * a.Wp; i += BTC_THREADS) sDTab[i] = 0.f;
-    const float* pp = pos + ((long long)b * a.G + g) * NS * 2;
+    const float* pp = pos + (((long long)b * a.G + g) * a.ns_total + n_off) * 2;
     for (int n = threadIdx.x; n < NS; n += BTC_THREADS) {
       const float px = pp[2 * n + 1];
       if (FAST && !(fabsf(px) <= 1.0f)) *oob_flag = 1u;     // benign race: every writer stores the same value
@@ -272,8 +278,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       // ---- TMA producer ------------------------------------------------------------------
       mbar_arrive_expect_tx(kv_full, 2u * NS * 64u);
-      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * NS);
-      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * NS);
+      tma_load_2d(sK, &tmK, kv_full, eta * 32, b * a.ns_total + n_off);
+      tma_load_2d(sV, &tmV, kv_full, eta * 32, b * a.ns_total + n_off);
       int it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int slot = it % a.nslots;
@@ -401,7 +407,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           pk8[i] = pack_bf16x2(__uint_as_float(qv[2 * i]) * a.scale, __uint_as_float(qv[2 * i + 1]) * a.scale);
-        uint4* dst = reinterpret_cast<uint4*>(dq + ((long long)b * a.HW + m_e) * a.C + eta * 32 + chalf * 16);
+        uint4* dst = reinterpret_cast<uint4*>(dq + (long long)blockIdx.z * a.dq_slab + ((long long)b * a.HW + m_e) * a.C + eta * 32 + chalf * 16);
         dst[0] = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
         dst[1] = make_uint4(pk8[4], pk8[5], pk8[6], pk8[7]);
       }
@@ -432,7 +438,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint8_t* prow_p = sP + chalf * 16384 + row * 128;
       uint8_t* prow_d = sDS + chalf * 16384 + row * 128;
       // dS for the table gradient: groups of 8 samples, [bh][NS / 8][m][8] - a warp's 32 rows write 512 contiguous bytes
-      bf16* ds_row = TBL ? nullptr : ds_out + (long long)bh * a.HW * NS + (long long)mm * 8;
+      bf16* ds_row = TBL ? nullptr : ds_out + (long long)bh * a.HW * a.ns_total + (long long)mm * 8;
 
       pf_setup += clock64() - pf_t;
 #pragma unroll 1
@@ -488,7 +494,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                   *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
                   *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
                   if (valid)      // the same 8 dS values, [m][n] layout, for the tensor-core table gradient
-                    *reinterpret_cast<uint4*>(ds_row + (long long)((nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                    *reinterpret_cast<uint4*>(ds_row + (long long)((n_off + nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
                 }
               }
               // d pos: column sums over this warp's 32 rows on bf16x2 pairs {x part, y part} (lane L ends up with
@@ -562,7 +568,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               *reinterpret_cast<uint4*>(prow_p + sw) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
               *reinterpret_cast<uint4*>(prow_d + sw) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
               if (!TBL && valid)      // the same 8 dS values, [m][n] layout, for the tensor-core table gradient
-                *reinterpret_cast<uint4*>(ds_row + (long long)((nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                *reinterpret_cast<uint4*>(ds_row + (long long)((n_off + nbase + j - 7) >> 3) * a.HW * 8) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
             }
             // ---- d rpe_table ----------------------------------------------------------------
             // Lanes = consecutive queries of an image row; the table step per query is < 1 cell,
@@ -688,7 +694,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int h = 0; h < NHALF; ++h) {
         const int n = h * NHC + row;
-        float* dst = outp + (((long long)blockIdx.x * a.B + b) * NS + n) * a.C + eta * 32;
+        float* dst = outp + (((long long)blockIdx.x * a.B + b) * a.ns_total + n_off + n) * a.C + eta * 32;
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t kv[16];
@@ -724,7 +730,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         sy += src[2 * n];
         sx += src[2 * n + 1];
       }
-      float* dpo = dpos_part + ((((long long)b * a.heads + eta) * a.chunks + blockIdx.x) * NS + n) * 2;
+      float* dpo = dpos_part + ((((long long)b * a.heads + eta) * a.chunks + blockIdx.x) * a.ns_total + n_off + n) * 2;
       dpo[0] = sy * (-a.ky / LOG2E);
       dpo[1] = sx * (-a.kx / LOG2E);
     }
@@ -757,8 +763,49 @@ int rows_spanned_max_b(int HW, int W) {
 
 }  // namespace
 
+// samples per CTA: the block's samples in chunks of 256 (128 when that is all that divides them)
+static int sample_chunk(int Ns) {
+  if (Ns <= 256) return Ns;
+  static const int off = [] { const char* e = std::getenv("DAT_B200_ATTN_BWD_SIMT_LARGE_NS"); return e && e[0] == '1' ? 1 : 0; }();
+  if (off) return 0;            // A/B: the CUDA-core backward for more than 256 samples (round 1)
+  return Ns % 256 == 0 ? 256 : (Ns % 128 == 0 ? 128 : 0);
+}
+int attention_bwd_tc_sample_chunks(const Shape& s) { return sample_chunk(s.Ns) > 0 ? s.Ns / sample_chunk(s.Ns) : 1; }
+
+// sum of the per-sample-chunk dQ slabs (bf16) in fp32, 8 elements per thread
+__global__ void __launch_bounds__(256) sum_slabs_bf16_kernel(const bf16* __restrict__ slabs, int nslab, long long count,
+                                                             bf16* __restrict__ out) {
+  pdl_enter();
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= count) return;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int z = 0; z < nslab; ++z) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(slabs + (long long)z * count + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h[e]);
+      acc[2 * e] += f.x;
+      acc[2 * e + 1] += f.y;
+    }
+  }
+  uint4 o;
+  __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+  *reinterpret_cast<uint4*>(out + i) = o;
+}
+
+// scratch for the dQ slabs of a multi-chunk backward (0 when the samples fit one chunk)
+size_t attention_bwd_tc_dq_scratch(const Shape& s) {
+  const int nsc = attention_bwd_tc_sample_chunks(s);
+  return nsc > 1 ? align_up((size_t)nsc * s.B * s.HW * s.C * 2, 256) : 0;
+}
+
 int attention_bwd_tc_chunks(const Shape& s) {
-  const int pairs = s.B * s.heads, n_tiles = (s.HW + TQ - 1) / TQ;
+  const int pairs = s.B * s.heads * attention_bwd_tc_sample_chunks(s), n_tiles = (s.HW + TQ - 1) / TQ;
   double best_cost = 1e30;
   int best = 1;
   for (int ch = 1; ch <= n_tiles && ch <= 16; ++ch) {
@@ -776,7 +823,8 @@ int attention_bwd_tc_chunks(const Shape& s) {
 struct BtcVariant { int ok, compact, priv, nslots; uint32_t smem; };
 BtcVariant pick_variant(const Shape& s, bool tbl = true) {
   BtcVariant v = {0, 0, 0, 2, 0};
-  if (s.act_dtype != DAT_BF16 || !(s.Ns == 128 || s.Ns == 256) || s.C % 8 != 0) return v;
+  const int NSc = sample_chunk(s.Ns);
+  if (s.act_dtype != DAT_BF16 || !(NSc == 128 || NSc == 256) || s.C % 8 != 0) return v;
   const int rows = rows_spanned_max_b(s.HW, s.W);
   const uint32_t lim = 227 * 1024;
   // private copies: a warp's queries lie in one image row, and runs of equal cells stay within
@@ -785,7 +833,7 @@ BtcVariant pick_variant(const Shape& s, bool tbl = true) {
   const int tries[4][3] = {{0, 1, 2}, {0, 0, 2}, {1, 0, 2}, {1, 0, 1}};   // {compact, priv, nslots}
   for (int t = 0; t < 4; ++t) {
     if (tries[t][1] && (!priv_ok || !tbl)) continue;
-    SmemPlanB sp = plan_smem_b(s.Ns, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, !tbl ? 0 : (tries[t][1] ? 8 : 1), tries[t][2],
+    SmemPlanB sp = plan_smem_b(NSc, s.Th + 3, s.Tw + 3, rows, tries[t][0] != 0, !tbl ? 0 : (tries[t][1] ? 8 : 1), tries[t][2],
                                (!tbl && tries[t][0] == 0) ? 16 : 8);
     if (sp.total <= lim) {
       v.ok = 1; v.compact = tries[t][0]; v.priv = tries[t][1]; v.nslots = tries[t][2]; v.smem = sp.total;
@@ -826,11 +874,15 @@ int attention_pack_table_compact(const Shape& s, const float* table, void* out, 
 int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
                      const float* lse, const float* delta, const float* pos, const void* tab_packed,
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
-                     cudaStream_t st, void* ds_out) {
+                     cudaStream_t st, void* ds_out, void* dq_scratch) {
   const bool tbl = ds_out == nullptr;      // dS streamed out: the table gradient is formed by rpe_table_grad_mma
   const BtcVariant var = pick_variant(s, tbl);
   DAT_REQUIRE(var.ok, "attention_bwd_tc: unsupported shape");
+  const int NSc = sample_chunk(s.Ns), nsc = s.Ns / NSc;
+  DAT_REQUIRE(nsc == 1 || dq_scratch != nullptr, "attention_bwd_tc: more than one sample chunk needs the dQ scratch");
   BtcArgs a;
+  a.ns_total = s.Ns;
+  a.dq_slab = (long long)s.B * s.HW * s.C;
   a.nslots = var.nslots;
   {   // light table-gradient path: 0.29 <= table cells per query step <= 1 (runs of <= 3.5 lanes)
     const float step = 0.5f * (float)(s.Tw - 1) / (float)(s.W - 1);
@@ -851,15 +903,16 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
   const uint64_t pitch = (uint64_t)s.C * 2;
   DAT_FWD(tc::make_tmap_2d(&tmQ, q, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, pitch, TQ, 32, 64));
   DAT_FWD(tc::make_tmap_2d(&tmDO, d_o, 2, false, (uint64_t)s.B * s.HW, (uint64_t)s.C, pitch, TQ, 32, 64));
-  DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
-  DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, s.Ns, 32, 64));
-  dim3 grid(a.chunks, s.B * s.heads);
+  DAT_FWD(tc::make_tmap_2d(&tmK, k, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, NSc, 32, 64));
+  DAT_FWD(tc::make_tmap_2d(&tmV, v, 2, false, (uint64_t)s.B * s.Ns, (uint64_t)s.C, pitch, NSc, 32, 64));
+  dim3 grid(a.chunks, s.B * s.heads, nsc);
+  void* dq_dst = nsc > 1 ? dq_scratch : dq;
 #define LAUNCH(NSV, CP, PV, TB)                                                                  \
   do {                                                                                           \
     auto kern = attn_bwd_tc_kernel<NSV, CP, PV, TB>;                                             \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem)); \
     launch_k(kern, grid, BTC_THREADS, var.smem, st, tmQ, tmDO, tmK, tmV, pos, tab_packed, lse, delta,  \
-                                              (bf16*)dq, dk_part, dv_part, d_table, dpos_part, (bf16*)ds_out, a); \
+                                              (bf16*)dq_dst, dk_part, dv_part, d_table, dpos_part, (bf16*)ds_out, a); \
   } while (0)
 #define LAUNCH_NS(NSV)                                   \
   do {                                                   \
@@ -869,10 +922,16 @@ int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v
     else if (var.priv) LAUNCH(NSV, false, true, true);   \
     else LAUNCH(NSV, false, false, true);                \
   } while (0)
-  if (s.Ns == 256) LAUNCH_NS(256); else LAUNCH_NS(128);
+  if (NSc == 256) LAUNCH_NS(256); else LAUNCH_NS(128);
 #undef LAUNCH_NS
 #undef LAUNCH
   DAT_LAUNCH_OK("attn_bwd_tc_kernel");
+  if (nsc > 1) {
+    const long long count = a.dq_slab;
+    DAT_REQUIRE(count % 8 == 0, "attention_bwd_tc: B * HW * C must be a multiple of 8");
+    launch_k(sum_slabs_bf16_kernel, ceil_div(count / 8, 256), 256, 0, st, (const bf16*)dq_scratch, nsc, count, (bf16*)dq);
+    DAT_LAUNCH_OK("sum_slabs_bf16_kernel");
+  }
   return DAT_OK;
 }
 

@@ -202,10 +202,11 @@ bool use_mma_table_grad(const Shape& s) {
 int bwd_qsplit(const Shape& s) {
   return use_tc_attn_bwd(s) ? attention_bwd_tc_chunks(s) : attention_bwd_qsplit(s);
 }
-// scratch of the tensor-core attention backward: delta | dk_part | dv_part | packed table
+// scratch of the tensor-core attention backward: delta | dk_part | dv_part | packed table | dQ slabs (> 256 samples)
 size_t tc_attn_bwd_scratch(const Shape& s) {
   const size_t part = align_up((size_t)attention_bwd_tc_chunks(s) * s.B * s.Ns * s.C * 4, 256);
-  return align_up((size_t)s.B * s.heads * s.HW * 4, 256) + 2 * part + attention_fwd_tc_workspace(s);
+  return align_up((size_t)s.B * s.heads * s.HW * 4, 256) + 2 * part + align_up(attention_fwd_tc_workspace(s), 256) +
+         attention_bwd_tc_dq_scratch(s);
 }
 
 BwdPlan plan_bwd(const Shape& s, void* ws) {
@@ -698,8 +699,9 @@ int dat_block_backward(const dat_block_desc* d, const dat_block_params* p, const
     const bool mma_table = use_mma_table_grad(s);
     if (!mma_table) DAT_CUDA_OK(cudaMemsetAsync(g->rpe_table, 0, (size_t)s.heads * s.Th * s.Tw * 4, st));
     DAT_FWD(attention_bwd_pack_table(s, p->rpe_table, tabp, !mma_table, st));
+    void* dq_slabs = attention_bwd_tc_dq_scratch(s) ? (char*)tabp + align_up(attention_fwd_tc_workspace(s), 256) : nullptr;
     DAT_FWD(attention_bwd_tc(s, sv->q, sv->k, sv->v, w.d_o, sv->lse, delta, sv->pos, tabp, w.dq, dk_part,
-                             dv_part, g->rpe_table, w.dpos_part, st, mma_table ? w.ds_tab : nullptr));
+                             dv_part, g->rpe_table, w.dpos_part, st, mma_table ? w.ds_tab : nullptr, dq_slabs));
     DAT_FWD(reduce_partials_pair(dk_part, dv_part, chunks, (long long)s.B * s.Ns * C, w.dk, w.dv, adt, st));
   } else {
     long long bias_bstride = 0;

@@ -108,7 +108,9 @@ int attention_bwd_tc_chunks(const Shape& s);
 int attention_bwd_tc(const Shape& s, const void* q, const void* k, const void* v, const void* d_o,
                      const float* lse, const float* delta, const float* pos, const void* tab_packed,
                      void* dq, float* dk_part, float* dv_part, float* d_table, float* dpos_part,
-                     cudaStream_t st, void* ds_out = nullptr);
+                     cudaStream_t st, void* ds_out = nullptr, void* dq_scratch = nullptr);
+int attention_bwd_tc_sample_chunks(const Shape& s);   // CTAs along the samples (1 up to 256 samples)
+size_t attention_bwd_tc_dq_scratch(const Shape& s);   // bytes of dQ slabs attention_bwd_tc needs as dq_scratch (0: none)
 }  // namespace dat
 
 namespace dat {

@@ -471,11 +471,14 @@ def test_block_backward_bf16_full_size_vs_oracle(stage):
 @pytest.mark.parametrize("H,W,heads,groups,stride,ksize,qs", [
     (32, 64, 4, 2, 4, 7, 28),      # 8 x 16 = 128 samples: the NS = 128 instantiation, non-square map, 2 x 2 table tiles
     (64, 32, 2, 1, 4, 7, 14),      # 16 x 8 = 128 samples, one 27 x 27 table tile shared by all warps
-    (32, 128, 2, 2, 2, 5, 7),      # 16 x 64 = 1024 samples: split-KV forward, CUDA-core backward
+    (32, 128, 2, 2, 2, 5, 7),      # 16 x 64 = 1024 samples: split-KV forward, tensor-core backward over 4 sample chunks
+    (32, 64, 2, 1, 2, 5, 7),       # 16 x 32 = 512 samples: 2 sample chunks
+    (16, 256, 2, 1, 2, 5, 7),      # 8 x 128 = 1024 samples on a 256-wide map (in-kernel table scatter, no dS stream)
 ])
 def test_block_backward_bf16_other_sample_counts(H, W, heads, groups, stride, ksize, qs):
     """bf16 block fwd+bwd at sample counts other than 256 (tensor-core backward with the table-gradient GEMMs for
-    Ns = 128; split-KV tensor-core forward + CUDA-core backward for Ns = 1024) against the fp32 analytic oracle."""
+    Ns = 128; split-KV tensor-core forward + tensor-core backward in chunks of 256 samples for Ns = 512 / 1024: the
+    saved log-sum-exp makes the chunks independent, their dQ slabs are summed) against the fp32 analytic oracle."""
     from dat_segmentation_b200.dattention import DAttentionBaseline
     torch.manual_seed(H + W + heads)
     m = DAttentionBaseline((qs, qs), (qs, qs), heads, 32, groups, 0.0, 0.0, stride, 2, True, False,
