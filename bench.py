@@ -199,8 +199,8 @@ def ncu_traffic():
 
 
 def kernel_roofline(dev, pk):
-    """Roofline of the dominant kernel of the step, `gemm_tc_persistent_kernel` (12 % of the kernel time, 174
-    launches: profiles/r01_launches_step_818.md), at the shape that carries most of its time - the stage-2 MLP fc1
+    """Roofline of the dominant kernel of the step, `gemm_tc_persistent_kernel` (13 % of the kernel time, 183
+    launches: profiles/r02_launches_step.md), at the shape that carries most of its time - the stage-2 MLP fc1
     (M = B*HW = 16384, N = 1024, K = 256, bf16; 18 MLPs per step run it forward and as the fc2 data gradient).
     Algorithmic bytes = X + W + Y once; its arithmetic intensity (202 FLOP/B) is below the measured
     ridge (1658 TF/s / 6541 GB/s = 254 FLOP/B), so the bound is HBM.  `others`: the attention forward (the
@@ -257,8 +257,8 @@ def kernel_roofline(dev, pk):
         "traffic": traffic.get("attention", {}).get("dram_bytes"), "traffic_source": traffic.get("attention", {}).get("source"),
         "hbm_frac": round(byts / (ms_a * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "ms": round(ms_a, 4),
         "algorithmic_bytes": byts,
-        "note": "attn_fwd_tc2_kernel; bound by CUDA-core issue rate + MUFU (bias interpolation + softmax, ~16 instructions "
-                "per score vs 128 MMA FLOP): DESIGN.md 3.1 row 7, profiles/r02_ncu_kernels.md"}]
+        "note": "attn_fwd_tc2_kernel; bound by CUDA-core issue rate + MUFU (bias interpolation + softmax, 23.7 thread "
+                "instructions per score vs 128 MMA FLOP): DESIGN.md 3.1 row 7, profiles/r02_ncu_kernels.md"}]
     roof["per_kernel_table"] = "profiles/r02_kernel_rooflines.md"
     return roof
 
@@ -540,7 +540,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "implementation": "deformable-attention blocks, LayerNorms, residual/drop-path, MLP 1x1 convs and "
-                                         "depthwise convs in dat_b200 kernels; conv stem / down-projections in library ops",
+                                         "depthwise convs, conv stem and down-projections (im2col + tcgen05 GEMMs) in dat_b200 kernels",
                        "per_gpu_batch": PER_GPU_BATCH, "global_batch": total,
                        "parallelism": (f"dp{world} (batch-sharded; NCCL gradient all-reduce in {len(ts.bucket_slices)} buckets "
                                        f"{'overlapped with the backward inside the captured step' if ts.overlap else 'after the step'})"

@@ -91,21 +91,40 @@ dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
   // The CTA's threads cover min(C, 256) consecutive channels (modulo C): their filters are staged cooperatively
   // with coalesced loads into w_s[49][256] (tap-major), each thread then reads its channel pair as one LDS.64.
   // (Per-thread staging - 98 scattered loads + 49 stores per thread - was ~40 % of the stall samples at stage 2.)
-  extern __shared__ __align__(16) float w_s[];             // [49][2 * D7_THREADS]
+  // WPACK (bf16 activations, i.e. autocast: the library convolution runs on bf16-rounded weights too): a channel
+  // pair's two taps are one bf16x2 word, [49][D7_THREADS] words.  The weight fetches were as expensive as the math: 49
+  // LDS.64 per 196 FFMA2 and warp = 200 KB of shared-memory reads per round of the SM's 16 warps = 1568 cycles at
+  // 128 B/clk, exactly the FMA pipe's 4 x 392 cycles per scheduler; halving the bytes leaves the FMA pipe as the bound.
+  constexpr bool WPACK = sizeof(TI) == 2 || sizeof(TO) == 2;
+  extern __shared__ __align__(16) float w_s[];             // [49][2 * D7_THREADS] floats or [49][D7_THREADS] words
   const int nst = C < 2 * D7_THREADS ? C : 2 * D7_THREADS;
   {
     const int c_first = (int)(((long long)blockIdx.x * D7_THREADS) % (C >> 1)) * 2;
-    for (int idx = threadIdx.x; idx < nst * 49; idx += D7_THREADS) {
-      const int cc = idx / 49, uv = idx - cc * 49;
-      int cg = c_first + cc;
-      if (cg >= C) cg -= C;
-      w_s[uv * (2 * D7_THREADS) + cc] = w[cg * 49 + (flip ? 48 - uv : uv)];   // row pitch fixed: immediate offsets below
+    if (WPACK) {
+      uint32_t* w_p = reinterpret_cast<uint32_t*>(w_s);
+      for (int idx = threadIdx.x; idx < (nst >> 1) * 49; idx += D7_THREADS) {
+        const int cp = idx / 49, uv = idx - cp * 49;
+        int cg = c_first + 2 * cp;
+        if (cg >= C) cg -= C;
+        const int t = flip ? 48 - uv : uv;
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(w[cg * 49 + t], w[(cg + 1) * 49 + t]);
+        w_p[uv * D7_THREADS + cp] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < nst * 49; idx += D7_THREADS) {
+        const int cc = idx / 49, uv = idx - cc * 49;
+        int cg = c_first + cc;
+        if (cg >= C) cg -= C;
+        w_s[uv * (2 * D7_THREADS) + cc] = w[cg * 49 + (flip ? 48 - uv : uv)];   // row pitch fixed: immediate offsets below
+      }
     }
   }
   __syncthreads();
   const Strip s = strip_of(B, C, th, strips_x, strips_y);
   if (!s.ok) return;
   const float* w_mine = w_s + (C < 2 * D7_THREADS ? (2 * (int)threadIdx.x) % C : 2 * (int)threadIdx.x);
+  const uint32_t* w_mine_p = reinterpret_cast<const uint32_t*>(w_s) +
+                             (C < 2 * D7_THREADS ? (int)threadIdx.x % (C >> 1) : (int)threadIdx.x);
   const float b0 = bias != nullptr ? bias[s.c] : 0.f, b1 = bias != nullptr ? bias[s.c + 1] : 0.f;
   const bool lval = s.x0 > 0, rval = s.x0 + TW < W;
   const int rstride = W * C;
@@ -143,7 +162,13 @@ dwconv7_fwd_kernel(const TI* __restrict__ x, const float* __restrict__ w, const 
               float2 (&a)[TW] = acc[(k - u + 7) % 7];
 #pragma unroll
               for (int v = 0; v < 7; ++v) {
-                const float2 wv = *reinterpret_cast<const float2*>(w_mine + (u * 7 + v) * (2 * D7_THREADS));
+                float2 wv;
+                if (WPACK) {
+                  const uint32_t pk = w_mine_p[(u * 7 + v) * D7_THREADS];
+                  wv = make_float2(__uint_as_float(pk << 16), __uint_as_float(pk & 0xffff0000u));
+                } else {
+                  wv = *reinterpret_cast<const float2*>(w_mine + (u * 7 + v) * (2 * D7_THREADS));
+                }
 #pragma unroll
                 for (int i = 0; i < TW; ++i) a[i] = __ffma2_rn(wv, in[i + v], a[i]);
               }
