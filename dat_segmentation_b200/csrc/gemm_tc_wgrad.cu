@@ -222,7 +222,8 @@ static void wg_plan(long long M, int N, int K, int* splits, int* cs) {
   double best = 1e30;
   *splits = 1;
   *cs = 1;
-  for (int c = 8; c >= 1; c >>= 1) {
+  static const int no_cluster = [] { const char* e = std::getenv("DAT_B200_WG_CLUSTER"); return e && e[0] == '0' ? 1 : 0; }();
+  for (int c = no_cluster ? 1 : 8; c >= 1; c >>= 1) {     // DAT_B200_WG_CLUSTER=0: one partial per slice (round 1), for A/B
     const int slots = wg_cluster_slots(c);
     long long s = slots / tiles / c * c;            // whole clusters, one wave
     if (s > cap) s = cap / c * c;
