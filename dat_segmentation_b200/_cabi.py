@@ -106,6 +106,7 @@ def lib():
     L.dat_offset_pos_fwd.argtypes = [dp, C.POINTER(BlockParams), vp, f32p, f32p, f32p, vp]
     L.dat_ref_points.argtypes = [i32, i32, f32p, f32p, vp]
     L.dat_sample_fwd.argtypes = [dp, vp, f32p, vp, vp, vp]
+    L.dat_gather_kv_fwd.argtypes = [dp, vp, f32p, vp, vp, f32p, f32p, vp, vp, vp, vp]
     L.dat_attention_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp, C.c_size_t, i32, vp]
     L.dat_attention_fwd_workspace_bytes.argtypes = [dp]
     L.dat_attention_fwd_workspace_bytes.restype = C.c_size_t
@@ -153,7 +154,7 @@ def lib():
         getattr(L, name).restype = C.c_int
     for name in ("dat_sample_grid", "dat_block_forward", "dat_block_backward", "dat_pointwise_fwd",
                  "dat_pointwise_fwd_tc", "dat_cast_bf16",
-                 "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd", "dat_attention_fwd",
+                 "dat_offset_pos_fwd", "dat_ref_points", "dat_sample_fwd", "dat_gather_kv_fwd", "dat_attention_fwd",
                  "dat_rpe_bias"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -175,7 +176,7 @@ def exported_symbols():
             "dat_cast_bf16_multi", "dat_pointwise_dgrad_tc",
             "dat_bias_grad",
             "dat_offset_pos_fwd",
-            "dat_ref_points", "dat_sample_fwd",
+            "dat_ref_points", "dat_sample_fwd", "dat_gather_kv_fwd",
             "dat_attention_fwd", "dat_attention_fwd_workspace_bytes", "dat_rpe_bias",
             "dat_layernorm_fwd", "dat_layernorm_bwd_workspace_bytes", "dat_layernorm_bwd",
             "dat_residual_layernorm_fwd", "dat_residual_layernorm_bwd",

@@ -434,6 +434,14 @@ int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, voi
   return sample_fwd(s, x, pos, xs, taps, (cudaStream_t)stream);
 }
 
+int dat_gather_kv_fwd(const dat_block_desc* d, const void* x, const float* pos, const void* wk_bf16,
+                      const void* wv_bf16, const float* bk, const float* bv, void* xs, void* k, void* v, void* stream) {
+  Shape s;
+  DAT_FWD(make_shape(d, &s));
+  DAT_REQUIRE(x && pos && wk_bf16 && wv_bf16 && xs && k && v, "gather_kv_fwd: NULL pointer");
+  return gather_kv_tc(s, x, pos, wk_bf16, wv_bf16, bk, bv, xs, k, v, (cudaStream_t)stream);
+}
+
 size_t dat_attention_fwd_workspace_bytes(const dat_block_desc* d) {
   Shape s;
   if (make_shape(d, &s) != DAT_OK) return 0;
@@ -572,14 +580,20 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
   } else {
     DAT_FWD(pointwise_fwd_simt(x, s.x_dtype, p->wq, p->bq, sv->q, adt, M, C, C, st));
   }
+  bool fused_kv = false;
   if (s.no_off) {   // dat_blocks.py:156-157,164-167: offsets zeroed, keys / values from the average-pooled map
     DAT_CUDA_OK(cudaMemsetAsync(sv->pos, 0, (size_t)s.B * s.G * s.Ns * 2 * 4, st));
     DAT_FWD(avgpool_fwd(s, x, sv->xs, st));
   } else {
     DAT_FWD(offset_pos_fwd(s, p, sv->q, sv->t_dw, sv->off_raw, sv->pos, st));
-    DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
+    // the gather is the A-operand producer of the k / v projections when the shape allows (one launch, no round trip
+    // of the sampled features between them); xs is still written: the backward reads it
+    fused_kv = tc && gather_kv_tc_supported(s);
+    if (fused_kv) DAT_FWD(gather_kv_tc(s, x, sv->pos, wk_b, wv_b, p->bk, p->bv, sv->xs, sv->k, sv->v, st));
+    else DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
   }
-  if (tc) {
+  if (fused_kv) {
+  } else if (tc) {
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wk_b, p->bk, sv->k, adt, Mk, C, C, st));
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wv_b, p->bv, sv->v, adt, Mk, C, C, st));
   } else {

@@ -20,6 +20,10 @@ int colsum_splits(long long M);
 size_t pointwise_wgrad_workspace(long long M, int N, int K);
 int pointwise_wgrad_simt(const void* dY, int dy_dt, const void* X, int x_dt, float* dW, float* db,
                          long long M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+// gather fused with the k / v projections (gather_kv_tc.cu): xs, k, v (B, Ns, C) bf16 from x, pos and the bf16 weights
+bool gather_kv_tc_supported(const Shape& s);
+int gather_kv_tc(const Shape& s, const void* x, const float* pos, const void* wk, const void* wv, const float* bk,
+                 const float* bv, void* xs, void* k, void* v, cudaStream_t st);
 int reduce_partials_pair(const float* partA, const float* partB, int nsplit, long long count, void* outA, void* outB,
                          int out_dt, cudaStream_t st);
 int reduce_partials(const float* part, int nsplit, long long count, void* out, int out_dt,

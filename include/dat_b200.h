@@ -216,6 +216,14 @@ int dat_ref_points(int32_t Hk, int32_t Wk, float* ref_y, float* ref_x, void* str
 int dat_sample_fwd(const dat_block_desc* d, const void* x, const float* pos, void* xs,
                    int32_t* taps, void* stream);
 
+/* The gather fused with the k / v projections (dat_blocks.py:169-178): xs = grid_sample(x, pos) (bf16, bit-identical
+ * to dat_sample_fwd), k = xs Wk^T + bk, v = xs Wv^T + bv (bf16) in ONE launch - the sampled tile is built in shared
+ * memory as the A operand of the tcgen05 GEMMs.  act_dtype must be DAT_BF16, C in {64, 128, 256, 512}, C / n_groups a
+ * multiple of 8; wk_bf16 / wv_bf16 are bf16 (C, C) copies of the weights; bk / bv fp32 (may be NULL).
+ * dat_block_forward uses it where it is faster than the three launches (C <= 128; DAT_B200_GATHER_KV_FUSION=0/1). */
+int dat_gather_kv_fwd(const dat_block_desc* d, const void* x, const float* pos, const void* wk_bf16,
+                      const void* wv_bf16, const float* bk, const float* bv, void* xs, void* k, void* v, void* stream);
+
 /* QK^T*scale + bilinear rpe bias + softmax + PV (dat_blocks.py:180-223).
  * act_dtype DAT_BF16 with Ns in {64,128,256} runs the tcgen05 kernel and needs
  * `dat_attention_fwd_workspace_bytes` of scratch (packed rpe table); any other case runs

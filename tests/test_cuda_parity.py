@@ -532,3 +532,45 @@ def test_proj_drop_in_training_is_a_dropout_of_the_block_output():
     torch.testing.assert_close(y1[kept], (y0 * 2.0)[kept], rtol=1e-6, atol=1e-6)
     with pytest.raises(NotImplementedError):
         make(0.1, 0.0)(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("x_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,C,heads,G,stride,ksize,qs", [
+    (32, 64, 2, 1, 2, 5, 14), (32, 128, 4, 2, 2, 5, 14), (32, 256, 8, 4, 2, 5, 14), (16, 512, 16, 8, 1, 3, 7),
+    (24, 128, 4, 2, 2, 5, 14),     # 12 x 12 = 144 samples per image: the last 128-row tile is partly empty
+])
+def test_gather_fused_with_the_kv_projections_equals_the_three_launch_path(H, C, heads, G, stride, ksize, qs, x_dtype):
+    """dat_gather_kv_fwd forms x_sampled inside the k / v projection kernel (gather_kv_tc.cu; dat_block_forward uses it
+    for C <= 128).  x_sampled must be bit-identical to dat_sample_fwd's (same index arithmetic; positions beyond
+    [-1, 1] included: zero padding), and k / v bit-identical to the stand-alone tcgen05 GEMM on that x_sampled
+    (dat_blocks.py:169-178)."""
+    import ctypes as C_
+    from dat_segmentation_b200 import _cabi
+    lib = _cabi.lib()
+    p = lambda t: C_.c_void_p(t.data_ptr() if t is not None else 0)
+    B = 3
+    st = C_.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Th = 2 * qs - 1
+    bf = torch.bfloat16
+    d = _cabi.BlockDesc(B, H, H, heads, G, stride, ksize, Th, Th, 2.0, _cabi.DAT_F32 if x_dtype == torch.float32 else _cabi.DAT_BF16,
+                        _cabi.DAT_BF16)
+    hk, wk = C_.c_int32(), C_.c_int32()
+    _cabi.check(lib.dat_sample_grid(C_.byref(d), C_.byref(hk), C_.byref(wk)), "grid")
+    Ns, HW = hk.value * wk.value, H * H
+    gen = torch.Generator(device="cuda").manual_seed(C + H)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    x = rn(B, HW, C).to(x_dtype)
+    pos = torch.rand(B, G, Ns, 2, device="cuda", generator=gen) * 2.6 - 1.3      # some taps fall outside the map
+    wk_b, wv_b = (rn(C, C) / C ** 0.5).to(bf), (rn(C, C) / C ** 0.5).to(bf)
+    bk, bv = rn(C) * 0.1, rn(C) * 0.1
+    e_ = lambda *sh: torch.empty(*sh, device="cuda", dtype=bf)
+    xs, k, v, xs_ref = e_(B, Ns, C), e_(B, Ns, C), e_(B, Ns, C), e_(B, Ns, C)
+    _cabi.check(lib.dat_gather_kv_fwd(C_.byref(d), p(x), p(pos), p(wk_b), p(wv_b), p(bk), p(bv), p(xs), p(k), p(v), st),
+                "gather_kv_fwd")
+    _cabi.check(lib.dat_sample_fwd(C_.byref(d), p(x), p(pos), p(xs_ref), None, st), "sample_fwd")
+    assert torch.equal(xs, xs_ref)
+    for w, b, out in ((wk_b, bk, k), (wv_b, bv, v)):
+        ref = e_(B * Ns, C)
+        _cabi.check(lib.dat_pointwise_fwd_tc(p(xs_ref), 1, p(w), p(b), p(ref), 1, B * Ns, C, C, st), "gemm")
+        assert torch.equal(out.reshape(B * Ns, C), ref)
