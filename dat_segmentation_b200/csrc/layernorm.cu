@@ -8,6 +8,8 @@
 // Backward: gamma / beta gradients are accumulated per lane over a grid-stride loop, reduced
 // per CTA in shared memory and across CTAs by a second tiny kernel in a fixed order
 // (deterministic, no atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -218,6 +220,197 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
   }
 }
 
+// ---- narrow rows (C = 64 / 128): LPR = C / 8 lanes per row, 8 contiguous channels per lane ------------------------
+// The warp-per-row kernels above give a lane 2 channels of a 64-channel row (8-byte accesses) and spend a full 5-level
+// butterfly per statistic and row: ~100 warp instructions per 64 elements, 40 % (forward) / 61 % (backward) of the HBM
+// peak at stage 0.  Here a warp works on 32 / LPR rows at once, a lane moves 32 (fp32) / 16 (bf16) bytes per access
+// and a row's statistics take log2(LPR) shuffle levels.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+__device__ __forceinline__ void round8(const float*, float (&)[8]) {}
+__device__ __forceinline__ void round8(const bf16*, float (&v)[8]) {     // the values as a bf16 stream holds them
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+}
+template <int LPR> __device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TI, typename TO, int LPR>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_sub_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         TO* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
+                         float eps, const TO* __restrict__ a, const float* __restrict__ scale,
+                         long long rows_per_sample, TI* __restrict__ xout) {
+  pdl_enter();
+  constexpr int C = LPR * 8, RPW = 32 / LPR, UNR = 2;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, cl = (lane % LPR) * 8;
+  float g[8], b[8];
+  ld8(gamma + cl, g);
+  ld8(beta + cl, b);
+  const float inv_c = 1.0f / (float)C;
+  const long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * (RPW * UNR) + sub;
+  float v[UNR][8];
+  bool ok[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const long long row = row0 + u * RPW;
+    ok[u] = row < rows;
+    if (ok[u]) {
+      ld8(x + row * C + cl, v[u]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+    }
+  }
+  if (a != nullptr) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long row = row0 + u * RPW;
+      if (ok[u]) {
+        float av[8];
+        ld8(a + row * C + cl, av);
+        const float sc = scale[row / rows_per_sample];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[u][e] = fmaf(av[e], sc, v[u][e]);
+        st8(xout + row * C + cl, v[u]);
+        round8(xout, v[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const long long row = row0 + u * RPW;
+    float s1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1 += v[u][e];
+    const float mean = row_sum<LPR>(s1) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = v[u][e] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.0f / sqrtf(row_sum<LPR>(q) * inv_c + eps);
+    if (ok[u]) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[u][e] - mean) * rstd * g[e] + b[e];
+      st8(y + row * C + cl, o);
+      if (cl == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+    }
+  }
+}
+
+template <typename TI, typename TDY, int LPR>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_sub_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TI* __restrict__ dx,
+                         const TI* __restrict__ dres, float* __restrict__ partial, long long rows,
+                         TDY* __restrict__ da, const float* __restrict__ scale, long long rows_per_sample) {
+  pdl_enter();
+  constexpr int C = LPR * 8, RPW = 32 / LPR;
+  extern __shared__ float red[];     // [LN_WARPS][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, cl = (lane % LPR) * 8;
+  float gam[8], gg[8], gb[8];
+  ld8(gamma + cl, gam);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) gg[e] = gb[e] = 0.f;
+  const float inv_c = 1.0f / (float)C;
+  for (long long row = ((long long)blockIdx.x * LN_WARPS + warp) * RPW + sub; row - sub < rows;
+       row += (long long)gridDim.x * LN_WARPS * RPW) {
+    const bool ok = row < rows;
+    float xv[8], dv[8], rv[8];
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] = dv[e] = rv[e] = 0.f;
+    if (ok) {
+      mean = mean_in[row];
+      rstd = rstd_in[row];
+      ld8(x + row * C + cl, xv);
+      ld8(dy + row * C + cl, dv);
+      if (dres != nullptr) ld8(dres + row * C + cl, rv);
+    }
+    float xh[8], dg[8];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      xh[e] = ok ? (xv[e] - mean) * rstd : 0.f;
+      gg[e] = fmaf(dv[e], xh[e], gg[e]);
+      gb[e] += dv[e];
+      dg[e] = dv[e] * gam[e];
+      m1 += dg[e];
+      m2 = fmaf(dg[e], xh[e], m2);
+    }
+    m1 = row_sum<LPR>(m1) * inv_c;
+    m2 = row_sum<LPR>(m2) * inv_c;
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (dg[e] - m1 - xh[e] * m2) + rv[e];   // + the residual-path gradient
+      st8(dx + row * C + cl, o);
+      if (da != nullptr) {
+        round8(dx, o);
+        const float sc = scale[row / rows_per_sample];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] *= sc;
+        st8(da + row * C + cl, o);
+      }
+    }
+  }
+  // the RPW row groups of the warp hold the same channels: add them (fixed order), then the warps of the CTA
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gg[e] += __shfl_xor_sync(0xffffffffu, gg[e], o);
+      gb[e] += __shfl_xor_sync(0xffffffffu, gb[e], o);
+    }
+  }
+  float* mine = red + (size_t)warp * 2 * C;
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mine[cl + e] = gg[e];
+      mine[C + cl + e] = gb[e];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += red[(size_t)w * 2 * C + idx];
+    partial[(size_t)blockIdx.x * 2 * C + idx] = s;
+  }
+}
+
 // block (32, 32): threadIdx.x = output within a 32-wide slice, threadIdx.y = partial lane; fixed
 // summation order (lane-strided partial sums, then lanes 0..31): deterministic.
 __global__ void layernorm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int C,
@@ -263,6 +456,26 @@ int residual_layernorm_fwd(const void* a, const float* scale, long long rows_per
   DAT_REQUIRE(rows > 0 && C >= 2 && C % 2 == 0 && C <= 64 * LN_MAXV, "layernorm: unsupported C=%d", C);
   DAT_REQUIRE(a == nullptr || (scale != nullptr && xout != nullptr && rows_per_sample > 0),
               "residual_layernorm_fwd: scale / xout missing");
+  static const int ln_v1 = [] { const char* e = std::getenv("DAT_B200_LN_V1"); return e && e[0] == '1' ? 1 : 0; }();
+  if ((C == 64 || C == 128) && !ln_v1) {      // narrow rows: several rows per warp, 8 channels per lane
+    const int rpw = 32 / (C / 8) * 2;         // rows per warp and pass x 2 passes in flight
+    const int grid_s = (int)ceil_div(rows, (long long)LN_WARPS * rpw);
+#define LAUNCH_S(TI, TO, L)                                                                                      \
+  launch_k(layernorm_fwd_sub_kernel<TI, TO, L>, grid_s, LN_WARPS * 32, 0, st, (const TI*)x, gamma, beta, (TO*)y, \
+           mean, rstd, rows, eps, (const TO*)a, scale, rows_per_sample, (TI*)xout)
+#define LAUNCH_SL(TI, TO)                                                   \
+  do {                                                                      \
+    if (C == 64) LAUNCH_S(TI, TO, 8); else LAUNCH_S(TI, TO, 16);            \
+  } while (0)
+    if (x_dt == DAT_F32 && y_dt == DAT_F32) LAUNCH_SL(float, float);
+    else if (x_dt == DAT_F32) LAUNCH_SL(float, bf16);
+    else if (y_dt == DAT_F32) LAUNCH_SL(bf16, float);
+    else LAUNCH_SL(bf16, bf16);
+#undef LAUNCH_SL
+#undef LAUNCH_S
+    DAT_LAUNCH_OK("layernorm_fwd_sub_kernel");
+    return DAT_OK;
+  }
   const int nv = nv_of(C);
   const int rows_per_warp = nv == 1 ? 4 : (nv == 2 ? 2 : 1);      // RowsOf<NV>::R
   const int grid = (int)ceil_div(rows, (long long)LN_WARPS * rows_per_warp);
@@ -304,6 +517,33 @@ int residual_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
   const int nv = nv_of(C);
   const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
   float* part = (float*)ws;
+  static const int ln_v1 = [] { const char* e = std::getenv("DAT_B200_LN_V1"); return e && e[0] == '1' ? 1 : 0; }();
+  if ((C == 64 || C == 128) && !ln_v1) {
+#define LAUNCH_S(TI, TD, L)                                                                                          \
+  do {                                                                                                               \
+    auto kern = layernorm_bwd_sub_kernel<TI, TD, L>;                                                                 \
+    int occ = 1;                                                                                                     \
+    DAT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LN_WARPS * 32, smem));                     \
+    if (occ < 1) occ = 1;                                                                                            \
+    if (nblk > 148 * occ) nblk = 148 * occ;                                                                          \
+    launch_k(kern, nblk, LN_WARPS * 32, smem, st, (const TD*)dy, (const TI*)x, gamma, mean, rstd, (TI*)dx,           \
+             (const TI*)dres, part, rows, (TD*)da, scale, rows_per_sample);                                          \
+  } while (0)
+#define LAUNCH_SL(TI, TD)                                                   \
+  do {                                                                      \
+    if (C == 64) LAUNCH_S(TI, TD, 8); else LAUNCH_S(TI, TD, 16);            \
+  } while (0)
+    if (x_dt == DAT_F32 && dy_dt == DAT_F32) LAUNCH_SL(float, float);
+    else if (x_dt == DAT_F32) LAUNCH_SL(float, bf16);
+    else if (dy_dt == DAT_F32) LAUNCH_SL(bf16, float);
+    else LAUNCH_SL(bf16, bf16);
+#undef LAUNCH_SL
+#undef LAUNCH_S
+    DAT_LAUNCH_OK("layernorm_bwd_sub_kernel");
+    launch_k(layernorm_bwd_reduce_kernel, ceil_div(2 * C, 32), dim3(32, 32), 0, st, part, nblk, C, dgamma, dbeta);
+    DAT_LAUNCH_OK("layernorm_bwd_reduce_kernel");
+    return DAT_OK;
+  }
 #define LAUNCH(TI, TD, NVV)                                                                       \
   do {                                                                                            \
     auto kern = layernorm_bwd_kernel<TI, TD, NVV>;                                                \
