@@ -284,7 +284,9 @@ gather_kv_tc_kernel(const __grid_constant__ CUtensorMap tmWk, const __grid_const
         }
       }
     }
-    if (lane == 0) bulk_wait_group<0>();
+    // the staging tile must have been read before the CTA's shared memory goes away; the global writes themselves
+      // complete asynchronously (they are ordered before the end of the grid, like any other store)
+      if (lane == 0) bulk_wait_group_read<0>();
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -455,7 +455,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
         }
       }
-      if (lane == 0) bulk_wait_group<0>();
+      // the staging tile must have been read before the CTA's shared memory goes away; the global writes themselves
+      // complete asynchronously (they are ordered before the end of the grid, like any other store)
+      if (lane == 0) bulk_wait_group_read<0>();
     } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const int buf = li & 1;
