@@ -51,6 +51,15 @@ constexpr unsigned FULL = 0xffffffffu;
 // TMEM column map (512 columns allocated)
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_DK = 288, TM_DV = 352;
 
+// Phase counters of the compute warps (tools/attn_bwd_phases.py): compiled in only with -DDAT_ATTN_BWD_PROFILE
+// (DAT_B200_BUILD_DEFS, tagged build) - six 64-bit counters and a clock read per 32 scores cost the production kernel
+// registers it does not have (168 per thread, spills).
+#ifdef DAT_ATTN_BWD_PROFILE
+#define PF(...) __VA_ARGS__
+#else
+#define PF(...)
+#endif
+
 struct BtcArgs {
   int B, H, W, HW, C, heads, G, hg, Th, Tw, Wp, Hp;
   int n_tiles, rows_max, chunks, nslots, light_table;
@@ -367,7 +376,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int i = 0; i < NHALF * 2; ++i) dpx_acc[i] = dpy_acc[i] = 0.f;
     int it = 0;
-    long long pf_total = clock64(), pf_wait = 0, pf_score = 0, pf_col = 0, pf_dq = 0, pf_setup = 0;
+    PF(long long pf_total = clock64(), pf_wait = 0, pf_score = 0, pf_col = 0, pf_dq = 0, pf_setup = 0;)
     // per-(image row of the tile, sample) y footprint, double-buffered: the table of tile i + 1 is built after the score
     // loops of tile i, so a tile starts with ONE barrier and no table build on its critical path
     const uint32_t yt_stride = (uint32_t)a.rows_max * NS * (FAST ? 16u : 8u);
@@ -416,7 +425,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int m_prev = 0;
     bool valid_prev = false;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      long long pf_t = clock64();
+      PF(long long pf_t = clock64();)
       const int m = tile * TQ + row;
       const bool valid = m < a.HW;
       const int mm = valid ? m : a.HW - 1;
@@ -440,14 +449,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // dS for the table gradient: groups of 8 samples, [bh][NS / 8][m][8] - a warp's 32 rows write 512 contiguous bytes
       bf16* ds_row = TBL ? nullptr : ds_out + (long long)bh * a.HW * a.ns_total + (long long)mm * 8;
 
-      pf_setup += clock64() - pf_t;
+      PF(pf_setup += clock64() - pf_t;)
 #pragma unroll 1
       for (int h = 0; h < NHALF; ++h) {
         const uint32_t e_idx = (uint32_t)(it * NHALF + h);
-        pf_t = clock64();
+        PF(pf_t = clock64();)
         mbar_wait(sdp_full, e_idx & 1u);
         tc_fence_after_sync();
-        pf_wait += clock64() - pf_t;
+        PF(pf_wait += clock64() - pf_t;)
         if constexpr (FAST) {
           auto fast_body = [&](auto xc_tag) {
             constexpr bool XC = decltype(xc_tag)::value;
@@ -455,7 +464,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int sub = 0; sub < 2; ++sub) {
               const int col0 = chalf * 64 + sub * 32;          // column within the half
               uint32_t sv[32], dpv[32];
-              pf_t = clock64();
+              PF(pf_t = clock64();)
               tmem_ld_32x32(t_lane + TM_S + (uint32_t)col0, sv);
               tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
               tmem_wait_ld();
@@ -499,12 +508,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
               // d pos: column sums over this warp's 32 rows on bf16x2 pairs {x part, y part} (lane L ends up with
               // column L); the running sums over tiles stay fp32
-              const long long pf_m = clock64();
-              pf_score += pf_m - pf_t;
+              PF(const long long pf_m = clock64();)
+              PF(pf_score += pf_m - pf_t;)
               const uint32_t cs = column_sums32_bf16x2(g2, lane);
               dpx_acc[h * 2 + sub] += __uint_as_float(cs << 16);
               dpy_acc[h * 2 + sub] += __uint_as_float(cs & 0xffff0000u);
-              pf_col += clock64() - pf_m;
+              PF(pf_col += clock64() - pf_m;)
             }
           };
           if (xclamp) fast_body(std::true_type{});
@@ -514,7 +523,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int sub = 0; sub < 2; ++sub) {
           const int col0 = chalf * 64 + sub * 32;          // column within the half
           uint32_t sv[32], dpv[32];
-          pf_t = clock64();
+          PF(pf_t = clock64();)
           tmem_ld_32x32(t_lane + TM_S + (uint32_t)col0, sv);
           tmem_ld_32x32(t_lane + TM_DP + (uint32_t)col0, dpv);
           tmem_wait_ld();
@@ -648,33 +657,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
           }
           // d pos: column sums over this warp's 32 rows (lane L ends up with column L)
-          const long long pf_m = clock64();
-          pf_score += pf_m - pf_t;
+          PF(const long long pf_m = clock64();)
+          PF(pf_score += pf_m - pf_t;)
           dpx_acc[h * 2 + sub] += column_sums32(gxs, lane);
           dpy_acc[h * 2 + sub] += column_sums32(gys, lane);
-          pf_col += clock64() - pf_m;
+          PF(pf_col += clock64() - pf_m;)
         }
         }
         if (h == 0 && it > 0) {         // the previous tile's dQ (its MMAs finished long ago); frees the accumulator
-          pf_t = clock64();             // before this half's dQ MMAs are issued (they follow pds_ready)
+          PF(pf_t = clock64();)  // before this half's dQ MMAs are issued (they follow pds_ready)
           dq_epilogue(it - 1, m_prev, valid_prev);
-          pf_dq += clock64() - pf_t;
+          PF(pf_dq += clock64() - pf_t;)
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(pds_ready);
       }
-      pf_t = clock64();
+      PF(pf_t = clock64();)
       if (tile + (int)gridDim.x < a.n_tiles) build_yt(tile + gridDim.x, (it + 1) & 1);
-      pf_setup += clock64() - pf_t;
+      PF(pf_setup += clock64() - pf_t;)
       m_prev = m;
       valid_prev = valid;
     }
     {
-      const long long pf_t = clock64();
+      PF(const long long pf_t = clock64();)
       dq_epilogue(it - 1, m_prev, valid_prev);      // the last tile's dQ; also: every MMA of the CTA has completed
-      pf_dq += clock64() - pf_t;
+      PF(pf_dq += clock64() - pf_t;)
     }
+#ifdef DAT_ATTN_BWD_PROFILE
     if (warp == 4 && lane == 0) {
       atomicAdd(&g_attn_bwd_prof[0], (unsigned long long)(clock64() - pf_total));
       atomicAdd(&g_attn_bwd_prof[1], (unsigned long long)pf_wait);
@@ -684,6 +694,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       atomicAdd(&g_attn_bwd_prof[5], (unsigned long long)pf_setup);
       atomicAdd(&g_attn_bwd_prof[6], 1ull);
     }
+#endif
 
     // ---- end of CTA: dK / dV accumulators, d pos, d table --------------------------------------
     // every MMA of this CTA has completed: the last dq_full commit covers all earlier MMAs

@@ -1,5 +1,7 @@
 """Phase breakdown of the tensor-core attention backward (dat_debug_attn_bwd_timing) for one block
-fwd+bwd at each DAT-T++ stage shape, B = 16, bf16."""
+fwd+bwd at each DAT-T++ stage shape, B = 16, bf16.  The counters are compiled in only with -DDAT_ATTN_BWD_PROFILE:
+  DAT_B200_BUILD_TAG=prof DAT_B200_BUILD_DEFS=-DDAT_ATTN_BWD_PROFILE python -m dat_segmentation_b200.build
+  DAT_B200_LIB=$PWD/dat_segmentation_b200/libdat_b200_prof.so python tools/attn_bwd_phases.py"""
 import ctypes as C
 import os
 import sys
