@@ -351,7 +351,10 @@ int dwconv3_fwd(const void* x, int x_dt, const float* w, const float* bias, void
                 int B, int H, int W, int C, int mode, int flip, cudaStream_t st) {
   DAT_REQUIRE(C % 2 == 0, "dwconv3: C must be even");
   DAT_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || z_out != nullptr), "dwconv3: bad mode");
-  const int th = dwconv3_rows_per_strip(B, H, W, C);
+  int th = dwconv3_rows_per_strip(B, H, W, C);
+  // the MLP middle (mode 2: z stored, GELU) runs best with half the strip height of the fused backward, whose optimum
+  // the common rule above tracks: 115 -> 101 us (stage 0), 60 -> 53 (stage 1), 32.1 -> 29.7 (stage 2), DAT_B200_DW3_TH sweep
+  if (mode == 2 && th >= 16 && std::getenv("DAT_B200_DW3_TH") == nullptr) th = th / 2;
   const int sx = ceil_div(W, TW), sy = ceil_div(H, th);
   const long long threads = (long long)B * sx * sy * (C / 2);
   const unsigned grid = (unsigned)ceil_div(threads, (long long)D3_THREADS);
