@@ -325,8 +325,9 @@ dwconv3_bwd_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, const TD
 int dwconv3_rows_per_strip(int B, int H, int W, int C) {
   const long long per_row_block = (long long)B * ceil_div(W, TW) * (C / 2);
   if (const char* e = std::getenv("DAT_B200_DW3_TH")) { const int v = std::atoi(e); if (v > 0) return v < H ? v : H; }
+  static const long long per_sm = [] { const char* e = std::getenv("DAT_B200_DW3_THREADS_PER_SM"); return e ? std::atoll(e) : 700ll; }();
   int th = H;
-  while (th > 8 && per_row_block * ceil_div(H, th) < 148ll * 700) th = (th + 1) / 2;
+  while (th > 8 && per_row_block * ceil_div(H, th) < 148ll * per_sm) th = (th + 1) / 2;
   return th;
 }
 
