@@ -139,17 +139,41 @@ sample_bwd_dx_kernel(const float* __restrict__ pos, const TD* __restrict__ dxs,
     keys[e] = key;
   }
   __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += blockDim.x) {
-        int ixj = i ^ j;
-        if (ixj > i) {
-          uint32_t a = keys[i], c2 = keys[ixj];
-          bool up = (i & k) == 0;
-          if ((a > c2) == up) { keys[i] = c2; keys[ixj] = a; }
+  if (P == (int)blockDim.x) {
+    // one key per thread: the compare-exchange stages with a partner inside the warp (j < 32: 40 of the 55 stages at
+    // P = 1024) run on registers with one shuffle each; only the cross-warp stages go through shared memory and a
+    // barrier (ncu: the all-shared-memory sort was ~35 % of this kernel's samples)
+    uint32_t key = keys[tid];
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        uint32_t other;
+        if (j >= 32) {
+          keys[tid] = key;
+          __syncthreads();
+          other = keys[tid ^ j];
+          __syncthreads();
+        } else {
+          other = __shfl_xor_sync(0xffffffffu, key, j);
         }
+        const bool take_min = ((tid & k) == 0) == ((tid & j) == 0);
+        key = take_min ? min(key, other) : max(key, other);
       }
-      __syncthreads();
+    }
+    keys[tid] = key;
+    __syncthreads();
+  } else {
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P; i += blockDim.x) {
+          int ixj = i ^ j;
+          if (ixj > i) {
+            uint32_t a = keys[i], c2 = keys[ixj];
+            bool up = (i & k) == 0;
+            if ((a > c2) == up) { keys[i] = c2; keys[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   // One THREAD per run head, 32 channels (this CTA's slice) as 8 independent 4-wide
