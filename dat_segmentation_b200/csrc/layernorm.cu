@@ -220,7 +220,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const TI* __restrict__ x,
   }
 }
 
-// ---- narrow rows (C = 64 / 128): LPR = C / 8 lanes per row, 8 contiguous channels per lane ------------------------
+// ---- rows of 64 / 128 / 256 channels: LPR = C / 8 lanes per row, 8 contiguous channels per lane ------------------------
 // The warp-per-row kernels above give a lane 2 channels of a 64-channel row (8-byte accesses) and spend a full 5-level
 // butterfly per statistic and row: ~100 warp instructions per 64 elements, 40 % (forward) / 61 % (backward) of the HBM
 // peak at stage 0.  Here a warp works on 32 / LPR rows at once, a lane moves 32 (fp32) / 16 (bf16) bytes per access
@@ -457,7 +457,7 @@ int residual_layernorm_fwd(const void* a, const float* scale, long long rows_per
   DAT_REQUIRE(a == nullptr || (scale != nullptr && xout != nullptr && rows_per_sample > 0),
               "residual_layernorm_fwd: scale / xout missing");
   static const int ln_v1 = [] { const char* e = std::getenv("DAT_B200_LN_V1"); return e && e[0] == '1' ? 1 : 0; }();
-  if ((C == 64 || C == 128) && !ln_v1) {      // narrow rows: several rows per warp, 8 channels per lane
+  if ((C == 64 || C == 128 || C == 256) && !ln_v1) {      // narrow rows: several rows per warp, 8 channels per lane
     const int rpw = 32 / (C / 8) * 2;         // rows per warp and pass x 2 passes in flight
     const int grid_s = (int)ceil_div(rows, (long long)LN_WARPS * rpw);
 #define LAUNCH_S(TI, TO, L)                                                                                      \
@@ -465,7 +465,7 @@ int residual_layernorm_fwd(const void* a, const float* scale, long long rows_per
            mean, rstd, rows, eps, (const TO*)a, scale, rows_per_sample, (TI*)xout)
 #define LAUNCH_SL(TI, TO)                                                   \
   do {                                                                      \
-    if (C == 64) LAUNCH_S(TI, TO, 8); else LAUNCH_S(TI, TO, 16);            \
+    if (C == 64) LAUNCH_S(TI, TO, 8); else if (C == 128) LAUNCH_S(TI, TO, 16); else LAUNCH_S(TI, TO, 32); \
   } while (0)
     if (x_dt == DAT_F32 && y_dt == DAT_F32) LAUNCH_SL(float, float);
     else if (x_dt == DAT_F32) LAUNCH_SL(float, bf16);
@@ -518,7 +518,7 @@ int residual_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
   const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
   float* part = (float*)ws;
   static const int ln_v1 = [] { const char* e = std::getenv("DAT_B200_LN_V1"); return e && e[0] == '1' ? 1 : 0; }();
-  if ((C == 64 || C == 128) && !ln_v1) {
+  if ((C == 64 || C == 128 || C == 256) && !ln_v1) {
 #define LAUNCH_S(TI, TD, L)                                                                                          \
   do {                                                                                                               \
     auto kern = layernorm_bwd_sub_kernel<TI, TD, L>;                                                                 \
@@ -531,7 +531,7 @@ int residual_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
   } while (0)
 #define LAUNCH_SL(TI, TD)                                                   \
   do {                                                                      \
-    if (C == 64) LAUNCH_S(TI, TD, 8); else LAUNCH_S(TI, TD, 16);            \
+    if (C == 64) LAUNCH_S(TI, TD, 8); else if (C == 128) LAUNCH_S(TI, TD, 16); else LAUNCH_S(TI, TD, 32); \
   } while (0)
     if (x_dt == DAT_F32 && dy_dt == DAT_F32) LAUNCH_SL(float, float);
     else if (x_dt == DAT_F32) LAUNCH_SL(float, bf16);
