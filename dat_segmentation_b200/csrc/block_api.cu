@@ -593,6 +593,9 @@ int dat_block_forward(const dat_block_desc* d, const dat_block_params* p, const 
     else DAT_FWD(sample_fwd(s, x, sv->pos, sv->xs, nullptr, st));
   }
   if (fused_kv) {
+  } else if (tc && pointwise_fwd_tc_two_outputs_supported(C)) {
+    // k and v = two products of the same sampled features: one launch of the persistent GEMM
+    DAT_FWD(pointwise_fwd_tc_dual(sv->xs, wk_b, nullptr, wv_b, adt, p->bk, sv->k, adt, Mk, C, C, st, false, p->bv, sv->v));
   } else if (tc) {
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wk_b, p->bk, sv->k, adt, Mk, C, C, st));
     DAT_FWD(pointwise_fwd_tc(sv->xs, adt, wv_b, p->bv, sv->v, adt, Mk, C, C, st));

@@ -270,7 +270,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                           const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias,
                           TOut* __restrict__ Y, int M, int N, int k_chunks, int k_chunks1, int BN, int stages,
-                          int tmem_cols, int m_tiles, int total_tiles, int stage_pitch, int bias_bytes, int dbg) {
+                          int tmem_cols, int m_tiles, int total_tiles, int stage_pitch, int bias_bytes, int dbg,
+                          const __grid_constant__ CUtensorMap tmY2, const float* __restrict__ bias2, int N1) {
+  // N1 < N: TWO products of the same A in one launch (the k and v projections of the sampled features): output
+  // columns [0, N1) are X W^T + bias into tmY, columns [N1, N) are X W2^T + bias2 into tmY2 (W2 behind tmB2, which is
+  // otherwise the second K-concatenated source; the two uses exclude each other).  N1 is a multiple of BN.
   pdl_enter();
   // dbg (DAT_B200_GEMM_DBG, timing decomposition only - results are wrong): 1 = no global stores, 2 = B loaded for the
   // CTA's first tile only, 4 = A loaded for the first tile only, 8 = epilogue only hands the accumulator back
@@ -300,6 +304,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tma_prefetch_desc(&tmB2);
     }
     if (BN % 64 == 0) tma_prefetch_desc(&tmY);
+    if (N1 < N) tma_prefetch_desc(&tmY2);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -330,14 +335,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (!ld_a && !ld_b) { mbar_arrive(&full[s]); continue; }
           mbar_arrive_expect_tx(&full[s], (uint32_t)((ld_a ? A_STAGE_BYTES : 0) + (ld_b ? b_stage_bytes : 0)));
           const bool second = kc >= k_chunks1;
+          const bool out2 = n0 >= N1;                       // second product: its weights sit behind tmB2
+          const int n0w = out2 ? n0 - N1 : n0;
           const int kcol = (second ? kc - k_chunks1 : kc) * CHUNK_ELEMS;
           if (ld_a) tma_load_2d(sA + s * A_STAGE_BYTES, second ? &tmA2 : &tmA, &full[s], kcol, m0);
           if (!ld_b) continue;
           if (BMN) {
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sB + s * b_stage_bytes + i * 8192, second ? &tmB2 : &tmB, &full[s], n0 + 64 * i, kcol);
+              tma_load_2d(sB + s * b_stage_bytes + i * 8192, (second || out2) ? &tmB2 : &tmB, &full[s], n0w + 64 * i, kcol);
           } else {
-            tma_load_2d(sB + s * b_stage_bytes, second ? &tmB2 : &tmB, &full[s], kcol, n0);
+            tma_load_2d(sB + s * b_stage_bytes, (second || out2) ? &tmB2 : &tmB, &full[s], kcol, n0w);
           }
         }
       }
@@ -380,7 +387,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     int li = 0;
     // the whole bias vector is staged once per CTA by the epilogue warps alone: the producer and the MMA issuer start
     // their first tile without waiting for this global load
-    for (int i = threadIdx.x - 64; i < N; i += 32 * TCP_EPI_WARPS) sBias[i] = bias != nullptr ? bias[i] : 0.f;
+    for (int i = threadIdx.x - 64; i < N; i += 32 * TCP_EPI_WARPS) {
+      const float* bsrc = i < N1 ? bias : bias2;
+      sBias[i] = bsrc != nullptr ? bsrc[i < N1 ? i : i - N1] : 0.f;
+    }
     asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
     if (BN % 64 == 0) {
       // TMA-store epilogue: a warp's 32 rows x 64 columns go TMEM -> registers -> (+ bias, convert) -> a 128B-swizzled
@@ -450,7 +460,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           __syncwarp();
           if (lane == 0 && !(dbg & 1) && m0 + quad * 32 < M) {
 #pragma unroll
-            for (int bx = 0; bx < NBOX; ++bx) tma_store_2d(&tmY, tstage + bx * 4096, n0 + cg + bx * BOX_COLS, m0 + quad * 32);
+            const bool out2 = n0 >= N1;
+            const int ncol = (out2 ? n0 - N1 : n0) + cg;
+            for (int bx = 0; bx < NBOX; ++bx)
+              tma_store_2d(out2 ? &tmY2 : &tmY, tstage + bx * 4096, ncol + bx * BOX_COLS, m0 + quad * 32);
             bulk_commit_group();
           }
         }
@@ -805,6 +818,11 @@ int cast_transpose_bf16(const float* w, void* out, int N, int K, cudaStream_t st
   return DAT_OK;
 }
 
+bool pointwise_fwd_tc_two_outputs_supported(int N) {
+  return pick_bn(N) != 0 && pick_bn(N) % 64 == 0 && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr &&
+         std::getenv("DAT_B200_KV_TWO_LAUNCHES") == nullptr;
+}
+
 int pointwise_fwd_tc(const void* X, int x_dt, const void* W, const float* b, void* Y, int y_dt,
                      long long M, int N, int K, cudaStream_t st) {
   return pointwise_fwd_tc_dual(X, W, nullptr, nullptr, x_dt, b, Y, y_dt, M, N, K, st);
@@ -830,11 +848,17 @@ int pointwise_dgrad_tc(const void* dY, const void* W, const void* dY2, const voi
 
 // Y = X W^T (+ X2 W2^T) + b.  W: fp32 when x_dt == DAT_F32 (tf32 MMA), bf16 when x_dt == DAT_BF16.
 // w_mn: W (and W2) are (K, N) row-major bf16 matrices read as MN-major B operands (see the kernel's BMN flag).
+// Y2 != NULL (two products of one X in one launch): Y = X W^T + b and Y2 = X W2^T + b2, both (M, N); needs a tile width
+// that is a multiple of 64, no second K source and K-major weights.
 int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
-                          cudaStream_t st, bool w_mn) {
+                          cudaStream_t st, bool w_mn, const float* b2, void* Y2) {
   DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
   const bool tf32 = x_dt == DAT_F32;
+  const bool two_out = Y2 != nullptr;
+  DAT_REQUIRE(!two_out || (X2 == nullptr && W2 != nullptr && !w_mn && pick_bn(N) % 64 == 0 &&
+                           std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
+              "pointwise_fwd_tc: two outputs need K-major weights, one K source and a tile width that is a multiple of 64");
   DAT_REQUIRE(!w_mn || (!tf32 && pick_bn_mn(N) != 0 && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
               "pointwise_fwd_tc: the MN-major weight operand needs bf16 and a tile width that is a multiple of 64");
   const int eb = tf32 ? 4 : 2;
@@ -855,6 +879,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     DAT_FWD(tc::make_tmap_2d(&tmA2, X2, eb, tf32, (uint64_t)M, (uint64_t)K, (uint64_t)K * eb, TC_BM, chunk_elems, 128));
     DAT_FWD(map_w(&tmB2, W2));
   }
+  if (two_out) DAT_FWD(map_w(&tmB2, W2));
   const int stage_bytes = A_STAGE_BYTES + BN * CHUNK_BYTES;
   // CTA pairs (cta_group::2, 256 x BN tiles): tiles of 128 or 256 columns, at least one full pair of row tiles.
   // Opt-in (DAT_B200_GEMM_PAIR=1): measured on B200 it halves the weight-panel fills but is no faster than the
@@ -862,7 +887,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   // fc1: profiles/r02_gemm_pair.md) - the kernel is bound by ring depth x fill latency and by its epilogue, not by
   // L2 -> shared-memory bandwidth.
   static const int pair_off = [] { const char* e = std::getenv("DAT_B200_GEMM_PAIR"); return e && e[0] == '1' ? 0 : 1; }();
-  if (!pair_off && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr && (BN == 256 || BN == 128) && M >= 2 * TC_BM) {
+  if (!pair_off && !two_out && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr && (BN == 256 || BN == 128) && M >= 2 * TC_BM) {
     const int gcols = persistent_gcols(BN);
     const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
     const int staging = TCP_EPI_WARPS * 32 * stage_pitch;
@@ -907,27 +932,32 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     // box (bf16) or two (fp32) per epilogue warp; other widths use the padded, row-coalesced st.global staging
     const bool tma_out = BN % 64 == 0;
     const int staging = tma_out ? TCP_EPI_WARPS * 4096 * (int)(dtype_size(y_dt) / 2) : TCP_EPI_WARPS * 32 * stage_pitch;
-    const int bias_bytes = (int)align_up((size_t)N * 4, 1024);
+    const int N1 = N;                                  // columns of the first output
+    const int Ntot = two_out ? 2 * N : N;              // the kernel's N: both outputs side by side
+    const int bias_bytes = (int)align_up((size_t)Ntot * 4, 1024);
     int stages = (226 * 1024 - 1024 - 1024 - bias_bytes - staging) / stage_bytes;
     if (stages > 8) stages = 8;
     DAT_REQUIRE(stages >= 2, "pointwise_fwd_tc: tile does not fit shared memory");
     const size_t smem = 1024 + 1024 + (size_t)bias_bytes + (size_t)stages * stage_bytes + staging;
     int tmem_cols = 32;
     while (tmem_cols < 2 * BN) tmem_cols <<= 1;
-    const int m_tiles = (int)ceil_div(M, (long long)TC_BM), total = m_tiles * (N / BN);
+    const int m_tiles = (int)ceil_div(M, (long long)TC_BM), total = m_tiles * (Ntot / BN);
     const int grid = total < 148 ? total : 148;
-    CUtensorMap tmY = tmA;
+    CUtensorMap tmY = tmA, tmY2 = tmA;
     if (tma_out) {
       const int eo = (int)dtype_size(y_dt);
       DAT_FWD(tc::make_tmap_2d(&tmY, Y, eo, y_dt == DAT_F32, (uint64_t)M, (uint64_t)N, (uint64_t)N * eo, 32, 128 / eo, 128));
+      tmY2 = tmY;
+      if (two_out)
+        DAT_FWD(tc::make_tmap_2d(&tmY2, Y2, eo, y_dt == DAT_F32, (uint64_t)M, (uint64_t)N, (uint64_t)N * eo, 32, 128 / eo, 128));
     }
     static const int gemm_dbg = [] { const char* e = std::getenv("DAT_B200_GEMM_DBG"); return e ? std::atoi(e) : 0; }();
 #define LAUNCH_P(TF, TO, MN)                                                                      \
   do {                                                                                            \
     auto kern = gemm_tc_persistent_kernel<TF, TO, MN>;                                            \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    launch_k(kern, grid, TCP_THREADS, smem, st, tmA, tmB, tmA2, tmB2, tmY, b, (TO*)Y, (int)M, N, k_chunks,     \
-                                         k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch, bias_bytes, gemm_dbg); \
+    launch_k(kern, grid, TCP_THREADS, smem, st, tmA, tmB, tmA2, tmB2, tmY, b, (TO*)Y, (int)M, Ntot, k_chunks,  \
+             k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch, bias_bytes, gemm_dbg, tmY2, b2, N1); \
   } while (0)
     if (w_mn && y_dt == DAT_F32) LAUNCH_P(false, float, true);
     else if (w_mn) LAUNCH_P(false, bf16, true);

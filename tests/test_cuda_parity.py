@@ -574,3 +574,51 @@ def test_gather_fused_with_the_kv_projections_equals_the_three_launch_path(H, C,
         ref = e_(B * Ns, C)
         _cabi.check(lib.dat_pointwise_fwd_tc(p(xs_ref), 1, p(w), p(b), p(ref), 1, B * Ns, C, C, st), "gemm")
         assert torch.equal(out.reshape(B * Ns, C), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,C,heads,G,stride,ksize,qs", [
+    (32, 64, 2, 1, 2, 5, 14), (32, 128, 4, 2, 2, 5, 14),       # gather fused with the k / v projections
+    (32, 256, 8, 4, 2, 5, 14), (16, 512, 16, 8, 1, 3, 7),      # stand-alone gather + ONE two-output GEMM launch
+    (16, 96, 3, 1, 1, 3, 7),                                   # 96 channels: 32-column tiles, two plain launches
+])
+def test_block_forward_k_and_v_equal_standalone_projections(H, C, heads, G, stride, ksize, qs):
+    """Whatever launch structure dat_block_forward picks for `k = proj_k(x_sampled)`, `v = proj_v(x_sampled)`
+    (dat_blocks.py:177-178), the saved k / v are bit-identical to the stand-alone tcgen05 GEMM on the saved x_sampled."""
+    import ctypes as C_
+    from dat_segmentation_b200 import _cabi
+    lib = _cabi.lib()
+    p = lambda t: C_.c_void_p(t.data_ptr() if t is not None else 0)
+    B = 2
+    st = C_.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Th = 2 * qs - 1
+    bf, f32 = torch.bfloat16, torch.float32
+    d = _cabi.BlockDesc(B, H, H, heads, G, stride, ksize, Th, Th, 2.0, _cabi.DAT_F32, _cabi.DAT_BF16)
+    hk, wk = C_.c_int32(), C_.c_int32()
+    _cabi.check(lib.dat_sample_grid(C_.byref(d), C_.byref(hk), C_.byref(wk)), "grid")
+    Ns, Cg, HW = hk.value * wk.value, C // G, H * H
+    gen = torch.Generator(device="cuda").manual_seed(C + H)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    prm = [rn(Cg, 1, ksize, ksize) / ksize, rn(Cg) * 0.1, torch.ones(Cg, device="cuda"), torch.zeros(Cg, device="cuda"),
+           rn(2, Cg, 1, 1) / Cg ** 0.5] + [t for _ in range(4) for t in (rn(C, C, 1, 1) / C ** 0.5, rn(C) * 0.1)] + \
+          [rn(heads, Th, Th) * 0.1]
+    ps = _cabi.BlockParams()
+    for n_, t_ in zip(_cabi.PARAM_FIELDS, prm):
+        setattr(ps, n_, t_.data_ptr())
+    x = rn(B, HW, C)
+    e_ = lambda *sh, dt=bf: torch.empty(*sh, device="cuda", dtype=dt)
+    saved = [e_(B, HW, C), e_(B, G, Ns, Cg, dt=f32), e_(B, G, Ns, 2, dt=f32), e_(B, G, Ns, 2, dt=f32), e_(B, Ns, C),
+             e_(B, Ns, C), e_(B, Ns, C), e_(B, HW, C), e_(B, heads, HW, dt=f32)]
+    ss = _cabi.BlockSaved()
+    for n_, t_ in zip(_cabi.SAVED_FIELDS, saved):
+        setattr(ss, n_, t_.data_ptr())
+    nf = lib.dat_block_fwd_workspace_bytes(C_.byref(d))
+    ws = torch.empty(max(nf, 64), device="cuda", dtype=torch.uint8)
+    y = e_(B, HW, C)
+    _cabi.check(lib.dat_block_forward(C_.byref(d), C_.byref(ps), p(x), p(y), C_.byref(ss), p(ws), nf, st), "block_forward")
+    xs, k, v = saved[4], saved[5], saved[6]
+    for w, b, out in ((prm[7], prm[8], k), (prm[9], prm[10], v)):
+        ref = e_(B * Ns, C)
+        wb = w.reshape(C, C).to(bf).contiguous()
+        _cabi.check(lib.dat_pointwise_fwd_tc(p(xs), 1, p(wb), p(b), p(ref), 1, B * Ns, C, C, st), "gemm")
+        assert torch.equal(out.reshape(B * Ns, C), ref)
