@@ -89,6 +89,8 @@ def lib():
                                      C.POINTER(BlockGrads), vp, C.c_size_t, vp]
     L.dat_pointwise_fwd.argtypes = [vp, i32, f32p, f32p, vp, i32, i64, i32, i32, vp]
     L.dat_pointwise_fwd_tc.argtypes = [vp, i32, vp, f32p, vp, i32, i64, i32, i32, vp]
+    L.dat_pointwise_fwd_tc_residual.argtypes = [vp, i32, vp, f32p, f32p, f32p, i64, f32p, i64, i32, i32, vp]
+    L.dat_pointwise_fwd_tc_residual.restype = C.c_int
     L.dat_cast_bf16.argtypes = [f32p, vp, i64, vp]
     L.dat_cast_transpose_bf16.argtypes = [f32p, vp, i32, i32, vp]
     L.dat_cast_bf16_multi.argtypes = [vp, i32, vp]
@@ -171,7 +173,7 @@ def exported_symbols():
     """Names declared in include/dat_b200.h (used by the CPU-side symbol test)."""
     return ["dat_sample_grid", "dat_block_fwd_workspace_bytes", "dat_block_bwd_workspace_bytes",
             "dat_last_error", "dat_version", "dat_launch_count", "dat_block_forward", "dat_block_backward",
-            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_cast_bf16", "dat_debug_gemm_timing", "dat_debug_attn_bwd_timing",
+            "dat_pointwise_fwd", "dat_pointwise_fwd_tc", "dat_pointwise_fwd_tc_residual", "dat_cast_bf16", "dat_debug_gemm_timing", "dat_debug_attn_bwd_timing",
             "dat_cast_transpose_bf16", "dat_pointwise_wgrad_tc_workspace_bytes", "dat_pointwise_wgrad_tc",
             "dat_cast_bf16_multi", "dat_pointwise_dgrad_tc",
             "dat_bias_grad",

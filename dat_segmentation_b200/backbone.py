@@ -107,6 +107,17 @@ class TransformerMLPWithConv(nn.Module):
         x = self.dwc(x) if self.b200_ops else self.act(x + self.dwc(x))
         return self.drop2(self.linear2(x))
 
+    def forward_residual(self, x, resid, scale):
+        """resid + scale[b] * mlp(x): with the dat_b200 ops the residual add with stochastic depth rides in the epilogue
+        of the last 1x1 conv (one kernel less and no bf16 round trip of the branch); else the separate add."""
+        h = self.drop1(self.linear1(x))
+        h = self.dwc(h) if self.b200_ops else self.act(h + self.dwc(h))
+        fc2 = self.linear2[0]
+        if (self.b200_ops and not (self.training and self.drop2.p > 0) and hasattr(fc2, "residual_fusable")
+                and fc2.residual_fusable(h, resid)):
+            return fc2.forward_residual(h, resid, scale)
+        return scale_residual(self.drop2(self.linear2(h)), resid, scale)
+
 
 class TransformerStage(nn.Module):
     """One resolution stage (dat.py:34-165).  Spec letters: 'D' deformable attention,
@@ -195,8 +206,11 @@ class TransformerStage(nn.Module):
                 # `x = drop_path(attn) + x` and the norm that follows it in one kernel (forward and backward)
                 x, ln = self.layer_norms[2 * d + 1].forward_residual_fork(self.layer_scales[2 * d](a), x, scales[si],
                                                                           out_dtype=mlp_in)
-                m = self.mlps[d](ln)
-                x = scale_residual(self.layer_scales[2 * d + 1](m), x, scales[si + 1])
+                if isinstance(self.layer_scales[2 * d + 1], nn.Identity) and hasattr(self.mlps[d], "forward_residual"):
+                    x = self.mlps[d].forward_residual(ln, x, scales[si + 1])
+                else:
+                    m = self.mlps[d](ln)
+                    x = scale_residual(self.layer_scales[2 * d + 1](m), x, scales[si + 1])
                 si += 2
         return x
 

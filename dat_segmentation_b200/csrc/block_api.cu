@@ -287,6 +287,18 @@ size_t dat_block_fwd_workspace_bytes(const dat_block_desc* d) {
   return fwd_fixed_bytes(s) + plan_fwd_var(s, nullptr).total;
 }
 
+int dat_pointwise_fwd_tc_residual(const void* X, int32_t x_dtype, const void* W, const float* b, const float* resid,
+                                  const float* scale, int64_t rows_per_sample, float* Y, int64_t M, int32_t N, int32_t K,
+                                  void* stream) {
+  DAT_REQUIRE(X && W && resid && scale && Y && rows_per_sample > 0, "pointwise_fwd_tc_residual: NULL pointer / bad size");
+  if (!pointwise_fwd_tc_supported(x_dtype, M, N, K) || !pointwise_fwd_tc_two_outputs_supported(N)) {
+    set_error("pointwise_fwd_tc_residual: shape M=%lld N=%d K=%d not tileable in 64-column groups", (long long)M, N, K);
+    return DAT_ERR_UNSUPPORTED;
+  }
+  return pointwise_fwd_tc_dual(X, W, nullptr, nullptr, x_dtype, b, Y, DAT_F32, M, N, K, (cudaStream_t)stream, false, nullptr,
+                               nullptr, resid, scale, rows_per_sample);
+}
+
 int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b, void* Y,
                          int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream) {
   DAT_REQUIRE(X && W && Y, "pointwise_fwd_tc: NULL pointer");

@@ -271,7 +271,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias,
                           TOut* __restrict__ Y, int M, int N, int k_chunks, int k_chunks1, int BN, int stages,
                           int tmem_cols, int m_tiles, int total_tiles, int stage_pitch, int bias_bytes, int dbg,
-                          const __grid_constant__ CUtensorMap tmY2, const float* __restrict__ bias2, int N1) {
+                          const __grid_constant__ CUtensorMap tmY2, const float* __restrict__ bias2, int N1,
+                          const float* __restrict__ resid, const float* __restrict__ rscale, int rows_per_sample) {
+  // resid != NULL (fp32 output): the residual add with stochastic depth that follows the product rides along in the
+  // epilogue - Y = resid + rscale[row / rows_per_sample] * bf16(X W^T + bias), i.e. `x = drop_path(mlp(x)) + x`
+  // (dat.py:151-156) with the branch rounded to bf16 as the autocast convolution returns it.
   // N1 < N: TWO products of the same A in one launch (the k and v projections of the sampled features): output
   // columns [0, N1) are X W^T + bias into tmY, columns [N1, N) are X W2^T + bias2 into tmY2 (W2 behind tmB2, which is
   // otherwise the second K-concatenated source; the two uses exclude each other).  N1 is a multiple of BN.
@@ -409,6 +413,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         tc_fence_after_sync();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
         const int cg_first = chalf * 64;
+        // fused residual: this lane's row of the residual stream (NULL beyond M) and its sample's scale
+        const int my_row = m0 + quad * 32 + lane;
+        const float* rrow = (resid != nullptr && my_row < M) ? resid + (long long)my_row * N + n0 : nullptr;
+        const float rsc = (resid != nullptr && my_row < M) ? rscale[my_row / rows_per_sample] : 0.f;
         if (cg_first >= BN || (dbg & 8)) {   // a single column group: this warp only hands the buffer back
           tc_fence_before_sync();
           __syncwarp();
@@ -434,10 +442,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             for (int j = 0; j < 32; j += 8) {
               const float4 b0 = *reinterpret_cast<const float4*>(bp + c * 32 + j);
               const float4 b1 = *reinterpret_cast<const float4*>(bp + c * 32 + j + 4);
-              const float v0 = __uint_as_float(r[c][j]) + b0.x, v1 = __uint_as_float(r[c][j + 1]) + b0.y;
-              const float v2 = __uint_as_float(r[c][j + 2]) + b0.z, v3 = __uint_as_float(r[c][j + 3]) + b0.w;
-              const float v4 = __uint_as_float(r[c][j + 4]) + b1.x, v5 = __uint_as_float(r[c][j + 5]) + b1.y;
-              const float v6 = __uint_as_float(r[c][j + 6]) + b1.z, v7 = __uint_as_float(r[c][j + 7]) + b1.w;
+              float v0 = __uint_as_float(r[c][j]) + b0.x, v1 = __uint_as_float(r[c][j + 1]) + b0.y;
+              float v2 = __uint_as_float(r[c][j + 2]) + b0.z, v3 = __uint_as_float(r[c][j + 3]) + b0.w;
+              float v4 = __uint_as_float(r[c][j + 4]) + b1.x, v5 = __uint_as_float(r[c][j + 5]) + b1.y;
+              float v6 = __uint_as_float(r[c][j + 6]) + b1.z, v7 = __uint_as_float(r[c][j + 7]) + b1.w;
+              if (sizeof(TOut) == 4 && resid != nullptr) {
+                const float4 x0 = rrow != nullptr ? *reinterpret_cast<const float4*>(rrow + cg + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x1 = rrow != nullptr ? *reinterpret_cast<const float4*>(rrow + cg + c * 32 + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                auto rb = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };
+                v0 = fmaf(rb(v0), rsc, x0.x); v1 = fmaf(rb(v1), rsc, x0.y); v2 = fmaf(rb(v2), rsc, x0.z); v3 = fmaf(rb(v3), rsc, x0.w);
+                v4 = fmaf(rb(v4), rsc, x1.x); v5 = fmaf(rb(v5), rsc, x1.y); v6 = fmaf(rb(v6), rsc, x1.z); v7 = fmaf(rb(v7), rsc, x1.w);
+              }
               if (sizeof(TOut) == 2) {     // 8 columns = one 16-byte chunk of the 64-column box
                 const uint32_t chunk = (uint32_t)(c * 4 + (j >> 3));
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((chunk ^ sxor) << 4)),
@@ -852,10 +867,14 @@ int pointwise_dgrad_tc(const void* dY, const void* W, const void* dY2, const voi
 // that is a multiple of 64, no second K source and K-major weights.
 int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
-                          cudaStream_t st, bool w_mn, const float* b2, void* Y2) {
+                          cudaStream_t st, bool w_mn, const float* b2, void* Y2, const float* resid, const float* rscale,
+                          long long rows_per_sample) {
   DAT_REQUIRE(pointwise_fwd_tc_supported(x_dt, M, N, K), "pointwise_fwd_tc: unsupported shape M=%lld N=%d K=%d", M, N, K);
   const bool tf32 = x_dt == DAT_F32;
   const bool two_out = Y2 != nullptr;
+  DAT_REQUIRE(resid == nullptr || (y_dt == DAT_F32 && !two_out && rscale != nullptr && rows_per_sample > 0 &&
+                                   pick_bn(N) % 64 == 0 && !w_mn && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
+              "pointwise_fwd_tc: the fused residual needs an fp32 output and a tile width that is a multiple of 64");
   DAT_REQUIRE(!two_out || (X2 == nullptr && W2 != nullptr && !w_mn && pick_bn(N) % 64 == 0 &&
                            std::getenv("DAT_B200_GEMM_LEGACY") == nullptr),
               "pointwise_fwd_tc: two outputs need K-major weights, one K source and a tile width that is a multiple of 64");
@@ -887,7 +906,7 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
   // fc1: profiles/r02_gemm_pair.md) - the kernel is bound by ring depth x fill latency and by its epilogue, not by
   // L2 -> shared-memory bandwidth.
   static const int pair_off = [] { const char* e = std::getenv("DAT_B200_GEMM_PAIR"); return e && e[0] == '1' ? 0 : 1; }();
-  if (!pair_off && !two_out && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr && (BN == 256 || BN == 128) && M >= 2 * TC_BM) {
+  if (!pair_off && !two_out && resid == nullptr && std::getenv("DAT_B200_GEMM_LEGACY") == nullptr && (BN == 256 || BN == 128) && M >= 2 * TC_BM) {
     const int gcols = persistent_gcols(BN);
     const int stage_pitch = gcols * (int)dtype_size(y_dt) + 16;
     const int staging = TCP_EPI_WARPS * 32 * stage_pitch;
@@ -957,7 +976,8 @@ int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const vo
     auto kern = gemm_tc_persistent_kernel<TF, TO, MN>;                                            \
     DAT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     launch_k(kern, grid, TCP_THREADS, smem, st, tmA, tmB, tmA2, tmB2, tmY, b, (TO*)Y, (int)M, Ntot, k_chunks,  \
-             k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch, bias_bytes, gemm_dbg, tmY2, b2, N1); \
+             k_chunks1, BN, stages, tmem_cols, m_tiles, total, stage_pitch, bias_bytes, gemm_dbg, tmY2, b2, N1,    \
+             resid, rscale, (int)rows_per_sample);                                                               \
   } while (0)
     if (w_mn && y_dt == DAT_F32) LAUNCH_P(false, float, true);
     else if (w_mn) LAUNCH_P(false, bf16, true);

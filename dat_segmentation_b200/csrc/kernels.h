@@ -95,7 +95,8 @@ int cast_transpose_weights_bf16(const float* w0, const float* w1, const float* w
                                 void* out, int C, cudaStream_t st);
 int pointwise_fwd_tc_dual(const void* X, const void* W, const void* X2, const void* W2, int x_dt,
                           const float* b, void* Y, int y_dt, long long M, int N, int K,
-                          cudaStream_t st, bool w_mn = false, const float* b2 = nullptr, void* Y2 = nullptr);
+                          cudaStream_t st, bool w_mn = false, const float* b2 = nullptr, void* Y2 = nullptr,
+                          const float* resid = nullptr, const float* rscale = nullptr, long long rows_per_sample = 0);
 bool pointwise_fwd_tc_two_outputs_supported(int N);   // Y2 != NULL: tile width a multiple of 64
 // dX[M, K] = dY[M, N] W[N, K] (+ dY2 W2): the bf16 weight is read in place as an MN-major operand (no transpose)
 bool pointwise_dgrad_tc_supported(long long M, int N, int K);

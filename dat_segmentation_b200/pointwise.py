@@ -72,7 +72,7 @@ class _PointwiseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         lib = _cabi.lib()
-        x_l, w32 = ctx.saved_tensors
+        x_l, w32 = ctx.saved_tensors[:2]
         M, K = x_l.shape
         N = w32.shape[0]
         dev = x_l.device
@@ -127,6 +127,49 @@ class _PointwiseFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _PointwiseResidualFn(torch.autograd.Function):
+    """(x_l (M, K) bf16, resid_l (M, N) fp32, scale (B,)) -> resid + scale[b] * bf16(x_l W^T + b): the last 1x1 conv of the
+    MLP and the residual add with stochastic depth that follows it (`x = drop_path(mlp(x)) + x`, dat.py:151-156) in ONE
+    kernel (the GEMM's epilogue reads the residual stream and writes the new one).  Backward: d resid = dy; the branch
+    gradient dy * scale[b] (bf16, the scale_residual kernel) feeds the usual data / weight gradients."""
+
+    @staticmethod
+    def forward(ctx, x_l, weight, bias, w_bf, resid_l, scale):
+        lib = _cabi.lib()
+        M, K = x_l.shape
+        N = weight.shape[0]
+        dev = x_l.device
+        w32 = weight.detach().float().reshape(N, K).contiguous()
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        with torch.cuda.device(dev):
+            y = torch.empty(M, N, device=dev, dtype=torch.float32)
+            if w_bf is None:
+                w_bf = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+                _cabi.check(lib.dat_cast_bf16(_ptr(w32), _ptr(w_bf), N * K, _stream(dev)), "dat_cast_bf16")
+            _cabi.check(lib.dat_pointwise_fwd_tc_residual(_ptr(x_l), _cabi.DAT_BF16, _ptr(w_bf), _ptr(b32), _ptr(resid_l),
+                                                          _ptr(scale), M // scale.numel(), _ptr(y), M, N, K, _stream(dev)),
+                        "dat_pointwise_fwd_tc_residual")
+        ctx.save_for_backward(x_l, w32, scale)
+        ctx.w_bf = w_bf
+        ctx.has_bias, ctx.wdtype, ctx.wshape = bias is not None, weight.dtype, weight.shape
+        ctx.param_refs = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.lib()
+        scale = ctx.saved_tensors[2]
+        dy = dy.float().contiguous()
+        M, N = dy.shape
+        dev = dy.device
+        with torch.cuda.device(dev):
+            dm = torch.empty(M, N, device=dev, dtype=torch.bfloat16)     # branch gradient dy * scale[b]
+            _cabi.check(lib.dat_scale_residual(_ptr(dy), _cabi.DAT_F32, None, 0, _ptr(scale), _ptr(dm), _cabi.DAT_BF16,
+                                               scale.numel(), (M // scale.numel()) * N, _stream(dev)), "dat_scale_residual")
+        dx, dw, db, _ = _PointwiseFn.backward(ctx, dm)
+        return dx, dw, db, None, dy, None
+
+
 class PointwiseConvCL(nn.Conv2d):
     """nn.Conv2d(cin, cout, 1) parameters; tcgen05 GEMMs under bf16 autocast on CUDA."""
 
@@ -145,4 +188,22 @@ class PointwiseConvCL(nn.Conv2d):
         if not x_l.is_contiguous():
             x_l = x_l.contiguous()
         y = _PointwiseFn.apply(x_l.reshape(B * H * W, K), self.weight, self.bias, cached_bf16(self))
+        return y.reshape(B, H, W, N).permute(0, 3, 1, 2)
+
+    def residual_fusable(self, x, resid):
+        """True when `forward_residual` runs as one kernel: bf16 input, fp32 channel-last residual stream of the output
+        shape, 64-column tiles."""
+        B, K, H, W = x.shape
+        N = self.out_channels
+        return (x.is_cuda and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+                and x.dtype == torch.bfloat16 and resid.dtype == torch.float32 and resid.shape == (B, N, H, W)
+                and x.permute(0, 2, 3, 1).is_contiguous() and resid.permute(0, 2, 3, 1).is_contiguous()
+                and N % 64 == 0 and _supported(B * H * W, N, K) and not _os.environ.get("DAT_B200_NO_GEMM_RESIDUAL"))
+
+    def forward_residual(self, x, resid, scale):
+        """resid + scale[b] * conv1x1(x) (the caller checked `residual_fusable`)."""
+        B, K, H, W = x.shape
+        N = self.out_channels
+        y = _PointwiseResidualFn.apply(x.permute(0, 2, 3, 1).reshape(B * H * W, K), self.weight, self.bias,
+                                       cached_bf16(self), resid.permute(0, 2, 3, 1).reshape(B * H * W, N), scale)
         return y.reshape(B, H, W, N).permute(0, 3, 1, 2)

@@ -162,6 +162,12 @@ int dat_pointwise_fwd(const void* X, int32_t x_dtype, const float* W, const floa
  * (the block driver then uses the CUDA-core path). */
 int dat_pointwise_fwd_tc(const void* X, int32_t x_dtype, const void* W, const float* b,
                          void* Y, int32_t y_dtype, int64_t M, int32_t N, int32_t K, void* stream);
+/* The same product with the residual add that follows it in the MLP branch (`x = drop_path(mlp(x)) + x`, dat.py:151-156)
+ * in the epilogue: Y (fp32) = resid + scale[row / rows_per_sample] * bf16(X W^T + b).  resid, Y: (M, N) fp32; scale: one
+ * float per sample (mask / keep_prob).  N must tile in 64-column groups (DAT_ERR_UNSUPPORTED otherwise). */
+int dat_pointwise_fwd_tc_residual(const void* X, int32_t x_dtype, const void* W, const float* b, const float* resid,
+                                  const float* scale, int64_t rows_per_sample, float* Y, int64_t M, int32_t N, int32_t K,
+                                  void* stream);
 /* Debug aid: globaltimer (ns) phase stamps of CTA (0,0) of the last dat_pointwise_fwd_tc
  * launch: entry, setup done, first TMA stage landed, MMAs issued, accumulator ready,
  * epilogue done (6 of 8 slots used).  Synchronises the device. */

@@ -64,3 +64,36 @@ def test_pointwise_fallbacks_match_library():
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y = m(x)
         assert torch.equal(y, F.conv2d(x, m.weight, m.bias))
+
+
+@pytest.mark.parametrize("C,B,H,W", [(64, 3, 16, 16), (256, 2, 32, 32), (512, 2, 8, 12)])
+def test_mlp_residual_in_the_gemm_epilogue_matches_the_two_kernel_path(C, B, H, W, monkeypatch):
+    """`x = drop_path(mlp(ln)) + x` (dat.py:151-156) with the add fused into the last 1x1 conv's epilogue
+    (TransformerMLPWithConv.forward_residual) == MLP + scale_residual: new stream, and the gradients of the MLP input,
+    the stream and every MLP parameter."""
+    from dat_segmentation_b200.backbone import TransformerMLPWithConv
+    from dat_segmentation_b200.residual import scale_residual
+    torch.manual_seed(C)
+    mlp = TransformerMLPWithConv(C, 4, 0.0, b200_ops=True).cuda().train()
+    scale = torch.tensor(([0.0, 1.0 / 0.7, 1.0 / 0.7])[:B], device="cuda")
+    ln0 = torch.randn(B, H, W, C, device="cuda").bfloat16().permute(0, 3, 1, 2)
+    x0 = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2)
+    g = torch.randn(B, H, W, C, device="cuda").permute(0, 3, 1, 2)
+    res = []
+    for fused in (True, False):
+        ln, x = ln0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        mlp.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if fused:
+                fc2 = mlp.linear2[0]
+                y = mlp.forward_residual(ln, x, scale)
+            else:
+                y = scale_residual(mlp(ln), x, scale)
+        assert y.dtype == torch.float32
+        (y * g).sum().backward()
+        torch.cuda.synchronize()
+        res.append([y.detach().clone(), ln.grad.float().clone(), x.grad.clone()] +
+                   [p.grad.float().clone() for p in mlp.parameters()])
+    names = ["stream", "d mlp input", "d stream"] + [n for n, _ in mlp.named_parameters()]
+    for f, u, name in zip(res[0], res[1], names):
+        torch.testing.assert_close(f, u, rtol=1e-5, atol=1e-5, msg=lambda m, name=name: f"{name}: {m}")
