@@ -249,7 +249,7 @@ __device__ __forceinline__ void store8(bf16* p, float4 a, float4 b) {
 
 // Persistent version: one CTA per SM walks the output tiles (m fastest, so neighbouring CTAs share
 // the weight tile in L2).  The TMA producer never drains its ring between tiles, the fp32
-// accumulator is double-buffered in TMEM (2 x BN columns), and the four epilogue warps store tile
+// accumulator is double-buffered in TMEM (2 x BN columns), and the eight epilogue warps store tile
 // i while the MMA warp accumulates tile i + 1: loads, MMAs and stores of a CTA overlap instead of
 // alternating (the one-tile kernel idles its loads ~60 % of a CTA's lifetime, profiles/r01_ncu_kernels.md).
 //   barriers: full/empty per ring stage, acc_full/acc_empty per TMEM buffer.
@@ -257,9 +257,13 @@ __device__ __forceinline__ void store8(bf16* p, float4 a, float4 b) {
 // groups shared by a quadrant's two warps), else the whole tile (32 / 96 columns, one warp)
 __host__ __device__ inline int persistent_gcols(int BN) { return BN % 64 == 0 ? 64 : BN; }
 
-// Epilogue: 8 warps, two per TMEM lane quadrant, taking alternate column groups of a tile.  With four warps the
-// epilogue (TMEM -> +bias -> bf16 -> staged, coalesced stores) bounded every wide-N / small-K shape: switching it off
-// took the stage-1 fc1 GEMM from 33 to 12.5 us and the stage-2 one from 22.9 to 12.6 us.
+// Epilogue: 8 warps, two per TMEM lane quadrant, taking alternate column groups of a tile.  Tiles that are a multiple
+// of 64 columns wide leave through TMA stores (TMEM -> + bias [-> fused residual] -> bf16 / fp32 -> 128B-swizzled
+// staging -> one cp.async.bulk.tensor store per warp and group); the round-1 epilogue (padded staging, ld.shared +
+// st.global write-out) remains for 32 / 96-column tiles.  The write-out bounded every wide-N / small-K shape: with the
+// epilogue switched off the stage-2 fc1 GEMM takes 12.7 us, with the old one 21.0, with TMA stores 15.2
+// (profiles/r02_gemm_decompose.md).  One launch can also form two products of the same A (N1 < N: the k and v
+// projections).
 // BMN: the B operand is MN-major - a (K, N) row-major matrix, i.e. the weight W (N_fwd, K_fwd) itself when the
 // product is the data gradient dX = dY W: 64 x 64 TMA boxes (128B swizzle) are the canonical MN-major core-matrix
 // layout (8-row groups 1 KB apart, 64-column blocks 8 KB apart, gemm_tc_wgrad.cu), so no transposed copy of the
